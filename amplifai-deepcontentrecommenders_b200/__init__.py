@@ -1,0 +1,6 @@
+"""amplifai-deepcontentrecommenders_b200: B200-native (sm_100a) DCUE training + scoring hot path
+behind the reference's DCUENet / DCUE API."""
+from . import _lib, eval, ops  # noqa: F401
+from .dcue.dcue import DCUENet  # noqa: F401
+
+__all__ = ["DCUENet"]

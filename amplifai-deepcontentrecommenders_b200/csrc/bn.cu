@@ -1,0 +1,506 @@
+// HBM-bound glue of the song tower: BatchNorm statistics / finalize / apply, the fused
+// transpose+convert of the NCL fp32 input into 16-bit panels (this also replaces the
+// reference's torch.cat([pos,neg]) copy, dcrecommend/dcue/dcue.py:90), and the backward pass
+// BatchNorm-backward + ReLU mask + MaxPool unpooling in one sweep.
+// Reference semantics: truedcuemel1dbn.py:77-101 (order conv -> pool -> relu -> bn).
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ NCL input statistics
+// block = 8 warps; warp w owns channels w, w+8, ... (<=16 per warp for C=128); lanes stride
+// the L frames of one (s,c) row; per-lane fp32 partials, reduced across lanes/blocks in fp64.
+constexpr int STAT_MAXC_PER_WARP = 16;
+
+__global__ void __launch_bounds__(256)
+ncl_stats_kernel(const float* __restrict__ pos, int S_pos, const float* __restrict__ neg, int S_neg, int C, int L,
+                 double* __restrict__ partial /* [grid][2][C] */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float s1[STAT_MAXC_PER_WARP], s2[STAT_MAXC_PER_WARP];
+#pragma unroll
+    for (int i = 0; i < STAT_MAXC_PER_WARP; ++i) s1[i] = s2[i] = 0.f;
+    const int S = S_pos + S_neg;
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        const float* base = s < S_pos ? pos + (long)s * C * L : neg + (long)(s - S_pos) * C * L;
+#pragma unroll
+        for (int i = 0; i < STAT_MAXC_PER_WARP; ++i) {
+            const int c = w + 8 * i;
+            if (c < C) {
+                const float* row = base + (long)c * L;
+                float a = 0.f, b = 0.f;
+                for (int t = lane; t < L; t += 32) {
+                    const float v = __ldg(row + t);
+                    a += v;
+                    b = fmaf(v, v, b);
+                }
+                s1[i] += a;
+                s2[i] += b;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < STAT_MAXC_PER_WARP; ++i) {
+        const int c = w + 8 * i;
+        const double a = warp_sum_d((double)s1[i]), b = warp_sum_d((double)s2[i]);
+        if (lane == 0 && c < C) {
+            partial[((long)blockIdx.x * 2 + 0) * C + c] = a;
+            partial[((long)blockIdx.x * 2 + 1) * C + c] = b;
+        }
+    }
+}
+
+// out[j] = sum_b partial[b][j], fixed order
+__global__ void reduce_partials_kernel(const double* __restrict__ partial, int nblk, int n, double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += partial[(long)b * n + j];
+    out[j] = s;
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
+                                   int64_t* __restrict__ nbt, float momentum, float eps, int training,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_o,
+                                   float* __restrict__ rstd_o) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && training && nbt) *nbt += 1;
+    if (c >= C) return;
+    double mean, var;
+    if (training) {
+        mean = sums[c] / count;
+        var = sums[C + c] / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        if (rmean) {
+            const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+            rmean[c] = (float)((1.0 - momentum) * (double)rmean[c] + momentum * mean);
+            rvar[c] = (float)((1.0 - momentum) * (double)rvar[c] + momentum * unb);
+        }
+    } else {
+        mean = rmean[c];
+        var = rvar[c];
+    }
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    const double g = gamma ? (double)gamma[c] : 1.0, b = beta ? (double)beta[c] : 0.0;
+    scale[c] = (float)(g * rstd);
+    shift[c] = (float)(b - mean * g * rstd);
+    mean_o[c] = (float)mean;
+    rstd_o[c] = (float)rstd;
+}
+
+// ------------------------------------------------------------------ NCL -> panel pack
+// thread <-> (spectrogram s, panel q, frame t): 8 coalesced loads (one per channel of the
+// panel), one 16-byte store; consecutive threads walk t so both sides are coalesced.
+__global__ void __launch_bounds__(256)
+ncl_pack_kernel(const float* __restrict__ pos, int S_pos, const float* __restrict__ neg, int S_neg, int C, int L,
+                const float* __restrict__ scale, const float* __restrict__ shift, uint4* __restrict__ panel,
+                long panel_rows, int Lp, int pad, int fmt) {
+    const long total = (long)(S_pos + S_neg) * (C / 8) * L;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % L);
+        const long sq = i / L;
+        const int q = (int)(sq % (C / 8));
+        const long s = sq / (C / 8);
+        const float* base = (s < S_pos ? pos + s * (long)C * L : neg + (s - S_pos) * (long)C * L) + (long)(q * 8) * L + t;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(base + (long)j * L);
+        unsigned short h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = q * 8 + j;
+            const float y = scale ? fmaf(v[j], scale[c], shift[c]) : v[j];
+            h[j] = cvt_f32_to16(y, fmt);
+        }
+        uint4 o;
+        o.x = h[0] | ((unsigned)h[1] << 16);
+        o.y = h[2] | ((unsigned)h[3] << 16);
+        o.z = h[4] | ((unsigned)h[5] << 16);
+        o.w = h[6] | ((unsigned)h[7] << 16);
+        panel[(long)q * panel_rows + s * Lp + pad + t] = o;
+    }
+}
+
+// ------------------------------------------------------------------ [rows, C] tile kernels
+constexpr int TR = 32;          // rows per tile
+constexpr int TLD = 129;        // padded smem row stride (C <= 128)
+
+// y = scale*z + shift -> panel rows (s*Lp + pad + p) and/or fp32 y
+__global__ void __launch_bounds__(256)
+affine_pack_kernel(const float* __restrict__ z, long rows, int P, int C, const float* __restrict__ scale,
+                   const float* __restrict__ shift, uint4* __restrict__ panel, long panel_rows, int Lp, int pad,
+                   int fmt, float* __restrict__ y) {
+    __shared__ float tile[TR][TLD];
+    const int tid = threadIdx.x;
+    for (long r0 = (long)blockIdx.x * TR; r0 < rows; r0 += (long)gridDim.x * TR) {
+        for (int e = tid; e < TR * C; e += 256) {
+            const int rl = e / C, c = e - rl * C;
+            const long r = r0 + rl;
+            float v = 0.f;
+            if (r < rows) {
+                v = __ldg(z + r * C + c);
+                if (scale) v = fmaf(v, scale[c], shift[c]);
+                if (y) y[r * C + c] = v;
+            }
+            tile[rl][c] = v;
+        }
+        __syncthreads();
+        if (panel) {
+            // thread <-> (row lane, panel q): lanes walk rows so each warp store is contiguous
+            const int rl = tid & 31;
+            const long r = r0 + rl;
+            if (r < rows) {
+                const long s = r / P;
+                const int p = (int)(r - s * P);
+                for (int q = tid >> 5; q < C / 8; q += 8) {
+                    unsigned short h[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) h[j] = cvt_f32_to16(tile[rl][q * 8 + j], fmt);
+                    uint4 o;
+                    o.x = h[0] | ((unsigned)h[1] << 16);
+                    o.y = h[2] | ((unsigned)h[3] << 16);
+                    o.z = h[4] | ((unsigned)h[5] << 16);
+                    o.w = h[6] | ((unsigned)h[7] << 16);
+                    panel[(long)q * panel_rows + s * Lp + pad + p] = o;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// tp[s, c] = mean_p (scale*z[s,p,c] + shift)
+__global__ void time_mean_kernel(const float* __restrict__ z, int S, int P, int C, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, float* __restrict__ tp, int ldtp) {
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= (long)S * C) return;
+    const int c = (int)(i % C);
+    const long s = i / C;
+    float a = 0.f;
+    for (int p = 0; p < P; ++p) a += z[(s * P + p) * C + c];
+    a /= (float)P;
+    tp[s * ldtp + c] = scale ? fmaf(a, scale[c], shift[c]) : a;
+}
+
+// BN backward reductions: per block partial of sum dy, sum dy*xhat  (C <= 128, C % 4 == 0)
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ dtp, int lddtp, const float* __restrict__ z,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, long rows, int P, int C,
+                     double* __restrict__ partial /* [grid][2][C] */) {
+    __shared__ float red[2][8][128];
+    const int cl = (threadIdx.x & 31) * 4, rg = threadIdx.x >> 5;
+    float a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+    if (cl < C) {
+        float m[4], rs[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { m[j] = mean[cl + j]; rs[j] = rstd[cl + j]; }
+        const float invP = 1.f / (float)P;
+        for (long r = (long)blockIdx.x * 8 + rg; r < rows; r += (long)gridDim.x * 8) {
+            const float4 g = *reinterpret_cast<const float4*>(dy + r * lddy + cl);
+            const float4 zz = *reinterpret_cast<const float4*>(z + r * C + cl);
+            float gv[4] = {g.x, g.y, g.z, g.w};
+            const float zv[4] = {zz.x, zz.y, zz.z, zz.w};
+            if (dtp) {
+                const long s = r / P;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gv[j] += dtp[s * lddtp + cl + j] * invP;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a1[j] += gv[j];
+                a2[j] = fmaf(gv[j], (zv[j] - m[j]) * rs[j], a2[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (cl + j < 128) { red[0][rg][cl + j] = a1[j]; red[1][rg][cl + j] = a2[j]; }
+    }
+    __syncthreads();
+    const int c = threadIdx.x & 127, which = threadIdx.x >> 7;
+    if (c < C) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += (double)red[which][k][c];
+        partial[((long)blockIdx.x * 2 + which) * C + c] = s;
+    }
+}
+
+// dz = relu'(z) * scale * (dy - s1/n - xhat*s2/n); unpool into the dY panel or dense output
+__global__ void __launch_bounds__(256)
+bn_relu_unpool_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ dtp, int lddtp,
+                          const float* __restrict__ z, const uint8_t* __restrict__ code, const float* __restrict__ scale,
+                          const float* __restrict__ mean, const float* __restrict__ rstd, const double* __restrict__ sums,
+                          double count, long rows, int P, int C, int pool, int Lp, uint4* __restrict__ panel,
+                          long panel_rows, int fmt, float* __restrict__ dz_out, double* __restrict__ bias_partial) {
+    __shared__ float tile[TR][TLD];
+    __shared__ uint8_t ctile[TR][TLD + 3];
+    const int tid = threadIdx.x;
+    double bias_acc = 0.0;  // thread tid<C accumulates channel tid
+    const float invn = (float)(1.0 / count);
+    const float invP = 1.f / (float)P;
+    for (long r0 = (long)blockIdx.x * TR; r0 < rows; r0 += (long)gridDim.x * TR) {
+        for (int e = tid; e < TR * C; e += 256) {
+            const int rl = e / C, c = e - rl * C;
+            const long r = r0 + rl;
+            float v = 0.f;
+            uint8_t cd = 0;
+            if (r < rows) {
+                float g = __ldg(dy + r * lddy + c);
+                if (dtp) g += dtp[(r / P) * lddtp + c] * invP;
+                const float zz = __ldg(z + r * C + c);
+                if (sums) {
+                    const float xh = (zz - mean[c]) * rstd[c];
+                    g = g - (float)sums[c] * invn - xh * ((float)sums[C + c] * invn);
+                }
+                if (scale) g *= scale[c];
+                v = zz > 0.f ? g : 0.f;
+                if (code) cd = code[r * C + c];
+                if (dz_out) dz_out[r * C + c] = v;
+            }
+            tile[rl][c] = v;
+            ctile[rl][c] = cd;
+        }
+        __syncthreads();
+        if (panel) {
+            const int rl = tid & 31;
+            const long r = r0 + rl;
+            if (r < rows) {
+                const long s = r / P;
+                const int p = (int)(r - s * P);
+                const long prow = s * Lp + (long)p * pool;
+                for (int q = tid >> 5; q < C / 8; q += 8) {
+                    unsigned short h[8];
+                    uint8_t cd[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        h[j] = cvt_f32_to16(tile[rl][q * 8 + j], fmt);
+                        cd[j] = ctile[rl][q * 8 + j];
+                    }
+                    for (int i = 0; i < pool; ++i) {
+                        unsigned short w[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) w[j] = cd[j] == i ? h[j] : (unsigned short)0;
+                        uint4 o;
+                        o.x = w[0] | ((unsigned)w[1] << 16);
+                        o.y = w[2] | ((unsigned)w[3] << 16);
+                        o.z = w[4] | ((unsigned)w[5] << 16);
+                        o.w = w[6] | ((unsigned)w[7] << 16);
+                        panel[(long)q * panel_rows + prow + i] = o;
+                    }
+                }
+            }
+        }
+        if (bias_partial && tid < C) {
+            float s = 0.f;
+#pragma unroll 8
+            for (int k = 0; k < TR; ++k) s += tile[k][tid];
+            bias_acc += (double)s;
+        }
+        __syncthreads();
+    }
+    if (bias_partial && tid < C) bias_partial[(long)blockIdx.x * C + tid] = bias_acc;
+}
+
+__global__ void cvt_f64_f32_kernel(const double* __restrict__ in, int n, double mul, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)(in[i] * mul);
+}
+
+// bn0 backward reductions: dx is channels-last [S*L, C] (L1 dgrad), x is the NCL fp32 input.
+// block (g, q) owns the 8 channels of panel q for spectrograms g, g+G, ...
+__global__ void __launch_bounds__(128)
+ncl_bn_bwd_reduce_kernel(const float* __restrict__ dx, const float* __restrict__ pos, int S_pos,
+                         const float* __restrict__ neg, int S_neg, int C, int L, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, double* __restrict__ partial /* [G][2][C] */) {
+    __shared__ float red[4][16];
+    const int q = blockIdx.x % (C / 8), gi = blockIdx.x / (C / 8), G = gridDim.x / (C / 8);
+    const int S = S_pos + S_neg;
+    float m[8], rs[8], a1[8], a2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { m[j] = mean[q * 8 + j]; rs[j] = rstd[q * 8 + j]; a1[j] = a2[j] = 0.f; }
+    double d1[8], d2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d1[j] = d2[j] = 0.0;
+    for (int s = gi; s < S; s += G) {
+        const float* xb = (s < S_pos ? pos + (long)s * C * L : neg + (long)(s - S_pos) * C * L) + (long)(q * 8) * L;
+        for (int t = threadIdx.x; t < L; t += 128) {
+            const float4 g0 = *reinterpret_cast<const float4*>(dx + ((long)s * L + t) * C + q * 8);
+            const float4 g1 = *reinterpret_cast<const float4*>(dx + ((long)s * L + t) * C + q * 8 + 4);
+            const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xv = __ldg(xb + (long)j * L + t);
+                a1[j] += gv[j];
+                a2[j] = fmaf(gv[j], (xv - m[j]) * rs[j], a2[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { d1[j] += (double)a1[j]; d2[j] += (double)a2[j]; a1[j] = a2[j] = 0.f; }
+    }
+    // block reduce the 16 doubles (as two float-free passes through smem of warp sums)
+    __shared__ double dred[4][16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double v1 = warp_sum_d(d1[j]), v2 = warp_sum_d(d2[j]);
+        if ((threadIdx.x & 31) == 0) { dred[threadIdx.x >> 5][j] = v1; dred[threadIdx.x >> 5][8 + j] = v2; }
+    }
+    (void)red;
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        const double v = dred[0][threadIdx.x] + dred[1][threadIdx.x] + dred[2][threadIdx.x] + dred[3][threadIdx.x];
+        const int which = threadIdx.x >> 3, j = threadIdx.x & 7;
+        partial[((long)gi * 2 + which) * C + q * 8 + j] = v;
+    }
+}
+
+int tile_grid(long rows) {
+    long tiles = (rows + TR - 1) / TR;
+    long cap = (long)dcue_num_sms() * 8;
+    return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+}
+constexpr int STAT_BLOCKS_PER_SM = 4;
+
+}  // namespace
+
+extern "C" size_t dcue_ncl_stats_ws_bytes(int C) {
+    return (size_t)dcue_num_sms() * STAT_BLOCKS_PER_SM * 2 * (size_t)C * sizeof(double) + 256;
+}
+
+extern "C" int dcue_ncl_stats(const float* pos, int S_pos, const float* neg, int S_neg, int C, int L, double* sums,
+                              void* ws, size_t ws_bytes, void* stream) {
+    DCUE_CHECK_ARG(sums && ws && S_pos >= 0 && S_neg >= 0 && (pos || S_pos == 0) && (neg || S_neg == 0) && L > 0);
+    DCUE_CHECK_ARG(C > 0 && C <= 8 * STAT_MAXC_PER_WARP);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = S_pos + S_neg;
+    int grid = dcue_num_sms() * STAT_BLOCKS_PER_SM;
+    if (grid > S) grid = S > 0 ? S : 1;
+    if (ws_bytes < (size_t)grid * 2 * C * sizeof(double)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_ncl_stats: workspace too small");
+    ncl_stats_kernel<<<grid, 256, 0, st>>>(pos, S_pos, neg, S_neg, C, L, (double*)ws);
+    DCUE_LAUNCH_CHECK();
+    reduce_partials_kernel<<<ceil_div_i(2 * C, 128), 128, 0, st>>>((const double*)ws, grid, 2 * C, sums);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcue_bn_finalize(const double* sums, double count, int C, const float* gamma, const float* beta,
+                                float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                                float eps, int training, float* scale, float* shift, float* mean, float* rstd,
+                                void* stream) {
+    DCUE_CHECK_ARG(C > 0 && scale && shift && mean && rstd);
+    DCUE_CHECK_ARG(training ? (sums != nullptr && count > 0) : (running_mean && running_var));
+    bn_finalize_kernel<<<ceil_div_i(C, 128), 128, 0, (cudaStream_t)stream>>>(
+        sums, count, C, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, training, scale,
+        shift, mean, rstd);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcue_ncl_pack(const float* pos, int S_pos, const float* neg, int S_neg, int C, int L, const float* scale,
+                             const float* shift, void* panel, long panel_rows, int Lp, int pad, int fmt, void* stream) {
+    DCUE_CHECK_ARG(panel && S_pos >= 0 && S_neg >= 0 && (pos || S_pos == 0) && (neg || S_neg == 0));
+    DCUE_CHECK_ARG(C > 0 && C % 8 == 0 && L > 0 && Lp >= L + pad && pad >= 0 && (!scale == !shift));
+    DCUE_CHECK_ARG(panel_rows >= (long)(S_pos + S_neg) * Lp);
+    const long total = (long)(S_pos + S_neg) * (C / 8) * L;
+    if (total == 0) return 0;
+    long blocks = (total + 255) / 256;
+    const long cap = (long)dcue_num_sms() * 32;
+    if (blocks > cap) blocks = cap;
+    ncl_pack_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pos, S_pos, neg, S_neg, C, L, scale, shift,
+                                                                   (uint4*)panel, panel_rows, Lp, pad, fmt);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcue_affine_pack(const float* z, int S, int P, int C, const float* scale, const float* shift, void* panel,
+                                long panel_rows, int Lp, int pad, int fmt, float* y, float* tp, int ldtp, void* stream) {
+    DCUE_CHECK_ARG(z && S >= 0 && P > 0 && C > 0 && C <= 128 && (!scale == !shift));
+    DCUE_CHECK_ARG(!panel || (C % 8 == 0 && Lp >= P + pad && panel_rows >= (long)S * Lp));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long rows = (long)S * P;
+    if (rows == 0) return 0;
+    if (panel || y) {
+        affine_pack_kernel<<<tile_grid(rows), 256, 0, st>>>(z, rows, P, C, scale, shift, (uint4*)panel, panel_rows, Lp,
+                                                            pad, fmt, y);
+        DCUE_LAUNCH_CHECK();
+    }
+    if (tp) {
+        DCUE_CHECK_ARG(ldtp >= C);
+        time_mean_kernel<<<ceil_div_i((long)S * C, 256), 256, 0, st>>>(z, S, P, C, scale, shift, tp, ldtp);
+        DCUE_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" size_t dcue_bn_bwd_ws_bytes(int C) {
+    return (size_t)dcue_num_sms() * 8 * 2 * (size_t)C * sizeof(double) + 256;
+}
+
+extern "C" int dcue_bn_bwd_reduce(const float* dy, int lddy, const float* dtp, int lddtp, const float* z, const float* mean,
+                                  const float* rstd, int S, int P, int C, double* sums, void* ws, size_t ws_bytes,
+                                  void* stream) {
+    DCUE_CHECK_ARG(dy && z && mean && rstd && sums && ws && S >= 0 && P > 0 && C > 0 && C <= 128 && C % 4 == 0);
+    DCUE_CHECK_ARG(lddy >= C && lddy % 4 == 0 && ((uintptr_t)dy & 15) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long rows = (long)S * P;
+    long g = (rows + 7) / 8;
+    const long cap = (long)dcue_num_sms() * 8;
+    int grid = (int)(g < cap ? (g > 0 ? g : 1) : cap);
+    if (ws_bytes < (size_t)grid * 2 * C * sizeof(double)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_bn_bwd_reduce: workspace too small");
+    bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, lddy, dtp, lddtp, z, mean, rstd, rows, P, C, (double*)ws);
+    DCUE_LAUNCH_CHECK();
+    reduce_partials_kernel<<<ceil_div_i(2 * C, 128), 128, 0, st>>>((const double*)ws, grid, 2 * C, sums);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcue_bn_relu_unpool_bwd(const float* dy, int lddy, const float* dtp, int lddtp, const float* z, const uint8_t* code,
+                                       const float* scale, const float* mean, const float* rstd, const double* sums,
+                                       double count, int S, int P, int C, int pool, int Lp, void* dy_panel,
+                                       long panel_rows, int fmt, float* dz_out, double* bias_sums, void* ws,
+                                       size_t ws_bytes, void* stream) {
+    DCUE_CHECK_ARG(dy && z && S >= 0 && P > 0 && C > 0 && C <= 128 && (dy_panel || dz_out) && lddy >= C);
+    DCUE_CHECK_ARG(!sums || (mean && rstd && count > 0));
+    DCUE_CHECK_ARG(!dy_panel || (code && C % 8 == 0 && pool >= 1 && pool <= 8 && Lp >= P * pool && panel_rows >= (long)S * Lp));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long rows = (long)S * P;
+    if (rows == 0) return 0;
+    const int grid = tile_grid(rows);
+    if (bias_sums && (!ws || ws_bytes < (size_t)grid * C * sizeof(double)))
+        DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_bn_relu_unpool_bwd: workspace too small");
+    bn_relu_unpool_bwd_kernel<<<grid, 256, 0, st>>>(dy, lddy, dtp, lddtp, z, code, scale, mean, rstd, sums,
+                                                    count > 0 ? count : 1.0, rows, P, C, pool, Lp, (uint4*)dy_panel,
+                                                    panel_rows, fmt, dz_out, bias_sums ? (double*)ws : nullptr);
+    DCUE_LAUNCH_CHECK();
+    if (bias_sums) {
+        reduce_partials_kernel<<<ceil_div_i(C, 128), 128, 0, st>>>((const double*)ws, grid, C, bias_sums);
+        DCUE_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int dcue_ncl_bn_bwd_reduce(const float* dx, const float* pos, int S_pos, const float* neg, int S_neg, int C,
+                                      int L, const float* mean, const float* rstd, double* sums, void* ws,
+                                      size_t ws_bytes, void* stream) {
+    DCUE_CHECK_ARG(dx && mean && rstd && sums && ws && S_pos >= 0 && S_neg >= 0 && (pos || S_pos == 0) &&
+                   (neg || S_neg == 0) && C > 0 && C % 8 == 0 && L > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = S_pos + S_neg;
+    int G = dcue_num_sms() * 8 / (C / 8);
+    if (G > S) G = S > 0 ? S : 1;
+    if (G < 1) G = 1;
+    if (ws_bytes < (size_t)G * 2 * C * sizeof(double)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_ncl_bn_bwd_reduce: workspace too small");
+    ncl_bn_bwd_reduce_kernel<<<G * (C / 8), 128, 0, st>>>(dx, pos, S_pos, neg, S_neg, C, L, mean, rstd, (double*)ws);
+    DCUE_LAUNCH_CHECK();
+    reduce_partials_kernel<<<ceil_div_i(2 * C, 128), 128, 0, st>>>((const double*)ws, G, 2 * C, sums);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcue_cvt_f64_f32(const double* in, int n, double mul, float* out, void* stream) {
+    DCUE_CHECK_ARG(in && out && n >= 0);
+    if (n == 0) return 0;
+    cvt_f64_f32_kernel<<<ceil_div_i(n, 256), 256, 0, (cudaStream_t)stream>>>(in, n, mul, out);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}

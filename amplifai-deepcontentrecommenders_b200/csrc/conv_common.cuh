@@ -1,0 +1,41 @@
+// Geometry of one conv stage in the flat padded row space (see dcue_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct ConvGeom {
+    int S;            // spectrograms
+    int Lp;           // rows per spectrogram in the flat layout
+    int Lin;          // data rows per spectrogram (dgrad epilogue)
+    int pad;          // zero rows in front of each spectrogram's data
+    int k;            // taps
+    int pool;         // max-pool width (forward epilogue)
+    int P;            // pooled outputs per spectrogram
+    int Cin;          // contraction channels (<=128)
+    int Cout;         // output channels (<=128)
+    long rows_total;  // S * Lp
+};
+
+// CUDA-core path (conv_simt.cu)
+int dcue_simt_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_packed, const float* bias,
+                       const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
+                       cudaStream_t st);
+int dcue_simt_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
+                         const ConvGeom& g, float* dx, cudaStream_t st);
+int dcue_simt_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const void* x_panel, long x_rows, int fmt_x,
+                         long rows_total, int k, int Cin, int Cout, float* dW, void* ws, size_t ws_bytes,
+                         cudaStream_t st);
+// tcgen05 path (conv_tc.cu)
+int dcue_tc_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_packed, const float* bias,
+                     const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
+int dcue_tc_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
+                       const ConvGeom& g, float* dx, cudaStream_t st);
+int dcue_tc_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const void* x_panel, long x_rows, int fmt_x,
+                       long rows_total, int k, int Cin, int Cout, float* dW, void* ws, size_t ws_bytes,
+                       cudaStream_t st);
+size_t dcue_tc_ws_bytes(int k);
+
+__global__ void dcue_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int Cout, int Cin, int k,
+                                         float* __restrict__ dW);
+__global__ void dcue_reduce_partials_d(const double* __restrict__ partial, int nblk, int n, double* __restrict__ out);

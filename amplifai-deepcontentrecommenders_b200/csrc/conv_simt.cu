@@ -1,0 +1,254 @@
+// CUDA-core implicit-GEMM Conv1d kernels over the 16-bit panel layout (see dcue_b200.h).
+// They consume exactly the operands the tcgen05 kernels consume (same packed weights, same
+// panels, fp32 accumulation), so they serve as the on-device validator of conv_tc.cu and as
+// the path for shapes the tensor-core kernels do not cover.
+//
+// Conv as shifted-row GEMM:  out[r, m] = sum_{j<k} sum_{c<128} A[m][j*128+c] * In[r+j, c]
+// over flat rows r = s*Lp + t (reference: nn.Conv1d in truedcuemel1dbn.py:25-27,33-35,41-43,49-51).
+#include "common.cuh"
+#include "conv_common.cuh"
+
+namespace {
+
+constexpr int TRW = 32;   // flat rows per tile (multiple of every pool width)
+constexpr int CH = 128;   // channels are padded to 128 in packed weights
+
+// load rows [r0, r0+nrows) x 128 channels of a panel into smem as fp32 (row stride CH)
+__device__ __forceinline__ void load_panel_tile(float* __restrict__ xs, const uint4* __restrict__ panel,
+                                                long panel_rows, long r0, int nrows, int nch, int fmt, int tid,
+                                                int nthreads) {
+    const int chunks = nrows * (CH / 8);
+    for (int e = tid; e < chunks; e += nthreads) {
+        const int rl = e % nrows, q = e / nrows;  // consecutive threads walk rows of one panel
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (q * 8 < nch) v = __ldg(panel + (long)q * panel_rows + r0 + rl);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+        float* dst = xs + rl * CH + q * 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            dst[2 * j] = cvt16_to_f32((unsigned short)(w[j] & 0xffffu), fmt);
+            dst[2 * j + 1] = cvt16_to_f32((unsigned short)(w[j] >> 16), fmt);
+        }
+    }
+}
+
+template <int POOL>
+__device__ __forceinline__ void epi_pool(const float (&acc)[TRW], long r0, int m, float bv, const ConvGeom& g,
+                                         float* __restrict__ out, uint8_t* __restrict__ code, double& st1, double& st2) {
+#pragma unroll
+    for (int t0 = 0; t0 < TRW; t0 += POOL) {
+        const long r = r0 + t0;
+        const long s = r / g.Lp;
+        const int p = (int)(r - s * g.Lp) / POOL;
+        float best = acc[t0];
+        int bi = 0;
+#pragma unroll
+        for (int i = 1; i < POOL; ++i)
+            if (acc[t0 + i] > best) { best = acc[t0 + i]; bi = i; }   // first maximum wins, like ATen
+        if (s < g.S && p < g.P) {
+            const float v = fmaxf(best + bv, 0.f);
+            const long o = (s * g.P + p) * g.Cout + m;
+            out[o] = v;
+            if (code) code[o] = (uint8_t)bi;
+            st1 += v;
+            st2 += (double)v * v;
+        }
+    }
+}
+
+// EPI 0: bias + maxpool + relu + code + BN partial sums.   EPI 1: dgrad store of data rows.
+template <int EPI>
+__global__ void __launch_bounds__(128)
+conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in, const uint4* __restrict__ wp, int fmt_w,
+                 const float* __restrict__ bias, ConvGeom g, float* __restrict__ out, uint8_t* __restrict__ code,
+                 double* __restrict__ partial) {
+    extern __shared__ float xs[];  // [TRW + k - 1][CH]
+    const int m = threadIdx.x;
+    const long ntiles = (g.rows_total + TRW - 1) / TRW;
+    const int kpan = g.k * (CH / 8);  // 8-wide K chunks of the packed weight
+    double st1 = 0.0, st2 = 0.0;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long r0 = tile * TRW;
+        __syncthreads();
+        load_panel_tile(xs, panel, panel_rows, r0, TRW + g.k - 1, g.Cin, fmt_in, m, 128);
+        __syncthreads();
+        float acc[TRW];
+#pragma unroll
+        for (int t = 0; t < TRW; ++t) acc[t] = 0.f;
+        for (int kk8 = 0; kk8 < kpan; ++kk8) {
+            const int j = kk8 / (CH / 8), c0 = (kk8 % (CH / 8)) * 8;
+            if (c0 >= g.Cin) continue;
+            const uint4 wv = __ldg(wp + (long)kk8 * CH + m);
+            const unsigned ww[4] = {wv.x, wv.y, wv.z, wv.w};
+            float w[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                w[2 * q] = cvt16_to_f32((unsigned short)(ww[q] & 0xffffu), fmt_w);
+                w[2 * q + 1] = cvt16_to_f32((unsigned short)(ww[q] >> 16), fmt_w);
+            }
+#pragma unroll
+            for (int t = 0; t < TRW; ++t) {
+                const float4 a = *reinterpret_cast<const float4*>(xs + (t + j) * CH + c0);
+                const float4 b = *reinterpret_cast<const float4*>(xs + (t + j) * CH + c0 + 4);
+                acc[t] = fmaf(w[0], a.x, acc[t]); acc[t] = fmaf(w[1], a.y, acc[t]);
+                acc[t] = fmaf(w[2], a.z, acc[t]); acc[t] = fmaf(w[3], a.w, acc[t]);
+                acc[t] = fmaf(w[4], b.x, acc[t]); acc[t] = fmaf(w[5], b.y, acc[t]);
+                acc[t] = fmaf(w[6], b.z, acc[t]); acc[t] = fmaf(w[7], b.w, acc[t]);
+            }
+        }
+        if (EPI == 0) {
+            if (m < g.Cout) {
+                const float bv = bias ? bias[m] : 0.f;
+                if (g.pool == 4) epi_pool<4>(acc, r0, m, bv, g, out, code, st1, st2);
+                else if (g.pool == 2) epi_pool<2>(acc, r0, m, bv, g, out, code, st1, st2);
+                else epi_pool<1>(acc, r0, m, bv, g, out, code, st1, st2);
+            }
+        } else {
+            if (m < g.Cout) {
+#pragma unroll
+                for (int t = 0; t < TRW; ++t) {
+                    const long r = r0 + t;
+                    const long s = r / g.Lp;
+                    const int tt = (int)(r - s * g.Lp) - g.pad;
+                    if (s < g.S && tt >= 0 && tt < g.Lin) out[(s * g.Lin + tt) * g.Cout + m] = acc[t];
+                }
+            }
+        }
+    }
+    if (EPI == 0 && partial && m < g.Cout) {
+        partial[((long)blockIdx.x * 2 + 0) * g.Cout + m] = st1;
+        partial[((long)blockIdx.x * 2 + 1) * g.Cout + m] = st2;
+    }
+}
+
+// wgrad partials: block (chunk, tap j, ci tile of 32): part[chunk][co][j][ci] += dY[r,co]*X[r+j,ci]
+__global__ void __launch_bounds__(128)
+wgrad_rows_kernel(const uint4* __restrict__ dyp, long dy_rows, int fmt_dy, const uint4* __restrict__ xp, long x_rows,
+                  int fmt_x, long rows_total, int k, int Cin, int Cout, float* __restrict__ part) {
+    __shared__ float dys[TRW * CH];
+    __shared__ float xs[(TRW + 3) * CH];
+    const int co = threadIdx.x, j = blockIdx.y, c0 = blockIdx.z * 32;
+    const long ntiles = (rows_total + TRW - 1) / TRW;
+    const long per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const long tbeg = blockIdx.x * per, tend = min(ntiles, tbeg + per);
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    for (long tile = tbeg; tile < tend; ++tile) {
+        const long r0 = tile * TRW;
+        __syncthreads();
+        load_panel_tile(dys, dyp, dy_rows, r0, TRW, Cout, fmt_dy, co, 128);
+        load_panel_tile(xs, xp, x_rows, r0, TRW + k - 1, Cin, fmt_x, co, 128);
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < TRW; ++r) {
+            const float d = dys[r * CH + co];
+            const float* xr = xs + (r + j) * CH + c0;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                const float4 x = *reinterpret_cast<const float4*>(xr + c);
+                acc[c] = fmaf(d, x.x, acc[c]);
+                acc[c + 1] = fmaf(d, x.y, acc[c + 1]);
+                acc[c + 2] = fmaf(d, x.z, acc[c + 2]);
+                acc[c + 3] = fmaf(d, x.w, acc[c + 3]);
+            }
+        }
+    }
+    float* dst = part + (((long)blockIdx.x * CH + co) * k + j) * CH + c0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) dst[c] = acc[c];
+}
+
+}  // namespace
+
+// dW[co][ci][j] = sum_parts part[p][co][j][ci]   (shared with the tcgen05 wgrad)
+__global__ void dcue_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int Cout, int Cin, int k,
+                                         float* __restrict__ dW) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Cout * Cin * k) return;
+    const int j = i % k, ci = (i / k) % Cin, co = i / (k * Cin);
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += part[(((long)p * 128 + co) * k + j) * 128 + ci];
+    dW[i] = s;
+}
+
+__global__ void dcue_reduce_partials_d(const double* __restrict__ partial, int nblk, int n, double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += partial[(long)b * n + j];
+    out[j] = s;
+}
+
+__global__ void pack_conv_weight_kernel(const float* __restrict__ W, int Cout, int Cin, int k, int mode, int fmt,
+                                        unsigned short* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int K = k * 128;
+    if (i >= 128 * K) return;
+    const int kk = i / 128, m = i % 128;          // consecutive threads -> consecutive m
+    const int j = kk / 128, c = kk % 128;
+    float v = 0.f;
+    if (mode == 0) {  // A[co=m][j*128+ci=c] = W[co][ci][j]
+        if (m < Cout && c < Cin) v = W[((long)m * Cin + c) * k + j];
+    } else {          // A[ci=m][jj*128+co=c] = W[co][ci][k-1-jj]
+        if (m < Cin && c < Cout) v = W[((long)c * Cin + m) * k + (k - 1 - j)];
+    }
+    out[((long)(kk >> 3) * 128 + m) * 8 + (kk & 7)] = cvt_f32_to16(v, fmt);
+}
+
+int dcue_simt_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_packed, const float* bias,
+                       const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
+                       cudaStream_t st) {
+    const long ntiles = (g.rows_total + TRW - 1) / TRW;
+    const long cap = (long)dcue_num_sms() * 4;
+    const int grid = (int)(ntiles < cap ? (ntiles > 0 ? ntiles : 1) : cap);
+    if (sums && (!ws || ws_bytes < (size_t)grid * 2 * g.Cout * sizeof(double)))
+        DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_pool_fwd(simt): workspace too small");
+    const size_t smem = (size_t)(TRW + g.k - 1) * CH * sizeof(float);
+    conv_rows_kernel<0><<<grid, 128, smem, st>>>((const uint4*)panel, panel_rows, fmt, (const uint4*)w_packed, fmt, bias,
+                                                 g, z, code, sums ? (double*)ws : nullptr);
+    DCUE_LAUNCH_CHECK();
+    if (sums) {
+        dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 128), 128, 0, st>>>((const double*)ws, grid, 2 * g.Cout, sums);
+        DCUE_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int dcue_simt_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
+                         const ConvGeom& g, float* dx, cudaStream_t st) {
+    const long ntiles = (g.rows_total + TRW - 1) / TRW;
+    const long cap = (long)dcue_num_sms() * 4;
+    const int grid = (int)(ntiles < cap ? (ntiles > 0 ? ntiles : 1) : cap);
+    const size_t smem = (size_t)(TRW + g.k - 1) * CH * sizeof(float);
+    conv_rows_kernel<1><<<grid, 128, smem, st>>>((const uint4*)dy_panel_shifted, panel_rows, fmt_dy,
+                                                 (const uint4*)w_packed, fmt_w, nullptr, g, dx, nullptr, nullptr);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+int dcue_simt_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const void* x_panel, long x_rows, int fmt_x,
+                         long rows_total, int k, int Cin, int Cout, float* dW, void* ws, size_t ws_bytes,
+                         cudaStream_t st) {
+    const int nchunks = 32;
+    if (!ws || ws_bytes < (size_t)nchunks * 128 * k * 128 * sizeof(float))
+        DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_wgrad(simt): workspace too small");
+    dim3 grid(nchunks, k, 4);
+    wgrad_rows_kernel<<<grid, 128, 0, st>>>((const uint4*)dy_panel, dy_rows, fmt_dy, (const uint4*)x_panel, x_rows,
+                                            fmt_x, rows_total, k, Cin, Cout, (float*)ws);
+    DCUE_LAUNCH_CHECK();
+    dcue_wgrad_reduce_kernel<<<ceil_div_i((long)Cout * Cin * k, 256), 256, 0, st>>>((const float*)ws, nchunks, Cout, Cin,
+                                                                                    k, dW);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcue_pack_conv_weight(const float* W, int Cout, int Cin, int k, int mode, int fmt, void* out,
+                                     void* stream) {
+    DCUE_CHECK_ARG(W && out && Cout > 0 && Cout <= 128 && Cin > 0 && Cin <= 128 && k >= 1 && k <= 4 &&
+                   (mode == 0 || mode == 1));
+    pack_conv_weight_kernel<<<ceil_div_i(128L * k * 128, 256), 256, 0, (cudaStream_t)stream>>>(
+        W, Cout, Cin, k, mode, fmt, (unsigned short*)out);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,474 @@
+// tcgen05 / TMEM / TMA-bulk implicit-GEMM kernels for the DCUE song tower (sm_100a only).
+//
+// Reference ops replaced: nn.Conv1d (+MaxPool1d+ReLU and BatchNorm statistics) forward, its
+// data gradient and its weight gradient (truedcuemel1dbn.py:25-54,80-95 and autograd thereof).
+//
+// Formulation (see dcue_b200.h for the panel layout): channels on the MMA M axis, flat time
+// rows on the N axis, so one TMEM lane = one output channel and
+//   * max-pooling over time is a per-thread register max over adjacent accumulator columns,
+//   * bias / ReLU / BatchNorm partial sums are per-thread scalars (no shuffles, no atomics),
+//   * the k conv taps are k K-blocks whose B descriptors differ by +16 bytes (one row): the
+//     no-swizzle panel layout makes a tap shift a plain descriptor address offset, so the
+//     activation tile is staged ONCE per tile by cp.async.bulk (no im2col, no re-load per tap).
+//
+//   forward / dgrad:  D[ch, r] = sum_{j<k} sum_{c<128} A[ch][j*128+c] * In[r+j, c]
+//       A = packed weights, resident in smem for the whole persistent CTA (K-major, 128 x k*128)
+//       B = activation tile of 128+8 rows x 128 channels (K-major), 2-stage mbarrier ring
+//       D = 128 lanes x 128 columns fp32 in TMEM, double buffered (epilogue overlaps next MMA)
+//   wgrad:            D_j[co, ci] = sum_r dY[r, co] * X[r+j, ci]      (both operands MN-major)
+//       k accumulators of 128 columns stay in TMEM for the CTA's whole row range.
+//
+// Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+#include "common.cuh"
+#include "conv_common.cuh"
+
+namespace {
+
+constexpr int BN = 128;                       // flat rows per tile (MMA N)
+constexpr int HALO = 8;                       // extra rows staged for the taps (>= k-1, keeps 128 B groups)
+constexpr int PANELS = 16;                    // 128 channels / 8
+constexpr int ROWB = 16;                      // bytes per (row, panel) chunk
+constexpr int B_PANEL_BYTES = (BN + HALO) * ROWB;          // 2176
+constexpr int B_STAGE_BYTES = PANELS * B_PANEL_BYTES;       // 34816
+constexpr int A_PANEL_BYTES = 128 * ROWB;                   // 2048 (128 M rows)
+constexpr int NSTAGE = 2;
+constexpr int NTHREADS = 192;
+
+// ----------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, SWIZZLE_NONE (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) leading byte offset>>4 | [32,46) stride byte offset>>4 | [46,48) version=1
+// K-major : LBO = distance between the two 8-element K chunks of one MMA, SBO = between 8-row groups
+// MN-major: LBO = distance between 8-row K groups,              SBO = between 8-element MN chunks
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor), dense, fp32 accumulate
+__device__ __forceinline__ uint32_t make_idesc(int a_fmt, int b_fmt, int a_mn_major, int b_mn_major, int M, int N) {
+    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
+           ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct Pipe {
+    int stage = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance(int n) {
+        if (++stage == n) { stage = 0; phase ^= 1; }
+    }
+};
+
+// ----------------------------------------------------------------------------- fwd / dgrad
+// EPI 0: bias + maxpool(POOL) + relu + argmax code + BN partial sums -> z[S*P, Cout]
+// EPI 1: store the data rows -> dx[S*Lin, Cout]
+template <int EPI, int POOL>
+__device__ __forceinline__ void epilogue_chunk(const float (&v)[32], long r, int m, float bv, const ConvGeom& g,
+                                               float* __restrict__ out, uint8_t* __restrict__ code, double& st1,
+                                               double& st2) {
+    if (EPI == 0) {
+        float ts1 = 0.f, ts2 = 0.f;
+#pragma unroll
+        for (int t0 = 0; t0 < 32; t0 += POOL) {
+            const long rr = r + t0;
+            const long s = rr / g.Lp;
+            const int p = (int)(rr - s * g.Lp) / POOL;
+            float best = v[t0];
+            int bi = 0;
+#pragma unroll
+            for (int i = 1; i < POOL; ++i)
+                if (v[t0 + i] > best) { best = v[t0 + i]; bi = i; }
+            if (s < g.S && p < g.P && m < g.Cout) {
+                const float val = fmaxf(best + bv, 0.f);
+                const long o = (s * g.P + p) * g.Cout + m;
+                out[o] = val;
+                if (code) code[o] = (uint8_t)bi;
+                ts1 += val;
+                ts2 = fmaf(val, val, ts2);
+            }
+        }
+        st1 += (double)ts1;
+        st2 += (double)ts2;
+    } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            const long rr = r + t;
+            const long s = rr / g.Lp;
+            const int tt = (int)(rr - s * g.Lp) - g.pad;
+            if (s < g.S && tt >= 0 && tt < g.Lin && m < g.Cout) out[(s * g.Lin + tt) * g.Cout + m] = v[t];
+        }
+    }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in, const uint4* __restrict__ wp, int fmt_w,
+                    const float* __restrict__ bias, ConvGeom g, float* __restrict__ out, uint8_t* __restrict__ code,
+                    double* __restrict__ partial) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a_bytes = g.k * PANELS * A_PANEL_BYTES;  // k * 32 KB
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + a_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NSTAGE * B_STAGE_BYTES);
+    // bars: [0..NSTAGE) full, [NSTAGE..2NSTAGE) empty, [2N] wfull, [2N+1,2N+2] tmem_full, [2N+3,2N+4] tmem_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+    const uint32_t WFULL = bar0 + 8u * (2 * NSTAGE);
+    auto TFULL = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 1 + a); };
+    auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 3 + a); };
+
+    const long ntiles = (g.rows_total + BN - 1) / BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        mbar_init(WFULL, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<256>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== producer: weights once, then one activation tile per stage =====
+        if (lane == 0) {
+            mbar_expect_tx(WFULL, (uint32_t)a_bytes);
+            for (int c = 0; c < g.k * 4; ++c)  // 8 KB pieces
+                bulk_g2s(smem_u32(sA + c * 8192), reinterpret_cast<const uint8_t*>(wp) + (size_t)c * 8192, 8192, WFULL);
+            Pipe pp;
+            for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                mbar_wait(EMPTY(pp.stage), pp.phase ^ 1);
+                mbar_expect_tx(FULL(pp.stage), B_STAGE_BYTES);
+                const long r0 = tile * BN;
+                uint8_t* dst = sB + pp.stage * B_STAGE_BYTES;
+#pragma unroll 4
+                for (int q = 0; q < PANELS; ++q)
+                    bulk_g2s(smem_u32(dst + q * B_PANEL_BYTES), panel + (long)q * panel_rows + r0, B_PANEL_BYTES,
+                             FULL(pp.stage));
+                pp.advance(NSTAGE);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(fmt_w, fmt_in, 0, 0, 128, BN);
+            mbar_wait(WFULL, 0);
+            Pipe pp;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                mbar_wait(TEMPTY(acc), acc_phase ^ 1);
+                mbar_wait(FULL(pp.stage), pp.phase);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + pp.stage * B_STAGE_BYTES);
+                const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+                for (int j = 0; j < g.k; ++j) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {  // 16 channels = 2 panels per MMA
+                        const uint64_t ad = make_desc(a0 + (uint32_t)((j * PANELS + 2 * c) * A_PANEL_BYTES), A_PANEL_BYTES, 128);
+                        const uint64_t bd = make_desc(b0 + (uint32_t)(2 * c * B_PANEL_BYTES + j * ROWB), B_PANEL_BYTES, 128);
+                        umma_f16(d, ad, bd, idesc, (j | c) != 0);
+                    }
+                }
+                umma_commit(EMPTY(pp.stage));  // smem stage reusable once these MMAs retire
+                umma_commit(TFULL(acc));       // accumulator ready for the epilogue
+                pp.advance(NSTAGE);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue warps: TMEM -> registers -> (pool, relu, stats) -> global =====
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;  // output channel == TMEM lane
+        const float bv = (EPI == 0 && bias && m < g.Cout) ? bias[m] : 0.f;
+        double st1 = 0.0, st2 = 0.0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            mbar_wait(TFULL(acc), acc_phase);
+            tc_fence_after();
+            const long r0 = tile * BN;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
+                if (EPI == 0) {
+                    if (g.pool == 4) epilogue_chunk<0, 4>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2);
+                    else if (g.pool == 2) epilogue_chunk<0, 2>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2);
+                    else epilogue_chunk<0, 1>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2);
+                } else {
+                    epilogue_chunk<1, 1>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(TEMPTY(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (EPI == 0 && partial && m < g.Cout) {
+            partial[((long)blockIdx.x * 2 + 0) * g.Cout + m] = st1;
+            partial[((long)blockIdx.x * 2 + 1) * g.Cout + m] = st2;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem_base);
+    }
+}
+
+// ----------------------------------------------------------------------------- wgrad
+constexpr int WG_DY_PANEL = BN * ROWB;                       // 2048
+constexpr int WG_STAGE_BYTES = PANELS * WG_DY_PANEL + B_STAGE_BYTES;   // 32768 + 34816
+constexpr int WG_NSTAGE = 3;
+
+template <int KTAPS>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_wgrad_kernel(const uint4* __restrict__ dyp, long dy_rows, int fmt_dy, const uint4* __restrict__ xp, long x_rows,
+                int fmt_x, long rows_total, float* __restrict__ part /* [grid][128][KTAPS][128] */) {
+    constexpr int TCOLS = KTAPS * 128 <= 128 ? 128 : (KTAPS * 128 <= 256 ? 256 : 512);
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_NSTAGE * WG_STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_NSTAGE + 1);
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (WG_NSTAGE + s); };
+    const uint32_t DONE = bar0 + 8u * (2 * WG_NSTAGE);
+
+    const long ntiles = (rows_total + BN - 1) / BN;
+    const long per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const long tbeg = blockIdx.x * per;
+    const long tend = tbeg + per < ntiles ? tbeg + per : ntiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WG_NSTAGE; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        mbar_init(DONE, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TCOLS>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            Pipe pp;
+            for (long tile = tbeg; tile < tend; ++tile) {
+                mbar_wait(EMPTY(pp.stage), pp.phase ^ 1);
+                mbar_expect_tx(FULL(pp.stage), WG_STAGE_BYTES);
+                const long r0 = tile * BN;
+                uint8_t* dy_dst = smem + pp.stage * WG_STAGE_BYTES;
+                uint8_t* x_dst = dy_dst + PANELS * WG_DY_PANEL;
+#pragma unroll 4
+                for (int q = 0; q < PANELS; ++q) {
+                    bulk_g2s(smem_u32(dy_dst + q * WG_DY_PANEL), dyp + (long)q * dy_rows + r0, WG_DY_PANEL, FULL(pp.stage));
+                    bulk_g2s(smem_u32(x_dst + q * B_PANEL_BYTES), xp + (long)q * x_rows + r0, B_PANEL_BYTES, FULL(pp.stage));
+                }
+                pp.advance(WG_NSTAGE);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(fmt_dy, fmt_x, 1, 1, 128, 128);
+            Pipe pp;
+            bool first = true;
+            for (long tile = tbeg; tile < tend; ++tile) {
+                mbar_wait(FULL(pp.stage), pp.phase);
+                tc_fence_after();
+                const uint32_t dy0 = smem_u32(smem + pp.stage * WG_STAGE_BYTES);
+                const uint32_t x0 = dy0 + PANELS * WG_DY_PANEL;
+#pragma unroll
+                for (int kk = 0; kk < BN / 16; ++kk) {  // 16 rows (MMA K) per instruction
+                    const uint64_t ad = make_desc(dy0 + (uint32_t)(kk * 16 * ROWB), 128, WG_DY_PANEL);
+#pragma unroll
+                    for (int j = 0; j < KTAPS; ++j) {
+                        const uint64_t bd = make_desc(x0 + (uint32_t)((kk * 16 + j) * ROWB), 128, B_PANEL_BYTES);
+                        umma_f16(tmem_base + (uint32_t)(j * 128), ad, bd, idesc, !(first && kk == 0));
+                    }
+                }
+                first = false;
+                umma_commit(EMPTY(pp.stage));
+                pp.advance(WG_NSTAGE);
+            }
+            umma_commit(DONE);
+        }
+        __syncwarp();
+    } else {
+        const int quarter = warp & 3;
+        const int co = quarter * 32 + lane;
+        mbar_wait(DONE, 0);
+        tc_fence_after();
+        float* dst = part + ((long)blockIdx.x * 128 + co) * KTAPS * 128;
+#pragma unroll 1
+        for (int j = 0; j < KTAPS; ++j) {
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * 128 + ch * 32), v);
+                float4* d4 = reinterpret_cast<float4*>(dst + j * 128 + ch * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TCOLS>(tmem_base);
+    }
+}
+
+size_t rows_smem_bytes(int k) { return (size_t)k * PANELS * A_PANEL_BYTES + NSTAGE * B_STAGE_BYTES + 8 * (2 * NSTAGE + 5) + 16; }
+constexpr size_t WG_SMEM = (size_t)WG_NSTAGE * WG_STAGE_BYTES + 8 * (2 * WG_NSTAGE + 1) + 16;
+
+int tc_grid(long rows_total) {
+    const long ntiles = (rows_total + BN - 1) / BN;
+    const int sms = dcue_num_sms();
+    return (int)(ntiles < sms ? (ntiles > 0 ? ntiles : 1) : sms);
+}
+
+template <int EPI>
+int launch_rows(const void* panel, long panel_rows, int fmt_in, const void* w_packed, int fmt_w, const float* bias,
+                const ConvGeom& g, float* out, uint8_t* code, double* partial, int grid, cudaStream_t st) {
+    const size_t smem = rows_smem_bytes(g.k);
+    DCUE_CUDA(cudaFuncSetAttribute(tc_conv_rows_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_conv_rows_kernel<EPI><<<grid, NTHREADS, smem, st>>>((const uint4*)panel, panel_rows, fmt_in, (const uint4*)w_packed,
+                                                           fmt_w, bias, g, out, code, partial);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+size_t dcue_tc_ws_bytes(int k) {
+    const size_t stats = (size_t)dcue_num_sms() * 2 * 128 * sizeof(double);
+    const size_t wg = (size_t)dcue_num_sms() * 128 * k * 128 * sizeof(float);
+    return stats > wg ? stats : wg;
+}
+
+int dcue_tc_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_packed, const float* bias,
+                     const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+    if (g.Cin != 128) DCUE_FAIL(DCUE_E_UNSUPPORTED, "tcgen05 conv needs Cin == 128 (got %d)", g.Cin);
+    const int grid = tc_grid(g.rows_total);
+    if (sums && (!ws || ws_bytes < (size_t)grid * 2 * g.Cout * sizeof(double)))
+        DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_pool_fwd(tc): workspace too small");
+    if (int e = launch_rows<0>(panel, panel_rows, fmt, w_packed, fmt, bias, g, z, code, sums ? (double*)ws : nullptr, grid, st))
+        return e;
+    if (sums) {
+        dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 128), 128, 0, st>>>((const double*)ws, grid, 2 * g.Cout, sums);
+        DCUE_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int dcue_tc_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
+                       const ConvGeom& g, float* dx, cudaStream_t st) {
+    if (g.Cin != 128) DCUE_FAIL(DCUE_E_UNSUPPORTED, "tcgen05 dgrad needs Cout == 128 (got %d)", g.Cin);
+    return launch_rows<1>(dy_panel_shifted, panel_rows, fmt_dy, w_packed, fmt_w, nullptr, g, dx, nullptr, nullptr,
+                          tc_grid(g.rows_total), st);
+}
+
+int dcue_tc_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const void* x_panel, long x_rows, int fmt_x,
+                       long rows_total, int k, int Cin, int Cout, float* dW, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (Cin != 128 || Cout != 128) DCUE_FAIL(DCUE_E_UNSUPPORTED, "tcgen05 wgrad needs Cin == Cout == 128");
+    const int grid = tc_grid(rows_total);
+    if (!ws || ws_bytes < (size_t)grid * 128 * k * 128 * sizeof(float))
+        DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_wgrad(tc): workspace too small");
+#define LAUNCH_WG(KT)                                                                                             \
+    do {                                                                                                          \
+        DCUE_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM)); \
+        tc_wgrad_kernel<KT><<<grid, NTHREADS, WG_SMEM, st>>>((const uint4*)dy_panel, dy_rows, fmt_dy, (const uint4*)x_panel, \
+                                                             x_rows, fmt_x, rows_total, (float*)ws);              \
+    } while (0)
+    switch (k) {
+        case 1: LAUNCH_WG(1); break;
+        case 2: LAUNCH_WG(2); break;
+        case 3: LAUNCH_WG(3); break;
+        case 4: LAUNCH_WG(4); break;
+        default: DCUE_FAIL(DCUE_E_BADARG, "k must be 1..4");
+    }
+#undef LAUNCH_WG
+    DCUE_LAUNCH_CHECK();
+    dcue_wgrad_reduce_kernel<<<ceil_div_i((long)Cout * Cin * k, 256), 256, 0, st>>>((const float*)ws, grid, Cout, Cin, k, dW);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}

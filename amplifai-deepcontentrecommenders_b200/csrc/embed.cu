@@ -1,0 +1,135 @@
+// User embedding table: vectorised coalesced gather (+ReLU) and a deterministic
+// sort-by-row + segment-sum backward that produces the reference's DENSE [U,E] gradient
+// (nn.Embedding(sparse=False), dcrecommend/dcue/embeddings/userembedding.py:27,40-41).
+#include "common.cuh"
+#include <cub/cub.cuh>
+
+namespace {
+
+// one warp per gathered row; 16 B per lane when E % 4 == 0
+__global__ void __launch_bounds__(256)
+gather_relu_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx, int B, int U, int E,
+                   float* __restrict__ out, float* __restrict__ raw, int* __restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int64_t r = idx[b];
+    if (r < 0 || r >= U) {
+        if (lane == 0) atomicExch(err, 1);
+        return;
+    }
+    const float* src = table + r * (long)E;
+    float* dst = out + (long)b * E;
+    float* rdst = raw ? raw + (long)b * E : nullptr;
+    if ((E & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        float4* r4 = reinterpret_cast<float4*>(rdst);
+        for (int i = lane; i < E / 4; i += 32) {
+            float4 v = __ldg(s4 + i);
+            if (r4) r4[i] = v;
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            d4[i] = v;
+        }
+    } else {
+        for (int i = lane; i < E; i += 32) {
+            float v = __ldg(src + i);
+            if (rdst) rdst[i] = v;
+            dst[i] = fmaxf(v, 0.f);
+        }
+    }
+}
+
+__global__ void iota_kernel(int32_t* p, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+// one warp per sorted entry; only segment heads work: they sum their run in position order
+__global__ void __launch_bounds__(256)
+segment_scatter_kernel(const float* __restrict__ gout, const float* __restrict__ fwd,
+                       const int64_t* __restrict__ sidx, const int32_t* __restrict__ spos, int B, int E,
+                       float* __restrict__ gtable) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= B) return;
+    const int64_t row = sidx[i];
+    if (i > 0 && sidx[i - 1] == row) return;
+    int end = i + 1;
+    while (end < B && sidx[end] == row) ++end;
+    float* dst = gtable + row * (long)E;
+    for (int e0 = lane * 4; e0 < E; e0 += 128) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = i; j < end; ++j) {
+            const long p = (long)spos[j] * E;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (e0 + t < E) {
+                    float g = __ldg(gout + p + e0 + t);
+                    float f = __ldg(fwd + p + e0 + t);
+                    a[t] += f > 0.f ? g : 0.f;
+                }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (e0 + t < E) dst[e0 + t] = a[t];
+    }
+}
+
+struct SortWs {
+    size_t keys_in_off, vals_in_off, temp_off, temp_bytes, total;
+};
+SortWs sort_layout(int B) {
+    SortWs w;
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const int64_t*)nullptr, (int64_t*)nullptr,
+                                    (const int32_t*)nullptr, (int32_t*)nullptr, B);
+    w.vals_in_off = 0;
+    w.temp_off = round_up_l((long)B * 4, 256);
+    w.temp_bytes = temp;
+    w.total = w.temp_off + round_up_l((long)temp, 256);
+    return w;
+}
+
+}  // namespace
+
+extern "C" int dcue_gather_relu_fwd(const float* table, const int64_t* idx, int B, int U, int E, float* out,
+                                    float* raw_out, int* err_flag, void* stream) {
+    DCUE_CHECK_ARG(table && idx && out && err_flag && B >= 0 && U > 0 && E > 0);
+    if (B == 0) return 0;
+    gather_relu_kernel<<<ceil_div_i(B, 8), 256, 0, (cudaStream_t)stream>>>(table, idx, B, U, E, out, raw_out,
+                                                                            err_flag);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" size_t dcue_sort_ws_bytes(int B) { return B > 0 ? sort_layout(B).total : 256; }
+
+extern "C" int dcue_sort_indices(const int64_t* idx, int B, int U, int64_t* sorted_idx, int32_t* sorted_pos,
+                                 void* ws, size_t ws_bytes, void* stream) {
+    DCUE_CHECK_ARG(idx && sorted_idx && sorted_pos && ws && B >= 0 && U > 0);
+    if (B == 0) return 0;
+    SortWs w = sort_layout(B);
+    if (ws_bytes < w.total) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_sort_indices: workspace %zu < %zu", ws_bytes, w.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t* iota = reinterpret_cast<int32_t*>((char*)ws + w.vals_in_off);
+    iota_kernel<<<ceil_div_i(B, 256), 256, 0, st>>>(iota, B);
+    DCUE_LAUNCH_CHECK();
+    int end_bit = 1;
+    while (end_bit < 63 && (1LL << end_bit) < (long long)U) ++end_bit;
+    size_t temp = w.temp_bytes;
+    DCUE_CUDA(cub::DeviceRadixSort::SortPairs((char*)ws + w.temp_off, temp, idx, sorted_idx, iota, sorted_pos, B,
+                                              0, end_bit, st));
+    return 0;
+}
+
+extern "C" int dcue_scatter_add_bwd(const float* grad_out, const float* fwd_out, const int64_t* sorted_idx,
+                                    const int32_t* sorted_pos, int B, int U, int E, float* grad_table,
+                                    void* stream) {
+    DCUE_CHECK_ARG(grad_out && fwd_out && sorted_idx && sorted_pos && grad_table && B >= 0 && U > 0 && E > 0);
+    if (B == 0) return 0;
+    segment_scatter_kernel<<<ceil_div_i(B, 8), 256, 0, (cudaStream_t)stream>>>(grad_out, fwd_out, sorted_idx,
+                                                                                sorted_pos, B, E, grad_table);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,200 @@
+// fp32 CUDA-core GEMMs for the small dense layers of DCUE: the user MLP
+// (dcrecommend/dcue/embeddings/userembedding.py:42-44), the k=1 conv and the fc of the song
+// tower (truedcuemel1dbn.py:57-59,101).  <0.2 % of the step's FLOPs; kept in fp32 so that the
+// user features match the reference to ~1e-6.
+//
+// One strided kernel:  C[i,j] = sum_r A(i,r) * B(r,j)  (+bias[j]) (relu) (* mask[i,j] > 0)
+// 64x64 tile, BK = 16, 256 threads, 4x4 outputs per thread, optional split over r (grid.z)
+// into a workspace that a second kernel reduces in fixed order (deterministic).
+#include "common.cuh"
+
+namespace {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+struct GemmP {
+    const float* A; long sAi, sAr;
+    const float* B; long sBr, sBj;
+    float* C; long ldc;       // C[i*ldc + j]   (or partial buffer when splits > 1)
+    const float* bias;        // [J] or null
+    const float* mask; long ldmask;
+    int I, J, R, relu, splits;
+    long split_stride;        // elements between partial buffers
+};
+
+__global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
+    __shared__ float As[TK][TM + 4];
+    __shared__ float Bs[TK][TN + 4];
+    const int tid = threadIdx.x;
+    const int i0 = blockIdx.y * TM, j0 = blockIdx.x * TN;
+    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 4x4
+    // split range over r
+    const int rchunk = ceil_div_i(ceil_div_i(p.R, TK), p.splits) * TK;
+    const int rbeg = blockIdx.z * rchunk;
+    const int rend = min(p.R, rbeg + rchunk);
+
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+    const bool a_r_contig = (p.sAr == 1);
+    const bool b_j_contig = (p.sBj == 1);
+
+    for (int r0 = rbeg; r0 < rend; r0 += TK) {
+        // ---- load A tile (TM x TK)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int li, lr;
+            if (a_r_contig) { li = tid >> 2; lr = (tid & 3) * 4 + q; }
+            else            { lr = tid >> 4; li = (tid & 15) * 4 + q; }
+            const int gi = i0 + li, gr = r0 + lr;
+            As[lr][li] = (gi < p.I && gr < rend) ? __ldg(p.A + gi * p.sAi + gr * p.sAr) : 0.f;
+        }
+        // ---- load B tile (TK x TN)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int lj, lr;
+            if (b_j_contig) { lr = tid >> 4; lj = (tid & 15) * 4 + q; }
+            else            { lj = tid >> 2; lr = (tid & 3) * 4 + q; }
+            const int gj = j0 + lj, gr = r0 + lr;
+            Bs[lr][lj] = (gj < p.J && gr < rend) ? __ldg(p.B + gr * p.sBr + gj * p.sBj) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { a[q] = As[k][ty * 4 + q]; b[q] = Bs[k][tx * 4 + q]; }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+        }
+        __syncthreads();
+    }
+    float* C = p.C + (long)blockIdx.z * p.split_stride;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        const int gi = i0 + ty * 4 + x;
+        if (gi >= p.I) continue;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int gj = j0 + tx * 4 + y;
+            if (gj >= p.J) continue;
+            float v = acc[x][y];
+            if (p.splits == 1) {
+                if (p.bias) v += p.bias[gj];
+                if (p.relu) v = fmaxf(v, 0.f);
+                if (p.mask) v = p.mask[gi * p.ldmask + gj] > 0.f ? v : 0.f;
+            }
+            C[gi * p.ldc + gj] = v;
+        }
+    }
+}
+
+__global__ void split_reduce_kernel(const float* __restrict__ part, int splits, long n, float* __restrict__ out) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += part[(long)k * n + i];
+    out[i] = s;
+}
+
+// column sums of a [M, N] matrix (row stride ld): out[n] = sum_m x[m,n]; fixed-order, deterministic
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int ld, int M, int N,
+                                                     float* __restrict__ out) {
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int rl = threadIdx.x >> 5;
+    float s = 0.f;
+    if (c < N)
+        for (int m = rl; m < M; m += 8) s += x[(long)m * ld + c];
+    red[rl][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (rl == 0 && c < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        out[c] = t;
+    }
+}
+
+int wgrad_splits(int M, int K, int N) {
+    const int tiles = ceil_div_i(N, TM) * ceil_div_i(K, TN);
+    int s = (2 * dcue_num_sms() + tiles - 1) / tiles;
+    const int maxs = ceil_div_i(M, 4 * TK);
+    if (s > maxs) s = maxs;
+    if (s < 1) s = 1;
+    if (s > 64) s = 64;
+    return s;
+}
+
+}  // namespace
+
+extern "C" int dcue_linear_fwd(const float* X, int ldx, const float* W, const float* b, int M, int K, int N,
+                               int relu, float* Y, int ldy, void* stream) {
+    DCUE_CHECK_ARG(X && W && Y && M >= 0 && K > 0 && N > 0 && ldx >= K && ldy >= N);
+    if (M == 0) return 0;
+    GemmP p{};
+    p.A = X; p.sAi = ldx; p.sAr = 1;
+    p.B = W; p.sBr = 1; p.sBj = K;  // B(r,j) = W[j,r]
+    p.C = Y; p.ldc = ldy; p.bias = b; p.mask = nullptr; p.ldmask = 0;
+    p.I = M; p.J = N; p.R = K; p.relu = relu; p.splits = 1; p.split_stride = 0;
+    dim3 grid(ceil_div_i(N, TN), ceil_div_i(M, TM), 1);
+    gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcue_linear_dgrad(const float* dY, int lddy, const float* W, int M, int K, int N,
+                                 const float* mask, int ldmask, float* dX, int lddx, void* stream) {
+    DCUE_CHECK_ARG(dY && W && dX && M >= 0 && K > 0 && N > 0 && lddy >= N && lddx >= K);
+    if (M == 0) return 0;
+    GemmP p{};
+    p.A = dY; p.sAi = lddy; p.sAr = 1;
+    p.B = W; p.sBr = K; p.sBj = 1;  // B(r=n, j=k) = W[n,k]
+    p.C = dX; p.ldc = lddx; p.bias = nullptr; p.mask = mask; p.ldmask = ldmask;
+    p.I = M; p.J = K; p.R = N; p.relu = 0; p.splits = 1; p.split_stride = 0;
+    dim3 grid(ceil_div_i(K, TN), ceil_div_i(M, TM), 1);
+    gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" size_t dcue_linear_wgrad_ws_bytes(int M, int K, int N) {
+    return (size_t)wgrad_splits(M, K, N) * (size_t)N * (size_t)K * sizeof(float) + 256;
+}
+
+extern "C" int dcue_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, int M, int K, int N,
+                                 float* dW, float* db, void* ws, size_t ws_bytes, void* stream) {
+    DCUE_CHECK_ARG(dY && X && dW && M >= 0 && K > 0 && N > 0 && lddy >= N && ldx >= K);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (M == 0) {
+        DCUE_CUDA(cudaMemsetAsync(dW, 0, (size_t)N * K * sizeof(float), st));
+        if (db) DCUE_CUDA(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
+        return 0;
+    }
+    const int splits = wgrad_splits(M, K, N);
+    if (splits > 1 && (!ws || ws_bytes < (size_t)splits * N * K * sizeof(float)))
+        DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_linear_wgrad: workspace too small");
+    GemmP p{};
+    p.A = dY; p.sAi = 1; p.sAr = lddy;  // A(i=n, r=m) = dY[m,n]
+    p.B = X; p.sBr = ldx; p.sBj = 1;    // B(r=m, j=k) = X[m,k]
+    p.C = splits > 1 ? (float*)ws : dW; p.ldc = K; p.bias = nullptr; p.mask = nullptr; p.ldmask = 0;
+    p.I = N; p.J = K; p.R = M; p.relu = 0; p.splits = splits; p.split_stride = (long)N * K;
+    dim3 grid(ceil_div_i(K, TN), ceil_div_i(N, TM), splits);
+    gemm_kernel<<<grid, 256, 0, st>>>(p);
+    DCUE_LAUNCH_CHECK();
+    if (splits > 1) {
+        const long n = (long)N * K;
+        split_reduce_kernel<<<ceil_div_i(n, 256), 256, 0, st>>>((const float*)ws, splits, n, dW);
+        DCUE_LAUNCH_CHECK();
+    }
+    if (db) {
+        colsum_kernel<<<ceil_div_i(N, 32), 256, 0, st>>>(dY, lddy, M, N, db);
+        DCUE_LAUNCH_CHECK();
+    }
+    return 0;
+}

@@ -1,0 +1,395 @@
+// Eval scorer: all-pairs cosine score GEMM (tcgen05, fp32 accumulate in TMEM) with a fused
+// streaming top-k kept in shared memory — the score matrix is never materialised.
+//
+// Generalises DCUE.predict (dcrecommend/nn/dcue.py:495-513: model.sim of one user's factor row
+// against every candidate song's factor row) to all users x all songs.
+//
+//   users on the MMA M axis (one TMEM lane = one user), songs on N.  CTA = 128 users x one
+//   contiguous range of songs; the user tile stays in smem, song tiles stream through a 2-stage
+//   cp.async.bulk ring; accumulators are double buffered so the filter overlaps the next MMA.
+//   Filter: each epilogue thread compares its user's 128 fresh scores with that user's running
+//   threshold (the smallest kept score, in a register).  Passing scores are rare after warm-up
+//   (~k ln(I/k) per user); they are inserted warp-cooperatively (ballot -> all 32 lanes find and
+//   replace the minimum of that user's 128-slot candidate list in smem).
+//   Finish: rank sort of the 128 slots per user, write the k best (descending, ties by index).
+#include "common.cuh"
+
+namespace {
+
+constexpr int TU = 128;        // users per CTA (MMA M)
+constexpr int TI = 128;        // songs per tile (MMA N)
+constexpr int SLOTS = 128;     // kept candidates per user (k <= SLOTS)
+constexpr int ROWB = 16;
+constexpr int PANEL_BYTES = 128 * ROWB;  // 2048: one 8-wide K chunk of a 128-row tile
+constexpr int NSTAGE = 2;
+constexpr int NTHREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t make_idesc(int a_fmt, int b_fmt, int M, int N) {
+    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+// warp-cooperative: replace the minimum of user `ul`'s slot list by (s, it); returns the new minimum
+__device__ __forceinline__ float insert_candidate(float* __restrict__ cs, int* __restrict__ ci, int ul, float s, int it,
+                                                  int lane) {
+    float4* row = reinterpret_cast<float4*>(cs + ul * SLOTS);
+    float4 c = row[lane];
+    float mv = c.x;
+    int ms = 0;
+    if (c.y < mv) { mv = c.y; ms = 1; }
+    if (c.z < mv) { mv = c.z; ms = 2; }
+    if (c.w < mv) { mv = c.w; ms = 3; }
+    ms += lane * 4;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, mv, o);
+        const int os = __shfl_xor_sync(0xffffffffu, ms, o);
+        if (ov < mv || (ov == mv && os < ms)) { mv = ov; ms = os; }
+    }
+    if ((ms >> 2) == lane) {
+        cs[ul * SLOTS + ms] = s;
+        ci[ul * SLOTS + ms] = it;
+        const int w = ms & 3;
+        if (w == 0) c.x = s; else if (w == 1) c.y = s; else if (w == 2) c.z = s; else c.w = s;
+    }
+    float nm = fminf(fminf(c.x, c.y), fminf(c.z, c.w));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nm = fminf(nm, __shfl_xor_sync(0xffffffffu, nm, o));
+    __syncwarp();
+    return nm;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long n_users, const uint4* __restrict__ items,
+            long i_rows, long n_items, int Kp, int fmt, int k, long item_offset, long items_per_split,
+            float* __restrict__ out_s, int64_t* __restrict__ out_i /* [splits][n_users][k] */) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int npan = Kp / 8;
+    const int tile_bytes = npan * PANEL_BYTES;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + tile_bytes;
+    float* cs = reinterpret_cast<float*>(sB + NSTAGE * tile_bytes);
+    int* ci = reinterpret_cast<int*>(cs + TU * SLOTS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ci + TU * SLOTS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+    const uint32_t AFULL = bar0 + 8u * (2 * NSTAGE);
+    auto TFULL = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 1 + a); };
+    auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 3 + a); };
+
+    const long u0 = (long)blockIdx.x * TU;
+    const long ibeg = (long)blockIdx.y * items_per_split;
+    const long iend = ibeg + items_per_split < n_items ? ibeg + items_per_split : n_items;
+    const long ntiles = iend > ibeg ? (iend - ibeg + TI - 1) / TI : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        mbar_init(AFULL, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 4); }
+        fence_barrier_init();
+    }
+    for (int e = threadIdx.x; e < TU * SLOTS; e += NTHREADS) { cs[e] = -INFINITY; ci[e] = -1; }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(AFULL, (uint32_t)tile_bytes);
+            for (int q = 0; q < npan; ++q)
+                bulk_g2s(smem_u32(sA + q * PANEL_BYTES), users + (long)q * u_rows + u0, PANEL_BYTES, AFULL);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long t = 0; t < ntiles; ++t) {
+                mbar_wait(EMPTY(stage), phase ^ 1);
+                mbar_expect_tx(FULL(stage), (uint32_t)tile_bytes);
+                const long r0 = ibeg + t * TI;
+                uint8_t* dst = sB + stage * tile_bytes;
+                for (int q = 0; q < npan; ++q)
+                    bulk_g2s(smem_u32(dst + q * PANEL_BYTES), items + (long)q * i_rows + r0, PANEL_BYTES, FULL(stage));
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(fmt, fmt, TU, TI);
+            mbar_wait(AFULL, 0);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (long t = 0; t < ntiles; ++t) {
+                mbar_wait(TEMPTY(acc), acc_phase ^ 1);
+                mbar_wait(FULL(stage), phase);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + stage * tile_bytes);
+                for (int c = 0; c < Kp / 16; ++c) {
+                    const uint64_t ad = make_desc(a0 + (uint32_t)(2 * c * PANEL_BYTES), PANEL_BYTES, 128);
+                    const uint64_t bd = make_desc(b0 + (uint32_t)(2 * c * PANEL_BYTES), PANEL_BYTES, 128);
+                    umma_f16(tmem_base + (uint32_t)(acc * TI), ad, bd, idesc, c != 0);
+                }
+                umma_commit(EMPTY(stage));
+                umma_commit(TFULL(acc));
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int quarter = warp & 3;
+        const int ul = quarter * 32 + lane;  // user within the tile == TMEM lane
+        float thr = -INFINITY;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long t = 0; t < ntiles; ++t) {
+            mbar_wait(TFULL(acc), acc_phase);
+            tc_fence_after();
+            const long it0 = ibeg + t * TI;
+#pragma unroll 1
+            for (int ch = 0; ch < TI / 32; ++ch) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TI + ch * 32), v);
+                const long ib = it0 + ch * 32;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const bool pass = v[j] > thr && (ib + j) < iend;
+                    unsigned mask = __ballot_sync(0xffffffffu, pass);
+                    while (mask) {
+                        const int l = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const float s = __shfl_sync(0xffffffffu, v[j], l);
+                        const float nt = insert_candidate(cs, ci, quarter * 32 + l, s, (int)(ib + j), lane);
+                        if (lane == l) thr = nt;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(TEMPTY(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        // ---- finish: rank sort each of this warp's 32 users' slot lists, write the k best
+        __syncwarp();
+        for (int uu = 0; uu < 32; ++uu) {
+            const int usr = quarter * 32 + uu;
+            const long gu = u0 + usr;
+            if (gu >= n_users) break;
+            float es[4];
+            int ei[4], rk[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { es[e] = cs[usr * SLOTS + lane * 4 + e]; ei[e] = ci[usr * SLOTS + lane * 4 + e]; }
+            for (int r = 0; r < SLOTS; ++r) {
+                const float sr = cs[usr * SLOTS + r];
+                const int ir = ci[usr * SLOTS + r];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) rk[e] += (sr > es[e]) || (sr == es[e] && (unsigned)ir < (unsigned)ei[e]);
+            }
+            const long ob = ((long)blockIdx.y * n_users + gu) * k;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (rk[e] < k) {
+                    out_s[ob + rk[e]] = es[e];
+                    out_i[ob + rk[e]] = ei[e] < 0 ? -1 : (int64_t)ei[e] + item_offset;
+                }
+        }
+        (void)ul;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// x[rows,F] fp32 -> x/max(|x|,eps) as 16-bit K-major panels [Kp/8][round_up(rows,128)][8]
+__global__ void __launch_bounds__(256)
+normalize_rows_kernel(const float* __restrict__ x, long rows, int F, float eps, int Kp, int fmt, uint4* __restrict__ out,
+                      long panel_rows) {
+    const int lane = threadIdx.x & 31;
+    const long r = blockIdx.x * 8L + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const float* xr = x + r * F;
+    float ss = 0.f;
+    for (int c = lane; c < F; c += 32) { const float v = xr[c]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+    for (int q = lane; q < Kp / 8; q += 32) {
+        unsigned short h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = q * 8 + j;
+            h[j] = cvt_f32_to16(c < F ? xr[c] * inv : 0.f, fmt);
+        }
+        uint4 o;
+        o.x = h[0] | ((unsigned)h[1] << 16);
+        o.y = h[2] | ((unsigned)h[3] << 16);
+        o.z = h[4] | ((unsigned)h[5] << 16);
+        o.w = h[6] | ((unsigned)h[7] << 16);
+        out[(long)q * panel_rows + r] = o;
+    }
+}
+
+// k-way merge of `parts` descending lists per user, one thread per user
+__global__ void topk_merge_kernel(const float* __restrict__ s, const int64_t* __restrict__ idx, int parts, long n_users,
+                                  int k, float* __restrict__ os, int64_t* __restrict__ oi) {
+    const long u = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (u >= n_users) return;
+    int head[16];
+    for (int p = 0; p < parts; ++p) head[p] = 0;
+    for (int r = 0; r < k; ++r) {
+        int bp = -1;
+        float bs = -INFINITY;
+        int64_t bi = -1;
+        for (int p = 0; p < parts; ++p) {
+            if (head[p] >= k) continue;
+            const long o = ((long)p * n_users + u) * k + head[p];
+            const float v = s[o];
+            const int64_t ii = idx[o];
+            if (ii < 0) continue;
+            if (bp < 0 || v > bs || (v == bs && ii < bi)) { bp = p; bs = v; bi = ii; }
+        }
+        os[u * k + r] = bp < 0 ? -INFINITY : bs;
+        oi[u * k + r] = bi;
+        if (bp >= 0) ++head[bp];
+    }
+}
+
+int topk_splits(long n_users, long n_items) {
+    const long ublocks = (n_users + TU - 1) / TU;
+    long want = (2L * dcue_num_sms() + ublocks - 1) / ublocks;
+    const long maxs = (n_items + 4 * TI - 1) / (4 * TI);
+    if (want > maxs) want = maxs;
+    if (want > 16) want = 16;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+}  // namespace
+
+extern "C" int dcue_normalize_rows(const float* x, long rows, int F, float eps, int Kp, int fmt, void* out, void* stream) {
+    DCUE_CHECK_ARG(x && out && rows >= 0 && F > 0 && Kp >= F && Kp % 16 == 0 && Kp <= 256);
+    if (rows == 0) return 0;
+    normalize_rows_kernel<<<ceil_div_i(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, F, eps, Kp, fmt, (uint4*)out,
+                                                                                 round_up_l(rows, 128));
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" size_t dcue_topk_ws_bytes(int impl, long n_users, long n_items, int k) {
+    (void)impl;
+    const int splits = topk_splits(n_users, n_items);
+    return splits > 1 ? (size_t)splits * n_users * k * (sizeof(float) + sizeof(int64_t)) + 256 : 256;
+}
+
+extern "C" int dcue_topk_scores(int impl, const void* users_n, long n_users, const void* items_n, long n_items, int Kp,
+                                int fmt, int k, long item_offset, float* top_scores, int64_t* top_idx, void* ws,
+                                size_t ws_bytes, void* stream) {
+    DCUE_CHECK_ARG(users_n && items_n && top_scores && top_idx && n_users >= 0 && n_items >= 0 && k > 0 && k <= SLOTS);
+    DCUE_CHECK_ARG(Kp % 16 == 0 && Kp >= 16 && Kp <= 128);
+    if (impl != DCUE_IMPL_TC) DCUE_FAIL(DCUE_E_UNSUPPORTED, "dcue_topk_scores: only the tcgen05 implementation exists");
+    if (n_users == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int splits = topk_splits(n_users, n_items);
+    long per = (n_items + splits - 1) / splits;
+    per = round_up_l(per > 0 ? per : 1, TI);
+    float* os = top_scores;
+    int64_t* oi = top_idx;
+    if (splits > 1) {
+        const size_t need = (size_t)splits * n_users * k * (sizeof(float) + sizeof(int64_t));
+        if (!ws || ws_bytes < need) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_topk_scores: workspace %zu < %zu", ws_bytes, need);
+        oi = (int64_t*)ws;
+        os = (float*)((char*)ws + (size_t)splits * n_users * k * sizeof(int64_t));
+    }
+    // slots that are never filled (fewer than k songs in a split) must read as "missing"
+    DCUE_CUDA(cudaMemsetAsync(oi, 0xff, (size_t)splits * n_users * k * sizeof(int64_t), st));
+    const size_t smem = (size_t)(1 + NSTAGE) * (Kp / 8) * PANEL_BYTES + (size_t)TU * SLOTS * 8 + 8 * (2 * NSTAGE + 5) + 16;
+    DCUE_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((n_users + TU - 1) / TU), splits);
+    topk_kernel<<<grid, NTHREADS, smem, st>>>((const uint4*)users_n, round_up_l(n_users, 128), n_users,
+                                              (const uint4*)items_n, round_up_l(n_items, 128), n_items, Kp, fmt, k,
+                                              item_offset, per, os, oi);
+    DCUE_LAUNCH_CHECK();
+    if (splits > 1) {
+        topk_merge_kernel<<<ceil_div_i(n_users, 128), 128, 0, st>>>(os, oi, splits, n_users, k, top_scores, top_idx);
+        DCUE_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int dcue_topk_merge(const float* scores, const int64_t* idx, int parts, long n_users, int k, float* out_scores,
+                               int64_t* out_idx, void* stream) {
+    DCUE_CHECK_ARG(scores && idx && out_scores && out_idx && parts >= 1 && parts <= 16 && n_users >= 0 && k > 0);
+    if (n_users == 0) return 0;
+    topk_merge_kernel<<<ceil_div_i(n_users, 128), 128, 0, (cudaStream_t)stream>>>(scores, idx, parts, n_users, k, out_scores,
+                                                                                  out_idx);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,82 @@
+"""B200 drop-in for dcrecommend/dcue/dcue.py: Deep Content-User Embedding network
+(Lee et al., DLRS 2018) with forward(u, pos, neg) on hand-written sm_100a kernels."""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .audiomodels.truedcuemel1d import TrueDcueNetMel1D
+from .audiomodels.truedcuemel1dbn import TrueDcueNetMel1DBn
+from .audiomodels.truedcuemel1dres import TrueDcueNetMel1DRes
+from .audiomodels.truedcuemel1dresbn import TrueDcueNetMel1DResBn
+from .embeddings.userembedding import UserEmbeddings
+
+
+class CosineSimilarity(nn.Module):
+    """nn.CosineSimilarity(dim=1) for row-wise [M,F] x [M,F] inputs (DCUE.predict,
+    dcrecommend/nn/dcue.py:513) on the score kernel."""
+
+    def __init__(self, dim=1, eps=1e-8):
+        super().__init__()
+        self.dim, self.eps = dim, eps
+
+    def forward(self, x1, x2):
+        if x1.dim() != 2 or x1.shape != x2.shape or self.dim != 1:
+            raise NotImplementedError("CosineSimilarity on B200 supports row-wise [M,F] x [M,F] inputs")
+        M, F = x1.shape
+        feats = torch.cat([x2, torch.zeros_like(x2)], dim=0)  # cos(x, 0) == 0 -> scores = cos(x1, x2)
+        return ops.ScoreFn.apply(x1, feats, M, 1).view(M)
+
+
+class DCUENet(nn.Module):
+
+    """DCUE model: user tower + mel-spectrogram ConvNet song tower + cosine scores."""
+
+    def __init__(self, dict_args):
+        """dict_args keys: feature_dim, conv_hidden, user_embdim, user_count, model_type."""
+        super().__init__()
+        self.feature_dim = dict_args["feature_dim"]
+        self.conv_hidden = dict_args["conv_hidden"]
+        self.user_embdim = dict_args["user_embdim"]
+        self.user_count = dict_args["user_count"]
+        self.model_type = dict_args["model_type"]
+
+        conv_args = {"output_size": self.feature_dim, "hidden_size": self.conv_hidden}
+        towers = {"truedcuemel1d": TrueDcueNetMel1D, "truedcuemel1dres": TrueDcueNetMel1DRes,
+                  "truedcuemel1dbn": TrueDcueNetMel1DBn, "truedcuemel1dresbn": TrueDcueNetMel1DResBn}
+        if self.model_type not in towers:
+            raise ValueError("{} is not a recognized model type!".format(self.model_type))
+        self.conv = towers[self.model_type](conv_args)
+
+        self.user_embd = UserEmbeddings({"user_embdim": self.user_embdim, "user_count": self.user_count,
+                                         "feature_dim": self.feature_dim})
+        self.sim = CosineSimilarity(dim=1)
+
+    def forward(self, u, pos, neg=None):
+        """u int64 [B]; pos f32 [B,128,L]; neg f32 [B,N,128,L] ->
+        (scores [B,N], u_featvects [B,F], pos_featvects [B,F], neg_featvects [B,N,F]).
+        With neg=None the reference raises NameError; here scores is [B,1] = cos(u,pos) and
+        neg_featvects is None."""
+        u_featvects = self.user_embd(u)
+        B = pos.shape[0]
+        if neg is not None:
+            N = neg.shape[1]
+            feats = self.conv.forward_posneg(pos, neg)
+            scores = ops.ScoreFn.apply(u_featvects, feats, B, N)
+            return scores, u_featvects, feats[:B], feats[B:].view(B, N, self.feature_dim)
+        pos_featvects = self.conv.forward_posneg(pos, None)
+        scores = self.sim(u_featvects, pos_featvects).view(B, 1)
+        return scores, u_featvects, pos_featvects, None
+
+    def hinge_loss_step(self, u, pos, neg, margin, batch_total=None, return_all=False):
+        """forward + DCUE._loss_func (max(0, margin - scores).sum(1).mean()) with the scoring, the
+        loss and their backward fused in one kernel.  batch_total = global batch size under data
+        parallelism (defaults to the local B)."""
+        u_featvects = self.user_embd(u)
+        B, N = neg.shape[0], neg.shape[1]
+        feats = self.conv.forward_posneg(pos, neg)
+        total = B if batch_total is None else batch_total
+        loss_rows, scores = ops.HingeScoreFn.apply(u_featvects, feats, B, N, margin, total)
+        loss = loss_rows.sum() / total
+        if return_all:
+            return loss, scores, u_featvects, feats[:B], feats[B:].view(B, N, self.feature_dim)
+        return loss

@@ -1,0 +1,448 @@
+"""Host-side orchestration of the DCUE hot path: thin ``torch.autograd.Function``s that hand raw
+device pointers of PyTorch-owned buffers to the C-ABI kernels (``_lib``).  No ATen compute and
+no CPU fallback here: PyTorch provides memory, streams and autograd bookkeeping only.
+
+Reference call sites replaced
+  song tower   dcrecommend/dcue/audiomodels/truedcuemel1d{,bn,res,resbn}.py  forward + autograd
+  user tower   dcrecommend/dcue/embeddings/userembedding.py:33-44            forward + autograd
+  scoring      dcrecommend/dcue/dcue.py:93-106, dcrecommend/nn/dcue.py:167-170
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib as L
+
+N_MELS = 128
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+COS_EPS = 1e-8
+
+#  (k, pad, pool) of layer1..layer4 (truedcuemel1dbn.py:25-54)
+STAGES = ((4, 2, 4), (4, 2, 4), (4, 2, 4), (2, 1, 2))
+
+
+def _roundup(a, b):
+    return (a + b - 1) // b * b
+
+
+def conv_impl():
+    """tcgen05 path unless DCUE_CONV_IMPL=simt (validator) is requested."""
+    return L.IMPL_SIMT if os.environ.get("DCUE_CONV_IMPL", "tc").lower() == "simt" else L.IMPL_TC
+
+
+def operand_fmt():
+    """16-bit format of the forward conv operands: fp16 (default) or bf16 (DCUE_OPERAND=bf16)."""
+    return L.FMT_BF16 if os.environ.get("DCUE_OPERAND", "f16").lower() == "bf16" else L.FMT_F16
+
+
+def tower_geometry(frames):
+    """Flat padded row geometry of the four conv stages for `frames` input frames."""
+    geo, lin = [], frames
+    for k, pad, pool in STAGES:
+        lout = lin + 2 * pad - k + 1
+        P = lout // pool
+        if P < 1:
+            raise ValueError("input of %d frames is too short for the DCUE tower" % frames)
+        # rows per spectrogram: all data rows, and a zero tail of >= k-1 rows after the last live
+        # conv output so neither the taps nor the dgrad ever see a neighbouring spectrogram
+        lp = _roundup(max(lin + pad, P * pool + k - 1), pool)
+        geo.append(dict(k=k, pad=pad, pool=pool, Lin=lin, Lout=lout, P=P, Lp=lp))
+        lin = P
+    if lin != 1:
+        raise ValueError("the DCUE tower needs an input length that pools down to 1 frame (got %d -> %d)"
+                         % (frames, lin))
+    return geo
+
+
+class Panel:
+    """16-bit [rows, 128] activation matrix in the panel layout, zero-initialised (padding rows
+    are never written afterwards)."""
+
+    def __init__(self, S, Lp, device):
+        self.rows_total = S * Lp
+        self.panel_rows = L.FRONT_HALO + _roundup(max(self.rows_total, 1), 128) + L.BACK_HALO
+        self.buf = torch.zeros(16 * self.panel_rows * 8, dtype=torch.int16, device=device)
+        self.base = self.buf.data_ptr() + L.FRONT_HALO * 16
+
+
+class TowerWorkspace:
+    """All device buffers of one tower forward(+backward) for a given (S, frames)."""
+
+    def __init__(self, S, frames, H, F, res, device):
+        self.key = (S, frames, H, F, res, str(device))
+        self.S, self.geo, self.device = S, tower_geometry(frames), device
+        f32 = dict(dtype=torch.float32, device=device)
+        self.X = [Panel(S, g["Lp"], device) for g in self.geo]
+        self.z = [torch.empty(S * g["P"], H, **f32) for g in self.geo]
+        self.code = [torch.empty(S * g["P"], H, dtype=torch.uint8, device=device) for g in self.geo]
+        self.y4 = torch.empty(S, H, **f32)
+        self.z5 = torch.empty(S, F, **f32)
+        self.fc_in = torch.empty(S, 4 * H + F if res else F, **f32)
+        self.sums = torch.zeros(6, 2 * 128, dtype=torch.float64, device=device)
+        self.bnp = torch.zeros(6, 4, 128, **f32)        # scale, shift, mean, rstd per BN layer
+        self.zero128 = torch.zeros(128, **f32)
+        self.one128 = torch.ones(128, **f32)
+        self.wp = [torch.empty(128 * g["k"] * 128, dtype=torch.int16, device=device) for g in self.geo]
+        nbytes = max(L.query("dcue_conv_ws_bytes", L.IMPL_TC, S, g["Lp"], 4, 128, 128) for g in self.geo)
+        nbytes = max(nbytes, L.query("dcue_ncl_stats_ws_bytes", 128), L.query("dcue_bn_bwd_ws_bytes", 128),
+                     L.query("dcue_linear_wgrad_ws_bytes", S, 4 * H + F, F),
+                     L.query("dcue_linear_wgrad_ws_bytes", S, H, F))
+        self.scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self._bwd = None
+
+    def bwd(self):
+        """Backward-only buffers, created on first use."""
+        if self._bwd is None:
+            S, dev = self.S, self.device
+            f32 = dict(dtype=torch.float32, device=dev)
+            b = {}
+            b["dY"] = [Panel(S, g["Lp"], dev) for g in self.geo]
+            b["dx"] = [torch.empty(S * g["Lin"], 128, **f32) for g in self.geo]
+            b["wpd"] = [torch.empty(128 * g["k"] * 128, dtype=torch.int16, device=dev) for g in self.geo]
+            b["bsum"] = torch.zeros(2 * 128, dtype=torch.float64, device=dev)
+            b["dsums"] = torch.zeros(6, 2 * 128, dtype=torch.float64, device=dev)
+            self._bwd = b
+        return self._bwd
+
+
+_POOL = {}
+
+
+def _acquire(S, frames, H, F, res, device):
+    key = (S, frames, H, F, res, str(device))
+    free = _POOL.get(key)
+    if free:
+        return free.pop()
+    return TowerWorkspace(S, frames, H, F, res, device)
+
+
+def _release(ws):
+    _POOL.setdefault(ws.key, []).append(ws)
+
+
+def clear_workspaces():
+    _POOL.clear()
+
+
+def _check_input(x, name):
+    if not x.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: the DCUE B200 path has no CPU fallback" % name)
+    if x.dtype != torch.float32:
+        raise TypeError("%s must be float32" % name)
+    return x.contiguous()
+
+
+class SongTowerFn(torch.autograd.Function):
+    """feats[S,F] = tower(cat(pos, neg))  without materialising the concatenation."""
+
+    @staticmethod
+    def forward(ctx, pos, neg, mod, training, *params):
+        has_bn, res = mod._has_bn, mod._res
+        H, F = mod.hidden_size, mod.output_size
+        if H != 128:
+            raise NotImplementedError("conv_hidden must be 128 for the B200 tower kernels (got %d)" % H)
+        if F > 128 or F % 4:
+            raise NotImplementedError("feature_dim must be a multiple of 4 and <= 128 (got %d)" % F)
+        pos = _check_input(pos, "pos")
+        S_pos, C, frames = pos.shape
+        if C != N_MELS:
+            raise ValueError("expected %d mel bins, got %d" % (N_MELS, C))
+        if neg is not None:
+            neg = _check_input(neg, "neg").view(-1, C, frames)
+        S_neg = 0 if neg is None else neg.shape[0]
+        S = S_pos + S_neg
+        dev = pos.device
+        st = L.stream()
+        impl, fmt = conv_impl(), operand_fmt()
+        ws = _acquire(S, frames, H, F, res, dev)
+        geo = ws.geo
+        scratch, nscr = ws.scratch.data_ptr(), ws.scratch.numel()
+        P = dict(zip(mod._param_names, params))
+        dp = mod._dp
+        world = 1 if dp is None else dp.world_size
+
+        def bn_finalize(i, count, C_):
+            """sums[i] -> scale/shift/mean/rstd of BN layer i (batch or running statistics)."""
+            bnm = getattr(mod, "bn%d" % i)
+            if training and dp is not None:
+                dp.all_reduce_sum(ws.sums[i])
+            L.call("dcue_bn_finalize", ws.sums[i].data_ptr(), float(count * world), C_, P["bn%d.weight" % i].data_ptr(),
+                   P["bn%d.bias" % i].data_ptr(), bnm.running_mean.data_ptr(), bnm.running_var.data_ptr(),
+                   bnm.num_batches_tracked.data_ptr(), BN_MOMENTUM, BN_EPS, int(training),
+                   ws.bnp[i, 0].data_ptr(), ws.bnp[i, 1].data_ptr(), ws.bnp[i, 2].data_ptr(), ws.bnp[i, 3].data_ptr(), st)
+
+        pos_p, neg_p = pos.data_ptr(), (None if neg is None else neg.data_ptr())
+        # ---- bn0 + transpose/convert into the layer1 operand panel
+        g0 = geo[0]
+        if has_bn:
+            if training:
+                L.call("dcue_ncl_stats", pos_p, S_pos, neg_p, S_neg, C, frames, ws.sums[0].data_ptr(), scratch, nscr, st)
+            bn_finalize(0, S * frames, C)
+            sc, sh = ws.bnp[0, 0].data_ptr(), ws.bnp[0, 1].data_ptr()
+        else:
+            sc = sh = None
+        L.call("dcue_ncl_pack", pos_p, S_pos, neg_p, S_neg, C, frames, sc, sh, ws.X[0].base, ws.X[0].panel_rows,
+               g0["Lp"], g0["pad"], fmt, st)
+        # ---- layer1..4: conv + pool + relu (+ BN statistics) -> affine -> next operand panel
+        for i, g in enumerate(geo, start=1):
+            Wt, bt = P["layer%d.weight" % i], P["layer%d.bias" % i]
+            L.call("dcue_pack_conv_weight", Wt.data_ptr(), H, 128, g["k"], 0, fmt, ws.wp[i - 1].data_ptr(), st)
+            want_stats = has_bn and training
+            L.call("dcue_conv_pool_fwd", impl, ws.X[i - 1].base, ws.X[i - 1].panel_rows, fmt, ws.wp[i - 1].data_ptr(),
+                   bt.data_ptr(), S, g["Lp"], g["P"], g["pool"], g["k"], 128, H, ws.z[i - 1].data_ptr(),
+                   ws.code[i - 1].data_ptr(), ws.sums[i].data_ptr() if want_stats else None, scratch, nscr, st)
+            if has_bn:
+                bn_finalize(i, S * g["P"], H)
+                sc, sh = ws.bnp[i, 0].data_ptr(), ws.bnp[i, 1].data_ptr()
+            else:
+                sc = sh = None
+            tp = ws.fc_in[:, (i - 1) * H:].data_ptr() if res else None
+            ldtp = ws.fc_in.shape[1]
+            if i < 4:
+                nx = geo[i]
+                L.call("dcue_affine_pack", ws.z[i - 1].data_ptr(), S, g["P"], H, sc, sh, ws.X[i].base, ws.X[i].panel_rows,
+                       nx["Lp"], nx["pad"], fmt, None, tp, ldtp, st)
+            else:
+                L.call("dcue_affine_pack", ws.z[3].data_ptr(), S, 1, H, sc, sh, None, 0, 1, 0, fmt, ws.y4.data_ptr(), tp,
+                       ldtp, st)
+        # ---- layer5 (k=1 conv == linear) + relu (+bn5), fc
+        L.call("dcue_linear_fwd", ws.y4.data_ptr(), H, P["layer5.weight"].data_ptr(), P["layer5.bias"].data_ptr(), S, H, F,
+               1, ws.z5.data_ptr(), F, st)
+        y5 = ws.fc_in[:, 4 * H:] if res else ws.fc_in
+        if has_bn:
+            if training:  # sum z, sum z^2 via the backward-reduce kernel with mean=0, rstd=1
+                L.call("dcue_bn_bwd_reduce", ws.z5.data_ptr(), F, None, 0, ws.z5.data_ptr(), ws.zero128.data_ptr(),
+                       ws.one128.data_ptr(), S, 1, F, ws.sums[5].data_ptr(), scratch, nscr, st)
+            bn_finalize(5, S, F)
+            sc, sh = ws.bnp[5, 0].data_ptr(), ws.bnp[5, 1].data_ptr()
+        else:
+            sc = sh = None
+        # strided affine copy of z5 into its slot of the fc input (time mean over P=1 rows)
+        L.call("dcue_affine_pack", ws.z5.data_ptr(), S, 1, F, sc, sh, None, 0, 1, 0, fmt, None, y5.data_ptr(),
+               ws.fc_in.shape[1], st)
+        out = torch.empty(S, F, dtype=torch.float32, device=dev)
+        Kfc = ws.fc_in.shape[1]
+        L.call("dcue_linear_fwd", ws.fc_in.data_ptr(), Kfc, P["fc.weight"].data_ptr(), P["fc.bias"].data_ptr(), S, Kfc, F,
+               0, out.data_ptr(), F, st)
+
+        needs_bwd = any(ctx.needs_input_grad)
+        if needs_bwd:
+            ctx.ws, ctx.mod, ctx.training = ws, mod, training
+            ctx.pos, ctx.neg, ctx.dims = pos, neg, (S_pos, S_neg, C, frames)
+            ctx.impl, ctx.fmt, ctx.world = impl, fmt, world
+            ctx.save_for_backward(*params)
+        else:
+            _release(ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        ws, mod, training = ctx.ws, ctx.mod, ctx.training
+        if ws is None:
+            raise RuntimeError("SongTowerFn backward called twice (workspace already released)")
+        has_bn, res = mod._has_bn, mod._res
+        H, F = mod.hidden_size, mod.output_size
+        S_pos, S_neg, C, frames = ctx.dims
+        S = S_pos + S_neg
+        geo, impl, fmt, world = ws.geo, ctx.impl, ctx.fmt, ctx.world
+        dp = mod._dp
+        params = ctx.saved_tensors
+        P = dict(zip(mod._param_names, params))
+        dev = gout.device
+        st = L.stream()
+        scratch, nscr = ws.scratch.data_ptr(), ws.scratch.numel()
+        b = ws.bwd()
+        f32 = dict(dtype=torch.float32, device=dev)
+        gout = gout.contiguous()
+        grads = {}
+        Kfc = ws.fc_in.shape[1]
+        gfmt = L.FMT_BF16  # gradients entering the conv backward are bf16 (fp16 would underflow)
+
+        def bn_sums(i, dy_ptr, lddy, dtp_ptr, lddtp, z, P_, C_):
+            """BN backward reductions of layer i (+ DP all-reduce); also emits dgamma/dbeta."""
+            L.call("dcue_bn_bwd_reduce", dy_ptr, lddy, dtp_ptr, lddtp, z.data_ptr(), ws.bnp[i, 2].data_ptr(),
+                   ws.bnp[i, 3].data_ptr(), S, P_, C_, b["dsums"][i].data_ptr(), scratch, nscr, st)
+            if dp is not None:
+                dp.all_reduce_sum(b["dsums"][i])
+            gw, gb = torch.empty(C_, **f32), torch.empty(C_, **f32)
+            L.call("dcue_cvt_f64_f32", b["dsums"][i][C_:].data_ptr(), C_, 1.0, gw.data_ptr(), st)
+            L.call("dcue_cvt_f64_f32", b["dsums"][i].data_ptr(), C_, 1.0, gb.data_ptr(), st)
+            grads["bn%d.weight" % i], grads["bn%d.bias" % i] = gw, gb
+
+        # ---- fc
+        gW, gb_ = torch.empty(F, Kfc, **f32), torch.empty(F, **f32)
+        L.call("dcue_linear_wgrad", gout.data_ptr(), F, ws.fc_in.data_ptr(), Kfc, S, Kfc, F, gW.data_ptr(), gb_.data_ptr(),
+               scratch, nscr, st)
+        grads["fc.weight"], grads["fc.bias"] = gW, gb_
+        dfc = torch.empty(S, Kfc, **f32)
+        L.call("dcue_linear_dgrad", gout.data_ptr(), F, P["fc.weight"].data_ptr(), S, Kfc, F, None, 0, dfc.data_ptr(), Kfc, st)
+        dy5 = dfc[:, 4 * H:] if res else dfc
+        # ---- bn5 + relu5 -> dz5 ; layer5
+        dz5 = torch.empty(S, F, **f32)
+        bn_train = has_bn and training
+        if bn_train:
+            bn_sums(5, dy5.data_ptr(), Kfc, None, 0, ws.z5, 1, F)
+        elif has_bn:
+            grads["bn5.weight"] = grads["bn5.bias"] = None  # eval-mode backward: affine treated as constant
+        L.call("dcue_bn_relu_unpool_bwd", dy5.data_ptr(), Kfc, None, 0, ws.z5.data_ptr(), None,
+               ws.bnp[5, 0].data_ptr() if has_bn else None, ws.bnp[5, 2].data_ptr() if has_bn else None,
+               ws.bnp[5, 3].data_ptr() if has_bn else None, b["dsums"][5].data_ptr() if bn_train else None,
+               float(S * world), S, 1, F, 1, 1, None, 0, gfmt, dz5.data_ptr(), None, scratch, nscr, st)
+        gW5, gb5 = torch.empty(F, H, 1, **f32), torch.empty(F, **f32)
+        L.call("dcue_linear_wgrad", dz5.data_ptr(), F, ws.y4.data_ptr(), H, S, H, F, gW5.data_ptr(), gb5.data_ptr(), scratch,
+               nscr, st)
+        grads["layer5.weight"], grads["layer5.bias"] = gW5, gb5
+        dy = torch.empty(S, H, **f32)  # gradient w.r.t. the stage-4 BN output
+        L.call("dcue_linear_dgrad", dz5.data_ptr(), F, P["layer5.weight"].data_ptr(), S, H, F, None, 0, dy.data_ptr(), H, st)
+        # ---- stages 4..1
+        for i in range(4, 0, -1):
+            g = geo[i - 1]
+            dtp = dfc[:, (i - 1) * H:].data_ptr() if res else None
+            if bn_train:
+                bn_sums(i, dy.data_ptr(), H, dtp, Kfc, ws.z[i - 1], g["P"], H)
+            elif has_bn:
+                grads["bn%d.weight" % i] = grads["bn%d.bias" % i] = None
+            dYp = b["dY"][i - 1]
+            L.call("dcue_bn_relu_unpool_bwd", dy.data_ptr(), H, dtp, Kfc, ws.z[i - 1].data_ptr(), ws.code[i - 1].data_ptr(),
+                   ws.bnp[i, 0].data_ptr() if has_bn else None, ws.bnp[i, 2].data_ptr() if has_bn else None,
+                   ws.bnp[i, 3].data_ptr() if has_bn else None, b["dsums"][i].data_ptr() if bn_train else None,
+                   float(S * g["P"] * world), S, g["P"], H, g["pool"], g["Lp"], dYp.base, dYp.panel_rows, gfmt, None,
+                   b["bsum"].data_ptr(), scratch, nscr, st)
+            gb_i = torch.empty(H, **f32)
+            L.call("dcue_cvt_f64_f32", b["bsum"].data_ptr(), H, 1.0, gb_i.data_ptr(), st)
+            gW_i = torch.empty(H, 128, g["k"], **f32)
+            L.call("dcue_conv_wgrad", impl, dYp.base, dYp.panel_rows, gfmt, ws.X[i - 1].base, ws.X[i - 1].panel_rows, fmt,
+                   S * g["Lp"], g["k"], 128, H, gW_i.data_ptr(), scratch, nscr, st)
+            grads["layer%d.weight" % i], grads["layer%d.bias" % i] = gW_i, gb_i
+            if i > 1 or has_bn:
+                L.call("dcue_pack_conv_weight", P["layer%d.weight" % i].data_ptr(), H, 128, g["k"], 1, fmt,
+                       b["wpd"][i - 1].data_ptr(), st)
+                dx = b["dx"][i - 1]
+                L.call("dcue_conv_dgrad", impl, dYp.base, dYp.panel_rows, gfmt, b["wpd"][i - 1].data_ptr(), fmt, S, g["Lp"],
+                       g["Lin"], g["pad"], g["k"], 128, H, dx.data_ptr(), scratch, nscr, st)
+                dy = dx
+        # ---- bn0
+        if bn_train:
+            L.call("dcue_ncl_bn_bwd_reduce", dy.data_ptr(), ctx.pos.data_ptr(), S_pos,
+                   None if ctx.neg is None else ctx.neg.data_ptr(), S_neg, C, frames, ws.bnp[0, 2].data_ptr(),
+                   ws.bnp[0, 3].data_ptr(), b["dsums"][0].data_ptr(), scratch, nscr, st)
+            if dp is not None:
+                dp.all_reduce_sum(b["dsums"][0])
+            gw, gb0 = torch.empty(C, **f32), torch.empty(C, **f32)
+            L.call("dcue_cvt_f64_f32", b["dsums"][0][C:].data_ptr(), C, 1.0, gw.data_ptr(), st)
+            L.call("dcue_cvt_f64_f32", b["dsums"][0].data_ptr(), C, 1.0, gb0.data_ptr(), st)
+            grads["bn0.weight"], grads["bn0.bias"] = gw, gb0
+        elif has_bn:
+            grads["bn0.weight"] = grads["bn0.bias"] = None
+        ctx.ws = None
+        _release(ws)
+        return (None, None, None, None) + tuple(grads.get(n) for n in mod._param_names)
+
+
+class UserTowerFn(torch.autograd.Function):
+    """u_f = linear2(relu(linear1(relu(table[idx]))))  (userembedding.py:40-44)."""
+
+    @staticmethod
+    def forward(ctx, idx, table, w1, b1, w2, b2):
+        if not table.is_cuda:
+            raise RuntimeError("the DCUE B200 path has no CPU fallback: move the model to a CUDA device")
+        if idx.dtype != torch.int64:
+            raise TypeError("user indices must be int64")
+        shape = idx.shape
+        idx = idx.to(table.device).contiguous().view(-1)
+        B, (U, E), F = idx.numel(), table.shape, w2.shape[0]
+        dev, st = table.device, L.stream()
+        f32 = dict(dtype=torch.float32, device=dev)
+        h0, h1, out = torch.empty(B, E, **f32), torch.empty(B, E, **f32), torch.empty(B, F, **f32)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.call("dcue_gather_relu_fwd", table.data_ptr(), idx.data_ptr(), B, U, E, h0.data_ptr(), None, err.data_ptr(), st)
+        L.call("dcue_linear_fwd", h0.data_ptr(), E, w1.data_ptr(), b1.data_ptr(), B, E, E, 1, h1.data_ptr(), E, st)
+        L.call("dcue_linear_fwd", h1.data_ptr(), E, w2.data_ptr(), b2.data_ptr(), B, E, F, 0, out.data_ptr(), F, st)
+        if int(err.item()):  # nn.Embedding raises on out-of-range indices; so do we
+            raise IndexError("index out of range in self")
+        ctx.save_for_backward(idx, table, w1, w2, h0, h1)
+        return out.view(*shape, F)
+
+    @staticmethod
+    def backward(ctx, gout):
+        idx, table, w1, w2, h0, h1 = ctx.saved_tensors
+        B, (U, E), F = idx.numel(), table.shape, w2.shape[0]
+        dev, st = table.device, L.stream()
+        f32 = dict(dtype=torch.float32, device=dev)
+        gout = gout.contiguous().view(B, F)
+        nscr = max(L.query("dcue_linear_wgrad_ws_bytes", B, E, F), L.query("dcue_linear_wgrad_ws_bytes", B, E, E),
+                   L.query("dcue_sort_ws_bytes", B))
+        scratch = torch.empty(nscr, dtype=torch.uint8, device=dev)
+        gw2, gb2 = torch.empty(F, E, **f32), torch.empty(F, **f32)
+        L.call("dcue_linear_wgrad", gout.data_ptr(), F, h1.data_ptr(), E, B, E, F, gw2.data_ptr(), gb2.data_ptr(),
+               scratch.data_ptr(), nscr, st)
+        dh1 = torch.empty(B, E, **f32)
+        L.call("dcue_linear_dgrad", gout.data_ptr(), F, w2.data_ptr(), B, E, F, h1.data_ptr(), E, dh1.data_ptr(), E, st)
+        gw1, gb1 = torch.empty(E, E, **f32), torch.empty(E, **f32)
+        L.call("dcue_linear_wgrad", dh1.data_ptr(), E, h0.data_ptr(), E, B, E, E, gw1.data_ptr(), gb1.data_ptr(),
+               scratch.data_ptr(), nscr, st)
+        gtable = None
+        if ctx.needs_input_grad[1]:
+            dh0 = torch.empty(B, E, **f32)  # ReLU mask of the gather is applied in the scatter kernel
+            L.call("dcue_linear_dgrad", dh1.data_ptr(), E, w1.data_ptr(), B, E, E, None, 0, dh0.data_ptr(), E, st)
+            sidx = torch.empty(B, dtype=torch.int64, device=dev)
+            spos = torch.empty(B, dtype=torch.int32, device=dev)
+            L.call("dcue_sort_indices", idx.data_ptr(), B, U, sidx.data_ptr(), spos.data_ptr(), scratch.data_ptr(), nscr, st)
+            gtable = torch.zeros(U, E, **f32)  # dense gradient, like nn.Embedding(sparse=False)
+            L.call("dcue_scatter_add_bwd", dh0.data_ptr(), h0.data_ptr(), sidx.data_ptr(), spos.data_ptr(), B, U, E,
+                   gtable.data_ptr(), st)
+        return None, gtable, gw1, gb1, gw2, gb2
+
+
+class ScoreFn(torch.autograd.Function):
+    """scores[b,n] = cos(u_b, pos_b) - cos(u_b, neg_bn)  (dcue.py:93-106); feats = [pos; neg]."""
+
+    @staticmethod
+    def forward(ctx, u_f, feats, B, N):
+        u_f, feats = u_f.contiguous(), feats.contiguous()
+        F = u_f.shape[1]
+        scores = torch.empty(B, N, dtype=torch.float32, device=u_f.device)
+        L.call("dcue_score_fwd", u_f.data_ptr(), feats.data_ptr(), B, N, F, COS_EPS, scores.data_ptr(), L.stream())
+        ctx.save_for_backward(u_f, feats)
+        ctx.dims = (B, N, F)
+        return scores
+
+    @staticmethod
+    def backward(ctx, gs):
+        u_f, feats = ctx.saved_tensors
+        B, N, F = ctx.dims
+        du, df = torch.empty_like(u_f), torch.empty_like(feats)
+        L.call("dcue_score_bwd", u_f.data_ptr(), feats.data_ptr(), gs.contiguous().data_ptr(), B, N, F, COS_EPS,
+               du.data_ptr(), df.data_ptr(), L.stream())
+        return du, df, None, None
+
+
+class HingeScoreFn(torch.autograd.Function):
+    """Fused scores + max-margin hinge loss + analytic backward in ONE kernel launch.
+    Returns (loss_rows[B], scores[B,N]); mean over the GLOBAL batch is folded into the gradient."""
+
+    @staticmethod
+    def forward(ctx, u_f, feats, B, N, margin, batch_total):
+        u_f, feats = u_f.contiguous(), feats.contiguous()
+        F = u_f.shape[1]
+        dev = u_f.device
+        scores = torch.empty(B, N, dtype=torch.float32, device=dev)
+        loss_rows = torch.empty(B, dtype=torch.float32, device=dev)
+        du, df = torch.empty_like(u_f), torch.empty_like(feats)
+        L.call("dcue_score_hinge_fwdbwd", u_f.data_ptr(), feats.data_ptr(), B, N, F, COS_EPS, float(margin), int(batch_total),
+               scores.data_ptr(), loss_rows.data_ptr(), du.data_ptr(), df.data_ptr(), L.stream())
+        ctx.save_for_backward(du, df)
+        ctx.batch_total = batch_total
+        ctx.mark_non_differentiable(scores)
+        return loss_rows, scores
+
+    @staticmethod
+    def backward(ctx, g_rows, _g_scores):
+        # du/df hold d(sum_b loss_rows / batch_total); the caller's loss is loss_rows.sum()/batch_total,
+        # i.e. g_rows == 1/batch_total for every row -> rescale by g_rows * batch_total (a scalar).
+        du, df = ctx.saved_tensors
+        scale = g_rows.reshape(-1)[:1] * float(ctx.batch_total)
+        return du * scale, df * scale, None, None, None, None

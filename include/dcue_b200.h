@@ -1,0 +1,211 @@
+/*
+ * dcue_b200.h — C ABI of libdcue_b200.so: hand-written sm_100a kernels for the DCUE
+ * (Lee et al. 2018) training + scoring hot path.
+ *
+ * The reference (estebandito22/Amplifai-DeepContentRecommenders) is pure Python/PyTorch and
+ * has no FFI; each entry point below replaces the implicit ATen/cuDNN/cuBLAS kernels that a
+ * reference call site issues (file:line given per function, paths relative to the reference
+ * root).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; buffers are owned by the caller
+ *     (PyTorch tensors on the Python side); nothing is allocated or freed here;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream;
+ *   - return value: 0 = ok, >0 = cudaError_t, <0 = DCUE_E_* argument error;
+ *     dcue_last_error() returns a static message for the calling thread's last failure;
+ *   - no global mutable state: re-entrant per stream.
+ *
+ * 16-bit activation "panel" layout (conv operands, HBM):
+ *   element (row r, channel c) of a [rows, C] matrix lives at
+ *       base[((c / 8) * panel_rows + r) * 8 + (c % 8)]
+ *   i.e. C/8 panels, each a column of 16-byte (8-channel) row chunks.  The same bytes are a
+ *   K-major UMMA operand (rows = M/N, channels = K) and an MN-major one (channels = M/N,
+ *   rows = K) with no swizzle, so tap shifts are plain 16-byte address offsets.
+ *   Rows are "flat": spectrogram s, padded time q -> r = s * Lp + q, with `pad` zero rows in
+ *   front of each spectrogram's data and zeros up to Lp.  `base` points at row 0; the buffer
+ *   holds DCUE_FRONT_HALO zero rows before it and at least DCUE_BACK_HALO after rows_total.
+ */
+#ifndef DCUE_B200_H
+#define DCUE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCUE_E_BADARG   (-1)
+#define DCUE_E_WORKSPACE (-2)
+#define DCUE_E_INDEX    (-3)   /* user index out of range (nn.Embedding raises IndexError) */
+#define DCUE_E_UNSUPPORTED (-4)
+
+#define DCUE_FMT_F16  0
+#define DCUE_FMT_BF16 1
+
+#define DCUE_IMPL_SIMT 0       /* CUDA-core implicit GEMM (bring-up / validator / tiny layers) */
+#define DCUE_IMPL_TC   1       /* tcgen05 + TMEM + TMA-bulk implicit GEMM                      */
+
+#define DCUE_FRONT_HALO 8
+#define DCUE_BACK_HALO  136
+
+const char* dcue_last_error(void);
+int dcue_version(void);
+/* number of kernels this library has launched in the calling process (all streams) */
+long dcue_launch_count(void);
+
+/* ---------------------------------------------------------------- user tower ------------- */
+
+/* nn.Embedding forward + ReLU   (dcrecommend/dcue/embeddings/userembedding.py:40-41).
+ * out[b,:] = relu(table[idx[b],:]); raw (pre-ReLU) rows are optionally copied to raw_out.
+ * err_flag (device int, pre-zeroed) is set to 1 if any index is outside [0,U). */
+int dcue_gather_relu_fwd(const float* table, const int64_t* idx, int B, int U, int E,
+                         float* out, float* raw_out, int* err_flag, void* stream);
+
+/* autograd of the above: dense [U,E] gradient = deterministic sorted segment sum of the
+ * ReLU-masked rows (replaces ATen embedding_dense_backward, userembedding.py:27,40).
+ * sorted_idx/sorted_pos: idx sorted ascending with the source position of each entry (stable);
+ * the sort itself is dcue_sort_indices.  grad_table must be zeroed by the caller. */
+int dcue_sort_indices(const int64_t* idx, int B, int U, int64_t* sorted_idx, int32_t* sorted_pos,
+                      void* ws, size_t ws_bytes, void* stream);
+size_t dcue_sort_ws_bytes(int B);
+int dcue_scatter_add_bwd(const float* grad_out, const float* fwd_out /* relu output, mask */,
+                         const int64_t* sorted_idx, const int32_t* sorted_pos, int B, int U, int E,
+                         float* grad_table, void* stream);
+
+/* nn.Linear (+ optional ReLU) forward / backward, fp32
+ * (userembedding.py:42-44; truedcuemel1dbn.py:57-59 (k=1 conv), :101 (fc)).
+ * Y[M,N] = act(X[M,K] W[N,K]^T + b[N]); ldx/ldy are row strides in elements. */
+int dcue_linear_fwd(const float* X, int ldx, const float* W, const float* b, int M, int K, int N,
+                    int relu, float* Y, int ldy, void* stream);
+/* dX[M,K] = dY[M,N] W[N,K]; if mask != NULL, dX *= (mask > 0) (ReLU that produced X). */
+int dcue_linear_dgrad(const float* dY, int lddy, const float* W, int M, int K, int N,
+                      const float* mask, int ldmask, float* dX, int lddx, void* stream);
+/* dW[N,K] = dY^T X ; db[N] = colsum(dY).  ws: dcue_linear_wgrad_ws_bytes(M,K,N). */
+int dcue_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, int M, int K, int N,
+                      float* dW, float* db, void* ws, size_t ws_bytes, void* stream);
+size_t dcue_linear_wgrad_ws_bytes(int M, int K, int N);
+
+/* ---------------------------------------------------------------- song tower ------------- */
+
+/* Per-channel sum / sum of squares of the NCL fp32 input batch, without torch.cat
+ * (dcrecommend/dcue/dcue.py:90 + bn0, truedcuemel1dbn.py:79).  sums = double[2*C]. */
+int dcue_ncl_stats(const float* pos, int S_pos, const float* neg, int S_neg, int C, int L,
+                   double* sums, void* ws, size_t ws_bytes, void* stream);
+size_t dcue_ncl_stats_ws_bytes(int C);
+
+/* BatchNorm finalize (truedcuemel1dbn.py:24,30,38,46,54,61): from sums/count produce
+ * scale = gamma*rstd, shift = beta - mean*scale, mean, rstd; training!=0 uses batch statistics
+ * and updates running_mean/var (momentum, unbiased var) and num_batches_tracked; otherwise the
+ * running statistics are used and nothing is updated.  gamma/beta NULL = identity affine. */
+int dcue_bn_finalize(const double* sums, double count, int C, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                     float momentum, float eps, int training,
+                     float* scale, float* shift, float* mean, float* rstd, void* stream);
+
+/* x[S,C,L] fp32 (pos rows then neg rows) -> scale*x+shift -> 16-bit panel rows
+ * r = s*Lp + pad + t  (fused transpose + convert; scale/shift NULL = identity). */
+int dcue_ncl_pack(const float* pos, int S_pos, const float* neg, int S_neg, int C, int L,
+                  const float* scale, const float* shift, void* panel, long panel_rows,
+                  int Lp, int pad, int fmt, void* stream);
+
+/* Conv1d weight [Cout,Cin,k] fp32 -> 16-bit UMMA A operand [128 x k*128], K-major panels:
+ * mode 0 (forward): A[co][j*Cin+ci] = W[co][ci][j];
+ * mode 1 (dgrad):   A[ci][jj*Cout+co] = W[co][ci][k-1-jj].   Rows/cols beyond C are zero. */
+int dcue_pack_conv_weight(const float* W, int Cout, int Cin, int k, int mode, int fmt, void* out,
+                          void* stream);
+
+/* Conv1d + bias + MaxPool1d(pool) + ReLU with BatchNorm partial sums, implicit GEMM over
+ * shifted row views of the panel (truedcuemel1dbn.py:80-83 etc.; all four tower variants).
+ * z[S*P, Cout] fp32 = relu(max_{i<pool} conv[s, p*pool+i, :] + bias); code[S*P,Cout] u8 = argmax i;
+ * sums (nullable) = double[2*Cout] sum z, sum z^2. */
+int dcue_conv_pool_fwd(int impl, const void* panel, long panel_rows, int fmt, const void* w_packed,
+                       const float* bias, int S, int Lp, int P, int pool, int k, int Cin, int Cout,
+                       float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes, void* stream);
+
+/* Conv1d data gradient: dX[s, t, ci] = sum_{j,co} W[co,ci,j] dY[s, t + pad - j, co] for the
+ * Lin data rows of every spectrogram; dY is a bf16/f16 panel in the forward's flat row space
+ * (conv output t at row s*Lp + t). dx[S*Lin, Cin] fp32. */
+int dcue_conv_dgrad(int impl, const void* dy_panel, long panel_rows, int fmt_dy, const void* w_packed_dgrad,
+                    int fmt_w, int S, int Lp, int Lin, int pad, int k, int Cin, int Cout, float* dx,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* Conv1d weight gradient dW[co,ci,j] = sum_r dY[r,co] X[r+j,ci] over all flat rows
+ * (reference layout [Cout,Cin,k] fp32 out). */
+int dcue_conv_wgrad(int impl, const void* dy_panel, long dy_panel_rows, int fmt_dy, const void* x_panel,
+                    long x_panel_rows, int fmt_x, long rows_total, int k, int Cin, int Cout, float* dW,
+                    void* ws, size_t ws_bytes, void* stream);
+size_t dcue_conv_ws_bytes(int impl, int S, int Lp, int k, int Cin, int Cout);
+
+/* y = scale*z+shift written (a) as the next layer's 16-bit panel rows s*Lp+pad+p (panel nullable)
+ * and/or (b) as fp32 [S*P, C] (y nullable); tp (nullable) [S, ldtp] gets the time average of y
+ * (AvgPool1d over the stage's whole extent, truedcuemel1dresbn.py:92,98,104,110). */
+int dcue_affine_pack(const float* z, int S, int P, int C, const float* scale, const float* shift,
+                     void* panel, long panel_rows, int Lp, int pad, int fmt, float* y, float* tp,
+                     int ldtp, void* stream);
+
+/* BatchNorm backward reductions: sums = double[2*C]: sum dy, sum dy*xhat, where xhat=(z-mean)*rstd.
+ * dy has row stride lddy (elements); dtp (nullable, [S, lddtp]) is the gradient of the time
+ * average, added as dtp/P to every row. */
+int dcue_bn_bwd_reduce(const float* dy, int lddy, const float* dtp, int lddtp, const float* z, const float* mean,
+                       const float* rstd, int S, int P, int C, double* sums, void* ws, size_t ws_bytes,
+                       void* stream);
+size_t dcue_bn_bwd_ws_bytes(int C);
+
+/* BatchNorm backward apply + ReLU mask + MaxPool unpooling in one pass:
+ *   dz = scale*(dy - s1/n - xhat*s2/n)   (training)   or   scale*dy (eval / no BN: sums NULL)
+ *   dz = 0 where z <= 0
+ * and writes (a) dY panel rows s*Lp + p*pool + code (the other pool-1 rows of the group zero)
+ * when dy_panel != NULL, or (b) dense dz[S*P,C] fp32 when dz_out != NULL.
+ * bias_sums double[C] (nullable) receives sum dz (the conv bias gradient). */
+int dcue_bn_relu_unpool_bwd(const float* dy, int lddy, const float* dtp, int lddtp, const float* z,
+                            const uint8_t* code, const float* scale, const float* mean, const float* rstd,
+                            const double* sums, double count, int S, int P, int C, int pool, int Lp,
+                            void* dy_panel, long panel_rows, int fmt, float* dz_out, double* bias_sums,
+                            void* ws, size_t ws_bytes, void* stream);
+
+/* bn0 backward reductions (truedcuemel1dbn.py:79): dx = channels-last [S*L, C] gradient of the
+ * normalised input (layer1 dgrad), pos/neg = the NCL fp32 input; sums = double[2*C] as above.
+ * ws: dcue_bn_bwd_ws_bytes(C). */
+int dcue_ncl_bn_bwd_reduce(const float* dx, const float* pos, int S_pos, const float* neg, int S_neg, int C,
+                           int L, const float* mean, const float* rstd, double* sums, void* ws,
+                           size_t ws_bytes, void* stream);
+
+/* double[n] -> float[n] with a scale (BN weight/bias grads, conv bias grads). */
+int dcue_cvt_f64_f32(const double* in, int n, double mul, float* out, void* stream);
+
+/* ---------------------------------------------------------------- scoring + loss --------- */
+
+/* nn.CosineSimilarity(dim=1) scores (dcrecommend/dcue/dcue.py:93-106):
+ * feats = [B positive rows ; B*N negative rows] x F.  scores[b,n] = cos(u_b,pos_b)-cos(u_b,neg_bn). */
+int dcue_score_fwd(const float* u, const float* feats, int B, int N, int F, float eps, float* scores,
+                   void* stream);
+int dcue_score_bwd(const float* u, const float* feats, const float* gscores, int B, int N, int F,
+                   float eps, float* du, float* dfeats, void* stream);
+/* Fused cosine scores + hinge loss (dcrecommend/nn/dcue.py:167-170) + analytic backward:
+ * loss_rows[b] = sum_n max(0, margin - scores[b,n]); du/dfeats = d(mean_b loss_rows)/d(.) with
+ * batch_total = global batch size (DP divides by the global B). */
+int dcue_score_hinge_fwdbwd(const float* u, const float* feats, int B, int N, int F, float eps,
+                            float margin, int batch_total, float* scores, float* loss_rows, float* du,
+                            float* dfeats, void* stream);
+
+/* ---------------------------------------------------------------- eval scorer ------------ */
+
+/* row-normalise factors (x / max(||x||,eps)) into 16-bit K-major rows padded to Kp (mult of 16). */
+int dcue_normalize_rows(const float* x, long rows, int F, float eps, int Kp, int fmt, void* out,
+                        void* stream);
+/* All-pairs cosine score GEMM + fused top-k (generalises DCUE.predict, nn/dcue.py:495-513):
+ * for each user row the k best (score, item index + item_offset) among `items` rows, sorted
+ * descending.  users_n/items_n: outputs of dcue_normalize_rows. */
+int dcue_topk_scores(int impl, const void* users_n, long n_users, const void* items_n, long n_items,
+                     int Kp, int fmt, int k, long item_offset, float* top_scores, int64_t* top_idx,
+                     void* ws, size_t ws_bytes, void* stream);
+size_t dcue_topk_ws_bytes(int impl, long n_users, long n_items, int k);
+/* merge `parts` per-shard top-k lists [parts][n_users][k] into one (song-sharded eval). */
+int dcue_topk_merge(const float* scores, const int64_t* idx, int parts, long n_users, int k,
+                    float* out_scores, int64_t* out_idx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCUE_B200_H */
