@@ -188,8 +188,10 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __rest
                      const float* __restrict__ mean, const float* __restrict__ rstd, long rows, int P, int C,
                      double* __restrict__ partial /* [grid][2][C] */) {
     __shared__ float red[2][8][128];
+    __shared__ float redm[8];
     const int cl = (threadIdx.x & 31) * 4, rg = threadIdx.x >> 5;
     float a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+    float amax = 0.f;
     if (cl < C) {
         float m[4], rs[4];
 #pragma unroll
@@ -209,6 +211,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __rest
             for (int j = 0; j < 4; ++j) {
                 a1[j] += gv[j];
                 a2[j] = fmaf(gv[j], (zv[j] - m[j]) * rs[j], a2[j]);
+                amax = fmaxf(amax, fabsf(gv[j]));
             }
         }
     }
@@ -216,7 +219,16 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __rest
     for (int j = 0; j < 4; ++j) {
         if (cl + j < 128) { red[0][rg][cl + j] = a1[j]; red[1][rg][cl + j] = a2[j]; }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) redm[rg] = amax;
     __syncthreads();
+    if (threadIdx.x == 0) {
+        float mm = redm[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) mm = fmaxf(mm, redm[k]);
+        partial[(long)gridDim.x * 2 * C + blockIdx.x] = (double)mm;   // after the [grid][2][C] sums
+    }
     const int c = threadIdx.x & 127, which = threadIdx.x >> 7;
     if (c < C) {
         double s = 0.0;
@@ -232,10 +244,12 @@ bn_relu_unpool_bwd_kernel(const float* __restrict__ dy, int lddy, const float* _
                           const float* __restrict__ z, const uint8_t* __restrict__ code, const float* __restrict__ scale,
                           const float* __restrict__ mean, const float* __restrict__ rstd, const double* __restrict__ sums,
                           double count, long rows, int P, int C, int pool, int Lp, uint4* __restrict__ panel,
-                          long panel_rows, int fmt, float* __restrict__ dz_out, double* __restrict__ bias_partial) {
+                          long panel_rows, int fmt, const float* __restrict__ gscale, float* __restrict__ dz_out,
+                          double* __restrict__ bias_partial) {
     __shared__ float tile[TR][TLD];
     __shared__ uint8_t ctile[TR][TLD + 3];
     const int tid = threadIdx.x;
+    const float gs = gscale ? gscale[0] : 1.f;
     double bias_acc = 0.0;  // thread tid<C accumulates channel tid
     const float invn = (float)(1.0 / count);
     const float invP = 1.f / (float)P;
@@ -274,7 +288,7 @@ bn_relu_unpool_bwd_kernel(const float* __restrict__ dy, int lddy, const float* _
                     uint8_t cd[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        h[j] = cvt_f32_to16(tile[rl][q * 8 + j], fmt);
+                        h[j] = cvt_f32_to16(tile[rl][q * 8 + j] * gs, fmt);
                         cd[j] = ctile[rl][q * 8 + j];
                     }
                     for (int i = 0; i < pool; ++i) {
@@ -300,6 +314,45 @@ bn_relu_unpool_bwd_kernel(const float* __restrict__ dy, int lddy, const float* _
         __syncthreads();
     }
     if (bias_partial && tid < C) bias_partial[(long)blockIdx.x * C + tid] = bias_acc;
+}
+
+__global__ void reduce_max_kernel(const double* __restrict__ pmax, int nblk, float* __restrict__ out) {
+    __shared__ float sm[256];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < nblk; i += 256) m = fmaxf(m, (float)pmax[i]);
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sm[0];
+}
+
+// gradient scale for the 16-bit conv-backward operand: the largest power of two s with
+// s * bound <= 2^14, bound >= max|dz| from |xhat| <= sqrt(n), mean|xhat| <= 1:
+//   |dz| <= max_c|scale_c| * max|dy| * (2 + sqrt(n))   (batch statistics)   or   max_c|scale_c| * max|dy|
+__global__ void grad_scale_kernel(const float* __restrict__ absmax, const float* __restrict__ scale, int C, double count,
+                                  float* __restrict__ out /* [2]: s, 1/s */) {
+    __shared__ float sm[128];
+    float m = 0.f;
+    for (int c = threadIdx.x; c < C; c += 128) m = fmaxf(m, scale ? fabsf(scale[c]) : 1.f);
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double bound = (double)sm[0] * (double)(*absmax) * (count > 0.0 ? 2.0 + sqrt(count) : 1.0);
+        int e = 0;
+        if (bound > 0.0 && isfinite(bound)) {
+            e = (int)floor(log2(16384.0 / bound));
+            e = max(-60, min(60, e));
+        }
+        out[0] = (float)ldexp(1.0, e);
+        out[1] = (float)ldexp(1.0, -e);
+    }
 }
 
 __global__ void cvt_f64_f32_kernel(const double* __restrict__ in, int n, double mul, float* __restrict__ out) {
@@ -433,12 +486,12 @@ extern "C" int dcue_affine_pack(const float* z, int S, int P, int C, const float
 }
 
 extern "C" size_t dcue_bn_bwd_ws_bytes(int C) {
-    return (size_t)dcue_num_sms() * 8 * 2 * (size_t)C * sizeof(double) + 256;
+    return (size_t)dcue_num_sms() * 8 * (2 * (size_t)C + 1) * sizeof(double) + 256;
 }
 
 extern "C" int dcue_bn_bwd_reduce(const float* dy, int lddy, const float* dtp, int lddtp, const float* z, const float* mean,
-                                  const float* rstd, int S, int P, int C, double* sums, void* ws, size_t ws_bytes,
-                                  void* stream) {
+                                  const float* rstd, int S, int P, int C, double* sums, float* absmax, void* ws,
+                                  size_t ws_bytes, void* stream) {
     DCUE_CHECK_ARG(dy && z && mean && rstd && sums && ws && S >= 0 && P > 0 && C > 0 && C <= 128 && C % 4 == 0);
     DCUE_CHECK_ARG(lddy >= C && lddy % 4 == 0 && ((uintptr_t)dy & 15) == 0);
     cudaStream_t st = (cudaStream_t)stream;
@@ -446,19 +499,23 @@ extern "C" int dcue_bn_bwd_reduce(const float* dy, int lddy, const float* dtp, i
     long g = (rows + 7) / 8;
     const long cap = (long)dcue_num_sms() * 8;
     int grid = (int)(g < cap ? (g > 0 ? g : 1) : cap);
-    if (ws_bytes < (size_t)grid * 2 * C * sizeof(double)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_bn_bwd_reduce: workspace too small");
+    if (ws_bytes < (size_t)grid * (2 * C + 1) * sizeof(double)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_bn_bwd_reduce: workspace too small");
     bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, lddy, dtp, lddtp, z, mean, rstd, rows, P, C, (double*)ws);
     DCUE_LAUNCH_CHECK();
     reduce_partials_kernel<<<ceil_div_i(2 * C, 128), 128, 0, st>>>((const double*)ws, grid, 2 * C, sums);
     DCUE_LAUNCH_CHECK();
+    if (absmax) {
+        reduce_max_kernel<<<1, 256, 0, st>>>((const double*)ws + (size_t)grid * 2 * C, grid, absmax);
+        DCUE_LAUNCH_CHECK();
+    }
     return 0;
 }
 
 extern "C" int dcue_bn_relu_unpool_bwd(const float* dy, int lddy, const float* dtp, int lddtp, const float* z, const uint8_t* code,
                                        const float* scale, const float* mean, const float* rstd, const double* sums,
                                        double count, int S, int P, int C, int pool, int Lp, void* dy_panel,
-                                       long panel_rows, int fmt, float* dz_out, double* bias_sums, void* ws,
-                                       size_t ws_bytes, void* stream) {
+                                       long panel_rows, int fmt, const float* gscale, float* dz_out, double* bias_sums,
+                                       void* ws, size_t ws_bytes, void* stream) {
     DCUE_CHECK_ARG(dy && z && S >= 0 && P > 0 && C > 0 && C <= 128 && (dy_panel || dz_out) && lddy >= C);
     DCUE_CHECK_ARG(!sums || (mean && rstd && count > 0));
     DCUE_CHECK_ARG(!dy_panel || (code && C % 8 == 0 && pool >= 1 && pool <= 8 && Lp >= P * pool && panel_rows >= (long)S * Lp));
@@ -470,7 +527,7 @@ extern "C" int dcue_bn_relu_unpool_bwd(const float* dy, int lddy, const float* d
         DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_bn_relu_unpool_bwd: workspace too small");
     bn_relu_unpool_bwd_kernel<<<grid, 256, 0, st>>>(dy, lddy, dtp, lddtp, z, code, scale, mean, rstd, sums,
                                                     count > 0 ? count : 1.0, rows, P, C, pool, Lp, (uint4*)dy_panel,
-                                                    panel_rows, fmt, dz_out, bias_sums ? (double*)ws : nullptr);
+                                                    panel_rows, fmt, gscale, dz_out, bias_sums ? (double*)ws : nullptr);
     DCUE_LAUNCH_CHECK();
     if (bias_sums) {
         reduce_partials_kernel<<<ceil_div_i(C, 128), 128, 0, st>>>((const double*)ws, grid, C, bias_sums);
@@ -493,6 +550,13 @@ extern "C" int dcue_ncl_bn_bwd_reduce(const float* dx, const float* pos, int S_p
     ncl_bn_bwd_reduce_kernel<<<G * (C / 8), 128, 0, st>>>(dx, pos, S_pos, neg, S_neg, C, L, mean, rstd, (double*)ws);
     DCUE_LAUNCH_CHECK();
     reduce_partials_kernel<<<ceil_div_i(2 * C, 128), 128, 0, st>>>((const double*)ws, G, 2 * C, sums);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcue_grad_scale(const float* absmax, const float* scale, int C, double count, float* out, void* stream) {
+    DCUE_CHECK_ARG(absmax && out && C > 0);
+    grad_scale_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(absmax, scale, C, count, out);
     DCUE_LAUNCH_CHECK();
     return 0;
 }

@@ -41,8 +41,8 @@ extern "C" int dcue_conv_pool_fwd(int impl, const void* panel, long panel_rows, 
 }
 
 extern "C" int dcue_conv_dgrad(int impl, const void* dy_panel, long panel_rows, int fmt_dy, const void* w_packed_dgrad,
-                               int fmt_w, int S, int Lp, int Lin, int pad, int k, int Cin, int Cout, float* dx, void* ws,
-                               size_t ws_bytes, void* stream) {
+                               int fmt_w, int S, int Lp, int Lin, int pad, int k, int Cin, int Cout, const float* gscale,
+                               float* dx, void* ws, size_t ws_bytes, void* stream) {
     (void)ws; (void)ws_bytes;
     DCUE_CHECK_ARG(dy_panel && w_packed_dgrad && dx && Lin > 0 && pad >= 0 && Lin + pad <= Lp && k - 1 <= DCUE_FRONT_HALO);
     // GEMM view: contraction over the conv's Cout, output channels = the conv's Cin
@@ -53,19 +53,19 @@ extern "C" int dcue_conv_dgrad(int impl, const void* dy_panel, long panel_rows, 
     // In'[r] = dY[r - (k-1)]: shift the base pointer back by k-1 rows (front halo rows are zero)
     const char* shifted = (const char*)dy_panel - (size_t)(k - 1) * 16;
     if (impl == DCUE_IMPL_TC)
-        return dcue_tc_conv_dgrad(shifted, panel_rows, fmt_dy, w_packed_dgrad, fmt_w, g, dx, (cudaStream_t)stream);
-    return dcue_simt_conv_dgrad(shifted, panel_rows, fmt_dy, w_packed_dgrad, fmt_w, g, dx, (cudaStream_t)stream);
+        return dcue_tc_conv_dgrad(shifted, panel_rows, fmt_dy, w_packed_dgrad, fmt_w, g, gscale, dx, (cudaStream_t)stream);
+    return dcue_simt_conv_dgrad(shifted, panel_rows, fmt_dy, w_packed_dgrad, fmt_w, g, gscale, dx, (cudaStream_t)stream);
 }
 
 extern "C" int dcue_conv_wgrad(int impl, const void* dy_panel, long dy_panel_rows, int fmt_dy, const void* x_panel,
-                               long x_panel_rows, int fmt_x, long rows_total, int k, int Cin, int Cout, float* dW,
-                               void* ws, size_t ws_bytes, void* stream) {
+                               long x_panel_rows, int fmt_x, long rows_total, int k, int Cin, int Cout,
+                               const float* gscale, float* dW, void* ws, size_t ws_bytes, void* stream) {
     DCUE_CHECK_ARG(dy_panel && x_panel && dW && rows_total >= 0 && k >= 1 && k <= 4 && Cin > 0 && Cin <= 128 &&
                    Cin % 8 == 0 && Cout > 0 && Cout <= 128 && Cout % 8 == 0);
     DCUE_CHECK_ARG(dy_panel_rows >= round_up_l(rows_total, 128) + 16 && x_panel_rows >= round_up_l(rows_total, 128) + 16);
     if (impl == DCUE_IMPL_TC)
         return dcue_tc_conv_wgrad(dy_panel, dy_panel_rows, fmt_dy, x_panel, x_panel_rows, fmt_x, rows_total, k, Cin, Cout,
-                                  dW, ws, ws_bytes, (cudaStream_t)stream);
+                                  gscale, dW, ws, ws_bytes, (cudaStream_t)stream);
     return dcue_simt_conv_wgrad(dy_panel, dy_panel_rows, fmt_dy, x_panel, x_panel_rows, fmt_x, rows_total, k, Cin, Cout,
-                                dW, ws, ws_bytes, (cudaStream_t)stream);
+                                gscale, dW, ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -21,21 +21,21 @@ int dcue_simt_conv_fwd(const void* panel, long panel_rows, int fmt, const void* 
                        const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
                        cudaStream_t st);
 int dcue_simt_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
-                         const ConvGeom& g, float* dx, cudaStream_t st);
+                         const ConvGeom& g, const float* gscale, float* dx, cudaStream_t st);
 int dcue_simt_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const void* x_panel, long x_rows, int fmt_x,
-                         long rows_total, int k, int Cin, int Cout, float* dW, void* ws, size_t ws_bytes,
-                         cudaStream_t st);
+                         long rows_total, int k, int Cin, int Cout, const float* gscale, float* dW, void* ws,
+                         size_t ws_bytes, cudaStream_t st);
 // tcgen05 path (conv_tc.cu)
 int dcue_tc_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_packed, const float* bias,
                      const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
                      cudaStream_t st);
 int dcue_tc_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
-                       const ConvGeom& g, float* dx, cudaStream_t st);
+                       const ConvGeom& g, const float* gscale, float* dx, cudaStream_t st);
 int dcue_tc_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const void* x_panel, long x_rows, int fmt_x,
-                       long rows_total, int k, int Cin, int Cout, float* dW, void* ws, size_t ws_bytes,
-                       cudaStream_t st);
+                       long rows_total, int k, int Cin, int Cout, const float* gscale, float* dW, void* ws,
+                       size_t ws_bytes, cudaStream_t st);
 size_t dcue_tc_ws_bytes(int k);
 
 __global__ void dcue_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int Cout, int Cin, int k,
-                                         float* __restrict__ dW);
+                                         const float* __restrict__ gscale, float* __restrict__ dW);
 __global__ void dcue_reduce_partials_d(const double* __restrict__ partial, int nblk, int n, double* __restrict__ out);

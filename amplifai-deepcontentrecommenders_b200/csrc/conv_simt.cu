@@ -61,8 +61,9 @@ template <int EPI>
 __global__ void __launch_bounds__(128)
 conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in, const uint4* __restrict__ wp, int fmt_w,
                  const float* __restrict__ bias, ConvGeom g, float* __restrict__ out, uint8_t* __restrict__ code,
-                 double* __restrict__ partial) {
+                 double* __restrict__ partial, const float* __restrict__ gscale) {
     extern __shared__ float xs[];  // [TRW + k - 1][CH]
+    const float oscale = (EPI == 1 && gscale) ? gscale[1] : 1.f;
     const int m = threadIdx.x;
     const long ntiles = (g.rows_total + TRW - 1) / TRW;
     const int kpan = g.k * (CH / 8);  // 8-wide K chunks of the packed weight
@@ -110,7 +111,7 @@ conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in, c
                     const long r = r0 + t;
                     const long s = r / g.Lp;
                     const int tt = (int)(r - s * g.Lp) - g.pad;
-                    if (s < g.S && tt >= 0 && tt < g.Lin) out[(s * g.Lin + tt) * g.Cout + m] = acc[t];
+                    if (s < g.S && tt >= 0 && tt < g.Lin) out[(s * g.Lin + tt) * g.Cout + m] = acc[t] * oscale;
                 }
             }
         }
@@ -163,13 +164,13 @@ wgrad_rows_kernel(const uint4* __restrict__ dyp, long dy_rows, int fmt_dy, const
 
 // dW[co][ci][j] = sum_parts part[p][co][j][ci]   (shared with the tcgen05 wgrad)
 __global__ void dcue_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int Cout, int Cin, int k,
-                                         float* __restrict__ dW) {
+                                         const float* __restrict__ gscale, float* __restrict__ dW) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Cout * Cin * k) return;
     const int j = i % k, ci = (i / k) % Cin, co = i / (k * Cin);
     float s = 0.f;
     for (int p = 0; p < nparts; ++p) s += part[(((long)p * 128 + co) * k + j) * 128 + ci];
-    dW[i] = s;
+    dW[i] = gscale ? s * gscale[1] : s;
 }
 
 __global__ void dcue_reduce_partials_d(const double* __restrict__ partial, int nblk, int n, double* __restrict__ out) {
@@ -206,7 +207,7 @@ int dcue_simt_conv_fwd(const void* panel, long panel_rows, int fmt, const void* 
         DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_pool_fwd(simt): workspace too small");
     const size_t smem = (size_t)(TRW + g.k - 1) * CH * sizeof(float);
     conv_rows_kernel<0><<<grid, 128, smem, st>>>((const uint4*)panel, panel_rows, fmt, (const uint4*)w_packed, fmt, bias,
-                                                 g, z, code, sums ? (double*)ws : nullptr);
+                                                 g, z, code, sums ? (double*)ws : nullptr, nullptr);
     DCUE_LAUNCH_CHECK();
     if (sums) {
         dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 128), 128, 0, st>>>((const double*)ws, grid, 2 * g.Cout, sums);
@@ -216,20 +217,20 @@ int dcue_simt_conv_fwd(const void* panel, long panel_rows, int fmt, const void* 
 }
 
 int dcue_simt_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
-                         const ConvGeom& g, float* dx, cudaStream_t st) {
+                         const ConvGeom& g, const float* gscale, float* dx, cudaStream_t st) {
     const long ntiles = (g.rows_total + TRW - 1) / TRW;
     const long cap = (long)dcue_num_sms() * 4;
     const int grid = (int)(ntiles < cap ? (ntiles > 0 ? ntiles : 1) : cap);
     const size_t smem = (size_t)(TRW + g.k - 1) * CH * sizeof(float);
     conv_rows_kernel<1><<<grid, 128, smem, st>>>((const uint4*)dy_panel_shifted, panel_rows, fmt_dy,
-                                                 (const uint4*)w_packed, fmt_w, nullptr, g, dx, nullptr, nullptr);
+                                                 (const uint4*)w_packed, fmt_w, nullptr, g, dx, nullptr, nullptr, gscale);
     DCUE_LAUNCH_CHECK();
     return 0;
 }
 
 int dcue_simt_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const void* x_panel, long x_rows, int fmt_x,
-                         long rows_total, int k, int Cin, int Cout, float* dW, void* ws, size_t ws_bytes,
-                         cudaStream_t st) {
+                         long rows_total, int k, int Cin, int Cout, const float* gscale, float* dW, void* ws,
+                         size_t ws_bytes, cudaStream_t st) {
     const int nchunks = 32;
     if (!ws || ws_bytes < (size_t)nchunks * 128 * k * 128 * sizeof(float))
         DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_wgrad(simt): workspace too small");
@@ -238,7 +239,7 @@ int dcue_simt_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const v
                                             fmt_x, rows_total, k, Cin, Cout, (float*)ws);
     DCUE_LAUNCH_CHECK();
     dcue_wgrad_reduce_kernel<<<ceil_div_i((long)Cout * Cin * k, 256), 256, 0, st>>>((const float*)ws, nchunks, Cout, Cin,
-                                                                                    k, dW);
+                                                                                    k, gscale, dW);
     DCUE_LAUNCH_CHECK();
     return 0;
 }

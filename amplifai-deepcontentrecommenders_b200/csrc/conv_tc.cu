@@ -163,7 +163,7 @@ __device__ __forceinline__ void epilogue_chunk(const float (&v)[32], long r, int
             const long rr = r + t;
             const long s = rr / g.Lp;
             const int tt = (int)(rr - s * g.Lp) - g.pad;
-            if (s < g.S && tt >= 0 && tt < g.Lin && m < g.Cout) out[(s * g.Lin + tt) * g.Cout + m] = v[t];
+            if (s < g.S && tt >= 0 && tt < g.Lin && m < g.Cout) out[(s * g.Lin + tt) * g.Cout + m] = v[t] * bv;
         }
     }
 }
@@ -172,7 +172,7 @@ template <int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in, const uint4* __restrict__ wp, int fmt_w,
                     const float* __restrict__ bias, ConvGeom g, float* __restrict__ out, uint8_t* __restrict__ code,
-                    double* __restrict__ partial) {
+                    double* __restrict__ partial, const float* __restrict__ gscale) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_bytes = g.k * PANELS * A_PANEL_BYTES;  // k * 32 KB
@@ -254,7 +254,8 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
         // ===== epilogue warps: TMEM -> registers -> (pool, relu, stats) -> global =====
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;  // output channel == TMEM lane
-        const float bv = (EPI == 0 && bias && m < g.Cout) ? bias[m] : 0.f;
+        // EPI 0: bv = conv bias.  EPI 1: bv = 1/s of the scaled 16-bit gradient operand.
+        const float bv = EPI == 0 ? ((bias && m < g.Cout) ? bias[m] : 0.f) : (gscale ? gscale[1] : 1.f);
         double st1 = 0.0, st2 = 0.0;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -407,11 +408,12 @@ int tc_grid(long rows_total) {
 
 template <int EPI>
 int launch_rows(const void* panel, long panel_rows, int fmt_in, const void* w_packed, int fmt_w, const float* bias,
-                const ConvGeom& g, float* out, uint8_t* code, double* partial, int grid, cudaStream_t st) {
+                const ConvGeom& g, float* out, uint8_t* code, double* partial, const float* gscale, int grid,
+                cudaStream_t st) {
     const size_t smem = rows_smem_bytes(g.k);
     DCUE_CUDA(cudaFuncSetAttribute(tc_conv_rows_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_conv_rows_kernel<EPI><<<grid, NTHREADS, smem, st>>>((const uint4*)panel, panel_rows, fmt_in, (const uint4*)w_packed,
-                                                           fmt_w, bias, g, out, code, partial);
+                                                           fmt_w, bias, g, out, code, partial, gscale);
     DCUE_LAUNCH_CHECK();
     return 0;
 }
@@ -431,7 +433,7 @@ int dcue_tc_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_
     const int grid = tc_grid(g.rows_total);
     if (sums && (!ws || ws_bytes < (size_t)grid * 2 * g.Cout * sizeof(double)))
         DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_pool_fwd(tc): workspace too small");
-    if (int e = launch_rows<0>(panel, panel_rows, fmt, w_packed, fmt, bias, g, z, code, sums ? (double*)ws : nullptr, grid, st))
+    if (int e = launch_rows<0>(panel, panel_rows, fmt, w_packed, fmt, bias, g, z, code, sums ? (double*)ws : nullptr, nullptr, grid, st))
         return e;
     if (sums) {
         dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 128), 128, 0, st>>>((const double*)ws, grid, 2 * g.Cout, sums);
@@ -441,14 +443,17 @@ int dcue_tc_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_
 }
 
 int dcue_tc_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
-                       const ConvGeom& g, float* dx, cudaStream_t st) {
+                       const ConvGeom& g, const float* gscale, float* dx, cudaStream_t st) {
     if (g.Cin != 128) DCUE_FAIL(DCUE_E_UNSUPPORTED, "tcgen05 dgrad needs Cout == 128 (got %d)", g.Cin);
-    return launch_rows<1>(dy_panel_shifted, panel_rows, fmt_dy, w_packed, fmt_w, nullptr, g, dx, nullptr, nullptr,
+    if (fmt_dy != fmt_w) DCUE_FAIL(DCUE_E_UNSUPPORTED, "tcgen05 kind::f16 needs both operands in the same 16-bit format");
+    return launch_rows<1>(dy_panel_shifted, panel_rows, fmt_dy, w_packed, fmt_w, nullptr, g, dx, nullptr, nullptr, gscale,
                           tc_grid(g.rows_total), st);
 }
 
 int dcue_tc_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const void* x_panel, long x_rows, int fmt_x,
-                       long rows_total, int k, int Cin, int Cout, float* dW, void* ws, size_t ws_bytes, cudaStream_t st) {
+                       long rows_total, int k, int Cin, int Cout, const float* gscale, float* dW, void* ws, size_t ws_bytes,
+                       cudaStream_t st) {
+    if (fmt_dy != fmt_x) DCUE_FAIL(DCUE_E_UNSUPPORTED, "tcgen05 kind::f16 needs both operands in the same 16-bit format");
     if (Cin != 128 || Cout != 128) DCUE_FAIL(DCUE_E_UNSUPPORTED, "tcgen05 wgrad needs Cin == Cout == 128");
     const int grid = tc_grid(rows_total);
     if (!ws || ws_bytes < (size_t)grid * 128 * k * 128 * sizeof(float))
@@ -468,7 +473,7 @@ int dcue_tc_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const voi
     }
 #undef LAUNCH_WG
     DCUE_LAUNCH_CHECK();
-    dcue_wgrad_reduce_kernel<<<ceil_div_i((long)Cout * Cin * k, 256), 256, 0, st>>>((const float*)ws, grid, Cout, Cin, k, dW);
+    dcue_wgrad_reduce_kernel<<<ceil_div_i((long)Cout * Cin * k, 256), 256, 0, st>>>((const float*)ws, grid, Cout, Cin, k, gscale, dW);
     DCUE_LAUNCH_CHECK();
     return 0;
 }

@@ -104,6 +104,8 @@ class TowerWorkspace:
             b["wpd"] = [torch.empty(128 * g["k"] * 128, dtype=torch.int16, device=dev) for g in self.geo]
             b["bsum"] = torch.zeros(2 * 128, dtype=torch.float64, device=dev)
             b["dsums"] = torch.zeros(6, 2 * 128, dtype=torch.float64, device=dev)
+            b["amax"] = torch.zeros(6, **f32)
+            b["gscale"] = torch.ones(6, 2, **f32)
             self._bwd = b
         return self._bwd
 
@@ -215,7 +217,7 @@ class SongTowerFn(torch.autograd.Function):
         if has_bn:
             if training:  # sum z, sum z^2 via the backward-reduce kernel with mean=0, rstd=1
                 L.call("dcue_bn_bwd_reduce", ws.z5.data_ptr(), F, None, 0, ws.z5.data_ptr(), ws.zero128.data_ptr(),
-                       ws.one128.data_ptr(), S, 1, F, ws.sums[5].data_ptr(), scratch, nscr, st)
+                       ws.one128.data_ptr(), S, 1, F, ws.sums[5].data_ptr(), None, scratch, nscr, st)
             bn_finalize(5, S, F)
             sc, sh = ws.bnp[5, 0].data_ptr(), ws.bnp[5, 1].data_ptr()
         else:
@@ -259,18 +261,30 @@ class SongTowerFn(torch.autograd.Function):
         gout = gout.contiguous()
         grads = {}
         Kfc = ws.fc_in.shape[1]
-        gfmt = L.FMT_BF16  # gradients entering the conv backward are bf16 (fp16 would underflow)
+        # tcgen05 kind::f16 wants both MMA operands in ONE 16-bit format, so the gradient operand dY
+        # uses the forward operand format; a per-layer power-of-two scale keeps fp16 in range.
+        gfmt = fmt
+        bn_train = has_bn and training
 
-        def bn_sums(i, dy_ptr, lddy, dtp_ptr, lddtp, z, P_, C_):
-            """BN backward reductions of layer i (+ DP all-reduce); also emits dgamma/dbeta."""
-            L.call("dcue_bn_bwd_reduce", dy_ptr, lddy, dtp_ptr, lddtp, z.data_ptr(), ws.bnp[i, 2].data_ptr(),
-                   ws.bnp[i, 3].data_ptr(), S, P_, C_, b["dsums"][i].data_ptr(), scratch, nscr, st)
-            if dp is not None:
-                dp.all_reduce_sum(b["dsums"][i])
-            gw, gb = torch.empty(C_, **f32), torch.empty(C_, **f32)
-            L.call("dcue_cvt_f64_f32", b["dsums"][i][C_:].data_ptr(), C_, 1.0, gw.data_ptr(), st)
-            L.call("dcue_cvt_f64_f32", b["dsums"][i].data_ptr(), C_, 1.0, gb.data_ptr(), st)
-            grads["bn%d.weight" % i], grads["bn%d.bias" % i] = gw, gb
+        def bn_sums(i, dy_ptr, lddy, dtp_ptr, lddtp, z, P_, C_, want_scale=True):
+            """Per-channel reductions over the gradient entering layer i's BN (+ DP all-reduce):
+            dgamma/dbeta when BN uses batch statistics, and max|dy| for the 16-bit gradient scale."""
+            mean_p = ws.bnp[i, 2].data_ptr() if bn_train else ws.zero128.data_ptr()
+            rstd_p = ws.bnp[i, 3].data_ptr() if bn_train else ws.one128.data_ptr()
+            L.call("dcue_bn_bwd_reduce", dy_ptr, lddy, dtp_ptr, lddtp, z.data_ptr(), mean_p, rstd_p, S, P_, C_,
+                   b["dsums"][i].data_ptr(), b["amax"][i:].data_ptr() if want_scale else None, scratch, nscr, st)
+            if bn_train:
+                if dp is not None:
+                    dp.all_reduce_sum(b["dsums"][i])
+                gw, gb = torch.empty(C_, **f32), torch.empty(C_, **f32)
+                L.call("dcue_cvt_f64_f32", b["dsums"][i][C_:].data_ptr(), C_, 1.0, gw.data_ptr(), st)
+                L.call("dcue_cvt_f64_f32", b["dsums"][i].data_ptr(), C_, 1.0, gb.data_ptr(), st)
+                grads["bn%d.weight" % i], grads["bn%d.bias" % i] = gw, gb
+            elif has_bn:
+                grads["bn%d.weight" % i] = grads["bn%d.bias" % i] = None  # eval-mode backward: constants
+            if want_scale:
+                L.call("dcue_grad_scale", b["amax"][i:].data_ptr(), ws.bnp[i, 0].data_ptr() if has_bn else None, C_,
+                       float(S * P_ * world) if bn_train else 0.0, b["gscale"][i].data_ptr(), st)
 
         # ---- fc
         gW, gb_ = torch.empty(F, Kfc, **f32), torch.empty(F, **f32)
@@ -282,15 +296,12 @@ class SongTowerFn(torch.autograd.Function):
         dy5 = dfc[:, 4 * H:] if res else dfc
         # ---- bn5 + relu5 -> dz5 ; layer5
         dz5 = torch.empty(S, F, **f32)
-        bn_train = has_bn and training
-        if bn_train:
-            bn_sums(5, dy5.data_ptr(), Kfc, None, 0, ws.z5, 1, F)
-        elif has_bn:
-            grads["bn5.weight"] = grads["bn5.bias"] = None  # eval-mode backward: affine treated as constant
+        if has_bn:
+            bn_sums(5, dy5.data_ptr(), Kfc, None, 0, ws.z5, 1, F, want_scale=False)
         L.call("dcue_bn_relu_unpool_bwd", dy5.data_ptr(), Kfc, None, 0, ws.z5.data_ptr(), None,
                ws.bnp[5, 0].data_ptr() if has_bn else None, ws.bnp[5, 2].data_ptr() if has_bn else None,
                ws.bnp[5, 3].data_ptr() if has_bn else None, b["dsums"][5].data_ptr() if bn_train else None,
-               float(S * world), S, 1, F, 1, 1, None, 0, gfmt, dz5.data_ptr(), None, scratch, nscr, st)
+               float(S * world), S, 1, F, 1, 1, None, 0, gfmt, None, dz5.data_ptr(), None, scratch, nscr, st)
         gW5, gb5 = torch.empty(F, H, 1, **f32), torch.empty(F, **f32)
         L.call("dcue_linear_wgrad", dz5.data_ptr(), F, ws.y4.data_ptr(), H, S, H, F, gW5.data_ptr(), gb5.data_ptr(), scratch,
                nscr, st)
@@ -301,28 +312,26 @@ class SongTowerFn(torch.autograd.Function):
         for i in range(4, 0, -1):
             g = geo[i - 1]
             dtp = dfc[:, (i - 1) * H:].data_ptr() if res else None
-            if bn_train:
-                bn_sums(i, dy.data_ptr(), H, dtp, Kfc, ws.z[i - 1], g["P"], H)
-            elif has_bn:
-                grads["bn%d.weight" % i] = grads["bn%d.bias" % i] = None
+            bn_sums(i, dy.data_ptr(), H, dtp, Kfc, ws.z[i - 1], g["P"], H)
+            gsc = b["gscale"][i].data_ptr()
             dYp = b["dY"][i - 1]
             L.call("dcue_bn_relu_unpool_bwd", dy.data_ptr(), H, dtp, Kfc, ws.z[i - 1].data_ptr(), ws.code[i - 1].data_ptr(),
                    ws.bnp[i, 0].data_ptr() if has_bn else None, ws.bnp[i, 2].data_ptr() if has_bn else None,
                    ws.bnp[i, 3].data_ptr() if has_bn else None, b["dsums"][i].data_ptr() if bn_train else None,
-                   float(S * g["P"] * world), S, g["P"], H, g["pool"], g["Lp"], dYp.base, dYp.panel_rows, gfmt, None,
+                   float(S * g["P"] * world), S, g["P"], H, g["pool"], g["Lp"], dYp.base, dYp.panel_rows, gfmt, gsc, None,
                    b["bsum"].data_ptr(), scratch, nscr, st)
             gb_i = torch.empty(H, **f32)
             L.call("dcue_cvt_f64_f32", b["bsum"].data_ptr(), H, 1.0, gb_i.data_ptr(), st)
             gW_i = torch.empty(H, 128, g["k"], **f32)
             L.call("dcue_conv_wgrad", impl, dYp.base, dYp.panel_rows, gfmt, ws.X[i - 1].base, ws.X[i - 1].panel_rows, fmt,
-                   S * g["Lp"], g["k"], 128, H, gW_i.data_ptr(), scratch, nscr, st)
+                   S * g["Lp"], g["k"], 128, H, gsc, gW_i.data_ptr(), scratch, nscr, st)
             grads["layer%d.weight" % i], grads["layer%d.bias" % i] = gW_i, gb_i
             if i > 1 or has_bn:
                 L.call("dcue_pack_conv_weight", P["layer%d.weight" % i].data_ptr(), H, 128, g["k"], 1, fmt,
                        b["wpd"][i - 1].data_ptr(), st)
                 dx = b["dx"][i - 1]
                 L.call("dcue_conv_dgrad", impl, dYp.base, dYp.panel_rows, gfmt, b["wpd"][i - 1].data_ptr(), fmt, S, g["Lp"],
-                       g["Lin"], g["pad"], g["k"], 128, H, dx.data_ptr(), scratch, nscr, st)
+                       g["Lin"], g["pad"], g["k"], 128, H, gsc, dx.data_ptr(), scratch, nscr, st)
                 dy = dx
         # ---- bn0
         if bn_train:
@@ -405,7 +414,8 @@ class ScoreFn(torch.autograd.Function):
         u_f, feats = u_f.contiguous(), feats.contiguous()
         F = u_f.shape[1]
         scores = torch.empty(B, N, dtype=torch.float32, device=u_f.device)
-        L.call("dcue_score_fwd", u_f.data_ptr(), feats.data_ptr(), B, N, F, COS_EPS, scores.data_ptr(), L.stream())
+        if B * N > 0:
+            L.call("dcue_score_fwd",     u_f.data_ptr(), feats.data_ptr(), B, N, F, COS_EPS, scores.data_ptr(), L.stream())
         ctx.save_for_backward(u_f, feats)
         ctx.dims = (B, N, F)
         return scores

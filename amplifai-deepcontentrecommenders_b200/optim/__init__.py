@@ -1,0 +1,2 @@
+from .cyclic_scheduler import CyclicLRWithRestarts  # noqa: F401
+from .ranger import Ranger  # noqa: F401

@@ -127,14 +127,16 @@ int dcue_conv_pool_fwd(int impl, const void* panel, long panel_rows, int fmt, co
  * Lin data rows of every spectrogram; dY is a bf16/f16 panel in the forward's flat row space
  * (conv output t at row s*Lp + t). dx[S*Lin, Cin] fp32. */
 int dcue_conv_dgrad(int impl, const void* dy_panel, long panel_rows, int fmt_dy, const void* w_packed_dgrad,
-                    int fmt_w, int S, int Lp, int Lin, int pad, int k, int Cin, int Cout, float* dx,
+                    int fmt_w, int S, int Lp, int Lin, int pad, int k, int Cin, int Cout,
+                    const float* gscale /* {s, 1/s} of the scaled dY operand, nullable */, float* dx,
                     void* ws, size_t ws_bytes, void* stream);
 
 /* Conv1d weight gradient dW[co,ci,j] = sum_r dY[r,co] X[r+j,ci] over all flat rows
  * (reference layout [Cout,Cin,k] fp32 out). */
 int dcue_conv_wgrad(int impl, const void* dy_panel, long dy_panel_rows, int fmt_dy, const void* x_panel,
-                    long x_panel_rows, int fmt_x, long rows_total, int k, int Cin, int Cout, float* dW,
-                    void* ws, size_t ws_bytes, void* stream);
+                    long x_panel_rows, int fmt_x, long rows_total, int k, int Cin, int Cout,
+                    const float* gscale /* {s, 1/s}, nullable */, float* dW, void* ws, size_t ws_bytes,
+                    void* stream);
 size_t dcue_conv_ws_bytes(int impl, int S, int Lp, int k, int Cin, int Cout);
 
 /* y = scale*z+shift written (a) as the next layer's 16-bit panel rows s*Lp+pad+p (panel nullable)
@@ -148,8 +150,12 @@ int dcue_affine_pack(const float* z, int S, int P, int C, const float* scale, co
  * dy has row stride lddy (elements); dtp (nullable, [S, lddtp]) is the gradient of the time
  * average, added as dtp/P to every row. */
 int dcue_bn_bwd_reduce(const float* dy, int lddy, const float* dtp, int lddtp, const float* z, const float* mean,
-                       const float* rstd, int S, int P, int C, double* sums, void* ws, size_t ws_bytes,
-                       void* stream);
+                       const float* rstd, int S, int P, int C, double* sums,
+                       float* absmax /* nullable: max |dy (+dtp/P)| */, void* ws, size_t ws_bytes, void* stream);
+/* Power-of-two scale for the 16-bit conv-backward operand (tcgen05 kind::f16 needs both operands in
+ * one format, and unscaled fp16 gradients would underflow): out = {s, 1/s}, s the largest power of two
+ * with s*bound <= 2^14, bound = max_c|scale_c| * absmax * (count > 0 ? 2 + sqrt(count) : 1) >= max|dz|. */
+int dcue_grad_scale(const float* absmax, const float* scale, int C, double count, float* out, void* stream);
 size_t dcue_bn_bwd_ws_bytes(int C);
 
 /* BatchNorm backward apply + ReLU mask + MaxPool unpooling in one pass:
@@ -161,8 +167,9 @@ size_t dcue_bn_bwd_ws_bytes(int C);
 int dcue_bn_relu_unpool_bwd(const float* dy, int lddy, const float* dtp, int lddtp, const float* z,
                             const uint8_t* code, const float* scale, const float* mean, const float* rstd,
                             const double* sums, double count, int S, int P, int C, int pool, int Lp,
-                            void* dy_panel, long panel_rows, int fmt, float* dz_out, double* bias_sums,
-                            void* ws, size_t ws_bytes, void* stream);
+                            void* dy_panel, long panel_rows, int fmt,
+                            const float* gscale /* panel values are multiplied by gscale[0]; nullable */,
+                            float* dz_out, double* bias_sums, void* ws, size_t ws_bytes, void* stream);
 
 /* bn0 backward reductions (truedcuemel1dbn.py:79): dx = channels-last [S*L, C] gradient of the
  * normalised input (layer1 dgrad), pos/neg = the NCL fp32 input; sums = double[2*C] as above.

@@ -23,7 +23,8 @@ Reference anchors (all under /root/reference):
 ``operand_dtype`` / ``grad_dtype`` reproduce the roundings of the B200 path:
 conv operands (activations entering layer1..4 and their weights) are rounded to
 ``operand_dtype`` (fp16 on B200) and the gradient entering each conv backward is
-rounded to ``grad_dtype`` (bf16); accumulation stays in the working dtype.  With
+rounded to ``grad_dtype`` ("fp16_scaled": fp16 under a per-layer power-of-two scale);
+accumulation stays in the working dtype.  With
 both ``None`` the oracle is the reference's exact fp32 (or fp64) arithmetic.
 """
 from __future__ import annotations
@@ -38,7 +39,16 @@ COS_EPS = 1e-8
 
 
 def _round(x, dt):
-    return x if dt is None else x.to(dt).to(x.dtype)
+    """Round to a 16-bit format.  dt == "fp16_scaled" is the B200 conv-backward operand: fp16 after
+    a power-of-two scale chosen per layer so that no value overflows (dcue_grad_scale), i.e. an
+    11-bit significand with effectively unbounded exponent."""
+    if dt is None:
+        return x
+    if isinstance(dt, str):
+        assert dt == "fp16_scaled"
+        m, e = torch.frexp(x.double())
+        return torch.ldexp(torch.round(m * 2048.0) / 2048.0, e).to(x.dtype)
+    return x.to(dt).to(x.dtype)
 
 
 class _RoundedConv(torch.autograd.Function):

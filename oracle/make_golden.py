@@ -77,6 +77,43 @@ def main():
     torch.save({"scores": s.detach(), "loss": l.detach(), "grad": s.grad, "tie_scores": t.detach(),
                 "tie_loss": lt.detach(), "tie_grad": t.grad}, os.path.join(OUT, "ref_hinge_kat.pt"))
     print("wrote hinge KAT", float(l), t.grad)
+    optim_goldens()
+
+
+def optim_goldens():
+    """Trajectories of the reference's Ranger and CyclicLRWithRestarts (host-side components the
+    drop-in trainer re-implements) on a tiny deterministic problem."""
+    import contextlib
+    import io
+    import warnings
+    warnings.simplefilter("ignore")
+    from dcrecommend.optim.cyclic_scheduler import CyclicLRWithRestarts
+    from dcrecommend.optim.ranger import Ranger
+    g = torch.Generator().manual_seed(5)
+    w0, A, b = torch.randn(7, 5, generator=g), torch.randn(5, 5, generator=g), torch.randn(7, generator=g)
+    w = torch.nn.Parameter(w0.clone())
+    bb = torch.nn.Parameter(b.clone())
+    with contextlib.redirect_stdout(io.StringIO()):
+        opt = Ranger([w, bb], lr=1e-2, alpha=0.5, k=6, N_sma_threshhold=5, betas=(0.9, 0.99), eps=1e-5, weight_decay=1e-2)
+    traj = []
+    for _ in range(40):
+        opt.zero_grad()
+        loss = ((w @ A).tanh().sum(1) + bb).pow(2).sum()
+        loss.backward()
+        opt.step()
+        traj.append(torch.cat([w.detach().flatten(), bb.detach()]).clone())
+    p = torch.nn.Parameter(torch.zeros(3))
+    sgd = torch.optim.SGD([p], lr=0.1, weight_decay=0.01)
+    sch = CyclicLRWithRestarts(sgd, 4, 18, restart_period=2, t_mult=2, policy="cosine")
+    lrs = []
+    for epoch in range(9):
+        sch.step()
+        for _ in range(4):
+            sch.batch_step()
+            lrs.append((sgd.param_groups[0]["lr"], sgd.param_groups[0]["weight_decay"]))
+    torch.save({"w0": w0, "A": A, "b": b, "ranger_traj": torch.stack(traj), "sched": torch.tensor(lrs, dtype=torch.float64)},
+               os.path.join(OUT, "ref_optim.pt"))
+    print("wrote optim goldens")
 
 
 if __name__ == "__main__":

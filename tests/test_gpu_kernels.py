@@ -97,7 +97,8 @@ def test_user_tower_forward_backward(zipf):
     h0 = torch.empty(B, 300, device=DEV)
     raw = torch.empty(B, 300, device=DEV)
     err = torch.zeros(1, dtype=torch.int32, device=DEV)
-    L.call("dcue_gather_relu_fwd", mod.embeddings.weight.data_ptr(), u.to(DEV).data_ptr(), B, U, 300, h0.data_ptr(),
+    ud = u.to(DEV)
+    L.call("dcue_gather_relu_fwd", mod.embeddings.weight.data_ptr(), ud.data_ptr(), B, U, 300, h0.data_ptr(),
            raw.data_ptr(), err.data_ptr(), L.stream())
     assert torch.equal(raw.cpu(), p["user_embd.embeddings.weight"][u])
     assert torch.equal(h0.cpu(), p["user_embd.embeddings.weight"][u].clamp_min(0))
@@ -147,12 +148,13 @@ def _conv_case(S, gi, seed):
     b = torch.randn(128, generator=g) * 0.1
     X = ops.Panel(S, geo["Lp"], DEV)
     st = L.stream()
-    xd = x.to(DEV)
+    xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
     L.call("dcue_ncl_pack", xd.data_ptr(), S, None, 0, 128, geo["Lin"], None, None, X.base, X.panel_rows, geo["Lp"],
            geo["pad"], L.FMT_F16, st)
     wp = torch.empty(128 * geo["k"] * 128, dtype=torch.int16, device=DEV)
-    L.call("dcue_pack_conv_weight", w.to(DEV).data_ptr(), 128, 128, geo["k"], 0, L.FMT_F16, wp.data_ptr(), st)
-    return dict(geo=geo, x=x, w=w, b=b, X=X, wp=wp, S=S)
+    L.call("dcue_pack_conv_weight", wd.data_ptr(), 128, 128, geo["k"], 0, L.FMT_F16, wp.data_ptr(), st)
+    torch.cuda.synchronize()
+    return dict(geo=geo, x=x, w=w, b=b, X=X, wp=wp, S=S, wd=wd, bd=bd)
 
 
 def _run_conv_fwd(c, impl):
@@ -162,7 +164,7 @@ def _run_conv_fwd(c, impl):
     sums = torch.zeros(256, dtype=torch.float64, device=DEV)
     nws = L.query("dcue_conv_ws_bytes", impl, S, geo["Lp"], geo["k"], 128, 128)
     ws = torch.empty(nws, dtype=torch.uint8, device=DEV)
-    L.call("dcue_conv_pool_fwd", impl, c["X"].base, c["X"].panel_rows, L.FMT_F16, c["wp"].data_ptr(), c["b"].to(DEV).data_ptr(),
+    L.call("dcue_conv_pool_fwd", impl, c["X"].base, c["X"].panel_rows, L.FMT_F16, c["wp"].data_ptr(), c["bd"].data_ptr(),
            S, geo["Lp"], geo["P"], geo["pool"], geo["k"], 128, 128, z.data_ptr(), code.data_ptr(), sums.data_ptr(),
            ws.data_ptr(), nws, L.stream())
     torch.cuda.synchronize()
@@ -191,7 +193,7 @@ def test_conv_pool_fwd(impl, gi, S):
     assert xp[:, :pad].abs().sum() == 0 and xp[:, pad + Lin:].abs().sum() == 0
     z, code, sums = _run_conv_fwd(c, impl)
     y_ref, z_ref, code_ref = _oracle_conv_fwd(c)
-    assert relerr(z, z_ref) < 2e-5                     # same fp16 operands, fp32 accumulate
+    assert relerr(z, z_ref) < 5e-5                     # same fp16 operands, fp32 accumulate
     live = z_ref > 1e-3                                  # argmax only matters where the ReLU passes
     mism = (code.cpu().long() != code_ref)[live].float().mean().item()
     assert mism < 1e-3, mism                             # ties / fp32-order near-ties only
@@ -206,23 +208,38 @@ def test_conv_backward_kernels(impl, gi, S):
     geo = c["geo"]
     z, code, _ = _run_conv_fwd(c, L.IMPL_SIMT)
     g = torch.Generator().manual_seed(300 + gi)
-    dyn = torch.randn(S * geo["P"], 128, generator=g)
+    dyn = torch.randn(S * geo["P"], 128, generator=g) * 1e-4   # tiny, like real gradients
+    dyn_d = dyn.to(DEV)
     dY = ops.Panel(S, geo["Lp"], DEV)
     bsum = torch.zeros(128, dtype=torch.float64, device=DEV)
     nws = max(L.query("dcue_conv_ws_bytes", impl, S, geo["Lp"], geo["k"], 128, 128), L.query("dcue_bn_bwd_ws_bytes", 128))
     ws = torch.empty(nws, dtype=torch.uint8, device=DEV)
     st = L.stream()
-    L.call("dcue_bn_relu_unpool_bwd", dyn.to(DEV).data_ptr(), 128, None, 0, z.data_ptr(), code.data_ptr(), None, None, None,
-           None, 1.0, S, geo["P"], 128, geo["pool"], geo["Lp"], dY.base, dY.panel_rows, L.FMT_BF16, None, bsum.data_ptr(),
-           ws.data_ptr(), nws, st)
+    # gradient scale from max|dy| (no BN here: bound = max|dy|)
+    sums = torch.zeros(256, dtype=torch.float64, device=DEV)
+    amax = torch.zeros(1, device=DEV)
+    gsc = torch.zeros(2, device=DEV)
+    zero, one = torch.zeros(128, device=DEV), torch.ones(128, device=DEV)
+    L.call("dcue_bn_bwd_reduce", dyn_d.data_ptr(), 128, None, 0, z.data_ptr(), zero.data_ptr(), one.data_ptr(), S, geo["P"], 128,
+           sums.data_ptr(), amax.data_ptr(), ws.data_ptr(), nws, st)
+    L.call("dcue_grad_scale", amax.data_ptr(), None, 128, 0.0, gsc.data_ptr(), st)
+    L.call("dcue_bn_relu_unpool_bwd", dyn_d.data_ptr(), 128, None, 0, z.data_ptr(), code.data_ptr(), None, None, None,
+           None, 1.0, S, geo["P"], 128, geo["pool"], geo["Lp"], dY.base, dY.panel_rows, L.FMT_F16, gsc.data_ptr(), None,
+           bsum.data_ptr(), ws.data_ptr(), nws, st)
+    assert abs(amax.item() - dyn.abs().max().item()) < 1e-12
+    sc = gsc.cpu()
+    import math
+    assert sc[0] * sc[1] == 1.0 and math.log2(sc[0].item()).is_integer()
+    assert 8192.0 < sc[0].item() * amax.item() <= 16384.0
     # oracle: same routing from the device's own z / code (so ties cannot differ)
     zc, cc = z.cpu(), code.cpu().long()
-    dz = (dyn * (zc > 0)).bfloat16().float()
+    dz = ((dyn * (zc > 0)) * sc[0]).half().float()            # the panel holds s * dz in fp16
     dy_ref = torch.zeros(S, geo["Lp"], 128)
     rows = (torch.arange(geo["P"]).view(1, -1, 1) * geo["pool"] + cc.view(S, geo["P"], 128))
     dy_ref.scatter_(1, rows, dz.view(S, geo["P"], 128))
-    got = _unpack_panel(dY, S * geo["Lp"], L.FMT_BF16).view(S, geo["Lp"], 128).cpu()
+    got = _unpack_panel(dY, S * geo["Lp"], L.FMT_F16).view(S, geo["Lp"], 128).cpu()
     assert torch.equal(got, dy_ref)
+    dy_ref = dy_ref / sc[0]                                    # kernels undo the scale on output
     assert relerr(bsum, (dyn * (zc > 0)).double().sum(0)) < 1e-5
     # wgrad / dgrad
     xr = c["x"].half().double().requires_grad_(True)
@@ -231,15 +248,15 @@ def test_conv_backward_kernels(impl, gi, S):
     gy = dy_ref[:, :geo["Lout"]].permute(0, 2, 1).double()
     y.backward(gy)
     dW = torch.empty(128, 128, geo["k"], device=DEV)
-    L.call("dcue_conv_wgrad", impl, dY.base, dY.panel_rows, L.FMT_BF16, c["X"].base, c["X"].panel_rows, L.FMT_F16,
-           S * geo["Lp"], geo["k"], 128, 128, dW.data_ptr(), ws.data_ptr(), nws, st)
-    assert relerr(dW, wr.grad) < 2e-5
+    L.call("dcue_conv_wgrad", impl, dY.base, dY.panel_rows, L.FMT_F16, c["X"].base, c["X"].panel_rows, L.FMT_F16,
+           S * geo["Lp"], geo["k"], 128, 128, gsc.data_ptr(), dW.data_ptr(), ws.data_ptr(), nws, st)
+    assert relerr(dW, wr.grad) < 5e-5
     wpd = torch.empty(128 * geo["k"] * 128, dtype=torch.int16, device=DEV)
-    L.call("dcue_pack_conv_weight", c["w"].to(DEV).data_ptr(), 128, 128, geo["k"], 1, L.FMT_F16, wpd.data_ptr(), st)
+    L.call("dcue_pack_conv_weight", c["wd"].data_ptr(), 128, 128, geo["k"], 1, L.FMT_F16, wpd.data_ptr(), st)
     dx = torch.full((S * geo["Lin"], 128), float("nan"), device=DEV)
-    L.call("dcue_conv_dgrad", impl, dY.base, dY.panel_rows, L.FMT_BF16, wpd.data_ptr(), L.FMT_F16, S, geo["Lp"], geo["Lin"],
-           geo["pad"], geo["k"], 128, 128, dx.data_ptr(), ws.data_ptr(), nws, st)
-    assert relerr(dx.view(S, geo["Lin"], 128), xr.grad.permute(0, 2, 1)) < 2e-5
+    L.call("dcue_conv_dgrad", impl, dY.base, dY.panel_rows, L.FMT_F16, wpd.data_ptr(), L.FMT_F16, S, geo["Lp"], geo["Lin"],
+           geo["pad"], geo["k"], 128, 128, gsc.data_ptr(), dx.data_ptr(), ws.data_ptr(), nws, st)
+    assert relerr(dx.view(S, geo["Lin"], 128), xr.grad.permute(0, 2, 1)) < 5e-5
 
 
 # ------------------------------------------------------------------ BatchNorm kernels
@@ -251,14 +268,16 @@ def test_ncl_stats_and_bn_finalize():
     nws = L.query("dcue_ncl_stats_ws_bytes", 128)
     ws = torch.empty(nws, dtype=torch.uint8, device=DEV)
     st = L.stream()
-    L.call("dcue_ncl_stats", pos.to(DEV).data_ptr(), 3, neg.to(DEV).data_ptr(), 11, 128, 131, sums.data_ptr(), ws.data_ptr(), nws, st)
+    pos_d, neg_d = pos.to(DEV), neg.to(DEV)
+    L.call("dcue_ncl_stats", pos_d.data_ptr(), 3, neg_d.data_ptr(), 11, 128, 131, sums.data_ptr(), ws.data_ptr(), nws, st)
     assert relerr(sums[:128], x.sum((0, 2))) < 1e-6 and relerr(sums[128:], (x * x).sum((0, 2))) < 1e-6
     gamma, beta = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g)
     rm, rv = torch.randn(128, generator=g), torch.rand(128, generator=g) + 0.5
     rmd, rvd, nbt = rm.to(DEV), rv.to(DEV), torch.tensor(3, device=DEV)
+    gam_d, bet_d = gamma.to(DEV), beta.to(DEV)
     out = torch.empty(4, 128, device=DEV)
     n = 14 * 131
-    L.call("dcue_bn_finalize", sums.data_ptr(), float(n), 128, gamma.to(DEV).data_ptr(), beta.to(DEV).data_ptr(), rmd.data_ptr(),
+    L.call("dcue_bn_finalize", sums.data_ptr(), float(n), 128, gam_d.data_ptr(), bet_d.data_ptr(), rmd.data_ptr(),
            rvd.data_ptr(), nbt.data_ptr(), 0.1, 1e-5, 1, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), st)
     mean, var = x.mean((0, 2)), x.var((0, 2), unbiased=False)
     rstd = 1 / torch.sqrt(var + 1e-5)
@@ -281,11 +300,13 @@ def test_topk_scores(nu, ni, k):
     sc = un @ inn.T
     kk = min(k, ni)
     v, i = torch.topk(sc, kk, dim=1)
-    assert relerr(ts[:, :kk], v) < 1e-5
-    # index sets equal wherever the k-th / (k+1)-th gap exceeds the fp32 accumulation tolerance
+    # x*(1/|x|) on device vs x/|x| here differ in the last fp32 bit, so a ~2^-13 fraction of the fp16
+    # roundings of the normalised factors differ by one fp16 ulp: score error <~ 1e-4 absolute
+    assert (ts[:, :kk].cpu().double() - v).abs().max() < 2e-4
+    # index sets equal wherever the k-th / (k+1)-th gap exceeds that tolerance
     if ni > kk:
         v1, _ = torch.topk(sc, kk + 1, dim=1)
-        clear = (v1[:, kk - 1] - v1[:, kk]) > 1e-5
+        clear = (v1[:, kk - 1] - v1[:, kk]) > 4e-4
     else:
         clear = torch.ones(nu, dtype=torch.bool)
     got = ti[:, :kk].cpu()
