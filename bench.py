@@ -1,0 +1,333 @@
+"""DCUE training-step benchmark (BASELINE.json metric: DCUE train triplets/sec).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+One "step" = zero_grad + DCUENet forward(u, pos, neg) + hinge loss + backward + optimizer.step +
+scheduler.batch_step over one batch (the loop body of the reference's _train_epoch,
+dcrecommend/nn/dcue.py:202-210).  Workload = BASELINE configs[1]: truedcuemel1dbn, 20k users,
+emb 300, batch 1024 per GPU, 20 sampled negatives, margin 0.2, Adam(1e-5, (0.9, 0.99), 1e-8).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC, UNIT = "DCUE train triplets/sec", "triplets/s"
+CFG = dict(model_type="truedcuemel1dbn", users=20000, emb=300, feat=100, hidden=128, frames=131, margin=0.2,
+           lr=1e-5, betas=(0.9, 0.99), eps=1e-8)
+L1_FLOP_PER_SPEC = 2 * 128 * 128 * 4 * 132  # live MACs*2 of layer1 per spectrogram
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------- CPU arm
+class OracleTrainer:
+    """The reference algorithm (oracle port) + torch Adam on host cores."""
+
+    def __init__(self, users):
+        from oracle import fixtures
+        self.p = fixtures.make_params(CFG["model_type"], seed=0, user_count=users)
+        self.names = [k for k, v in self.p.items() if v.is_floating_point() and "running_" not in k]
+        self.leaves = [torch.nn.Parameter(self.p[k].clone()) for k in self.names]
+        self.opt = torch.optim.Adam(self.leaves, CFG["lr"], CFG["betas"], CFG["eps"], 0)
+
+    def step(self, u, pos, neg):
+        from oracle import dcue_oracle as O
+        cur = dict(self.p)
+        cur.update({k: l.detach() for k, l in zip(self.names, self.leaves)})
+        r = O.train_step_grads(cur, u, pos, neg, CFG["model_type"], CFG["margin"])
+        for l, k in zip(self.leaves, self.names):
+            l.grad = r["grads"].get(k)
+        self.opt.step()
+        self.p.update(r["new_stats"])
+        return r["loss"].item()
+
+
+def cpu_arm(batch, negs, steps, warmup, budget_s=None):
+    """-> (triplets/s, seconds per step, steps run).  Uses every host thread torch will take."""
+    from oracle import fixtures
+    tr = OracleTrainer(CFG["users"])
+    u, pos, neg = fixtures.make_inputs(batch, negs, CFG["users"], seed=1)
+    for _ in range(warmup):
+        tr.step(u, pos, neg)
+    t0, n = time.perf_counter(), 0
+    while n < steps:
+        tr.step(u, pos, neg)
+        n += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s and n >= 2:
+            break
+    dt = time.perf_counter() - t0
+    return batch * n / dt, dt / n, n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_b = 64
+    value, sps, n = cpu_arm(sample_b, args.negs, args.steps, min(args.warmup, 1))
+    cores = torch.get_num_threads()
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+           "warmup": min(args.warmup, 1), "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config(args, extra={"sample": "each step = %d of the %d triplets of a batch" % (sample_b, args.batch)}),
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": "oracle port of the reference train step, batch %d x %d negs, %d steps" % (sample_b, args.negs, n)},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, extra=None):
+    c = {"workload": "cfg2: DCUE %s, %d users x %d emb, feature %d, batch %d per GPU, 1 pos + %d sampled negs, hinge margin %.1f, Adam lr 1e-5"
+                     % (CFG["model_type"], CFG["users"], CFG["emb"], CFG["feat"], args.batch, args.negs, CFG["margin"]),
+         "global_batch": args.batch * args.gpus, "negatives": args.negs, "parallelism": "dp%d" % args.gpus,
+         "l2": "inputs (%.2f GB/step/GPU fp32 spectrograms) exceed the 126 MB L2; no flush needed" %
+               (args.batch * (1 + args.negs) * 128 * CFG["frames"] * 4 / 1e9)}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ------------------------------------------------------------------------------------- GPU arm
+def kernel_roofline(pkg, S, dev):
+    """CUDA-event timing of the three layer-1 tensor-core kernels on this stream; the slowest is the
+    dominant kernel of the step.  achieved = algorithmic FLOPs per launch / avg launch time."""
+    L, ops = pkg._lib, pkg.ops
+    geo = ops.tower_geometry(CFG["frames"])[0]
+    st = L.stream()
+    X, dY = ops.Panel(S, geo["Lp"], dev), ops.Panel(S, geo["Lp"], dev)
+    X.buf.random_(0, 15000)   # arbitrary finite positive fp16 bit patterns (values < 1)
+    dY.buf.random_(0, 15000)
+    wp = torch.randint(0, 15000, (128 * 4 * 128,), dtype=torch.int16, device=dev)
+    bias = torch.zeros(128, device=dev)
+    z = torch.empty(S * geo["P"], 128, device=dev)
+    code = torch.empty(S * geo["P"], 128, dtype=torch.uint8, device=dev)
+    sums = torch.zeros(256, dtype=torch.float64, device=dev)
+    dx = torch.empty(S * geo["Lin"], 128, device=dev)
+    dW = torch.empty(128, 128, 4, device=dev)
+    nws = L.query("dcue_conv_ws_bytes", L.IMPL_TC, S, geo["Lp"], 4, 128, 128)
+    ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+    calls = {
+        "conv1_fwd_pool": lambda: L.call("dcue_conv_pool_fwd", L.IMPL_TC, X.base, X.panel_rows, 0, wp.data_ptr(), bias.data_ptr(), S,
+                                         geo["Lp"], geo["P"], 4, 4, 128, 128, z.data_ptr(), code.data_ptr(), sums.data_ptr(),
+                                         ws.data_ptr(), nws, st),
+        "conv1_dgrad": lambda: L.call("dcue_conv_dgrad", L.IMPL_TC, dY.base, dY.panel_rows, 0, wp.data_ptr(), 0, S, geo["Lp"], geo["Lin"],
+                                      2, 4, 128, 128, None, dx.data_ptr(), ws.data_ptr(), nws, st),
+        "conv1_wgrad": lambda: L.call("dcue_conv_wgrad", L.IMPL_TC, dY.base, dY.panel_rows, 0, X.base, X.panel_rows, 0, S * geo["Lp"], 4,
+                                      128, 128, None, dW.data_ptr(), ws.data_ptr(), nws, st),
+    }
+    res = {}
+    for name, fn in calls.items():
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        reps = 10
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        res[name] = {"ms": ms, "tflops": L1_FLOP_PER_SPEC * S / (ms * 1e-3) / 1e12}
+    return res
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = importlib.import_module("amplifai-deepcontentrecommenders_b200")
+    par = importlib.import_module("amplifai-deepcontentrecommenders_b200.parallel")
+    optim = importlib.import_module("amplifai-deepcontentrecommenders_b200.optim")
+    L = pkg._lib
+    B, N, U = args.batch, args.negs, CFG["users"]
+
+    torch.manual_seed(0)
+    model = pkg.DCUENet({"feature_dim": CFG["feat"], "conv_hidden": CFG["hidden"], "user_embdim": CFG["emb"], "user_count": U,
+                         "model_type": CFG["model_type"]}).to(dev).train()
+    dp = par.DataParallelDCUE(model)
+    opt = torch.optim.Adam(model.parameters(), CFG["lr"], CFG["betas"], CFG["eps"], 0)
+    sched = optim.CyclicLRWithRestarts(opt, B * world, epoch_size=B * world * 100000, restart_period=30, t_mult=2, policy="cosine")
+    sched.step()
+
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    u = torch.randint(0, U, (B,), generator=g, device=dev)
+    pos = torch.randn(B, 128, CFG["frames"], generator=g, device=dev)
+    neg = torch.randn(B, N, 128, CFG["frames"], generator=g, device=dev)
+    loss_acc = torch.zeros((), device=dev)
+
+    def step(u_, pos_, neg_):
+        opt.zero_grad(set_to_none=True)
+        loss = dp.loss_step(u_, pos_, neg_, CFG["margin"])
+        loss.backward()
+        dp.reduce_gradients()
+        opt.step()
+        sched.batch_step()
+        return loss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing ("value")
+    for _ in range(args.warmup):
+        step(u, pos, neg)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = L.lib().dcue_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss_acc += step(u, pos, neg)
+    e1.record()
+    barrier()
+    launches = L.lib().dcue_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    value = B * world * args.steps / (ms_total * 1e-3)
+    final_loss = dp.reduce_loss(loss_acc / args.steps).item()
+
+    # ---------------- end to end: pinned host inputs -> H2D -> step -> loss D2H, every step
+    hu, hpos, hneg = (t.cpu().pin_memory() for t in (u, pos, neg))
+    bufs = [(torch.empty_like(u), torch.empty_like(pos), torch.empty_like(neg)) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def enqueue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[slot])
+            for d, h in zip(bufs[slot], (hu, hpos, hneg)):
+                d.copy_(h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_loop(n):
+        for s in range(2):
+            freed[s].record(torch.cuda.current_stream())
+        enqueue_copy(0)
+        for i in range(n):
+            slot = i & 1
+            if i + 1 < n:
+                enqueue_copy(slot ^ 1)          # overlaps with this step's kernels
+            torch.cuda.current_stream().wait_event(ready[slot])
+            lossv = step(*bufs[slot])
+            freed[slot].record(torch.cuda.current_stream())
+            lossv.item()                        # device -> host read of the step's result
+
+    e2e_steps = max(2, min(args.steps, 6))
+    e2e_loop(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(e2e_steps)
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * e2e_steps / dt.item()
+    h2d = u.numel() * 8 + (pos.numel() + neg.numel()) * 4
+
+    out = None
+    if rank == 0:
+        tf_peak, hbm_peak, which = peaks()
+        kern = kernel_roofline(pkg, B * (1 + N), dev)
+        top = max(kern, key=lambda k: kern[k]["ms"])
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f16", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps},
+               "gpu_launches": int(launches), "final_loss": final_loss,
+               "roofline": {"bound": "tensor", "kernel": top, "achieved": kern[top]["tflops"], "peak": tf_peak, "unit": "TFLOP/s",
+                            "frac": kern[top]["tflops"] / tf_peak, "traffic": None, "peak_source": which + " (burst bf16 cuBLAS)",
+                            "kernels": kern}}
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            v, sps, n = cpu_arm(64, N, 1000, 1, budget_s=args.cpu_seconds)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                   "sample": "oracle port of the reference train step (cfg1: batch 64 x %d negs), %d steps, %.1f s/step" % (N, n, sps)}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="triplets per GPU")
+    ap.add_argument("--negs", type=int, default=20)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
