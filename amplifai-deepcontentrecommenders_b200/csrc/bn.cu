@@ -22,19 +22,45 @@ ncl_stats_kernel(const float* __restrict__ pos, int S_pos, const float* __restri
     const int S = S_pos + S_neg;
     for (int s = blockIdx.x; s < S; s += gridDim.x) {
         const float* base = s < S_pos ? pos + (long)s * C * L : neg + (long)(s - S_pos) * C * L;
+        if (L <= 160) {
+            // 4 channel rows x 5 strided frames = 20 independent loads in flight per lane
 #pragma unroll
-        for (int i = 0; i < STAT_MAXC_PER_WARP; ++i) {
-            const int c = w + 8 * i;
-            if (c < C) {
-                const float* row = base + (long)c * L;
-                float a = 0.f, b = 0.f;
-                for (int t = lane; t < L; t += 32) {
-                    const float v = __ldg(row + t);
-                    a += v;
-                    b = fmaf(v, v, b);
+            for (int i0 = 0; i0 < STAT_MAXC_PER_WARP; i0 += 4) {
+                float v[4][5];
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const int c = w + 8 * (i0 + ii);
+                    const float* row = base + (long)c * L;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const int t = lane + 32 * k;
+                        v[ii][k] = (c < C && t < L) ? __ldg(row + t) : 0.f;
+                    }
                 }
-                s1[i] += a;
-                s2[i] += b;
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    float a = 0.f, b = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) { a += v[ii][k]; b = fmaf(v[ii][k], v[ii][k], b); }
+                    s1[i0 + ii] += a;
+                    s2[i0 + ii] += b;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < STAT_MAXC_PER_WARP; ++i) {
+                const int c = w + 8 * i;
+                if (c < C) {
+                    const float* row = base + (long)c * L;
+                    float a = 0.f, b = 0.f;
+                    for (int t = lane; t < L; t += 32) {
+                        const float v = __ldg(row + t);
+                        a += v;
+                        b = fmaf(v, v, b);
+                    }
+                    s1[i] += a;
+                    s2[i] += b;
+                }
             }
         }
     }
@@ -49,13 +75,23 @@ ncl_stats_kernel(const float* __restrict__ pos, int S_pos, const float* __restri
     }
 }
 
-// out[j] = sum_b partial[b][j], fixed order
-__global__ void reduce_partials_kernel(const double* __restrict__ partial, int nblk, int n, double* __restrict__ out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+// out[j] = sum_b partial[b][j]; block = 32 columns x 8 row lanes, fixed summation order
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const double* __restrict__ partial, int nblk, int n, double* __restrict__ out) {
+    __shared__ double red[8][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + cl;
     double s = 0.0;
-    for (int b = 0; b < nblk; ++b) s += partial[(long)b * n + j];
-    out[j] = s;
+    if (j < n)
+        for (int b = rl; b < nblk; b += 8) s += partial[(long)b * n + j];
+    red[rl][cl] = s;
+    __syncthreads();
+    if (rl == 0 && j < n) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][cl];
+        out[j] = t;
+    }
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, const float* __restrict__ gamma,
@@ -133,16 +169,20 @@ affine_pack_kernel(const float* __restrict__ z, long rows, int P, int C, const f
     __shared__ float tile[TR][TLD];
     const int tid = threadIdx.x;
     for (long r0 = (long)blockIdx.x * TR; r0 < rows; r0 += (long)gridDim.x * TR) {
-        for (int e = tid; e < TR * C; e += 256) {
-            const int rl = e / C, c = e - rl * C;
+        const int C4 = C >> 2;  // C % 4 == 0 (checked by the host wrapper)
+        for (int e = tid; e < TR * C4; e += 256) {
+            const int rl = e / C4, c = (e - rl * C4) * 4;
             const long r = r0 + rl;
-            float v = 0.f;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < rows) {
-                v = __ldg(z + r * C + c);
-                if (scale) v = fmaf(v, scale[c], shift[c]);
-                if (y) y[r * C + c] = v;
+                v = __ldg(reinterpret_cast<const float4*>(z + r * C + c));
+                if (scale) {
+                    const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+                    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                }
+                if (y) *reinterpret_cast<float4*>(y + r * C + c) = v;
             }
-            tile[rl][c] = v;
+            tile[rl][c] = v.x; tile[rl][c + 1] = v.y; tile[rl][c + 2] = v.z; tile[rl][c + 3] = v.w;
         }
         __syncthreads();
         if (panel) {
@@ -254,26 +294,40 @@ bn_relu_unpool_bwd_kernel(const float* __restrict__ dy, int lddy, const float* _
     const float invn = (float)(1.0 / count);
     const float invP = 1.f / (float)P;
     for (long r0 = (long)blockIdx.x * TR; r0 < rows; r0 += (long)gridDim.x * TR) {
-        for (int e = tid; e < TR * C; e += 256) {
-            const int rl = e / C, c = e - rl * C;
+        const int C4 = C >> 2;  // C % 4 == 0 (checked by the host wrapper)
+        for (int e = tid; e < TR * C4; e += 256) {
+            const int rl = e / C4, c = (e - rl * C4) * 4;
             const long r = r0 + rl;
-            float v = 0.f;
-            uint8_t cd = 0;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            uint8_t cd[4] = {0, 0, 0, 0};
             if (r < rows) {
-                float g = __ldg(dy + r * lddy + c);
-                if (dtp) g += dtp[(r / P) * lddtp + c] * invP;
-                const float zz = __ldg(z + r * C + c);
-                if (sums) {
-                    const float xh = (zz - mean[c]) * rstd[c];
-                    g = g - (float)sums[c] * invn - xh * ((float)sums[C + c] * invn);
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(dy + r * lddy + c));
+                const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + r * C + c));
+                float g[4] = {g4.x, g4.y, g4.z, g4.w};
+                const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+                if (dtp) {
+                    const float* dp = dtp + (r / P) * lddtp + c;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) g[j] += dp[j] * invP;
                 }
-                if (scale) g *= scale[c];
-                v = zz > 0.f ? g : 0.f;
-                if (code) cd = code[r * C + c];
-                if (dz_out) dz_out[r * C + c] = v;
+                if (code) {
+                    const uchar4 c4 = *reinterpret_cast<const uchar4*>(code + r * C + c);
+                    cd[0] = c4.x; cd[1] = c4.y; cd[2] = c4.z; cd[3] = c4.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float gg = g[j];
+                    if (sums) {
+                        const float xh = (zz[j] - mean[c + j]) * rstd[c + j];
+                        gg = gg - (float)sums[c + j] * invn - xh * ((float)sums[C + c + j] * invn);
+                    }
+                    if (scale) gg *= scale[c + j];
+                    v[j] = zz[j] > 0.f ? gg : 0.f;
+                }
+                if (dz_out) *reinterpret_cast<float4*>(dz_out + r * C + c) = make_float4(v[0], v[1], v[2], v[3]);
             }
-            tile[rl][c] = v;
-            ctile[rl][c] = cd;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { tile[rl][c + j] = v[j]; ctile[rl][c + j] = cd[j]; }
         }
         __syncthreads();
         if (panel) {
@@ -431,7 +485,7 @@ extern "C" int dcue_ncl_stats(const float* pos, int S_pos, const float* neg, int
     if (ws_bytes < (size_t)grid * 2 * C * sizeof(double)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_ncl_stats: workspace too small");
     ncl_stats_kernel<<<grid, 256, 0, st>>>(pos, S_pos, neg, S_neg, C, L, (double*)ws);
     DCUE_LAUNCH_CHECK();
-    reduce_partials_kernel<<<ceil_div_i(2 * C, 128), 128, 0, st>>>((const double*)ws, grid, 2 * C, sums);
+    reduce_partials_kernel<<<ceil_div_i(2 * C, 32), 256, 0, st>>>((const double*)ws, grid, 2 * C, sums);
     DCUE_LAUNCH_CHECK();
     return 0;
 }
@@ -467,7 +521,7 @@ extern "C" int dcue_ncl_pack(const float* pos, int S_pos, const float* neg, int 
 
 extern "C" int dcue_affine_pack(const float* z, int S, int P, int C, const float* scale, const float* shift, void* panel,
                                 long panel_rows, int Lp, int pad, int fmt, float* y, float* tp, int ldtp, void* stream) {
-    DCUE_CHECK_ARG(z && S >= 0 && P > 0 && C > 0 && C <= 128 && (!scale == !shift));
+    DCUE_CHECK_ARG(z && S >= 0 && P > 0 && C > 0 && C <= 128 && C % 4 == 0 && (!scale == !shift));
     DCUE_CHECK_ARG(!panel || (C % 8 == 0 && Lp >= P + pad && panel_rows >= (long)S * Lp));
     cudaStream_t st = (cudaStream_t)stream;
     const long rows = (long)S * P;
@@ -502,7 +556,7 @@ extern "C" int dcue_bn_bwd_reduce(const float* dy, int lddy, const float* dtp, i
     if (ws_bytes < (size_t)grid * (2 * C + 1) * sizeof(double)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_bn_bwd_reduce: workspace too small");
     bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, lddy, dtp, lddtp, z, mean, rstd, rows, P, C, (double*)ws);
     DCUE_LAUNCH_CHECK();
-    reduce_partials_kernel<<<ceil_div_i(2 * C, 128), 128, 0, st>>>((const double*)ws, grid, 2 * C, sums);
+    reduce_partials_kernel<<<ceil_div_i(2 * C, 32), 256, 0, st>>>((const double*)ws, grid, 2 * C, sums);
     DCUE_LAUNCH_CHECK();
     if (absmax) {
         reduce_max_kernel<<<1, 256, 0, st>>>((const double*)ws + (size_t)grid * 2 * C, grid, absmax);
@@ -516,7 +570,8 @@ extern "C" int dcue_bn_relu_unpool_bwd(const float* dy, int lddy, const float* d
                                        double count, int S, int P, int C, int pool, int Lp, void* dy_panel,
                                        long panel_rows, int fmt, const float* gscale, float* dz_out, double* bias_sums,
                                        void* ws, size_t ws_bytes, void* stream) {
-    DCUE_CHECK_ARG(dy && z && S >= 0 && P > 0 && C > 0 && C <= 128 && (dy_panel || dz_out) && lddy >= C);
+    DCUE_CHECK_ARG(dy && z && S >= 0 && P > 0 && C > 0 && C <= 128 && C % 4 == 0 && (dy_panel || dz_out) && lddy >= C &&
+                   lddy % 4 == 0 && ((uintptr_t)dy & 15) == 0);
     DCUE_CHECK_ARG(!sums || (mean && rstd && count > 0));
     DCUE_CHECK_ARG(!dy_panel || (code && C % 8 == 0 && pool >= 1 && pool <= 8 && Lp >= P * pool && panel_rows >= (long)S * Lp));
     cudaStream_t st = (cudaStream_t)stream;
@@ -530,7 +585,7 @@ extern "C" int dcue_bn_relu_unpool_bwd(const float* dy, int lddy, const float* d
                                                     panel_rows, fmt, gscale, dz_out, bias_sums ? (double*)ws : nullptr);
     DCUE_LAUNCH_CHECK();
     if (bias_sums) {
-        reduce_partials_kernel<<<ceil_div_i(C, 128), 128, 0, st>>>((const double*)ws, grid, C, bias_sums);
+        reduce_partials_kernel<<<ceil_div_i(C, 32), 256, 0, st>>>((const double*)ws, grid, C, bias_sums);
         DCUE_LAUNCH_CHECK();
     }
     return 0;
@@ -549,7 +604,7 @@ extern "C" int dcue_ncl_bn_bwd_reduce(const float* dx, const float* pos, int S_p
     if (ws_bytes < (size_t)G * 2 * C * sizeof(double)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_ncl_bn_bwd_reduce: workspace too small");
     ncl_bn_bwd_reduce_kernel<<<G * (C / 8), 128, 0, st>>>(dx, pos, S_pos, neg, S_neg, C, L, mean, rstd, (double*)ws);
     DCUE_LAUNCH_CHECK();
-    reduce_partials_kernel<<<ceil_div_i(2 * C, 128), 128, 0, st>>>((const double*)ws, G, 2 * C, sums);
+    reduce_partials_kernel<<<ceil_div_i(2 * C, 32), 256, 0, st>>>((const double*)ws, G, 2 * C, sums);
     DCUE_LAUNCH_CHECK();
     return 0;
 }

@@ -13,6 +13,7 @@ extern "C" long dcue_launch_count(void) { return g_dcue_launches; }
 static int check_geom(const ConvGeom& g, long panel_rows) {
     DCUE_CHECK_ARG(g.S >= 0 && g.Lp > 0 && g.k >= 1 && g.k <= 4 && g.Cin > 0 && g.Cin <= 128 && g.Cin % 8 == 0);
     DCUE_CHECK_ARG(g.Cout > 0 && g.Cout <= 128);
+    DCUE_CHECK_ARG(g.rows_total < (1L << 31) - 4096);  // flat rows are indexed with 32-bit ints in the epilogues
     // tiles may read k-1 rows past a 128-row boundary: the back halo covers it
     DCUE_CHECK_ARG(panel_rows >= round_up_l(g.rows_total, 128) + 16);
     return 0;

@@ -130,40 +130,44 @@ struct Pipe {
 // ----------------------------------------------------------------------------- fwd / dgrad
 // EPI 0: bias + maxpool(POOL) + relu + argmax code + BN partial sums -> z[S*P, Cout]
 // EPI 1: store the data rows -> dx[S*Lin, Cout]
+// `r` = first flat row of the 32-column chunk.  Row -> (spectrogram s, padded time q) is one 32-bit
+// division per chunk, then incremental (the per-element 64-bit divisions used to dominate dgrad).
 template <int EPI, int POOL>
-__device__ __forceinline__ void epilogue_chunk(const float (&v)[32], long r, int m, float bv, const ConvGeom& g,
+__device__ __forceinline__ void epilogue_chunk(const float (&v)[32], int r, int m, float bv, const ConvGeom& g,
                                                float* __restrict__ out, uint8_t* __restrict__ code, double& st1,
                                                double& st2) {
+    int s = r / g.Lp;
+    int q = r - s * g.Lp;
+    const bool chan_ok = m < g.Cout;
     if (EPI == 0) {
         float ts1 = 0.f, ts2 = 0.f;
 #pragma unroll
         for (int t0 = 0; t0 < 32; t0 += POOL) {
-            const long rr = r + t0;
-            const long s = rr / g.Lp;
-            const int p = (int)(rr - s * g.Lp) / POOL;
             float best = v[t0];
             int bi = 0;
 #pragma unroll
             for (int i = 1; i < POOL; ++i)
                 if (v[t0 + i] > best) { best = v[t0 + i]; bi = i; }
-            if (s < g.S && p < g.P && m < g.Cout) {
+            const int p = q / POOL;  // POOL is a power of two
+            if (chan_ok && s < g.S && p < g.P) {
                 const float val = fmaxf(best + bv, 0.f);
-                const long o = (s * g.P + p) * g.Cout + m;
+                const long o = ((long)s * g.P + p) * g.Cout + m;
                 out[o] = val;
                 if (code) code[o] = (uint8_t)bi;
                 ts1 += val;
                 ts2 = fmaf(val, val, ts2);
             }
+            q += POOL;
+            if (q >= g.Lp) { q -= g.Lp; ++s; }
         }
         st1 += (double)ts1;
         st2 += (double)ts2;
     } else {
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
-            const long rr = r + t;
-            const long s = rr / g.Lp;
-            const int tt = (int)(rr - s * g.Lp) - g.pad;
-            if (s < g.S && tt >= 0 && tt < g.Lin && m < g.Cout) out[(s * g.Lin + tt) * g.Cout + m] = v[t] * bv;
+            const int tt = q - g.pad;
+            if (chan_ok && s < g.S && tt >= 0 && tt < g.Lin) out[((long)s * g.Lin + tt) * g.Cout + m] = v[t] * bv;
+            if (++q == g.Lp) { q = 0; ++s; }
         }
     }
 }
@@ -262,7 +266,7 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
         for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             mbar_wait(TFULL(acc), acc_phase);
             tc_fence_after();
-            const long r0 = tile * BN;
+            const int r0 = (int)(tile * BN);
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ++ch) {
                 float v[32];
@@ -436,7 +440,7 @@ int dcue_tc_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_
     if (int e = launch_rows<0>(panel, panel_rows, fmt, w_packed, fmt, bias, g, z, code, sums ? (double*)ws : nullptr, nullptr, grid, st))
         return e;
     if (sums) {
-        dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 128), 128, 0, st>>>((const double*)ws, grid, 2 * g.Cout, sums);
+        dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 32), 256, 0, st>>>((const double*)ws, grid, 2 * g.Cout, sums);
         DCUE_LAUNCH_CHECK();
     }
     return 0;

@@ -102,22 +102,24 @@ __global__ void split_reduce_kernel(const float* __restrict__ part, int splits, 
     out[i] = s;
 }
 
-// column sums of a [M, N] matrix (row stride ld): out[n] = sum_m x[m,n]; fixed-order, deterministic
+// column sums of a [M, N] matrix (row stride ld): block (column chunk, row chunk g) writes
+// part[g][n]; split_reduce_kernel then sums the row chunks in fixed order (deterministic).
+constexpr int COLSUM_G = 64;
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int ld, int M, int N,
-                                                     float* __restrict__ out) {
+                                                     float* __restrict__ part) {
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int rl = threadIdx.x >> 5;
     float s = 0.f;
     if (c < N)
-        for (int m = rl; m < M; m += 8) s += x[(long)m * ld + c];
+        for (int m = blockIdx.y * 8 + rl; m < M; m += 8 * gridDim.y) s += x[(long)m * ld + c];
     red[rl][threadIdx.x & 31] = s;
     __syncthreads();
     if (rl == 0 && c < N) {
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
-        out[c] = t;
+        part[(long)blockIdx.y * N + c] = t;
     }
 }
 
@@ -164,7 +166,7 @@ extern "C" int dcue_linear_dgrad(const float* dY, int lddy, const float* W, int 
 }
 
 extern "C" size_t dcue_linear_wgrad_ws_bytes(int M, int K, int N) {
-    return (size_t)wgrad_splits(M, K, N) * (size_t)N * (size_t)K * sizeof(float) + 256;
+    return ((size_t)wgrad_splits(M, K, N) * (size_t)N * (size_t)K + (size_t)COLSUM_G * N) * sizeof(float) + 256;
 }
 
 extern "C" int dcue_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, int M, int K, int N,
@@ -177,7 +179,7 @@ extern "C" int dcue_linear_wgrad(const float* dY, int lddy, const float* X, int 
         return 0;
     }
     const int splits = wgrad_splits(M, K, N);
-    if (splits > 1 && (!ws || ws_bytes < (size_t)splits * N * K * sizeof(float)))
+    if (!ws || ws_bytes < ((size_t)splits * N * K + (size_t)COLSUM_G * N) * sizeof(float))
         DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_linear_wgrad: workspace too small");
     GemmP p{};
     p.A = dY; p.sAi = 1; p.sAr = lddy;  // A(i=n, r=m) = dY[m,n]
@@ -193,7 +195,11 @@ extern "C" int dcue_linear_wgrad(const float* dY, int lddy, const float* X, int 
         DCUE_LAUNCH_CHECK();
     }
     if (db) {
-        colsum_kernel<<<ceil_div_i(N, 32), 256, 0, st>>>(dY, lddy, M, N, db);
+        float* part = (float*)ws + (size_t)splits * N * K;
+        dim3 cg(ceil_div_i(N, 32), COLSUM_G);
+        colsum_kernel<<<cg, 256, 0, st>>>(dY, lddy, M, N, part);
+        DCUE_LAUNCH_CHECK();
+        split_reduce_kernel<<<ceil_div_i(N, 256), 256, 0, st>>>(part, COLSUM_G, N, db);
         DCUE_LAUNCH_CHECK();
     }
     return 0;
