@@ -29,16 +29,18 @@ extern "C" size_t dcue_conv_ws_bytes(int impl, int S, int Lp, int k, int Cin, in
 }
 
 extern "C" int dcue_conv_pool_fwd(int impl, const void* panel, long panel_rows, int fmt, const void* w_packed,
-                                  const float* bias, int S, int Lp, int P, int pool, int k, int Cin, int Cout, float* z,
-                                  uint8_t* code, double* sums, void* ws, size_t ws_bytes, void* stream) {
+                                  const float* bias, const float* tap_bias, int S, int Lp, int Lin, int pad, int P, int pool,
+                                  int k, int Cin, int Cout, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
+                                  void* stream) {
     DCUE_CHECK_ARG(panel && w_packed && z && (pool == 1 || pool == 2 || pool == 4) && P > 0 && P * pool <= Lp &&
                    Lp % pool == 0);
-    ConvGeom g{S, Lp, 0, 0, k, pool, P, Cin, Cout, (long)S * Lp};
+    DCUE_CHECK_ARG(Lin > 0 && pad >= 0 && Lin + pad <= Lp);
+    ConvGeom g{S, Lp, Lin, pad, k, pool, P, Cin, Cout, (long)S * Lp};
     if (int e = check_geom(g, panel_rows)) return e;
     if (S == 0) return 0;
     if (impl == DCUE_IMPL_TC)
-        return dcue_tc_conv_fwd(panel, panel_rows, fmt, w_packed, bias, g, z, code, sums, ws, ws_bytes, (cudaStream_t)stream);
-    return dcue_simt_conv_fwd(panel, panel_rows, fmt, w_packed, bias, g, z, code, sums, ws, ws_bytes, (cudaStream_t)stream);
+        return dcue_tc_conv_fwd(panel, panel_rows, fmt, w_packed, bias, tap_bias, g, z, code, sums, ws, ws_bytes, (cudaStream_t)stream);
+    return dcue_simt_conv_fwd(panel, panel_rows, fmt, w_packed, bias, tap_bias, g, z, code, sums, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int dcue_conv_dgrad(int impl, const void* dy_panel, long panel_rows, int fmt_dy, const void* w_packed_dgrad,

@@ -16,9 +16,21 @@ struct ConvGeom {
     long rows_total;  // S * Lp
 };
 
+// Sum of the per-tap constants tb[j] whose tap falls outside the data rows for conv output t
+// (zero padding): used when an input-side BatchNorm shift is folded into the conv bias.
+__device__ __forceinline__ float missing_taps(const float (&tb)[4], int t, int k, int pad, int Lin) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int tt = t + j - pad;
+        if (j < k && (tt < 0 || tt >= Lin)) a += tb[j];
+    }
+    return a;
+}
+
 // CUDA-core path (conv_simt.cu)
 int dcue_simt_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_packed, const float* bias,
-                       const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
+                       const float* tap_bias, const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
                        cudaStream_t st);
 int dcue_simt_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
                          const ConvGeom& g, const float* gscale, float* dx, cudaStream_t st);
@@ -27,7 +39,7 @@ int dcue_simt_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const v
                          size_t ws_bytes, cudaStream_t st);
 // tcgen05 path (conv_tc.cu)
 int dcue_tc_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_packed, const float* bias,
-                     const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
+                     const float* tap_bias, const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
                      cudaStream_t st);
 int dcue_tc_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
                        const ConvGeom& g, const float* gscale, float* dx, cudaStream_t st);

@@ -34,17 +34,26 @@ __device__ __forceinline__ void load_panel_tile(float* __restrict__ xs, const ui
 
 template <int POOL>
 __device__ __forceinline__ void epi_pool(const float (&acc)[TRW], long r0, int m, float bv, const ConvGeom& g,
-                                         float* __restrict__ out, uint8_t* __restrict__ code, double& st1, double& st2) {
+                                         float* __restrict__ out, uint8_t* __restrict__ code, double& st1, double& st2,
+                                         bool has_tb, const float (&tb)[4]) {
 #pragma unroll
     for (int t0 = 0; t0 < TRW; t0 += POOL) {
         const long r = r0 + t0;
         const long s = r / g.Lp;
-        const int p = (int)(r - s * g.Lp) / POOL;
-        float best = acc[t0];
+        const int q = (int)(r - s * g.Lp);
+        const int p = q / POOL;
+        float w[POOL];
+#pragma unroll
+        for (int i = 0; i < POOL; ++i) w[i] = acc[t0 + i];
+        if (has_tb && (q < g.pad || q + POOL - 1 > g.Lin + g.pad - g.k)) {
+#pragma unroll
+            for (int i = 0; i < POOL; ++i) w[i] -= missing_taps(tb, q + i, g.k, g.pad, g.Lin);
+        }
+        float best = w[0];
         int bi = 0;
 #pragma unroll
         for (int i = 1; i < POOL; ++i)
-            if (acc[t0 + i] > best) { best = acc[t0 + i]; bi = i; }   // first maximum wins, like ATen
+            if (w[i] > best) { best = w[i]; bi = i; }   // first maximum wins, like ATen
         if (s < g.S && p < g.P) {
             const float v = fmaxf(best + bv, 0.f);
             const long o = (s * g.P + p) * g.Cout + m;
@@ -61,7 +70,7 @@ template <int EPI>
 __global__ void __launch_bounds__(128)
 conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in, const uint4* __restrict__ wp, int fmt_w,
                  const float* __restrict__ bias, ConvGeom g, float* __restrict__ out, uint8_t* __restrict__ code,
-                 double* __restrict__ partial, const float* __restrict__ gscale) {
+                 double* __restrict__ partial, const float* __restrict__ gscale, const float* __restrict__ tap_bias) {
     extern __shared__ float xs[];  // [TRW + k - 1][CH]
     const float oscale = (EPI == 1 && gscale) ? gscale[1] : 1.f;
     const int m = threadIdx.x;
@@ -99,10 +108,14 @@ conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in, c
         }
         if (EPI == 0) {
             if (m < g.Cout) {
-                const float bv = bias ? bias[m] : 0.f;
-                if (g.pool == 4) epi_pool<4>(acc, r0, m, bv, g, out, code, st1, st2);
-                else if (g.pool == 2) epi_pool<2>(acc, r0, m, bv, g, out, code, st1, st2);
-                else epi_pool<1>(acc, r0, m, bv, g, out, code, st1, st2);
+                float bv = bias ? bias[m] : 0.f;
+                float tb[4] = {0.f, 0.f, 0.f, 0.f};
+                const bool has_tb = tap_bias != nullptr;
+                if (has_tb)
+                    for (int j = 0; j < g.k; ++j) { tb[j] = tap_bias[j * g.Cout + m]; bv += tb[j]; }
+                if (g.pool == 4) epi_pool<4>(acc, r0, m, bv, g, out, code, st1, st2, has_tb, tb);
+                else if (g.pool == 2) epi_pool<2>(acc, r0, m, bv, g, out, code, st1, st2, has_tb, tb);
+                else epi_pool<1>(acc, r0, m, bv, g, out, code, st1, st2, has_tb, tb);
             }
         } else {
             if (m < g.Cout) {
@@ -192,7 +205,7 @@ dcue_reduce_partials_d(const double* __restrict__ partial, int nblk, int n, doub
 }
 
 __global__ void pack_conv_weight_kernel(const float* __restrict__ W, int Cout, int Cin, int k, int mode, int fmt,
-                                        unsigned short* __restrict__ out) {
+                                        const float* __restrict__ col_scale, unsigned short* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int K = k * 128;
     if (i >= 128 * K) return;
@@ -200,7 +213,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ W, int Cout, i
     const int j = kk / 128, c = kk % 128;
     float v = 0.f;
     if (mode == 0) {  // A[co=m][j*128+ci=c] = W[co][ci][j]
-        if (m < Cout && c < Cin) v = W[((long)m * Cin + c) * k + j];
+        if (m < Cout && c < Cin) v = W[((long)m * Cin + c) * k + j] * (col_scale ? col_scale[c] : 1.f);
     } else {          // A[ci=m][jj*128+co=c] = W[co][ci][k-1-jj]
         if (m < Cin && c < Cout) v = W[((long)c * Cin + m) * k + (k - 1 - j)];
     }
@@ -208,7 +221,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ W, int Cout, i
 }
 
 int dcue_simt_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_packed, const float* bias,
-                       const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
+                       const float* tap_bias, const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
                        cudaStream_t st) {
     const long ntiles = (g.rows_total + TRW - 1) / TRW;
     const long cap = (long)dcue_num_sms() * 4;
@@ -217,7 +230,7 @@ int dcue_simt_conv_fwd(const void* panel, long panel_rows, int fmt, const void* 
         DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_pool_fwd(simt): workspace too small");
     const size_t smem = (size_t)(TRW + g.k - 1) * CH * sizeof(float);
     conv_rows_kernel<0><<<grid, 128, smem, st>>>((const uint4*)panel, panel_rows, fmt, (const uint4*)w_packed, fmt, bias,
-                                                 g, z, code, sums ? (double*)ws : nullptr, nullptr);
+                                                 g, z, code, sums ? (double*)ws : nullptr, nullptr, tap_bias);
     DCUE_LAUNCH_CHECK();
     if (sums) {
         dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 32), 256, 0, st>>>((const double*)ws, grid, 2 * g.Cout, sums);
@@ -233,7 +246,7 @@ int dcue_simt_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_
     const int grid = (int)(ntiles < cap ? (ntiles > 0 ? ntiles : 1) : cap);
     const size_t smem = (size_t)(TRW + g.k - 1) * CH * sizeof(float);
     conv_rows_kernel<1><<<grid, 128, smem, st>>>((const uint4*)dy_panel_shifted, panel_rows, fmt_dy,
-                                                 (const uint4*)w_packed, fmt_w, nullptr, g, dx, nullptr, nullptr, gscale);
+                                                 (const uint4*)w_packed, fmt_w, nullptr, g, dx, nullptr, nullptr, gscale, nullptr);
     DCUE_LAUNCH_CHECK();
     return 0;
 }
@@ -254,12 +267,125 @@ int dcue_simt_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const v
     return 0;
 }
 
-extern "C" int dcue_pack_conv_weight(const float* W, int Cout, int Cin, int k, int mode, int fmt, void* out,
-                                     void* stream) {
+extern "C" int dcue_pack_conv_weight(const float* W, int Cout, int Cin, int k, int mode, int fmt, const float* col_scale,
+                                     void* out, void* stream) {
     DCUE_CHECK_ARG(W && out && Cout > 0 && Cout <= 128 && Cin > 0 && Cin <= 128 && k >= 1 && k <= 4 &&
                    (mode == 0 || mode == 1));
     pack_conv_weight_kernel<<<ceil_div_i(128L * k * 128, 256), 256, 0, (cudaStream_t)stream>>>(
-        W, Cout, Cin, k, mode, fmt, (unsigned short*)out);
+        W, Cout, Cin, k, mode, fmt, col_scale, (unsigned short*)out);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+
+// tapB[j][co] = sum_ci W[co][ci][j] * beta[ci]   (input-BatchNorm shift folded into the conv bias)
+__global__ void tap_bias_kernel(const float* __restrict__ W, int Cout, int Cin, int k, const float* __restrict__ beta,
+                                float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k * Cout) return;
+    const int j = i / Cout, co = i % Cout;
+    float s = 0.f;
+    for (int c = 0; c < Cin; ++c) s = fmaf(W[((long)co * Cin + c) * k + j], beta[c], s);
+    out[i] = s;
+}
+
+extern "C" int dcue_conv_tap_bias(const float* W, int Cout, int Cin, int k, const float* beta, float* tap_bias, void* stream) {
+    DCUE_CHECK_ARG(W && beta && tap_bias && Cout > 0 && Cin > 0 && k >= 1 && k <= 4);
+    tap_bias_kernel<<<ceil_div_i(k * Cout, 128), 128, 0, (cudaStream_t)stream>>>(W, Cout, Cin, k, beta, tap_bias);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+// out[i][c] = inv_scale * sum_s panel[s*Lp + rows[i]][c]  for up to 4 rows per spectrogram
+__global__ void __launch_bounds__(256)
+panel_row_sums_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt, int S, int Lp, int4 rows,
+                      const float* __restrict__ gscale, float* __restrict__ out /* [4][128] */) {
+    __shared__ float red[8][8][33];
+    const int q = blockIdx.x, ri = blockIdx.y;
+    const int row = ri == 0 ? rows.x : ri == 1 ? rows.y : ri == 2 ? rows.z : rows.w;
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (row >= 0)
+        for (int s = threadIdx.x; s < S; s += 256) {
+            const uint4 v = __ldg(panel + (long)q * panel_rows + (long)s * Lp + row);
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a[2 * j] += cvt16_to_f32((unsigned short)(w[j] & 0xffffu), fmt);
+                a[2 * j + 1] += cvt16_to_f32((unsigned short)(w[j] >> 16), fmt);
+            }
+        }
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float v = warp_sum(a[j]);
+        if (lane == 0) red[wp][j][0] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float t = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < 8; ++w2) t += red[w2][threadIdx.x][0];
+        out[ri * 128 + q * 8 + threadIdx.x] = t * (gscale ? gscale[1] : 1.f);
+    }
+}
+
+extern "C" int dcue_panel_row_sums(const void* panel, long panel_rows, int fmt, int S, int Lp, int r0, int r1, int r2, int r3,
+                                   const float* gscale, float* out, void* stream) {
+    DCUE_CHECK_ARG(panel && out && S >= 0 && Lp > 0 && r0 < Lp && r1 < Lp && r2 < Lp && r3 < Lp);
+    dim3 grid(16, 4);
+    panel_row_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)panel, panel_rows, fmt, S, Lp,
+                                                                  make_int4(r0, r1, r2, r3), gscale, out);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+// Gradients of a conv whose input BatchNorm (gamma, beta) was folded into it:
+//   conv input = gamma*xhat + beta inside the data rows, zero padding outside;  G = sum dY * xhat (wgrad on xhat)
+//   dW[co,ci,j] = gamma[ci]*G + beta[ci]*T[co,j],  dgamma[ci] = sum W*G,  dbeta[ci] = sum W*T,
+//   T[co,j] = sum over conv outputs t whose tap j reads a data row of dY[.,co,t]
+//           = Tall[co] - sum_{border rows t with tap j outside} E[t][co]
+__global__ void __launch_bounds__(128)
+bn_fold_grads_kernel(const float* __restrict__ G, const float* __restrict__ W, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ Tall, const float* __restrict__ E /* [4][128] */,
+                     int4 erows, int Cout, int Cin, int k, int pad, int Lin, float* __restrict__ dW,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float r1[128], r2[128];
+    const int ci = blockIdx.x, co = threadIdx.x;
+    float sg = 0.f, sb = 0.f;
+    if (co < Cout) {
+        const int er[4] = {erows.x, erows.y, erows.z, erows.w};
+        const float ga = gamma[ci], be = beta[ci];
+        for (int j = 0; j < k; ++j) {
+            float T = Tall[co];
+            for (int e = 0; e < 4; ++e) {
+                if (er[e] < 0) continue;
+                const int tt = er[e] + j - pad;
+                if (tt < 0 || tt >= Lin) T -= E[e * 128 + co];
+            }
+            const long o = ((long)co * Cin + ci) * k + j;
+            const float g = G[o], w = W[o];
+            dW[o] = ga * g + be * T;
+            sg = fmaf(w, g, sg);
+            sb = fmaf(w, T, sb);
+        }
+    }
+    r1[co] = sg;
+    r2[co] = sb;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (co < o) { r1[co] += r1[co + o]; r2[co] += r2[co + o]; }
+        __syncthreads();
+    }
+    if (co == 0) { dgamma[ci] = r1[0]; dbeta[ci] = r2[0]; }
+}
+
+extern "C" int dcue_bn_fold_grads(const float* G, const float* W, const float* gamma, const float* beta, const float* Tall,
+                                  const float* E, int r0, int r1, int r2, int r3, int Cout, int Cin, int k, int pad, int Lin,
+                                  float* dW, float* dgamma, float* dbeta, void* stream) {
+    DCUE_CHECK_ARG(G && W && gamma && beta && Tall && E && dW && dgamma && dbeta && Cout > 0 && Cout <= 128 && Cin > 0 &&
+                   k >= 1 && k <= 4);
+    bn_fold_grads_kernel<<<Cin, 128, 0, (cudaStream_t)stream>>>(G, W, gamma, beta, Tall, E, make_int4(r0, r1, r2, r3), Cout,
+                                                                Cin, k, pad, Lin, dW, dgamma, dbeta);
     DCUE_LAUNCH_CHECK();
     return 0;
 }

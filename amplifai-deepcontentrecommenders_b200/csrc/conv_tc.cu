@@ -135,7 +135,7 @@ struct Pipe {
 template <int EPI, int POOL>
 __device__ __forceinline__ void epilogue_chunk(const float (&v)[32], int r, int m, float bv, const ConvGeom& g,
                                                float* __restrict__ out, uint8_t* __restrict__ code, double& st1,
-                                               double& st2) {
+                                               double& st2, bool has_tb, const float (&tb)[4]) {
     int s = r / g.Lp;
     int q = r - s * g.Lp;
     const bool chan_ok = m < g.Cout;
@@ -143,11 +143,19 @@ __device__ __forceinline__ void epilogue_chunk(const float (&v)[32], int r, int 
         float ts1 = 0.f, ts2 = 0.f;
 #pragma unroll
         for (int t0 = 0; t0 < 32; t0 += POOL) {
-            float best = v[t0];
+            float w[POOL];
+#pragma unroll
+            for (int i = 0; i < POOL; ++i) w[i] = v[t0 + i];
+            // folded input-BatchNorm shift: outputs whose taps hang over the zero padding lack those taps' constant
+            if (has_tb && (q < g.pad || q + POOL - 1 > g.Lin + g.pad - g.k)) {
+#pragma unroll
+                for (int i = 0; i < POOL; ++i) w[i] -= missing_taps(tb, q + i, g.k, g.pad, g.Lin);
+            }
+            float best = w[0];
             int bi = 0;
 #pragma unroll
             for (int i = 1; i < POOL; ++i)
-                if (v[t0 + i] > best) { best = v[t0 + i]; bi = i; }
+                if (w[i] > best) { best = w[i]; bi = i; }
             const int p = q / POOL;  // POOL is a power of two
             if (chan_ok && s < g.S && p < g.P) {
                 const float val = fmaxf(best + bv, 0.f);
@@ -176,7 +184,7 @@ template <int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in, const uint4* __restrict__ wp, int fmt_w,
                     const float* __restrict__ bias, ConvGeom g, float* __restrict__ out, uint8_t* __restrict__ code,
-                    double* __restrict__ partial, const float* __restrict__ gscale) {
+                    double* __restrict__ partial, const float* __restrict__ gscale, const float* __restrict__ tap_bias) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_bytes = g.k * PANELS * A_PANEL_BYTES;  // k * 32 KB
@@ -259,7 +267,12 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;  // output channel == TMEM lane
         // EPI 0: bv = conv bias.  EPI 1: bv = 1/s of the scaled 16-bit gradient operand.
-        const float bv = EPI == 0 ? ((bias && m < g.Cout) ? bias[m] : 0.f) : (gscale ? gscale[1] : 1.f);
+        float bv = EPI == 0 ? ((bias && m < g.Cout) ? bias[m] : 0.f) : (gscale ? gscale[1] : 1.f);
+        float tb[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool has_tb = EPI == 0 && tap_bias != nullptr;
+        if (has_tb && m < g.Cout) {
+            for (int j = 0; j < g.k; ++j) { tb[j] = tap_bias[j * g.Cout + m]; bv += tb[j]; }
+        }
         double st1 = 0.0, st2 = 0.0;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -272,11 +285,11 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
                 if (EPI == 0) {
-                    if (g.pool == 4) epilogue_chunk<0, 4>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2);
-                    else if (g.pool == 2) epilogue_chunk<0, 2>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2);
-                    else epilogue_chunk<0, 1>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2);
+                    if (g.pool == 4) epilogue_chunk<0, 4>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2, has_tb, tb);
+                    else if (g.pool == 2) epilogue_chunk<0, 2>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2, has_tb, tb);
+                    else epilogue_chunk<0, 1>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2, has_tb, tb);
                 } else {
-                    epilogue_chunk<1, 1>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2);
+                    epilogue_chunk<1, 1>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2, false, tb);
                 }
             }
             tc_fence_before();
@@ -412,12 +425,12 @@ int tc_grid(long rows_total) {
 
 template <int EPI>
 int launch_rows(const void* panel, long panel_rows, int fmt_in, const void* w_packed, int fmt_w, const float* bias,
-                const ConvGeom& g, float* out, uint8_t* code, double* partial, const float* gscale, int grid,
-                cudaStream_t st) {
+                const ConvGeom& g, float* out, uint8_t* code, double* partial, const float* gscale,
+                const float* tap_bias, int grid, cudaStream_t st) {
     const size_t smem = rows_smem_bytes(g.k);
     DCUE_CUDA(cudaFuncSetAttribute(tc_conv_rows_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_conv_rows_kernel<EPI><<<grid, NTHREADS, smem, st>>>((const uint4*)panel, panel_rows, fmt_in, (const uint4*)w_packed,
-                                                           fmt_w, bias, g, out, code, partial, gscale);
+                                                           fmt_w, bias, g, out, code, partial, gscale, tap_bias);
     DCUE_LAUNCH_CHECK();
     return 0;
 }
@@ -431,13 +444,13 @@ size_t dcue_tc_ws_bytes(int k) {
 }
 
 int dcue_tc_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_packed, const float* bias,
-                     const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
+                     const float* tap_bias, const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
                      cudaStream_t st) {
     if (g.Cin != 128) DCUE_FAIL(DCUE_E_UNSUPPORTED, "tcgen05 conv needs Cin == 128 (got %d)", g.Cin);
     const int grid = tc_grid(g.rows_total);
     if (sums && (!ws || ws_bytes < (size_t)grid * 2 * g.Cout * sizeof(double)))
         DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_pool_fwd(tc): workspace too small");
-    if (int e = launch_rows<0>(panel, panel_rows, fmt, w_packed, fmt, bias, g, z, code, sums ? (double*)ws : nullptr, nullptr, grid, st))
+    if (int e = launch_rows<0>(panel, panel_rows, fmt, w_packed, fmt, bias, g, z, code, sums ? (double*)ws : nullptr, nullptr, tap_bias, grid, st))
         return e;
     if (sums) {
         dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 32), 256, 0, st>>>((const double*)ws, grid, 2 * g.Cout, sums);
@@ -451,7 +464,7 @@ int dcue_tc_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy
     if (g.Cin != 128) DCUE_FAIL(DCUE_E_UNSUPPORTED, "tcgen05 dgrad needs Cout == 128 (got %d)", g.Cin);
     if (fmt_dy != fmt_w) DCUE_FAIL(DCUE_E_UNSUPPORTED, "tcgen05 kind::f16 needs both operands in the same 16-bit format");
     return launch_rows<1>(dy_panel_shifted, panel_rows, fmt_dy, w_packed, fmt_w, nullptr, g, dx, nullptr, nullptr, gscale,
-                          tc_grid(g.rows_total), st);
+                          nullptr, tc_grid(g.rows_total), st);
 }
 
 int dcue_tc_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const void* x_panel, long x_rows, int fmt_x,

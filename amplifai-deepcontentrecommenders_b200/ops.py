@@ -83,6 +83,7 @@ class TowerWorkspace:
         self.fc_in = torch.empty(S, 4 * H + F if res else F, **f32)
         self.sums = torch.zeros(6, 2 * 128, dtype=torch.float64, device=device)
         self.bnp = torch.zeros(6, 4, 128, **f32)        # scale, shift, mean, rstd per BN layer
+        self.tapb = torch.zeros(4, 128, **f32)          # layer-1 per-tap constants of the folded bn0 shift
         self.zero128 = torch.zeros(128, **f32)
         self.one128 = torch.ones(128, **f32)
         self.wp = [torch.empty(128 * g["k"] * 128, dtype=torch.int16, device=device) for g in self.geo]
@@ -104,6 +105,7 @@ class TowerWorkspace:
             b["wpd"] = [torch.empty(128 * g["k"] * 128, dtype=torch.int16, device=dev) for g in self.geo]
             b["bsum"] = torch.zeros(2 * 128, dtype=torch.float64, device=dev)
             b["dsums"] = torch.zeros(6, 2 * 128, dtype=torch.float64, device=dev)
+            b["E"] = torch.zeros(4, 128, **f32)
             b["amax"] = torch.zeros(6, **f32)
             b["gscale"] = torch.ones(6, 2, **f32)
             self._bwd = b
@@ -166,24 +168,30 @@ class SongTowerFn(torch.autograd.Function):
         dp = mod._dp
         world = 1 if dp is None else dp.world_size
 
-        def bn_finalize(i, count, C_):
-            """sums[i] -> scale/shift/mean/rstd of BN layer i (batch or running statistics)."""
+        def bn_finalize(i, count, C_, affine=True):
+            """sums[i] -> scale/shift/mean/rstd of BN layer i (batch or running statistics).
+            affine=False gives the plain normalisation (scale = rstd, shift = -mean*rstd)."""
             bnm = getattr(mod, "bn%d" % i)
             if training and dp is not None:
                 dp.all_reduce_sum(ws.sums[i])
-            L.call("dcue_bn_finalize", ws.sums[i].data_ptr(), float(count * world), C_, P["bn%d.weight" % i].data_ptr(),
-                   P["bn%d.bias" % i].data_ptr(), bnm.running_mean.data_ptr(), bnm.running_var.data_ptr(),
+            L.call("dcue_bn_finalize", ws.sums[i].data_ptr(), float(count * world), C_,
+                   P["bn%d.weight" % i].data_ptr() if affine else None,
+                   P["bn%d.bias" % i].data_ptr() if affine else None, bnm.running_mean.data_ptr(), bnm.running_var.data_ptr(),
                    bnm.num_batches_tracked.data_ptr(), BN_MOMENTUM, BN_EPS, int(training),
                    ws.bnp[i, 0].data_ptr(), ws.bnp[i, 1].data_ptr(), ws.bnp[i, 2].data_ptr(), ws.bnp[i, 3].data_ptr(), st)
 
         pos_p, neg_p = pos.data_ptr(), (None if neg is None else neg.data_ptr())
-        # ---- bn0 + transpose/convert into the layer1 operand panel
+        # ---- bn0 + transpose/convert into the layer1 operand panel.  The panel holds the plain
+        # normalised input xhat; bn0's gamma is folded into layer1's packed weights and its beta into a
+        # border-aware bias (dcue_conv_tap_bias), which lets the backward skip layer1's data gradient.
         g0 = geo[0]
         if has_bn:
             if training:
                 L.call("dcue_ncl_stats", pos_p, S_pos, neg_p, S_neg, C, frames, ws.sums[0].data_ptr(), scratch, nscr, st)
-            bn_finalize(0, S * frames, C)
+            bn_finalize(0, S * frames, C, affine=False)
             sc, sh = ws.bnp[0, 0].data_ptr(), ws.bnp[0, 1].data_ptr()
+            L.call("dcue_conv_tap_bias", P["layer1.weight"].data_ptr(), H, 128, g0["k"], P["bn0.bias"].data_ptr(),
+                   ws.tapb.data_ptr(), st)
         else:
             sc = sh = None
         L.call("dcue_ncl_pack", pos_p, S_pos, neg_p, S_neg, C, frames, sc, sh, ws.X[0].base, ws.X[0].panel_rows,
@@ -191,10 +199,13 @@ class SongTowerFn(torch.autograd.Function):
         # ---- layer1..4: conv + pool + relu (+ BN statistics) -> affine -> next operand panel
         for i, g in enumerate(geo, start=1):
             Wt, bt = P["layer%d.weight" % i], P["layer%d.bias" % i]
-            L.call("dcue_pack_conv_weight", Wt.data_ptr(), H, 128, g["k"], 0, fmt, ws.wp[i - 1].data_ptr(), st)
+            fold = has_bn and i == 1
+            L.call("dcue_pack_conv_weight", Wt.data_ptr(), H, 128, g["k"], 0, fmt,
+                   P["bn0.weight"].data_ptr() if fold else None, ws.wp[i - 1].data_ptr(), st)
             want_stats = has_bn and training
             L.call("dcue_conv_pool_fwd", impl, ws.X[i - 1].base, ws.X[i - 1].panel_rows, fmt, ws.wp[i - 1].data_ptr(),
-                   bt.data_ptr(), S, g["Lp"], g["P"], g["pool"], g["k"], 128, H, ws.z[i - 1].data_ptr(),
+                   bt.data_ptr(), ws.tapb.data_ptr() if fold else None, S, g["Lp"], g["Lin"], g["pad"], g["P"], g["pool"],
+                   g["k"], 128, H, ws.z[i - 1].data_ptr(),
                    ws.code[i - 1].data_ptr(), ws.sums[i].data_ptr() if want_stats else None, scratch, nscr, st)
             if has_bn:
                 bn_finalize(i, S * g["P"], H)
@@ -325,27 +336,28 @@ class SongTowerFn(torch.autograd.Function):
             gW_i = torch.empty(H, 128, g["k"], **f32)
             L.call("dcue_conv_wgrad", impl, dYp.base, dYp.panel_rows, gfmt, ws.X[i - 1].base, ws.X[i - 1].panel_rows, fmt,
                    S * g["Lp"], g["k"], 128, H, gsc, gW_i.data_ptr(), scratch, nscr, st)
+            if i == 1 and has_bn:
+                # gW_i is G = sum dY * xhat.  bn0 was folded into this conv: its gradients and the true
+                # weight gradient follow from G and a few border row sums -- no data gradient needed.
+                k_, pad_, lin_ = g["k"], g["pad"], g["Lin"]
+                brow = list(range(pad_)) + list(range(lin_ + pad_ - k_ + 1, lin_ + 2 * pad_ - k_ + 1))
+                brow = (brow + [-1, -1, -1, -1])[:4]
+                L.call("dcue_panel_row_sums", dYp.base, dYp.panel_rows, gfmt, S, g["Lp"], brow[0], brow[1], brow[2], brow[3],
+                       gsc, b["E"].data_ptr(), st)
+                dW1, dg0, db0 = torch.empty(H, 128, k_, **f32), torch.empty(128, **f32), torch.empty(128, **f32)
+                L.call("dcue_bn_fold_grads", gW_i.data_ptr(), P["layer1.weight"].data_ptr(), P["bn0.weight"].data_ptr(),
+                       P["bn0.bias"].data_ptr(), gb_i.data_ptr(), b["E"].data_ptr(), brow[0], brow[1], brow[2], brow[3], H, 128,
+                       k_, pad_, lin_, dW1.data_ptr(), dg0.data_ptr(), db0.data_ptr(), st)
+                gW_i = dW1
+                grads["bn0.weight"], grads["bn0.bias"] = dg0, db0
             grads["layer%d.weight" % i], grads["layer%d.bias" % i] = gW_i, gb_i
-            if i > 1 or has_bn:
-                L.call("dcue_pack_conv_weight", P["layer%d.weight" % i].data_ptr(), H, 128, g["k"], 1, fmt,
+            if i > 1:
+                L.call("dcue_pack_conv_weight", P["layer%d.weight" % i].data_ptr(), H, 128, g["k"], 1, fmt, None,
                        b["wpd"][i - 1].data_ptr(), st)
                 dx = b["dx"][i - 1]
                 L.call("dcue_conv_dgrad", impl, dYp.base, dYp.panel_rows, gfmt, b["wpd"][i - 1].data_ptr(), fmt, S, g["Lp"],
                        g["Lin"], g["pad"], g["k"], 128, H, gsc, dx.data_ptr(), scratch, nscr, st)
                 dy = dx
-        # ---- bn0
-        if bn_train:
-            L.call("dcue_ncl_bn_bwd_reduce", dy.data_ptr(), ctx.pos.data_ptr(), S_pos,
-                   None if ctx.neg is None else ctx.neg.data_ptr(), S_neg, C, frames, ws.bnp[0, 2].data_ptr(),
-                   ws.bnp[0, 3].data_ptr(), b["dsums"][0].data_ptr(), scratch, nscr, st)
-            if dp is not None:
-                dp.all_reduce_sum(b["dsums"][0])
-            gw, gb0 = torch.empty(C, **f32), torch.empty(C, **f32)
-            L.call("dcue_cvt_f64_f32", b["dsums"][0][C:].data_ptr(), C, 1.0, gw.data_ptr(), st)
-            L.call("dcue_cvt_f64_f32", b["dsums"][0].data_ptr(), C, 1.0, gb0.data_ptr(), st)
-            grads["bn0.weight"], grads["bn0.bias"] = gw, gb0
-        elif has_bn:
-            grads["bn0.weight"] = grads["bn0.bias"] = None
         ctx.ws = None
         _release(ws)
         return (None, None, None, None) + tuple(grads.get(n) for n in mod._param_names)

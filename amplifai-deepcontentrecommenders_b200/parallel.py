@@ -7,7 +7,7 @@ batch.  To equal the single-process reference at the GLOBAL batch size,
     ``all_reduce_sum`` hook installed here),
   * the hinge loss divides by the global batch (``hinge_loss_step(batch_total=...)``), so local
     gradients are partial sums and one flat SUM all-reduce of all non-BatchNorm gradients (tower,
-    user MLP and the dense table gradient) yields exactly the reference's gradient on every rank.
+    user MLP, the dense table gradient, and bn0 which is folded into layer1) yields exactly the reference's gradient on every rank.
 Eval (BASELINE cfg5) shards songs across ranks and merges per-rank top-k lists.
 """
 from __future__ import annotations
@@ -25,9 +25,10 @@ def shard_slice(n, rank, world):
 
 
 def flat_bucket_names(named_grads):
-    """Names of the gradients that need the SUM all-reduce: everything except BatchNorm affine
-    parameters, whose gradients are already global (computed from all-reduced sums)."""
-    return [n for n, _ in named_grads if ".bn" not in n]
+    """Names of the gradients that need the SUM all-reduce: everything except the affine parameters
+    of bn1..bn5, whose gradients are already global (computed from all-reduced sums).  bn0 is folded
+    into layer1, so its gradients are local partial sums like any weight gradient."""
+    return [n for n, _ in named_grads if ".bn" not in n or ".bn0." in n]
 
 
 class DataParallelDCUE:

@@ -157,8 +157,8 @@ def kernel_roofline(pkg, S, dev):
     nws = L.query("dcue_conv_ws_bytes", L.IMPL_TC, S, geo["Lp"], 4, 128, 128)
     ws = torch.empty(nws, dtype=torch.uint8, device=dev)
     calls = {
-        "conv1_fwd_pool": lambda: L.call("dcue_conv_pool_fwd", L.IMPL_TC, X.base, X.panel_rows, 0, wp.data_ptr(), bias.data_ptr(), S,
-                                         geo["Lp"], geo["P"], 4, 4, 128, 128, z.data_ptr(), code.data_ptr(), sums.data_ptr(),
+        "conv1_fwd_pool": lambda: L.call("dcue_conv_pool_fwd", L.IMPL_TC, X.base, X.panel_rows, 0, wp.data_ptr(), bias.data_ptr(), None, S,
+                                         geo["Lp"], geo["Lin"], 2, geo["P"], 4, 4, 128, 128, z.data_ptr(), code.data_ptr(), sums.data_ptr(),
                                          ws.data_ptr(), nws, st),
         "conv1_dgrad": lambda: L.call("dcue_conv_dgrad", L.IMPL_TC, dY.base, dY.panel_rows, 0, wp.data_ptr(), 0, S, geo["Lp"], geo["Lin"],
                                       2, 4, 128, 128, None, dx.data_ptr(), ws.data_ptr(), nws, st),

@@ -112,15 +112,32 @@ int dcue_ncl_pack(const float* pos, int S_pos, const float* neg, int S_neg, int 
 /* Conv1d weight [Cout,Cin,k] fp32 -> 16-bit UMMA A operand [128 x k*128], K-major panels:
  * mode 0 (forward): A[co][j*Cin+ci] = W[co][ci][j];
  * mode 1 (dgrad):   A[ci][jj*Cout+co] = W[co][ci][k-1-jj].   Rows/cols beyond C are zero. */
-int dcue_pack_conv_weight(const float* W, int Cout, int Cin, int k, int mode, int fmt, void* out,
+int dcue_pack_conv_weight(const float* W, int Cout, int Cin, int k, int mode, int fmt,
+                          const float* col_scale /* mode 0: W[co][ci][j] *= col_scale[ci]; nullable */, void* out,
                           void* stream);
+
+/* Folding an input-side BatchNorm (gamma, beta) into the conv that consumes it, so that the conv
+ * operand is the plain normalised input xhat (truedcuemel1dbn.py:79-80):
+ *   conv(gamma*xhat + beta) = conv_{W*gamma}(xhat) + sum over taps j that hit a data row of tapB[j],
+ * tapB[j][co] = sum_ci W[co][ci][j]*beta[ci].  tap_bias out = float[k][Cout]. */
+int dcue_conv_tap_bias(const float* W, int Cout, int Cin, int k, const float* beta, float* tap_bias, void* stream);
+/* out[i][c] = gscale[1] * sum_s panel[s*Lp + r_i][c], i < 4 (r_i < 0 = unused): border row sums of dY. out = float[4][128] */
+int dcue_panel_row_sums(const void* panel, long panel_rows, int fmt, int S, int Lp, int r0, int r1, int r2, int r3,
+                        const float* gscale, float* out, void* stream);
+/* Backward of the folded pair from G = wgrad(dY, xhat):  dW = gamma*G + beta*T, dgamma = sum W*G,
+ * dbeta = sum W*T, with T[co][j] = Tall[co] - sum of the border row sums E whose tap j is padding.
+ * This replaces the layer-1 data gradient and the BatchNorm-backward pass over the input batch. */
+int dcue_bn_fold_grads(const float* G, const float* W, const float* gamma, const float* beta, const float* Tall,
+                       const float* E, int r0, int r1, int r2, int r3, int Cout, int Cin, int k, int pad, int Lin,
+                       float* dW, float* dgamma, float* dbeta, void* stream);
 
 /* Conv1d + bias + MaxPool1d(pool) + ReLU with BatchNorm partial sums, implicit GEMM over
  * shifted row views of the panel (truedcuemel1dbn.py:80-83 etc.; all four tower variants).
  * z[S*P, Cout] fp32 = relu(max_{i<pool} conv[s, p*pool+i, :] + bias); code[S*P,Cout] u8 = argmax i;
  * sums (nullable) = double[2*Cout] sum z, sum z^2. */
 int dcue_conv_pool_fwd(int impl, const void* panel, long panel_rows, int fmt, const void* w_packed,
-                       const float* bias, int S, int Lp, int P, int pool, int k, int Cin, int Cout,
+                       const float* bias, const float* tap_bias /* dcue_conv_tap_bias output, nullable */,
+                       int S, int Lp, int Lin, int pad, int P, int pool, int k, int Cin, int Cout,
                        float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes, void* stream);
 
 /* Conv1d data gradient: dX[s, t, ci] = sum_{j,co} W[co,ci,j] dY[s, t + pad - j, co] for the

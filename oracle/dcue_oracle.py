@@ -71,13 +71,47 @@ class _RoundedConv(torch.autograd.Function):
         return gx, gw, gb, None, None, None
 
 
+class _FoldedBNConv(torch.autograd.Function):
+    """layer1(bn0(x)) as the B200 path evaluates it: the conv operand is the plain normalised input
+    xhat, bn0.weight is folded into the weights and bn0.bias into a border-aware bias; backward gets
+    dW, dgamma, dbeta from G = sum dY*xhat (no data gradient).  Same function, different roundings."""
+
+    @staticmethod
+    def forward(ctx, xhat, w, b, gamma, beta, padding, op_dt, g_dt):
+        xr = _round(xhat, op_dt)
+        wg = _round(w * gamma[None, :, None], op_dt)
+        S, C, L = xhat.shape
+        beta_img = beta.view(1, C, 1).expand(1, C, L)
+        y = F.conv1d(xr, wg, None, padding=padding) + F.conv1d(beta_img, w, None, padding=padding) + b.view(1, -1, 1)
+        ctx.save_for_backward(xr, w, gamma, beta)
+        ctx.padding, ctx.g_dt = padding, g_dt
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xr, w, gamma, beta = ctx.saved_tensors
+        pad, k, L = ctx.padding, w.shape[2], xr.shape[2]
+        gr = _round(gy, ctx.g_dt)
+        G = torch.nn.grad.conv1d_weight(xr, w.shape, gr, padding=pad)
+        tall = gy.sum(dim=(0, 2))
+        T = tall[:, None].repeat(1, k)
+        for j in range(k):
+            for t in range(gy.shape[2]):
+                if not 0 <= t + j - pad < L:
+                    T[:, j] = T[:, j] - gr[:, :, t].sum(0)
+        dW = gamma[None, :, None] * G + beta[None, :, None] * T[:, None, :]
+        dgamma = (w * G).sum(dim=(0, 2))
+        dbeta = (w * T[:, None, :]).sum(dim=(0, 2))
+        return None, dW, tall, dgamma, dbeta, None, None, None
+
+
 def _conv(x, w, b, padding, op_dt, g_dt):
     if op_dt is None and g_dt is None:
         return F.conv1d(x, w, b, padding=padding)
     return _RoundedConv.apply(x, w, b, padding, op_dt, g_dt)
 
 
-def _bn(x, p, name, training, new_stats):
+def _bn(x, p, name, training, new_stats, affine=True):
     """BatchNorm1d over [S, C, L] (truedcuemel1dbn.py:24,30,...): batch statistics with
     biased variance when training, running statistics otherwise; running_var is updated
     with the unbiased variance, momentum 0.1, eps 1e-5."""
@@ -95,6 +129,8 @@ def _bn(x, p, name, training, new_stats):
     else:
         mean, var = rm.to(x.dtype), rv.to(x.dtype)
     xhat = (x - mean[None, :, None]) * torch.rsqrt(var[None, :, None] + BN_EPS)
+    if not affine:
+        return xhat
     return xhat * w[None, :, None] + b[None, :, None]
 
 
@@ -112,11 +148,16 @@ def tower_forward(p, x, model_type, training=True, prefix="conv.", operand_dtype
     stats = None
     if new_stats is not None:
         stats = {}
+    fold = bn and (operand_dtype is not None or grad_dtype is not None)
     if bn:
-        x = _bn(x, q, "bn0", training, stats)
+        x = _bn(x, q, "bn0", training, stats, affine=not fold)
     tps = []
     for i, (pad, pool) in enumerate(((2, 4), (2, 4), (2, 4), (1, 2)), start=1):
-        x = _conv(x, q["layer%d.weight" % i], q["layer%d.bias" % i], pad, operand_dtype, grad_dtype)
+        if fold and i == 1:
+            x = _FoldedBNConv.apply(x, q["layer1.weight"], q["layer1.bias"], q["bn0.weight"], q["bn0.bias"], pad,
+                                    operand_dtype, grad_dtype)
+        else:
+            x = _conv(x, q["layer%d.weight" % i], q["layer%d.bias" % i], pad, operand_dtype, grad_dtype)
         x = F.max_pool1d(x, pool)
         x = F.relu(x)
         if bn:

@@ -152,7 +152,7 @@ def _conv_case(S, gi, seed):
     L.call("dcue_ncl_pack", xd.data_ptr(), S, None, 0, 128, geo["Lin"], None, None, X.base, X.panel_rows, geo["Lp"],
            geo["pad"], L.FMT_F16, st)
     wp = torch.empty(128 * geo["k"] * 128, dtype=torch.int16, device=DEV)
-    L.call("dcue_pack_conv_weight", wd.data_ptr(), 128, 128, geo["k"], 0, L.FMT_F16, wp.data_ptr(), st)
+    L.call("dcue_pack_conv_weight", wd.data_ptr(), 128, 128, geo["k"], 0, L.FMT_F16, None, wp.data_ptr(), st)
     torch.cuda.synchronize()
     return dict(geo=geo, x=x, w=w, b=b, X=X, wp=wp, S=S, wd=wd, bd=bd)
 
@@ -165,7 +165,7 @@ def _run_conv_fwd(c, impl):
     nws = L.query("dcue_conv_ws_bytes", impl, S, geo["Lp"], geo["k"], 128, 128)
     ws = torch.empty(nws, dtype=torch.uint8, device=DEV)
     L.call("dcue_conv_pool_fwd", impl, c["X"].base, c["X"].panel_rows, L.FMT_F16, c["wp"].data_ptr(), c["bd"].data_ptr(),
-           S, geo["Lp"], geo["P"], geo["pool"], geo["k"], 128, 128, z.data_ptr(), code.data_ptr(), sums.data_ptr(),
+           None, S, geo["Lp"], geo["Lin"], geo["pad"], geo["P"], geo["pool"], geo["k"], 128, 128, z.data_ptr(), code.data_ptr(), sums.data_ptr(),
            ws.data_ptr(), nws, L.stream())
     torch.cuda.synchronize()
     return z, code, sums
@@ -252,7 +252,7 @@ def test_conv_backward_kernels(impl, gi, S):
            S * geo["Lp"], geo["k"], 128, 128, gsc.data_ptr(), dW.data_ptr(), ws.data_ptr(), nws, st)
     assert relerr(dW, wr.grad) < 5e-5
     wpd = torch.empty(128 * geo["k"] * 128, dtype=torch.int16, device=DEV)
-    L.call("dcue_pack_conv_weight", c["wd"].data_ptr(), 128, 128, geo["k"], 1, L.FMT_F16, wpd.data_ptr(), st)
+    L.call("dcue_pack_conv_weight", c["wd"].data_ptr(), 128, 128, geo["k"], 1, L.FMT_F16, None, wpd.data_ptr(), st)
     dx = torch.full((S * geo["Lin"], 128), float("nan"), device=DEV)
     L.call("dcue_conv_dgrad", impl, dY.base, dY.panel_rows, L.FMT_F16, wpd.data_ptr(), L.FMT_F16, S, geo["Lp"], geo["Lin"],
            geo["pad"], geo["k"], 128, 128, gsc.data_ptr(), dx.data_ptr(), ws.data_ptr(), nws, st)

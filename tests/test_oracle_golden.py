@@ -106,3 +106,21 @@ def test_embedding_dense_grad():
     g = torch.arange(8.0).view(4, 2)
     d = O.embedding_dense_grad(idx, g, 5)
     assert torch.equal(d[3], g[0] + g[2]) and torch.equal(d[2], torch.zeros(2))
+
+
+@pytest.mark.parametrize("mt", ["truedcuemel1dbn", "truedcuemel1dresbn"])
+def test_bn0_fold_is_exact_algebra(mt):
+    """The B200 path feeds layer1 the normalised input and folds bn0's affine into layer1
+    (weights * gamma, border-aware bias from beta; dW/dgamma/dbeta from G = sum dY*xhat).
+    With identity roundings the folded oracle must reproduce the plain reference math."""
+    p = fixtures.make_params(mt, seed=0, user_count=30)
+    u, pos, neg = fixtures.make_inputs(4, 2, 30, seed=1)
+    a = O.train_step_grads(p, u, pos, neg, mt, 0.2, dtype=torch.float64)
+    b = O.train_step_grads(p, u, pos, neg, mt, 0.2, operand_dtype=torch.float64, grad_dtype=torch.float64,
+                           dtype=torch.float64)
+    assert abs(a["loss"].item() - b["loss"].item()) < 1e-12
+    for k in a["grads"]:
+        _close(b["grads"][k], a["grads"][k], 1e-9)
+    for k in a["new_stats"]:
+        if a["new_stats"][k].is_floating_point():
+            _close(b["new_stats"][k], a["new_stats"][k], 1e-12)

@@ -22,7 +22,8 @@ def test_shard_slice_covers_everything():
 def test_bucket_excludes_batchnorm_affine():
     names = [("conv.bn0.weight", 0), ("conv.layer1.weight", 0), ("conv.bn3.bias", 0), ("user_embd.embeddings.weight", 0),
              ("conv.fc.bias", 0)]
-    assert par.flat_bucket_names(names) == ["conv.layer1.weight", "user_embd.embeddings.weight", "conv.fc.bias"]
+    assert par.flat_bucket_names(names) == ["conv.bn0.weight", "conv.layer1.weight", "user_embd.embeddings.weight",
+                                            "conv.fc.bias"]
 
 
 def _worker(rank, world, port, out):
