@@ -463,7 +463,7 @@ ncl_bn_bwd_reduce_kernel(const float* __restrict__ dx, const float* __restrict__
 
 int tile_grid(long rows) {
     long tiles = (rows + TR - 1) / TR;
-    long cap = (long)dcue_num_sms() * 8;
+    long cap = (long)dcue_num_sms() * 6;
     return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
 constexpr int STAT_BLOCKS_PER_SM = 4;
@@ -551,7 +551,7 @@ extern "C" int dcue_bn_bwd_reduce(const float* dy, int lddy, const float* dtp, i
     cudaStream_t st = (cudaStream_t)stream;
     const long rows = (long)S * P;
     long g = (rows + 7) / 8;
-    const long cap = (long)dcue_num_sms() * 8;
+    const long cap = (long)dcue_num_sms() * 4;
     int grid = (int)(g < cap ? (g > 0 ? g : 1) : cap);
     if (ws_bytes < (size_t)grid * (2 * C + 1) * sizeof(double)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_bn_bwd_reduce: workspace too small");
     bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, lddy, dtp, lddtp, z, mean, rstd, rows, P, C, (double*)ws);

@@ -14,8 +14,9 @@ gather_relu_kernel(const float* __restrict__ table, const int64_t* __restrict__ 
     const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (b >= B) return;
     const int64_t r = idx[b];
-    if (r < 0 || r >= U) {
+    if (r < 0 || r >= U) {  // nn.Embedding raises: flag it and poison the row so the loss cannot look sane
         if (lane == 0) atomicExch(err, 1);
+        for (int i = lane; i < E; i += 32) out[(long)b * E + i] = __int_as_float(0x7fc00000);
         return;
     }
     const float* src = table + r * (long)E;

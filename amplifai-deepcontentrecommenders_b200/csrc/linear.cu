@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
             float v = acc[x][y];
             if (p.splits == 1) {
                 if (p.bias) v += p.bias[gj];
-                if (p.relu) v = fmaxf(v, 0.f);
+                if (p.relu) v = v < 0.f ? 0.f : v;  // NaN-propagating (an out-of-range user row must stay loud)
                 if (p.mask) v = p.mask[gi * p.ldmask + gj] > 0.f ? v : 0.f;
             }
             C[gi * p.ldc + gj] = v;

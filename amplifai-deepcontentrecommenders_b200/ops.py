@@ -367,7 +367,7 @@ class UserTowerFn(torch.autograd.Function):
     """u_f = linear2(relu(linear1(relu(table[idx]))))  (userembedding.py:40-44)."""
 
     @staticmethod
-    def forward(ctx, idx, table, w1, b1, w2, b2):
+    def forward(ctx, idx, table, w1, b1, w2, b2, err):
         if not table.is_cuda:
             raise RuntimeError("the DCUE B200 path has no CPU fallback: move the model to a CUDA device")
         if idx.dtype != torch.int64:
@@ -378,12 +378,11 @@ class UserTowerFn(torch.autograd.Function):
         dev, st = table.device, L.stream()
         f32 = dict(dtype=torch.float32, device=dev)
         h0, h1, out = torch.empty(B, E, **f32), torch.empty(B, E, **f32), torch.empty(B, F, **f32)
-        err = torch.zeros(1, dtype=torch.int32, device=dev)
         L.call("dcue_gather_relu_fwd", table.data_ptr(), idx.data_ptr(), B, U, E, h0.data_ptr(), None, err.data_ptr(), st)
         L.call("dcue_linear_fwd", h0.data_ptr(), E, w1.data_ptr(), b1.data_ptr(), B, E, E, 1, h1.data_ptr(), E, st)
         L.call("dcue_linear_fwd", h1.data_ptr(), E, w2.data_ptr(), b2.data_ptr(), B, E, F, 0, out.data_ptr(), F, st)
-        if int(err.item()):  # nn.Embedding raises on out-of-range indices; so do we
-            raise IndexError("index out of range in self")
+        # out-of-range indices set `err` and poison their rows with NaN; the flag is read lazily
+        # (UserEmbeddings.raise_if_index_error) so that the forward never synchronises with the host
         ctx.save_for_backward(idx, table, w1, w2, h0, h1)
         return out.view(*shape, F)
 
@@ -415,7 +414,7 @@ class UserTowerFn(torch.autograd.Function):
             gtable = torch.zeros(U, E, **f32)  # dense gradient, like nn.Embedding(sparse=False)
             L.call("dcue_scatter_add_bwd", dh0.data_ptr(), h0.data_ptr(), sidx.data_ptr(), spos.data_ptr(), B, U, E,
                    gtable.data_ptr(), st)
-        return None, gtable, gw1, gb1, gw2, gb2
+        return None, gtable, gw1, gb1, gw2, gb2, None
 
 
 class ScoreFn(torch.autograd.Function):

@@ -106,8 +106,12 @@ def test_user_tower_forward_backward(zipf):
 
 def test_user_index_out_of_range_raises():
     mod = pkg.dcue.embeddings.userembedding.UserEmbeddings({"user_embdim": 300, "user_count": 10, "feature_dim": 100}).to(DEV)
+    out = mod(torch.tensor([3, 10], device=DEV))
+    assert torch.isnan(out[1]).all() and not torch.isnan(out[0]).any()
     with pytest.raises(IndexError):
-        mod(torch.tensor([3, 10], device=DEV))
+        mod.raise_if_index_error()
+    mod(torch.tensor([3, 9], device=DEV))
+    mod.raise_if_index_error()  # flag was cleared
 
 
 # ------------------------------------------------------------------ fp32 linear kernels

@@ -73,7 +73,7 @@ def test_forward_backward_marshalling(dry, monkeypatch, mt):
 
 
 def _user_fwd_nocuda(orig):
-    def fwd(ctx, idx, table, *rest):
+    def fwd(ctx, idx, table, *rest):  # rest = w1, b1, w2, b2, err
         class _T:  # pretend the table is on a CUDA device for the is_cuda guard only
             pass
         real_is_cuda = torch.Tensor.is_cuda
