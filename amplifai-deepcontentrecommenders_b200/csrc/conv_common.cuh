@@ -42,7 +42,7 @@ int dcue_tc_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_
                      const float* tap_bias, const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
                      cudaStream_t st);
 int dcue_tc_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
-                       const ConvGeom& g, const float* gscale, float* dx, cudaStream_t st);
+                       const ConvGeom& g, const float* gscale, float* dx, void* ws, size_t ws_bytes, cudaStream_t st);
 int dcue_tc_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const void* x_panel, long x_rows, int fmt_x,
                        long rows_total, int k, int Cin, int Cout, const float* gscale, float* dW, void* ws,
                        size_t ws_bytes, cudaStream_t st);

@@ -22,6 +22,7 @@
 // warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
 #include "common.cuh"
 #include "conv_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -88,6 +89,29 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// A operand from TMEM (TS mode): lane = row of A, each 32-bit column = two consecutive K elements
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
@@ -130,85 +154,49 @@ struct Pipe {
 // ----------------------------------------------------------------------------- fwd / dgrad
 // EPI 0: bias + maxpool(POOL) + relu + argmax code + BN partial sums -> z[S*P, Cout]
 // EPI 1: store the data rows -> dx[S*Lin, Cout]
-// `r` = first flat row of the 32-column chunk.  Row -> (spectrogram s, padded time q) is one 32-bit
-// division per chunk, then incremental (the per-element 64-bit divisions used to dominate dgrad).
-template <int EPI, int POOL>
-__device__ __forceinline__ void epilogue_chunk(const float (&v)[32], int r, int m, float bv, const ConvGeom& g,
-                                               float* __restrict__ out, uint8_t* __restrict__ code, double& st1,
-                                               double& st2, bool has_tb, const float (&tb)[4]) {
-    int s = r / g.Lp;
-    int q = r - s * g.Lp;
-    const bool chan_ok = m < g.Cout;
-    if (EPI == 0) {
-        float ts1 = 0.f, ts2 = 0.f;
-#pragma unroll
-        for (int t0 = 0; t0 < 32; t0 += POOL) {
-            float w[POOL];
-#pragma unroll
-            for (int i = 0; i < POOL; ++i) w[i] = v[t0 + i];
-            // folded input-BatchNorm shift: outputs whose taps hang over the zero padding lack those taps' constant
-            if (has_tb && (q < g.pad || q + POOL - 1 > g.Lin + g.pad - g.k)) {
-#pragma unroll
-                for (int i = 0; i < POOL; ++i) w[i] -= missing_taps(tb, q + i, g.k, g.pad, g.Lin);
-            }
-            float best = w[0];
-            int bi = 0;
-#pragma unroll
-            for (int i = 1; i < POOL; ++i)
-                if (w[i] > best) { best = w[i]; bi = i; }
-            const int p = q / POOL;  // POOL is a power of two
-            if (chan_ok && s < g.S && p < g.P) {
-                const float val = fmaxf(best + bv, 0.f);
-                const long o = ((long)s * g.P + p) * g.Cout + m;
-                out[o] = val;
-                if (code) code[o] = (uint8_t)bi;
-                ts1 += val;
-                ts2 = fmaf(val, val, ts2);
-            }
-            q += POOL;
-            if (q >= g.Lp) { q -= g.Lp; ++s; }
-        }
-        st1 += (double)ts1;
-        st2 += (double)ts2;
-    } else {
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-            const int tt = q - g.pad;
-            if (chan_ok && s < g.S && tt >= 0 && tt < g.Lin) out[((long)s * g.Lin + tt) * g.Cout + m] = v[t] * bv;
-            if (++q == g.Lp) { q = 0; ++s; }
-        }
-    }
-}
+// Epilogue work split: 16 warps, warp e owns TMEM lane quarter (warp_id % 4) x column chunk e/4 of
+// every tile, i.e. exactly one tcgen05.ld.32x32b.x32 per tile; 4 warps per scheduler hide each other's
+// latencies (ncu showed a single epilogue warp per scheduler stalling on fixed-latency dependencies).
+constexpr int NEPI = 16;
+constexpr int NTHREADS_ROWS = 64 + NEPI * 32;
 
-template <int EPI>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// EPI 0: bias + maxpool(POOL) + relu + argmax code + BN partial sums -> z[S*P, Cout]
+// EPI 1: store the data rows (scaled by 1/s of the gradient operand)   -> dx[S*Lin, Cout]
+// ATMEM: the packed weights live in TMEM columns [0, k*64) (TS-mode MMA) instead of shared memory, which
+// leaves room for NST = 6 activation stages instead of 2 (the 2-stage ring was load-latency bound) and
+// removes the A-operand shared-memory reads.
+template <int EPI, int POOL, bool ATMEM>
+__global__ void __launch_bounds__(NTHREADS_ROWS, 1)
 tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in, const uint4* __restrict__ wp, int fmt_w,
                     const float* __restrict__ bias, ConvGeom g, float* __restrict__ out, uint8_t* __restrict__ code,
-                    double* __restrict__ partial, const float* __restrict__ gscale, const float* __restrict__ tap_bias) {
+                    double* __restrict__ partial, const float* __restrict__ gscale, const float* __restrict__ tap_bias,
+                    float* __restrict__ dummy) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a_bytes = g.k * PANELS * A_PANEL_BYTES;  // k * 32 KB
+    constexpr int NST = ATMEM ? 6 : NSTAGE;
+    constexpr int ACC0 = ATMEM ? 256 : 0;              // first accumulator column
+    const int a_bytes = ATMEM ? 0 : g.k * PANELS * A_PANEL_BYTES;  // k * 32 KB
     uint8_t* sA = smem;
     uint8_t* sB = smem + a_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NSTAGE * B_STAGE_BYTES);
-    // bars: [0..NSTAGE) full, [NSTAGE..2NSTAGE) empty, [2N] wfull, [2N+1,2N+2] tmem_full, [2N+3,2N+4] tmem_empty
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NST * B_STAGE_BYTES);
+    // bars: [0..NST) full, [NST..2NST) empty, [2N] wfull, [2N+1,2N+2] tmem_full, [2N+3,2N+4] tmem_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 5);
     const uint32_t bar0 = smem_u32(bars);
     auto FULL = [&](int s) { return bar0 + 8u * s; };
-    auto EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
-    const uint32_t WFULL = bar0 + 8u * (2 * NSTAGE);
-    auto TFULL = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 1 + a); };
-    auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 3 + a); };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (NST + s); };
+    const uint32_t WFULL = bar0 + 8u * (2 * NST);
+    auto TFULL = [&](int a) { return bar0 + 8u * (2 * NST + 1 + a); };
+    auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * NST + 3 + a); };
 
     const long ntiles = (g.rows_total + BN - 1) / BN;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-        mbar_init(WFULL, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 4); }
+        for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        mbar_init(WFULL, ATMEM ? 4 : 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), NEPI); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<256>(smem_u32(tmem_slot));
+    if (warp == 1) tmem_alloc<ATMEM ? 512 : 256>(smem_u32(tmem_slot));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -217,9 +205,11 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
     if (warp == 0) {
         // ===== producer: weights once, then one activation tile per stage =====
         if (lane == 0) {
-            mbar_expect_tx(WFULL, (uint32_t)a_bytes);
-            for (int c = 0; c < g.k * 4; ++c)  // 8 KB pieces
-                bulk_g2s(smem_u32(sA + c * 8192), reinterpret_cast<const uint8_t*>(wp) + (size_t)c * 8192, 8192, WFULL);
+            if (!ATMEM) {
+                mbar_expect_tx(WFULL, (uint32_t)a_bytes);
+                for (int c = 0; c < g.k * 4; ++c)  // 8 KB pieces
+                    bulk_g2s(smem_u32(sA + c * 8192), reinterpret_cast<const uint8_t*>(wp) + (size_t)c * 8192, 8192, WFULL);
+            }
             Pipe pp;
             for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 mbar_wait(EMPTY(pp.stage), pp.phase ^ 1);
@@ -230,7 +220,7 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
                 for (int q = 0; q < PANELS; ++q)
                     bulk_g2s(smem_u32(dst + q * B_PANEL_BYTES), panel + (long)q * panel_rows + r0, B_PANEL_BYTES,
                              FULL(pp.stage));
-                pp.advance(NSTAGE);
+                pp.advance(NST);
             }
         }
     } else if (warp == 1) {
@@ -238,6 +228,7 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
         if (lane == 0) {
             const uint32_t idesc = make_idesc(fmt_w, fmt_in, 0, 0, 128, BN);
             mbar_wait(WFULL, 0);
+            tc_fence_after();
             Pipe pp;
             int acc = 0;
             uint32_t acc_phase = 0;
@@ -246,32 +237,53 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
                 mbar_wait(FULL(pp.stage), pp.phase);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + pp.stage * B_STAGE_BYTES);
-                const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t d = tmem_base + (uint32_t)(ACC0 + acc * BN);
                 for (int j = 0; j < g.k; ++j) {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {  // 16 channels = 2 panels per MMA
-                        const uint64_t ad = make_desc(a0 + (uint32_t)((j * PANELS + 2 * c) * A_PANEL_BYTES), A_PANEL_BYTES, 128);
                         const uint64_t bd = make_desc(b0 + (uint32_t)(2 * c * B_PANEL_BYTES + j * ROWB), B_PANEL_BYTES, 128);
-                        umma_f16(d, ad, bd, idesc, (j | c) != 0);
+                        if (ATMEM) {
+                            umma_f16_ts(d, tmem_base + (uint32_t)(j * 64 + c * 8), bd, idesc, (j | c) != 0);
+                        } else {
+                            const uint64_t ad = make_desc(a0 + (uint32_t)((j * PANELS + 2 * c) * A_PANEL_BYTES), A_PANEL_BYTES, 128);
+                            umma_f16(d, ad, bd, idesc, (j | c) != 0);
+                        }
                     }
                 }
                 umma_commit(EMPTY(pp.stage));  // smem stage reusable once these MMAs retire
                 umma_commit(TFULL(acc));       // accumulator ready for the epilogue
-                pp.advance(NSTAGE);
+                pp.advance(NST);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
         __syncwarp();
     } else {
         // ===== epilogue warps: TMEM -> registers -> (pool, relu, stats) -> global =====
-        const int quarter = warp & 3;
-        const int m = quarter * 32 + lane;  // output channel == TMEM lane
-        // EPI 0: bv = conv bias.  EPI 1: bv = 1/s of the scaled 16-bit gradient operand.
-        float bv = EPI == 0 ? ((bias && m < g.Cout) ? bias[m] : 0.f) : (gscale ? gscale[1] : 1.f);
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+        const int chunk = (warp - 2) >> 2;       // 32-column chunk of every tile
+        const int m = quarter * 32 + lane;       // output channel == TMEM lane
+        const bool chan_ok = m < g.Cout;
+        float bv = EPI == 0 ? ((bias && chan_ok) ? bias[m] : 0.f) : (gscale ? gscale[1] : 1.f);
         float tb[4] = {0.f, 0.f, 0.f, 0.f};
         const bool has_tb = EPI == 0 && tap_bias != nullptr;
-        if (has_tb && m < g.Cout) {
+        if (has_tb && chan_ok)
             for (int j = 0; j < g.k; ++j) { tb[j] = tap_bias[j * g.Cout + m]; bv += tb[j]; }
+        if (ATMEM && chunk == 0) {
+            // the four chunk-0 warps cover the four lane quarters: copy this thread's weight row into TMEM.
+            // packed weights [K/8][128 rows][8] -> row m, K chunk kk8 is one uint4 = columns 4*kk8 .. 4*kk8+3
+            for (int c0 = 0; c0 < g.k * 16; c0 += 8) {
+                uint32_t r[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 w = __ldg(wp + (long)(c0 + i) * 128 + m);
+                    r[4 * i] = w.x; r[4 * i + 1] = w.y; r[4 * i + 2] = w.z; r[4 * i + 3] = w.w;
+                }
+                tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c0 * 4), r);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(WFULL);
         }
         double st1 = 0.0, st2 = 0.0;
         int acc = 0;
@@ -279,34 +291,80 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
         for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             mbar_wait(TFULL(acc), acc_phase);
             tc_fence_after();
-            const int r0 = (int)(tile * BN);
-#pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
-                if (EPI == 0) {
-                    if (g.pool == 4) epilogue_chunk<0, 4>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2, has_tb, tb);
-                    else if (g.pool == 2) epilogue_chunk<0, 2>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2, has_tb, tb);
-                    else epilogue_chunk<0, 1>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2, has_tb, tb);
-                } else {
-                    epilogue_chunk<1, 1>(v, r0 + ch * 32, m, bv, g, out, code, st1, st2, false, tb);
-                }
-            }
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ACC0 + acc * BN + chunk * 32), v);
+            // accumulator columns are in registers: release the TMEM buffer before the global stores
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(TEMPTY(acc));
+            const int r = (int)(tile * BN) + chunk * 32;
+            int s = r / g.Lp;
+            int q = r - s * g.Lp;
+            if (EPI == 0) {
+                float ts1 = 0.f, ts2 = 0.f;
+#pragma unroll
+                for (int t0 = 0; t0 < 32; t0 += POOL) {
+                    float w[POOL];
+#pragma unroll
+                    for (int i = 0; i < POOL; ++i) w[i] = v[t0 + i];
+                    // folded input-BatchNorm shift: outputs whose taps hang over the zero padding lack those constants
+                    if (has_tb && (q < g.pad || q + POOL - 1 > g.Lin + g.pad - g.k)) {
+#pragma unroll
+                        for (int i = 0; i < POOL; ++i) w[i] -= missing_taps(tb, q + i, g.k, g.pad, g.Lin);
+                    }
+                    float best = w[0];
+                    int bi = 0;
+#pragma unroll
+                    for (int i = 1; i < POOL; ++i) {
+                        const bool gt = w[i] > best;   // first maximum wins, like ATen
+                        best = gt ? w[i] : best;
+                        bi = gt ? i : bi;
+                    }
+                    const int p = q / POOL;  // POOL is a power of two
+                    const bool ok = chan_ok && s < g.S && p < g.P;
+                    const float val = ok ? fmaxf(best + bv, 0.f) : 0.f;
+                    const long o = ((long)s * g.P + p) * g.Cout + m;
+                    // branch-free stores: dead lanes write to a scratch word instead of diverging
+                    float* zp = ok ? out + o : dummy;
+                    uint8_t* cp = ok ? code + o : reinterpret_cast<uint8_t*>(dummy);
+                    *zp = val;
+                    *cp = (uint8_t)bi;
+                    ts1 += val;
+                    ts2 = fmaf(val, val, ts2);
+                    q += POOL;
+                    const bool wrap = q >= g.Lp;
+                    q = wrap ? q - g.Lp : q;
+                    s += wrap ? 1 : 0;
+                }
+                st1 += (double)ts1;
+                st2 += (double)ts2;
+            } else {
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    const int tt = q - g.pad;
+                    const bool ok = chan_ok && s < g.S && tt >= 0 && tt < g.Lin;
+                    float* dp = ok ? out + ((long)s * g.Lin + tt) * g.Cout + m : dummy;
+                    *dp = v[t] * bv;
+                    ++q;
+                    const bool wrap = q == g.Lp;
+                    q = wrap ? 0 : q;
+                    s += wrap ? 1 : 0;
+                }
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (EPI == 0 && partial && m < g.Cout) {
-            partial[((long)blockIdx.x * 2 + 0) * g.Cout + m] = st1;
-            partial[((long)blockIdx.x * 2 + 1) * g.Cout + m] = st2;
+        if (EPI == 0 && partial && chan_ok) {
+            // 4 chunk-warps per channel: partial rows are (block, chunk)
+            const long prow = (long)blockIdx.x * 4 + chunk;
+            partial[(prow * 2 + 0) * g.Cout + m] = st1;
+            partial[(prow * 2 + 1) * g.Cout + m] = st2;
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<256>(tmem_base);
+        tmem_dealloc<ATMEM ? 512 : 256>(tmem_base);
     }
 }
 
@@ -414,7 +472,18 @@ tc_wgrad_kernel(const uint4* __restrict__ dyp, long dy_rows, int fmt_dy, const u
     }
 }
 
-size_t rows_smem_bytes(int k) { return (size_t)k * PANELS * A_PANEL_BYTES + NSTAGE * B_STAGE_BYTES + 8 * (2 * NSTAGE + 5) + 16; }
+size_t rows_smem_bytes(int k, bool atmem) {
+    if (atmem) return (size_t)6 * B_STAGE_BYTES + 8 * (2 * 6 + 5) + 16;
+    return (size_t)k * PANELS * A_PANEL_BYTES + NSTAGE * B_STAGE_BYTES + 8 * (2 * NSTAGE + 5) + 16;
+}
+bool use_atmem() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DCUE_TC_ATMEM");
+        v = (e && e[0] == '1') ? 1 : 0;  // default: weights in shared memory (SS); DCUE_TC_ATMEM=1 selects TMEM (TS)
+    }
+    return v != 0;
+}
 constexpr size_t WG_SMEM = (size_t)WG_NSTAGE * WG_STAGE_BYTES + 8 * (2 * WG_NSTAGE + 1) + 16;
 
 int tc_grid(long rows_total) {
@@ -423,14 +492,23 @@ int tc_grid(long rows_total) {
     return (int)(ntiles < sms ? (ntiles > 0 ? ntiles : 1) : sms);
 }
 
-template <int EPI>
-int launch_rows(const void* panel, long panel_rows, int fmt_in, const void* w_packed, int fmt_w, const float* bias,
-                const ConvGeom& g, float* out, uint8_t* code, double* partial, const float* gscale,
-                const float* tap_bias, int grid, cudaStream_t st) {
-    const size_t smem = rows_smem_bytes(g.k);
-    DCUE_CUDA(cudaFuncSetAttribute(tc_conv_rows_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_conv_rows_kernel<EPI><<<grid, NTHREADS, smem, st>>>((const uint4*)panel, panel_rows, fmt_in, (const uint4*)w_packed,
-                                                           fmt_w, bias, g, out, code, partial, gscale, tap_bias);
+template <int EPI, int POOL>
+int launch_rows_t(const void* panel, long panel_rows, int fmt_in, const void* w_packed, int fmt_w, const float* bias,
+                  const ConvGeom& g, float* out, uint8_t* code, double* partial, const float* gscale,
+                  const float* tap_bias, float* dummy, int grid, cudaStream_t st) {
+    const bool atm = use_atmem();
+    const size_t smem = rows_smem_bytes(g.k, atm);
+    if (atm) {
+        DCUE_CUDA(cudaFuncSetAttribute(tc_conv_rows_kernel<EPI, POOL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_conv_rows_kernel<EPI, POOL, true><<<grid, NTHREADS_ROWS, smem, st>>>((const uint4*)panel, panel_rows, fmt_in,
+                                                                                (const uint4*)w_packed, fmt_w, bias, g, out,
+                                                                                code, partial, gscale, tap_bias, dummy);
+    } else {
+        DCUE_CUDA(cudaFuncSetAttribute(tc_conv_rows_kernel<EPI, POOL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_conv_rows_kernel<EPI, POOL, false><<<grid, NTHREADS_ROWS, smem, st>>>((const uint4*)panel, panel_rows, fmt_in,
+                                                                                 (const uint4*)w_packed, fmt_w, bias, g, out,
+                                                                                 code, partial, gscale, tap_bias, dummy);
+    }
     DCUE_LAUNCH_CHECK();
     return 0;
 }
@@ -438,7 +516,8 @@ int launch_rows(const void* panel, long panel_rows, int fmt_in, const void* w_pa
 }  // namespace
 
 size_t dcue_tc_ws_bytes(int k) {
-    const size_t stats = (size_t)dcue_num_sms() * 2 * 128 * sizeof(double);
+    // [grid*4][2][128] stat partials + one scratch line for dead-lane stores
+    const size_t stats = (size_t)dcue_num_sms() * 4 * 2 * 128 * sizeof(double) + 256;
     const size_t wg = (size_t)dcue_num_sms() * 128 * k * 128 * sizeof(float);
     return stats > wg ? stats : wg;
 }
@@ -447,24 +526,31 @@ int dcue_tc_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_
                      const float* tap_bias, const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,
                      cudaStream_t st) {
     if (g.Cin != 128) DCUE_FAIL(DCUE_E_UNSUPPORTED, "tcgen05 conv needs Cin == 128 (got %d)", g.Cin);
+    if (!code) DCUE_FAIL(DCUE_E_BADARG, "tcgen05 conv forward needs the argmax code buffer");
     const int grid = tc_grid(g.rows_total);
-    if (sums && (!ws || ws_bytes < (size_t)grid * 2 * g.Cout * sizeof(double)))
-        DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_pool_fwd(tc): workspace too small");
-    if (int e = launch_rows<0>(panel, panel_rows, fmt, w_packed, fmt, bias, g, z, code, sums ? (double*)ws : nullptr, nullptr, tap_bias, grid, st))
-        return e;
+    const size_t part_bytes = (size_t)grid * 4 * 2 * g.Cout * sizeof(double);
+    if (!ws || ws_bytes < part_bytes + 256) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_pool_fwd(tc): workspace too small");
+    double* part = sums ? (double*)ws : nullptr;
+    float* dummy = (float*)((char*)ws + part_bytes);
+    int e;
+    if (g.pool == 4) e = launch_rows_t<0, 4>(panel, panel_rows, fmt, w_packed, fmt, bias, g, z, code, part, nullptr, tap_bias, dummy, grid, st);
+    else if (g.pool == 2) e = launch_rows_t<0, 2>(panel, panel_rows, fmt, w_packed, fmt, bias, g, z, code, part, nullptr, tap_bias, dummy, grid, st);
+    else e = launch_rows_t<0, 1>(panel, panel_rows, fmt, w_packed, fmt, bias, g, z, code, part, nullptr, tap_bias, dummy, grid, st);
+    if (e) return e;
     if (sums) {
-        dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 32), 256, 0, st>>>((const double*)ws, grid, 2 * g.Cout, sums);
+        dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 32), 256, 0, st>>>((const double*)ws, grid * 4, 2 * g.Cout, sums);
         DCUE_LAUNCH_CHECK();
     }
     return 0;
 }
 
 int dcue_tc_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
-                       const ConvGeom& g, const float* gscale, float* dx, cudaStream_t st) {
+                       const ConvGeom& g, const float* gscale, float* dx, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (g.Cin != 128) DCUE_FAIL(DCUE_E_UNSUPPORTED, "tcgen05 dgrad needs Cout == 128 (got %d)", g.Cin);
     if (fmt_dy != fmt_w) DCUE_FAIL(DCUE_E_UNSUPPORTED, "tcgen05 kind::f16 needs both operands in the same 16-bit format");
-    return launch_rows<1>(dy_panel_shifted, panel_rows, fmt_dy, w_packed, fmt_w, nullptr, g, dx, nullptr, nullptr, gscale,
-                          nullptr, tc_grid(g.rows_total), st);
+    if (!ws || ws_bytes < 256) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_dgrad(tc): workspace too small");
+    return launch_rows_t<1, 1>(dy_panel_shifted, panel_rows, fmt_dy, w_packed, fmt_w, nullptr, g, dx, nullptr, nullptr, gscale,
+                               nullptr, (float*)ws, tc_grid(g.rows_total), st);
 }
 
 int dcue_tc_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const void* x_panel, long x_rows, int fmt_x,
