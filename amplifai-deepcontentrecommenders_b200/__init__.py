@@ -1,6 +1,7 @@
 """amplifai-deepcontentrecommenders_b200: B200-native (sm_100a) DCUE training + scoring hot path
-behind the reference's DCUENet / DCUE API."""
+behind the reference's DCUENet / DCUE API  (reference: `from dcrecommend import DCUE`)."""
 from . import _lib, eval, ops  # noqa: F401
 from .dcue.dcue import DCUENet  # noqa: F401
+from .nn.dcue import DCUE  # noqa: F401
 
-__all__ = ["DCUENet"]
+__all__ = ["DCUE", "DCUENet"]
