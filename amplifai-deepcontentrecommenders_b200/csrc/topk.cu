@@ -90,34 +90,48 @@ __device__ __forceinline__ uint32_t make_idesc(int a_fmt, int b_fmt, int M, int 
            ((uint32_t)(M >> 4) << 24);
 }
 
-// warp-cooperative: replace the minimum of user `ul`'s slot list by (s, it); returns the new minimum
-__device__ __forceinline__ float insert_candidate(float* __restrict__ cs, int* __restrict__ ci, int ul, float s, int it,
-                                                  int lane) {
-    float4* row = reinterpret_cast<float4*>(cs + ul * SLOTS);
-    float4 c = row[lane];
-    float mv = c.x;
-    int ms = 0;
-    if (c.y < mv) { mv = c.y; ms = 1; }
-    if (c.z < mv) { mv = c.z; ms = 2; }
-    if (c.w < mv) { mv = c.w; ms = 3; }
-    ms += lane * 4;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, mv, o);
-        const int os = __shfl_xor_sync(0xffffffffu, ms, o);
-        if (ov < mv || (ov == mv && os < ms)) { mv = ov; ms = os; }
+// Each user's SLOTS candidates are kept sorted (descending) and spread over the warp: lane L holds
+// slots 4L..4L+3.  Inserting (s, it) is a shift: lanes whose slots all beat s are untouched, the first
+// lane that does not is the boundary (s lands at its local position n), every later lane takes its
+// predecessor's last slot in front.  3 shuffles + selects, no reduction; the user's new threshold is
+// simply the last slot (lane 31).  One non-inlined copy of this code serves all 32 unrolled columns.
+__device__ __noinline__ float process_column(unsigned mask, float vj, int item, float thr, float* __restrict__ cs,
+                                             int* __restrict__ ci, int ubase, int lane) {
+    while (mask) {
+        const int l = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float s = __shfl_sync(0xffffffffu, vj, l);
+        float4* srow = reinterpret_cast<float4*>(cs + (ubase + l) * SLOTS);
+        int4* irow = reinterpret_cast<int4*>(ci + (ubase + l) * SLOTS);
+        const float4 c = srow[lane];
+        const int4 d = irow[lane];
+        // items stream in increasing index order, so ties stay behind the entries already kept (>=)
+        const int n = (c.x >= s) + (c.y >= s) + (c.z >= s) + (c.w >= s);
+        const float pc = __shfl_up_sync(0xffffffffu, c.w, 1);
+        const int pd = __shfl_up_sync(0xffffffffu, d.w, 1);
+        const int np = __shfl_up_sync(0xffffffffu, n, 1);
+        const bool boundary = n < 4 && (lane == 0 || np == 4);
+        const float x = boundary ? s : pc;
+        const int xi = boundary ? item : pd;
+        float4 r = c;
+        int4 q = d;
+        if (n < 4) {
+            r.x = n == 0 ? x : c.x;
+            r.y = n == 0 ? c.x : (n == 1 ? x : c.y);
+            r.z = n <= 1 ? c.y : (n == 2 ? x : c.z);
+            r.w = n <= 2 ? c.z : x;
+            q.x = n == 0 ? xi : d.x;
+            q.y = n == 0 ? d.x : (n == 1 ? xi : d.y);
+            q.z = n <= 1 ? d.y : (n == 2 ? xi : d.z);
+            q.w = n <= 2 ? d.z : xi;
+            srow[lane] = r;
+            irow[lane] = q;
+        }
+        const float nt = __shfl_sync(0xffffffffu, r.w, 31);
+        if (lane == l) thr = nt;
+        __syncwarp();
     }
-    if ((ms >> 2) == lane) {
-        cs[ul * SLOTS + ms] = s;
-        ci[ul * SLOTS + ms] = it;
-        const int w = ms & 3;
-        if (w == 0) c.x = s; else if (w == 1) c.y = s; else if (w == 2) c.z = s; else c.w = s;
-    }
-    float nm = fminf(fminf(c.x, c.y), fminf(c.z, c.w));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nm = fminf(nm, __shfl_xor_sync(0xffffffffu, nm, o));
-    __syncwarp();
-    return nm;
+    return thr;
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -217,17 +231,11 @@ topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long 
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TI + ch * 32), v);
                 const long ib = it0 + ch * 32;
+                const int ncol = (iend - ib) < 32 ? (int)(iend - ib) : 32;   // < 32 only in the last tile
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const bool pass = v[j] > thr && (ib + j) < iend;
-                    unsigned mask = __ballot_sync(0xffffffffu, pass);
-                    while (mask) {
-                        const int l = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const float s = __shfl_sync(0xffffffffu, v[j], l);
-                        const float nt = insert_candidate(cs, ci, quarter * 32 + l, s, (int)(ib + j), lane);
-                        if (lane == l) thr = nt;
-                    }
+                    const unsigned mask = __ballot_sync(0xffffffffu, v[j] > thr && j < ncol);
+                    if (mask) thr = process_column(mask, v[j], (int)(ib + j), thr, cs, ci, quarter * 32, lane);
                 }
             }
             tc_fence_before();
@@ -235,29 +243,22 @@ topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long 
             if (lane == 0) mbar_arrive(TEMPTY(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        // ---- finish: rank sort each of this warp's 32 users' slot lists, write the k best
+        // ---- finish: the lists are already sorted; lane L writes slots 4L..4L+3 of each user
         __syncwarp();
         for (int uu = 0; uu < 32; ++uu) {
             const int usr = quarter * 32 + uu;
             const long gu = u0 + usr;
             if (gu >= n_users) break;
-            float es[4];
-            int ei[4], rk[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { es[e] = cs[usr * SLOTS + lane * 4 + e]; ei[e] = ci[usr * SLOTS + lane * 4 + e]; }
-            for (int r = 0; r < SLOTS; ++r) {
-                const float sr = cs[usr * SLOTS + r];
-                const int ir = ci[usr * SLOTS + r];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) rk[e] += (sr > es[e]) || (sr == es[e] && (unsigned)ir < (unsigned)ei[e]);
-            }
             const long ob = ((long)blockIdx.y * n_users + gu) * k;
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (rk[e] < k) {
-                    out_s[ob + rk[e]] = es[e];
-                    out_i[ob + rk[e]] = ei[e] < 0 ? -1 : (int64_t)ei[e] + item_offset;
+            for (int e = 0; e < 4; ++e) {
+                const int slot = lane * 4 + e;
+                if (slot < k) {
+                    const int it = ci[usr * SLOTS + slot];
+                    out_s[ob + slot] = cs[usr * SLOTS + slot];
+                    out_i[ob + slot] = it < 0 ? -1 : (int64_t)it + item_offset;
                 }
+            }
         }
         (void)ul;
     }

@@ -53,6 +53,7 @@ class SynthPredSet(Dataset):
         self.rows = []
         self.user_has_songs = False
         self.song_has_users = False
+        self.create_user_data(self.uniq_users[0])   # like DCUEPredset: never empty
 
     def create_user_data(self, user):
         pos = [s for u, s in self.pairs if u == user]

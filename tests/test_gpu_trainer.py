@@ -105,12 +105,12 @@ def test_factors_predict_score_topk_and_checkpoint(tmp_path):
 
 
 def test_fit_runs_end_to_end(tmp_path):
-    w = SynthWorld(n_users=12, n_songs=20)
-    tr, va = SynthTrainSet(w, w.pairs[:48]), SynthTrainSet(w, w.pairs[48:64])
+    w = SynthWorld(n_users=20, n_songs=20)   # 120 (user, song) pairs -> epoch_size 8 (one batch per sub-epoch)
+    tr, va = SynthTrainSet(w, w.pairs[:96]), SynthTrainSet(w, w.pairs[96:])
     t = pkg.DCUE(batch_size=8, neg_batch_size=w.negs, lr=1e-4, num_epochs=1, eval_pct=1.0)
     t.num_workers = 0
     np.random.seed(0)
-    t.fit(tr, va, va, SynthPredSet(w, w.pairs[48:64]), SynthPredSet(w, w.pairs[:48]), SynthItemSet(w), w.n_users,
+    t.fit(tr, va, va, SynthPredSet(w, w.pairs[96:]), SynthPredSet(w, w.pairs[:96]), SynthItemSet(w), w.n_users,
           w.n_songs, "triplets.txt", "metadata.csv", str(tmp_path))
     assert t.nn_epoch == 2 and t.user_factors is not None
     assert os.listdir(os.path.join(str(tmp_path), t._format_model_subdir()))
