@@ -48,7 +48,7 @@ def main():
             e = ((p.grad - q.grad).norm() / q.grad.norm().clamp_min(1e-30)).item()
             worst = max(worst, e)
         berr = max(((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)).item()
-                   for (_, a), (_, b) in zip(net.named_buffers(), ref.named_buffers()))
+                   for (_, a), (_, b) in zip(net.named_buffers(), ref.named_buffers())) if list(net.named_buffers()) else 0.0
         lerr = abs(total.item() - loss_ref.item()) / abs(loss_ref.item())
         if rank == 0:
             print("DP_PARITY %s world=%d loss_rel=%.2e worst_grad_l2=%.2e buffers=%.2e" % (mt, world, lerr, worst, berr), flush=True)
