@@ -7,11 +7,15 @@
 //   users on the MMA M axis (one TMEM lane = one user), songs on N.  CTA = 128 users x one
 //   contiguous range of songs; the user tile stays in smem, song tiles stream through a 2-stage
 //   cp.async.bulk ring; accumulators are double buffered so the filter overlaps the next MMA.
-//   Filter: each epilogue thread compares its user's 128 fresh scores with that user's running
-//   threshold (the smallest kept score, in a register).  Passing scores are rare after warm-up
-//   (~k ln(I/k) per user); they are inserted warp-cooperatively (ballot -> all 32 lanes find and
-//   replace the minimum of that user's 128-slot candidate list in smem).
-//   Finish: rank sort of the 128 slots per user, write the k best (descending, ties by index).
+//   Filter: one TMEM lane = one user, so each epilogue thread owns one user: its threshold (the k-th
+//   best score at the last compaction) and its list length live in registers.  A chunk of 32 fresh scores
+//   is first reduced with a max tree; only if some lane beats its threshold are the columns scanned,
+//   and a passing score is APPENDED to that user's unsorted list in shared memory by its own lane (plain
+//   predicated stores, all 32 users in parallel).  When a list reaches CAP entries the warp sorts it
+//   cooperatively (bitonic network, 4 entries per lane, 15 shuffle steps), keeps the k best and raises the
+//   threshold: one ~400-instruction compaction per CAP-k appends instead of a dependent
+//   shuffle/LDS/STS chain per insert (ncu of the first version: 3 % tensor pipe, 780 cycles per insert).
+//   Finish: one last sort per user, write the k best (descending, ties by lower song index).
 #include "common.cuh"
 
 namespace {
@@ -90,48 +94,84 @@ __device__ __forceinline__ uint32_t make_idesc(int a_fmt, int b_fmt, int M, int 
            ((uint32_t)(M >> 4) << 24);
 }
 
-// Each user's SLOTS candidates are kept sorted (descending) and spread over the warp: lane L holds
-// slots 4L..4L+3.  Inserting (s, it) is a shift: lanes whose slots all beat s are untouched, the first
-// lane that does not is the boundary (s lands at its local position n), every later lane takes its
-// predecessor's last slot in front.  3 shuffles + selects, no reduction; the user's new threshold is
-// simply the last slot (lane 31).  One non-inlined copy of this code serves all 32 unrolled columns.
-__device__ __noinline__ float process_column(unsigned mask, float vj, int item, float thr, float* __restrict__ cs,
-                                             int* __restrict__ ci, int ubase, int lane) {
-    while (mask) {
-        const int l = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const float s = __shfl_sync(0xffffffffu, vj, l);
-        float4* srow = reinterpret_cast<float4*>(cs + (ubase + l) * SLOTS);
-        int4* irow = reinterpret_cast<int4*>(ci + (ubase + l) * SLOTS);
-        const float4 c = srow[lane];
-        const int4 d = irow[lane];
-        // items stream in increasing index order, so ties stay behind the entries already kept (>=)
-        const int n = (c.x >= s) + (c.y >= s) + (c.z >= s) + (c.w >= s);
-        const float pc = __shfl_up_sync(0xffffffffu, c.w, 1);
-        const int pd = __shfl_up_sync(0xffffffffu, d.w, 1);
-        const int np = __shfl_up_sync(0xffffffffu, n, 1);
-        const bool boundary = n < 4 && (lane == 0 || np == 4);
-        const float x = boundary ? s : pc;
-        const int xi = boundary ? item : pd;
-        float4 r = c;
-        int4 q = d;
-        if (n < 4) {
-            r.x = n == 0 ? x : c.x;
-            r.y = n == 0 ? c.x : (n == 1 ? x : c.y);
-            r.z = n <= 1 ? c.y : (n == 2 ? x : c.z);
-            r.w = n <= 2 ? c.z : x;
-            q.x = n == 0 ? xi : d.x;
-            q.y = n == 0 ? d.x : (n == 1 ? xi : d.y);
-            q.z = n <= 1 ? d.y : (n == 2 ? xi : d.z);
-            q.w = n <= 2 ? d.z : xi;
-            srow[lane] = r;
-            irow[lane] = q;
+constexpr int CAP = SLOTS;      // list capacity per user
+constexpr int LD = SLOTS + 1;   // row stride (floats): (user + slot) % 32 banks -> lane-parallel appends do not collide
+
+struct Cand {
+    float s;
+    int i;
+};
+// a ranks before b: higher score, ties by lower song index (-1 = empty sorts last among equals)
+__device__ __forceinline__ bool before(const Cand& a, const Cand& b) {
+    return a.s > b.s || (a.s == b.s && (unsigned)a.i < (unsigned)b.i);
+}
+
+// Warp-cooperative bitonic sort (descending) of 128 candidates, element g = lane*4 + e.
+__device__ __forceinline__ void bitonic_sort128(Cand (&c)[4], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 128; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 4) {
+                const int lx = stride >> 2;
+                const bool lower = (lane & lx) == 0;                    // g < partner
+                const bool desc = ((lane * 4) & size) == 0;             // size >= 8: uniform over e
+                const bool keep_first = lower == desc;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    Cand o;
+                    o.s = __shfl_xor_sync(0xffffffffu, c[e].s, lx);
+                    o.i = __shfl_xor_sync(0xffffffffu, c[e].i, lx);
+                    const bool mine_first = before(c[e], o);
+                    if (mine_first != keep_first) c[e] = o;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int pe = e ^ stride;
+                    if (pe > e) {
+                        const bool desc = ((lane * 4 + e) & size) == 0;
+                        const bool in_order = before(c[e], c[pe]);
+                        if (in_order != desc) { const Cand t = c[e]; c[e] = c[pe]; c[pe] = t; }
+                    }
+                }
+            }
         }
-        const float nt = __shfl_sync(0xffffffffu, r.w, 31);
-        if (lane == l) thr = nt;
-        __syncwarp();
     }
-    return thr;
+}
+
+// Sort user `u`'s list (entries >= n are empty), write it back sorted; returns the k-th best score.
+__device__ __forceinline__ float compact_user(float* __restrict__ cs, int* __restrict__ ci, int u, int n, int k, int lane) {
+    Cand c[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int g = lane * 4 + e;
+        c[e].s = g < n ? cs[u * LD + g] : -INFINITY;
+        c[e].i = g < n ? ci[u * LD + g] : -1;
+    }
+    bitonic_sort128(c, lane);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        cs[u * LD + lane * 4 + e] = c[e].s;
+        ci[u * LD + lane * 4 + e] = c[e].i;
+    }
+    // k-th best = element k-1 = lane (k-1)/4, e = (k-1)%4
+    const int ke = (k - 1) & 3;
+    const float mine = ke == 0 ? c[0].s : ke == 1 ? c[1].s : ke == 2 ? c[2].s : c[3].s;
+    const float kth = __shfl_sync(0xffffffffu, mine, (k - 1) >> 2);
+    __syncwarp();
+    return kth;
+}
+
+// compaction of every user whose list is full (one non-inlined copy)
+__device__ __noinline__ void compact_full(unsigned full, float* __restrict__ cs, int* __restrict__ ci, int ubase, int k,
+                                          int lane, float& thr, int& cnt) {
+    while (full) {
+        const int l = __ffs(full) - 1;
+        full &= full - 1;
+        const float kth = compact_user(cs, ci, ubase + l, CAP, k, lane);
+        if (lane == l) { thr = kth; cnt = k; }
+    }
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -145,8 +185,8 @@ topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long 
     uint8_t* sA = smem;
     uint8_t* sB = smem + tile_bytes;
     float* cs = reinterpret_cast<float*>(sB + NSTAGE * tile_bytes);
-    int* ci = reinterpret_cast<int*>(cs + TU * SLOTS);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ci + TU * SLOTS);
+    int* ci = reinterpret_cast<int*>(cs + TU * LD);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uintptr_t>(ci + TU * LD + 1) & ~(uintptr_t)7);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
     const uint32_t bar0 = smem_u32(bars);
     auto FULL = [&](int s) { return bar0 + 8u * s; };
@@ -166,7 +206,6 @@ topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long 
         for (int a = 0; a < 2; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 4); }
         fence_barrier_init();
     }
-    for (int e = threadIdx.x; e < TU * SLOTS; e += NTHREADS) { cs[e] = -INFINITY; ci[e] = -1; }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -218,8 +257,10 @@ topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long 
         __syncwarp();
     } else {
         const int quarter = warp & 3;
-        const int ul = quarter * 32 + lane;  // user within the tile == TMEM lane
-        float thr = -INFINITY;
+        const int ubase = quarter * 32;
+        const int u = ubase + lane;          // this lane's user within the tile == TMEM lane
+        float thr = -INFINITY;               // k-th best score at the last compaction
+        int cnt = 0;                         // entries in this user's list
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long t = 0; t < ntiles; ++t) {
@@ -231,11 +272,24 @@ topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long 
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TI + ch * 32), v);
                 const long ib = it0 + ch * 32;
-                const int ncol = (iend - ib) < 32 ? (int)(iend - ib) : 32;   // < 32 only in the last tile
+                if (iend - ib < 32) {  // last tile: columns beyond the song range never qualify
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (ib + j >= iend) v[j] = -INFINITY;
+                }
+                float mx = v[0];
+#pragma unroll
+                for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+                if (!__any_sync(0xffffffffu, mx > thr)) continue;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const unsigned mask = __ballot_sync(0xffffffffu, v[j] > thr && j < ncol);
-                    if (mask) thr = process_column(mask, v[j], (int)(ib + j), thr, cs, ci, quarter * 32, lane);
+                    if (v[j] > thr) {
+                        cs[u * LD + cnt] = v[j];
+                        ci[u * LD + cnt] = (int)(ib + j);
+                        ++cnt;
+                    }
+                    const unsigned full = __ballot_sync(0xffffffffu, cnt == CAP);
+                    if (full) compact_full(full, cs, ci, ubase, k, lane, thr, cnt);
                 }
             }
             tc_fence_before();
@@ -243,24 +297,25 @@ topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long 
             if (lane == 0) mbar_arrive(TEMPTY(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        // ---- finish: the lists are already sorted; lane L writes slots 4L..4L+3 of each user
+        // ---- finish: final sort of every user's list; lane L writes slots 4L..4L+3
         __syncwarp();
         for (int uu = 0; uu < 32; ++uu) {
-            const int usr = quarter * 32 + uu;
+            const int usr = ubase + uu;
             const long gu = u0 + usr;
             if (gu >= n_users) break;
+            const int n = __shfl_sync(0xffffffffu, cnt, uu);
+            compact_user(cs, ci, usr, n, k, lane);
             const long ob = ((long)blockIdx.y * n_users + gu) * k;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int slot = lane * 4 + e;
                 if (slot < k) {
-                    const int it = ci[usr * SLOTS + slot];
-                    out_s[ob + slot] = cs[usr * SLOTS + slot];
+                    const int it = ci[usr * LD + slot];
+                    out_s[ob + slot] = cs[usr * LD + slot];
                     out_i[ob + slot] = it < 0 ? -1 : (int64_t)it + item_offset;
                 }
             }
         }
-        (void)ul;
     }
     tc_fence_before();
     __syncthreads();
@@ -353,7 +408,8 @@ extern "C" size_t dcue_topk_ws_bytes(int impl, long n_users, long n_items, int k
 extern "C" int dcue_topk_scores(int impl, const void* users_n, long n_users, const void* items_n, long n_items, int Kp,
                                 int fmt, int k, long item_offset, float* top_scores, int64_t* top_idx, void* ws,
                                 size_t ws_bytes, void* stream) {
-    DCUE_CHECK_ARG(users_n && items_n && top_scores && top_idx && n_users >= 0 && n_items >= 0 && k > 0 && k <= SLOTS);
+    DCUE_CHECK_ARG(users_n && items_n && top_scores && top_idx && n_users >= 0 && n_items >= 0 && k > 0 &&
+                   k <= SLOTS - 8);  // a compaction must free at least 8 slots
     DCUE_CHECK_ARG(Kp % 16 == 0 && Kp >= 16 && Kp <= 128);
     if (impl != DCUE_IMPL_TC) DCUE_FAIL(DCUE_E_UNSUPPORTED, "dcue_topk_scores: only the tcgen05 implementation exists");
     if (n_users == 0) return 0;
@@ -371,7 +427,8 @@ extern "C" int dcue_topk_scores(int impl, const void* users_n, long n_users, con
     }
     // slots that are never filled (fewer than k songs in a split) must read as "missing"
     DCUE_CUDA(cudaMemsetAsync(oi, 0xff, (size_t)splits * n_users * k * sizeof(int64_t), st));
-    const size_t smem = (size_t)(1 + NSTAGE) * (Kp / 8) * PANEL_BYTES + (size_t)TU * SLOTS * 8 + 8 * (2 * NSTAGE + 5) + 16;
+    const size_t smem = (size_t)(1 + NSTAGE) * (Kp / 8) * PANEL_BYTES + (size_t)TU * (SLOTS + 1) * 8 + 16 +
+                        8 * (2 * NSTAGE + 5) + 16;
     DCUE_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((n_users + TU - 1) / TU), splits);
     topk_kernel<<<grid, NTHREADS, smem, st>>>((const uint4*)users_n, round_up_l(n_users, 128), n_users,
