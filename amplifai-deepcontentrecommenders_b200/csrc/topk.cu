@@ -5,8 +5,8 @@
 // against every candidate song's factor row) to all users x all songs.
 //
 //   users on the MMA M axis (one TMEM lane = one user), songs on N.  CTA = 128 users x one
-//   contiguous range of songs; the user tile stays in smem, song tiles stream through a 2-stage
-//   cp.async.bulk ring; accumulators are double buffered so the filter overlaps the next MMA.
+//   contiguous range of songs; the user tile lives in TMEM (TS-mode MMA), song tiles stream through a
+//   3-stage cp.async.bulk ring; accumulators are double buffered so the filter overlaps the next MMA.
 //   Filter: one TMEM lane = one user, so each epilogue thread owns one user: its threshold (the k-th
 //   best score at the last compaction) and its list length live in registers.  A chunk of 32 fresh scores
 //   is first reduced with a max tree; only if some lane beats its threshold are the columns scanned,
@@ -17,6 +17,7 @@
 //   shuffle/LDS/STS chain per insert (ncu of the first version: 3 % tensor pipe, 780 cycles per insert).
 //   Finish: one last sort per user, write the k best (descending, ties by lower song index).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -25,8 +26,10 @@ constexpr int TI = 128;        // songs per tile (MMA N)
 constexpr int SLOTS = 128;     // kept candidates per user (k <= SLOTS)
 constexpr int ROWB = 16;
 constexpr int PANEL_BYTES = 128 * ROWB;  // 2048: one 8-wide K chunk of a 128-row tile
-constexpr int NSTAGE = 2;
+constexpr int NSTAGE = 3;
 constexpr int NTHREADS = 192;
+constexpr int ACC0 = 64;         // accumulator columns start (the user tile occupies TMEM columns [0, Kp/2 <= 64))
+constexpr int NACC = 3;          // accumulator stages: absorbs the jitter of rare compactions / slow scans
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -68,6 +71,49 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+// asynchronous TMEM load: the registers are valid only after tmem_ld_fence() on the same array
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// ties the registers to a point after tmem_wait_ld() so no consumer is scheduled before the wait
+__device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[32]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+    asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                      "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -163,37 +209,68 @@ __device__ __forceinline__ float compact_user(float* __restrict__ cs, int* __res
     return kth;
 }
 
-// compaction of every user whose list is full (one non-inlined copy)
-__device__ __noinline__ void compact_full(unsigned full, float* __restrict__ cs, int* __restrict__ ci, int ubase, int k,
-                                          int lane, float& thr, int& cnt) {
+struct UserState {   // per-lane (= per-user) filter state, kept in registers
+    float thr;       // k-th best score at the last compaction
+    int cnt;         // entries in this user's list
+};
+
+// Rare path, ONE non-inlined copy (keeps the hot loop small enough for the instruction cache): re-read a
+// 32-column chunk of the accumulator from TMEM, append every score that beats its user's threshold (each
+// lane appends to its own user's list), and compact any list that fills up.
+__device__ __noinline__ UserState scan_chunk(uint32_t taddr, long ib, long iend, UserState st, bool enable,
+                                             float* __restrict__ cs, int* __restrict__ ci, int ubase, int k, int lane) {
+    float v[32];
+    tmem_ld32(taddr, v);
+    const int u = ubase + lane;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (enable && v[j] > st.thr && ib + j < iend) {
+            cs[u * LD + st.cnt] = v[j];
+            ci[u * LD + st.cnt] = (int)(ib + j);
+            ++st.cnt;
+        }
+        unsigned full = __ballot_sync(0xffffffffu, st.cnt == CAP);
+        while (full) {
+            const int l = __ffs(full) - 1;
+            full &= full - 1;
+            const float kth = compact_user(cs, ci, ubase + l, CAP, k, lane);
+            if (lane == l) { st.thr = kth; st.cnt = k; }
+        }
+    }
+    return st;
+}
+
+// compaction of every user whose list is full (state by value: keeps thr/cnt in registers)
+__device__ __noinline__ UserState compact_full(unsigned full, UserState st, float* __restrict__ cs, int* __restrict__ ci,
+                                               int ubase, int k, int lane) {
     while (full) {
         const int l = __ffs(full) - 1;
         full &= full - 1;
         const float kth = compact_user(cs, ci, ubase + l, CAP, k, lane);
-        if (lane == l) { thr = kth; cnt = k; }
+        if (lane == l) { st.thr = kth; st.cnt = k; }
     }
+    return st;
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long n_users, const uint4* __restrict__ items,
-            long i_rows, long n_items, int Kp, int fmt, int k, long item_offset, long items_per_split,
+            long i_rows, long n_items, int Kp, int fmt, int k, long item_offset, long items_per_split, int dbg,
             float* __restrict__ out_s, int64_t* __restrict__ out_i /* [splits][n_users][k] */) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int npan = Kp / 8;
     const int tile_bytes = npan * PANEL_BYTES;
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + tile_bytes;
+    uint8_t* sB = smem;
     float* cs = reinterpret_cast<float*>(sB + NSTAGE * tile_bytes);
     int* ci = reinterpret_cast<int*>(cs + TU * LD);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uintptr_t>(ci + TU * LD + 1) & ~(uintptr_t)7);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1 + 2 * NACC);
     const uint32_t bar0 = smem_u32(bars);
     auto FULL = [&](int s) { return bar0 + 8u * s; };
     auto EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
     const uint32_t AFULL = bar0 + 8u * (2 * NSTAGE);
     auto TFULL = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 1 + a); };
-    auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 3 + a); };
+    auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 1 + NACC + a); };
 
     const long u0 = (long)blockIdx.x * TU;
     const long ibeg = (long)blockIdx.y * items_per_split;
@@ -202,12 +279,12 @@ topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-        mbar_init(AFULL, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 4); }
+        mbar_init(AFULL, 4);
+        for (int a = 0; a < NACC; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 4); }
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -217,41 +294,36 @@ topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long 
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_expect_tx(AFULL, (uint32_t)tile_bytes);
-            for (int q = 0; q < npan; ++q)
-                bulk_g2s(smem_u32(sA + q * PANEL_BYTES), users + (long)q * u_rows + u0, PANEL_BYTES, AFULL);
             int stage = 0;
             uint32_t phase = 0;
             for (long t = 0; t < ntiles; ++t) {
                 mbar_wait(EMPTY(stage), phase ^ 1);
                 mbar_expect_tx(FULL(stage), (uint32_t)tile_bytes);
-                const long r0 = ibeg + t * TI;
-                uint8_t* dst = sB + stage * tile_bytes;
-                for (int q = 0; q < npan; ++q)
-                    bulk_g2s(smem_u32(dst + q * PANEL_BYTES), items + (long)q * i_rows + r0, PANEL_BYTES, FULL(stage));
+                const long r0 = ibeg + t * TI;   // multiple of 128: tile index r0 >> 7
+                bulk_g2s(smem_u32(sB + stage * tile_bytes), items + (r0 >> 7) * (long)npan * 128, (uint32_t)tile_bytes, FULL(stage));
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(fmt, fmt, TU, TI);
-            mbar_wait(AFULL, 0);
+            mbar_wait(AFULL, 0);   // the four epilogue warps have copied the user tile into TMEM
+            tc_fence_after();
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (long t = 0; t < ntiles; ++t) {
                 mbar_wait(TEMPTY(acc), acc_phase ^ 1);
                 mbar_wait(FULL(stage), phase);
                 tc_fence_after();
-                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + stage * tile_bytes);
+                const uint32_t b0 = smem_u32(sB + stage * tile_bytes);
                 for (int c = 0; c < Kp / 16; ++c) {
-                    const uint64_t ad = make_desc(a0 + (uint32_t)(2 * c * PANEL_BYTES), PANEL_BYTES, 128);
                     const uint64_t bd = make_desc(b0 + (uint32_t)(2 * c * PANEL_BYTES), PANEL_BYTES, 128);
-                    umma_f16(tmem_base + (uint32_t)(acc * TI), ad, bd, idesc, c != 0);
+                    umma_f16_ts(tmem_base + (uint32_t)(ACC0 + acc * TI), tmem_base + (uint32_t)(c * 8), bd, idesc, c != 0);
                 }
                 umma_commit(EMPTY(stage));
                 umma_commit(TFULL(acc));
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
         __syncwarp();
@@ -259,43 +331,98 @@ topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long 
         const int quarter = warp & 3;
         const int ubase = quarter * 32;
         const int u = ubase + lane;          // this lane's user within the tile == TMEM lane
-        float thr = -INFINITY;               // k-th best score at the last compaction
-        int cnt = 0;                         // entries in this user's list
+        {   // user tile -> TMEM (TS-mode A operand): row m, K chunk kk8 = one uint4 = columns 4*kk8..4*kk8+3
+            for (int c0 = 0; c0 < 16; c0 += 8) {
+                uint32_t r[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                    if (c0 + i < npan) w = __ldg(users + ((u0 >> 7) * (long)npan + (c0 + i)) * 128 + u);
+                    r[4 * i] = w.x; r[4 * i + 1] = w.y; r[4 * i + 2] = w.z; r[4 * i + 3] = w.w;
+                }
+                tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c0 * 4), r);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(AFULL);
+        }
+        UserState st;
+        st.thr = -INFINITY;
+        st.cnt = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long t = 0; t < ntiles; ++t) {
             mbar_wait(TFULL(acc), acc_phase);
             tc_fence_after();
             const long it0 = ibeg + t * TI;
-#pragma unroll 1
-            for (int ch = 0; ch < TI / 32; ++ch) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TI + ch * 32), v);
-                const long ib = it0 + ch * 32;
-                if (iend - ib < 32) {  // last tile: columns beyond the song range never qualify
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (ib + j >= iend) v[j] = -INFINITY;
+            // hot path: all four 32-column loads in flight, one wait, a max tree per chunk
+            uint32_t r0[32], r1[32], r2[32], r3[32];
+            const uint32_t tb = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ACC0 + acc * TI);
+            if (dbg >= 3) {  // timing experiment: no TMEM reads at all
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(TEMPTY(acc));
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
+            tmem_ld32_async(tb, r0);
+            tmem_ld32_async(tb + 32, r1);
+            tmem_ld32_async(tb + 64, r2);
+            tmem_ld32_async(tb + 96, r3);
+            tmem_wait_ld();
+            tmem_ld_fence(r0); tmem_ld_fence(r1); tmem_ld_fence(r2); tmem_ld_fence(r3);
+            float mx[4];
+#define DCUE_CHUNK_MAX(R, C)                                                                              \
+            {                                                                                             \
+                float m0 = __uint_as_float(R[0]), m1 = __uint_as_float(R[1]), m2 = __uint_as_float(R[2]),  \
+                      m3 = __uint_as_float(R[3]);                                                         \
+                _Pragma("unroll") for (int j = 4; j < 32; j += 4) {                                         \
+                    m0 = fmaxf(m0, __uint_as_float(R[j])); m1 = fmaxf(m1, __uint_as_float(R[j + 1]));     \
+                    m2 = fmaxf(m2, __uint_as_float(R[j + 2])); m3 = fmaxf(m3, __uint_as_float(R[j + 3])); \
+                }                                                                                         \
+                mx[C] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));                                              \
+            }
+            DCUE_CHUNK_MAX(r0, 0)
+            DCUE_CHUNK_MAX(r1, 1)
+            DCUE_CHUNK_MAX(r2, 2)
+            DCUE_CHUNK_MAX(r3, 3)
+#undef DCUE_CHUNK_MAX
+            if (it0 + TI > iend) {
+                // last tile: the slow path masks the columns beyond the song range
+                for (int c = 0; c < 4; ++c)
+                    st = scan_chunk(tb + (uint32_t)(c * 32), it0 + c * 32, iend, st, true, cs, ci, ubase, k, lane);
+            } else if (dbg < 1) {
+                // A chunk is examined only if some user of this warp beat its threshold there.  Each lane then
+                // builds the mask of its passing columns; with exactly one (the common case) the value is the
+                // chunk maximum it already holds, so it appends directly -- all 32 users in parallel.  Lanes with
+                // several candidates (warm-up) take the slow path that re-reads the chunk from TMEM.
+#define DCUE_CHUNK_SCAN(R, C)                                                                                   \
+                if (__any_sync(0xffffffffu, mx[C] > st.thr)) {                                                  \
+                    unsigned bits = 0;                                                                          \
+                    _Pragma("unroll") for (int j = 0; j < 32; ++j)                                                \
+                        bits |= (__uint_as_float(R[j]) > st.thr) ? (1u << j) : 0u;                              \
+                    const int pc = __popc(bits);                                                                \
+                    if (pc == 1) {                                                                              \
+                        cs[u * LD + st.cnt] = mx[C];                                                            \
+                        ci[u * LD + st.cnt] = (int)(it0 + (C) * 32 + __ffs(bits) - 1);                          \
+                        ++st.cnt;                                                                               \
+                    }                                                                                           \
+                    const unsigned full = __ballot_sync(0xffffffffu, st.cnt == CAP);                            \
+                    if (full) st = compact_full(full, st, cs, ci, ubase, k, lane);                              \
+                    if (__any_sync(0xffffffffu, pc > 1))                                                        \
+                        st = scan_chunk(tb + (uint32_t)((C) * 32), it0 + (C) * 32, iend, st, pc > 1, cs, ci, ubase, k, lane); \
                 }
-                float mx = v[0];
-#pragma unroll
-                for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-                if (!__any_sync(0xffffffffu, mx > thr)) continue;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (v[j] > thr) {
-                        cs[u * LD + cnt] = v[j];
-                        ci[u * LD + cnt] = (int)(ib + j);
-                        ++cnt;
-                    }
-                    const unsigned full = __ballot_sync(0xffffffffu, cnt == CAP);
-                    if (full) compact_full(full, cs, ci, ubase, k, lane, thr, cnt);
-                }
+                DCUE_CHUNK_SCAN(r0, 0)
+                DCUE_CHUNK_SCAN(r1, 1)
+                DCUE_CHUNK_SCAN(r2, 2)
+                DCUE_CHUNK_SCAN(r3, 3)
+#undef DCUE_CHUNK_SCAN
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(TEMPTY(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
         }
         // ---- finish: final sort of every user's list; lane L writes slots 4L..4L+3
         __syncwarp();
@@ -303,7 +430,7 @@ topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long 
             const int usr = ubase + uu;
             const long gu = u0 + usr;
             if (gu >= n_users) break;
-            const int n = __shfl_sync(0xffffffffu, cnt, uu);
+            const int n = __shfl_sync(0xffffffffu, st.cnt, uu);
             compact_user(cs, ci, usr, n, k, lane);
             const long ob = ((long)blockIdx.y * n_users + gu) * k;
 #pragma unroll
@@ -321,11 +448,12 @@ topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long 
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
 
-// x[rows,F] fp32 -> x/max(|x|,eps) as 16-bit K-major panels [Kp/8][round_up(rows,128)][8]
+// x[rows,F] fp32 -> x/max(|x|,eps) as 16-bit K-major operand tiles: [rows/128 tiles][Kp/8 panels][128 rows][8]
+// (tile-major, so one 128-row operand tile is ONE contiguous cp.async.bulk of Kp*256 bytes)
 __global__ void __launch_bounds__(256)
 normalize_rows_kernel(const float* __restrict__ x, long rows, int F, float eps, int Kp, int fmt, uint4* __restrict__ out,
                       long panel_rows) {
@@ -349,7 +477,7 @@ normalize_rows_kernel(const float* __restrict__ x, long rows, int F, float eps, 
         o.y = h[2] | ((unsigned)h[3] << 16);
         o.z = h[4] | ((unsigned)h[5] << 16);
         o.w = h[6] | ((unsigned)h[7] << 16);
-        out[(long)q * panel_rows + r] = o;
+        out[((r >> 7) * (Kp / 8) + q) * 128 + (r & 127)] = o;
     }
 }
 
@@ -427,13 +555,13 @@ extern "C" int dcue_topk_scores(int impl, const void* users_n, long n_users, con
     }
     // slots that are never filled (fewer than k songs in a split) must read as "missing"
     DCUE_CUDA(cudaMemsetAsync(oi, 0xff, (size_t)splits * n_users * k * sizeof(int64_t), st));
-    const size_t smem = (size_t)(1 + NSTAGE) * (Kp / 8) * PANEL_BYTES + (size_t)TU * (SLOTS + 1) * 8 + 16 +
-                        8 * (2 * NSTAGE + 5) + 16;
+    const size_t smem = (size_t)NSTAGE * (Kp / 8) * PANEL_BYTES + (size_t)TU * (SLOTS + 1) * 8 + 16 +
+                        8 * (2 * NSTAGE + 1 + 2 * NACC) + 16;
     DCUE_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((n_users + TU - 1) / TU), splits);
     topk_kernel<<<grid, NTHREADS, smem, st>>>((const uint4*)users_n, round_up_l(n_users, 128), n_users,
                                               (const uint4*)items_n, round_up_l(n_items, 128), n_items, Kp, fmt, k,
-                                              item_offset, per, os, oi);
+                                              item_offset, per, getenv("DCUE_TOPK_DEBUG") ? atoi(getenv("DCUE_TOPK_DEBUG")) : 0, os, oi);
     DCUE_LAUNCH_CHECK();
     if (splits > 1) {
         topk_merge_kernel<<<ceil_div_i(n_users, 128), 128, 0, st>>>(os, oi, splits, n_users, k, top_scores, top_idx);
