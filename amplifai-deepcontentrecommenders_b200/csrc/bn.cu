@@ -77,7 +77,8 @@ ncl_stats_kernel(const float* __restrict__ pos, int S_pos, const float* __restri
 
 // out[j] = sum_b partial[b][j]; block = 32 columns x 8 row lanes, fixed summation order
 __global__ void __launch_bounds__(256)
-reduce_partials_kernel(const double* __restrict__ partial, int nblk, int n, double* __restrict__ out) {
+reduce_partials_kernel(const double* __restrict__ partial, int nblk, int n, double* __restrict__ out,
+                       float* __restrict__ fout0 = nullptr, float* __restrict__ fout1 = nullptr, int half = 0) {
     __shared__ double red[8][33];
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + cl;
@@ -91,6 +92,9 @@ reduce_partials_kernel(const double* __restrict__ partial, int nblk, int n, doub
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += red[k][cl];
         out[j] = t;
+        // optional fp32 copies of the two halves (e.g. dbeta = sums[0:C], dgamma = sums[C:2C])
+        if (fout0 && j < half) fout0[j] = (float)t;
+        if (fout1 && j >= half) fout1[j - half] = (float)t;
     }
 }
 
@@ -170,12 +174,24 @@ affine_pack_kernel(const float* __restrict__ z, long rows, int P, int C, const f
     const int tid = threadIdx.x;
     for (long r0 = (long)blockIdx.x * TR; r0 < rows; r0 += (long)gridDim.x * TR) {
         const int C4 = C >> 2;  // C % 4 == 0 (checked by the host wrapper)
-        for (int e = tid; e < TR * C4; e += 256) {
+        constexpr int NIT = TR * 32 / 256;
+        float4 v4[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {   // issue every load of the tile first
+            const int e = tid + it * 256;
             const int rl = e / C4, c = (e - rl * C4) * 4;
             const long r = r0 + rl;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            v4[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < TR * C4 && r < rows) v4[it] = __ldg(reinterpret_cast<const float4*>(z + r * C + c));
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int e = tid + it * 256;
+            if (e >= TR * C4) continue;
+            const int rl = e / C4, c = (e - rl * C4) * 4;
+            const long r = r0 + rl;
+            float4 v = v4[it];
             if (r < rows) {
-                v = __ldg(reinterpret_cast<const float4*>(z + r * C + c));
                 if (scale) {
                     const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
                     v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
@@ -288,40 +304,69 @@ bn_relu_unpool_bwd_kernel(const float* __restrict__ dy, int lddy, const float* _
                           double* __restrict__ bias_partial) {
     __shared__ float tile[TR][TLD];
     __shared__ uint8_t ctile[TR][TLD + 3];
+    __shared__ long prow_s[TR];
+    __shared__ float k_s1[128], k_mean[128], k_rs2[128], k_scale[128];
     const int tid = threadIdx.x;
     const float gs = gscale ? gscale[0] : 1.f;
+    if (tid < 128) {
+        // dz = scale * (dy - s1/n - (z - mean) * rstd * s2/n): per-channel constants once per block
+        const bool on = tid < C;
+        const double inv_n = 1.0 / count;
+        k_s1[tid] = (on && sums) ? (float)(sums[tid] * inv_n) : 0.f;
+        k_mean[tid] = (on && sums) ? mean[tid] : 0.f;
+        k_rs2[tid] = (on && sums) ? (float)((double)rstd[tid] * sums[C + tid] * inv_n) : 0.f;
+        k_scale[tid] = (on && scale) ? scale[tid] : 1.f;
+    }
+    __syncthreads();
     double bias_acc = 0.0;  // thread tid<C accumulates channel tid
-    const float invn = (float)(1.0 / count);
     const float invP = 1.f / (float)P;
     for (long r0 = (long)blockIdx.x * TR; r0 < rows; r0 += (long)gridDim.x * TR) {
         const int C4 = C >> 2;  // C % 4 == 0 (checked by the host wrapper)
-        for (int e = tid; e < TR * C4; e += 256) {
+        if (tid < TR) {  // first panel row of each pooled row of this tile (-1 = beyond the end)
+            const long r = r0 + tid;
+            const long s = r / P;
+            prow_s[tid] = r < rows ? s * Lp + (r - s * P) * pool : -1;
+        }
+        // all global loads of the tile are issued before any is consumed: 12 independent requests per thread
+        // in flight (Little's law: the one-load-at-a-time version sat at 2.5 TB/s)
+        constexpr int NIT = TR * 32 / 256;   // 4 iterations cover 32 rows x (C/4 <= 32) float4 columns
+        float4 g4[NIT], z4[NIT];
+        uchar4 c4[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int e = tid + it * 256;
+            const int rl = e / C4, c = (e - rl * C4) * 4;
+            const long r = r0 + rl;
+            g4[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            z4[it] = g4[it];
+            c4[it] = make_uchar4(0, 0, 0, 0);
+            if (e < TR * C4 && r < rows) {
+                g4[it] = __ldg(reinterpret_cast<const float4*>(dy + r * lddy + c));
+                z4[it] = __ldg(reinterpret_cast<const float4*>(z + r * C + c));
+                if (code) c4[it] = *reinterpret_cast<const uchar4*>(code + r * C + c);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int e = tid + it * 256;
+            if (e >= TR * C4) continue;
             const int rl = e / C4, c = (e - rl * C4) * 4;
             const long r = r0 + rl;
             float v[4] = {0.f, 0.f, 0.f, 0.f};
-            uint8_t cd[4] = {0, 0, 0, 0};
+            const uint8_t cd[4] = {c4[it].x, c4[it].y, c4[it].z, c4[it].w};
             if (r < rows) {
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(dy + r * lddy + c));
-                const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + r * C + c));
-                float g[4] = {g4.x, g4.y, g4.z, g4.w};
-                const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+                float g[4] = {g4[it].x, g4[it].y, g4[it].z, g4[it].w};
+                const float zz[4] = {z4[it].x, z4[it].y, z4[it].z, z4[it].w};
                 if (dtp) {
                     const float* dp = dtp + (r / P) * lddtp + c;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) g[j] += dp[j] * invP;
                 }
-                if (code) {
-                    const uchar4 c4 = *reinterpret_cast<const uchar4*>(code + r * C + c);
-                    cd[0] = c4.x; cd[1] = c4.y; cd[2] = c4.z; cd[3] = c4.w;
-                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float gg = g[j];
-                    if (sums) {
-                        const float xh = (zz[j] - mean[c + j]) * rstd[c + j];
-                        gg = gg - (float)sums[c + j] * invn - xh * ((float)sums[C + c + j] * invn);
-                    }
-                    if (scale) gg *= scale[c + j];
+                    if (sums) gg = gg - k_s1[c + j] - (zz[j] - k_mean[c + j]) * k_rs2[c + j];
+                    gg *= k_scale[c + j];
                     v[j] = zz[j] > 0.f ? gg : 0.f;
                 }
                 if (dz_out) *reinterpret_cast<float4*>(dz_out + r * C + c) = make_float4(v[0], v[1], v[2], v[3]);
@@ -331,31 +376,27 @@ bn_relu_unpool_bwd_kernel(const float* __restrict__ dy, int lddy, const float* _
         }
         __syncthreads();
         if (panel) {
-            const int rl = tid & 31;
-            const long r = r0 + rl;
-            if (r < rows) {
-                const long s = r / P;
-                const int p = (int)(r - s * P);
-                const long prow = s * Lp + (long)p * pool;
-                for (int q = tid >> 5; q < C / 8; q += 8) {
-                    unsigned short h[8];
-                    uint8_t cd[8];
+            // consecutive lanes write consecutive 16-byte chunks of one panel: chunk = (pooled row, pool slot),
+            // so every store instruction covers 512 contiguous bytes (rows of a tile are consecutive in the panel)
+            const int lane = tid & 31;
+            const int chunks = TR * pool;
+            const int sh = pool == 4 ? 2 : (pool == 2 ? 1 : 0);
+            for (int q = tid >> 5; q < C / 8; q += 8) {
+                for (int cidx = lane; cidx < chunks; cidx += 32) {
+                    const int rl = pool == 8 ? cidx >> 3 : cidx >> sh;
+                    const int pi = cidx - (pool == 8 ? rl << 3 : rl << sh);
+                    const long prow = prow_s[rl];
+                    if (prow < 0) continue;
+                    unsigned short w[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        h[j] = cvt_f32_to16(tile[rl][q * 8 + j] * gs, fmt);
-                        cd[j] = ctile[rl][q * 8 + j];
-                    }
-                    for (int i = 0; i < pool; ++i) {
-                        unsigned short w[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) w[j] = cd[j] == i ? h[j] : (unsigned short)0;
-                        uint4 o;
-                        o.x = w[0] | ((unsigned)w[1] << 16);
-                        o.y = w[2] | ((unsigned)w[3] << 16);
-                        o.z = w[4] | ((unsigned)w[5] << 16);
-                        o.w = w[6] | ((unsigned)w[7] << 16);
-                        panel[(long)q * panel_rows + prow + i] = o;
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        w[j] = ctile[rl][q * 8 + j] == pi ? cvt_f32_to16(tile[rl][q * 8 + j] * gs, fmt) : (unsigned short)0;
+                    uint4 o;
+                    o.x = w[0] | ((unsigned)w[1] << 16);
+                    o.y = w[2] | ((unsigned)w[3] << 16);
+                    o.z = w[4] | ((unsigned)w[5] << 16);
+                    o.w = w[6] | ((unsigned)w[7] << 16);
+                    panel[(long)q * panel_rows + prow + pi] = o;
                 }
             }
         }
@@ -544,8 +585,8 @@ extern "C" size_t dcue_bn_bwd_ws_bytes(int C) {
 }
 
 extern "C" int dcue_bn_bwd_reduce(const float* dy, int lddy, const float* dtp, int lddtp, const float* z, const float* mean,
-                                  const float* rstd, int S, int P, int C, double* sums, float* absmax, void* ws,
-                                  size_t ws_bytes, void* stream) {
+                                  const float* rstd, int S, int P, int C, double* sums, float* absmax, float* dbeta,
+                                  float* dgamma, void* ws, size_t ws_bytes, void* stream) {
     DCUE_CHECK_ARG(dy && z && mean && rstd && sums && ws && S >= 0 && P > 0 && C > 0 && C <= 128 && C % 4 == 0);
     DCUE_CHECK_ARG(lddy >= C && lddy % 4 == 0 && ((uintptr_t)dy & 15) == 0);
     cudaStream_t st = (cudaStream_t)stream;
@@ -556,7 +597,7 @@ extern "C" int dcue_bn_bwd_reduce(const float* dy, int lddy, const float* dtp, i
     if (ws_bytes < (size_t)grid * (2 * C + 1) * sizeof(double)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_bn_bwd_reduce: workspace too small");
     bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, lddy, dtp, lddtp, z, mean, rstd, rows, P, C, (double*)ws);
     DCUE_LAUNCH_CHECK();
-    reduce_partials_kernel<<<ceil_div_i(2 * C, 32), 256, 0, st>>>((const double*)ws, grid, 2 * C, sums);
+    reduce_partials_kernel<<<ceil_div_i(2 * C, 32), 256, 0, st>>>((const double*)ws, grid, 2 * C, sums, dbeta, dgamma, C);
     DCUE_LAUNCH_CHECK();
     if (absmax) {
         reduce_max_kernel<<<1, 256, 0, st>>>((const double*)ws + (size_t)grid * 2 * C, grid, absmax);
@@ -569,11 +610,11 @@ extern "C" int dcue_bn_relu_unpool_bwd(const float* dy, int lddy, const float* d
                                        const float* scale, const float* mean, const float* rstd, const double* sums,
                                        double count, int S, int P, int C, int pool, int Lp, void* dy_panel,
                                        long panel_rows, int fmt, const float* gscale, float* dz_out, double* bias_sums,
-                                       void* ws, size_t ws_bytes, void* stream) {
+                                       float* bias_out, void* ws, size_t ws_bytes, void* stream) {
     DCUE_CHECK_ARG(dy && z && S >= 0 && P > 0 && C > 0 && C <= 128 && C % 4 == 0 && (dy_panel || dz_out) && lddy >= C &&
                    lddy % 4 == 0 && ((uintptr_t)dy & 15) == 0);
     DCUE_CHECK_ARG(!sums || (mean && rstd && count > 0));
-    DCUE_CHECK_ARG(!dy_panel || (code && C % 8 == 0 && pool >= 1 && pool <= 8 && Lp >= P * pool && panel_rows >= (long)S * Lp));
+    DCUE_CHECK_ARG(!dy_panel || (code && C % 8 == 0 && (pool == 1 || pool == 2 || pool == 4 || pool == 8) && Lp >= P * pool && panel_rows >= (long)S * Lp));
     cudaStream_t st = (cudaStream_t)stream;
     const long rows = (long)S * P;
     if (rows == 0) return 0;
@@ -585,7 +626,7 @@ extern "C" int dcue_bn_relu_unpool_bwd(const float* dy, int lddy, const float* d
                                                     panel_rows, fmt, gscale, dz_out, bias_sums ? (double*)ws : nullptr);
     DCUE_LAUNCH_CHECK();
     if (bias_sums) {
-        reduce_partials_kernel<<<ceil_div_i(C, 32), 256, 0, st>>>((const double*)ws, grid, C, bias_sums);
+        reduce_partials_kernel<<<ceil_div_i(C, 32), 256, 0, st>>>((const double*)ws, grid, C, bias_sums, bias_out, nullptr, C);
         DCUE_LAUNCH_CHECK();
     }
     return 0;

@@ -228,7 +228,7 @@ class SongTowerFn(torch.autograd.Function):
         if has_bn:
             if training:  # sum z, sum z^2 via the backward-reduce kernel with mean=0, rstd=1
                 L.call("dcue_bn_bwd_reduce", ws.z5.data_ptr(), F, None, 0, ws.z5.data_ptr(), ws.zero128.data_ptr(),
-                       ws.one128.data_ptr(), S, 1, F, ws.sums[5].data_ptr(), None, scratch, nscr, st)
+                       ws.one128.data_ptr(), S, 1, F, ws.sums[5].data_ptr(), None, None, None, scratch, nscr, st)
             bn_finalize(5, S, F)
             sc, sh = ws.bnp[5, 0].data_ptr(), ws.bnp[5, 1].data_ptr()
         else:
@@ -282,14 +282,18 @@ class SongTowerFn(torch.autograd.Function):
             dgamma/dbeta when BN uses batch statistics, and max|dy| for the 16-bit gradient scale."""
             mean_p = ws.bnp[i, 2].data_ptr() if bn_train else ws.zero128.data_ptr()
             rstd_p = ws.bnp[i, 3].data_ptr() if bn_train else ws.one128.data_ptr()
+            gw = gb = None
+            direct = bn_train and dp is None  # single GPU: the reducer emits dgamma / dbeta in fp32 directly
+            if bn_train:
+                gw, gb = torch.empty(C_, **f32), torch.empty(C_, **f32)
             L.call("dcue_bn_bwd_reduce", dy_ptr, lddy, dtp_ptr, lddtp, z.data_ptr(), mean_p, rstd_p, S, P_, C_,
-                   b["dsums"][i].data_ptr(), b["amax"][i:].data_ptr() if want_scale else None, scratch, nscr, st)
+                   b["dsums"][i].data_ptr(), b["amax"][i:].data_ptr() if want_scale else None,
+                   gb.data_ptr() if direct else None, gw.data_ptr() if direct else None, scratch, nscr, st)
             if bn_train:
                 if dp is not None:
                     dp.all_reduce_sum(b["dsums"][i])
-                gw, gb = torch.empty(C_, **f32), torch.empty(C_, **f32)
-                L.call("dcue_cvt_f64_f32", b["dsums"][i][C_:].data_ptr(), C_, 1.0, gw.data_ptr(), st)
-                L.call("dcue_cvt_f64_f32", b["dsums"][i].data_ptr(), C_, 1.0, gb.data_ptr(), st)
+                    L.call("dcue_cvt_f64_f32", b["dsums"][i][C_:].data_ptr(), C_, 1.0, gw.data_ptr(), st)
+                    L.call("dcue_cvt_f64_f32", b["dsums"][i].data_ptr(), C_, 1.0, gb.data_ptr(), st)
                 grads["bn%d.weight" % i], grads["bn%d.bias" % i] = gw, gb
             elif has_bn:
                 grads["bn%d.weight" % i] = grads["bn%d.bias" % i] = None  # eval-mode backward: constants
@@ -312,7 +316,7 @@ class SongTowerFn(torch.autograd.Function):
         L.call("dcue_bn_relu_unpool_bwd", dy5.data_ptr(), Kfc, None, 0, ws.z5.data_ptr(), None,
                ws.bnp[5, 0].data_ptr() if has_bn else None, ws.bnp[5, 2].data_ptr() if has_bn else None,
                ws.bnp[5, 3].data_ptr() if has_bn else None, b["dsums"][5].data_ptr() if bn_train else None,
-               float(S * world), S, 1, F, 1, 1, None, 0, gfmt, None, dz5.data_ptr(), None, scratch, nscr, st)
+               float(S * world), S, 1, F, 1, 1, None, 0, gfmt, None, dz5.data_ptr(), None, None, scratch, nscr, st)
         gW5, gb5 = torch.empty(F, H, 1, **f32), torch.empty(F, **f32)
         L.call("dcue_linear_wgrad", dz5.data_ptr(), F, ws.y4.data_ptr(), H, S, H, F, gW5.data_ptr(), gb5.data_ptr(), scratch,
                nscr, st)
@@ -326,13 +330,12 @@ class SongTowerFn(torch.autograd.Function):
             bn_sums(i, dy.data_ptr(), H, dtp, Kfc, ws.z[i - 1], g["P"], H)
             gsc = b["gscale"][i].data_ptr()
             dYp = b["dY"][i - 1]
+            gb_i = torch.empty(H, **f32)
             L.call("dcue_bn_relu_unpool_bwd", dy.data_ptr(), H, dtp, Kfc, ws.z[i - 1].data_ptr(), ws.code[i - 1].data_ptr(),
                    ws.bnp[i, 0].data_ptr() if has_bn else None, ws.bnp[i, 2].data_ptr() if has_bn else None,
                    ws.bnp[i, 3].data_ptr() if has_bn else None, b["dsums"][i].data_ptr() if bn_train else None,
                    float(S * g["P"] * world), S, g["P"], H, g["pool"], g["Lp"], dYp.base, dYp.panel_rows, gfmt, gsc, None,
-                   b["bsum"].data_ptr(), scratch, nscr, st)
-            gb_i = torch.empty(H, **f32)
-            L.call("dcue_cvt_f64_f32", b["bsum"].data_ptr(), H, 1.0, gb_i.data_ptr(), st)
+                   b["bsum"].data_ptr(), gb_i.data_ptr(), scratch, nscr, st)
             gW_i = torch.empty(H, 128, g["k"], **f32)
             L.call("dcue_conv_wgrad", impl, dYp.base, dYp.panel_rows, gfmt, ws.X[i - 1].base, ws.X[i - 1].panel_rows, fmt,
                    S * g["Lp"], g["k"], 128, H, gsc, gW_i.data_ptr(), scratch, nscr, st)

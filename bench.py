@@ -38,35 +38,48 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled every 20 ms DURING the timed region (NVML in-process;
+    falls back to `nvidia-smi -lms` when pynvml is unavailable)."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.samples, self.stop_flag, self.maxclk, self.err = [], False, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.maxclk = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except OSError:
-            self.proc = None
+        except Exception as e:  # noqa: BLE001
+            self.err = "nvml unavailable: %s" % e
+            self.t = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((clk, rs))
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+                return
+            time.sleep(0.02)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
-        if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(int(r[0]) for r in rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+        self.stop_flag = True
+        if self.t is not None:
+            self.t.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.maxclk, "reasons": [self.err or "no samples"]}
+        clk = sorted(c for c, _ in self.samples)
+        reasons = [n for n, bit in self.BAD.items() if any(r & bit for _, r in self.samples)]
+        return {"sm_mhz": clk[len(clk) // 2], "sm_max_mhz": self.maxclk, "reasons": reasons, "samples": len(self.samples)}
 
 
 # ------------------------------------------------------------------------------------- CPU arm
@@ -138,9 +151,14 @@ def workload_config(args, extra=None):
 
 
 # ------------------------------------------------------------------------------------- GPU arm
+# DRAM bytes per launch at S = 21504 from the ncu --set full captures in profiles/ (scaled linearly with S)
+NCU_TRAFFIC_S21504 = {"conv1_fwd_pool": 749.1e6 + 419.6e6}
+
+
 def kernel_roofline(pkg, S, dev):
-    """CUDA-event timing of the three layer-1 tensor-core kernels on this stream; the slowest is the
-    dominant kernel of the step.  achieved = algorithmic FLOPs per launch / avg launch time."""
+    """CUDA-event timing, on this stream, of the step's heaviest kernels at layer-1 size: the two tcgen05
+    GEMMs (tensor-bound) and the BatchNorm-backward/unpool sweep (HBM-bound).  achieved = algorithmic
+    FLOPs (bytes) per launch / average launch time."""
     L, ops = pkg._lib, pkg.ops
     geo = ops.tower_geometry(CFG["frames"])[0]
     st = L.stream()
@@ -149,24 +167,31 @@ def kernel_roofline(pkg, S, dev):
     dY.buf.random_(0, 15000)
     wp = torch.randint(0, 15000, (128 * 4 * 128,), dtype=torch.int16, device=dev)
     bias = torch.zeros(128, device=dev)
-    z = torch.empty(S * geo["P"], 128, device=dev)
-    code = torch.empty(S * geo["P"], 128, dtype=torch.uint8, device=dev)
+    rows = S * geo["P"]
+    z = torch.rand(rows, 128, device=dev)
+    dyn = torch.randn(rows, 128, device=dev)
+    code = torch.randint(0, 4, (rows, 128), dtype=torch.uint8, device=dev)
     sums = torch.zeros(256, dtype=torch.float64, device=dev)
-    dx = torch.empty(S * geo["Lin"], 128, device=dev)
+    bsum = torch.zeros(128, dtype=torch.float64, device=dev)
+    bn = torch.ones(4, 128, device=dev)
+    gsc = torch.ones(2, device=dev)
     dW = torch.empty(128, 128, 4, device=dev)
-    nws = L.query("dcue_conv_ws_bytes", L.IMPL_TC, S, geo["Lp"], 4, 128, 128)
+    nws = max(L.query("dcue_conv_ws_bytes", L.IMPL_TC, S, geo["Lp"], 4, 128, 128), L.query("dcue_bn_bwd_ws_bytes", 128))
     ws = torch.empty(nws, dtype=torch.uint8, device=dev)
     calls = {
-        "conv1_fwd_pool": lambda: L.call("dcue_conv_pool_fwd", L.IMPL_TC, X.base, X.panel_rows, 0, wp.data_ptr(), bias.data_ptr(), None, S,
-                                         geo["Lp"], geo["Lin"], 2, geo["P"], 4, 4, 128, 128, z.data_ptr(), code.data_ptr(), sums.data_ptr(),
-                                         ws.data_ptr(), nws, st),
-        "conv1_dgrad": lambda: L.call("dcue_conv_dgrad", L.IMPL_TC, dY.base, dY.panel_rows, 0, wp.data_ptr(), 0, S, geo["Lp"], geo["Lin"],
-                                      2, 4, 128, 128, None, dx.data_ptr(), ws.data_ptr(), nws, st),
-        "conv1_wgrad": lambda: L.call("dcue_conv_wgrad", L.IMPL_TC, dY.base, dY.panel_rows, 0, X.base, X.panel_rows, 0, S * geo["Lp"], 4,
-                                      128, 128, None, dW.data_ptr(), ws.data_ptr(), nws, st),
+        "conv1_fwd_pool": (lambda: L.call("dcue_conv_pool_fwd", L.IMPL_TC, X.base, X.panel_rows, 0, wp.data_ptr(), bias.data_ptr(), None, S,
+                                          geo["Lp"], geo["Lin"], 2, geo["P"], 4, 4, 128, 128, z.data_ptr(), code.data_ptr(),
+                                          sums.data_ptr(), ws.data_ptr(), nws, st), "tensor", L1_FLOP_PER_SPEC * S),
+        "conv1_wgrad": (lambda: L.call("dcue_conv_wgrad", L.IMPL_TC, dY.base, dY.panel_rows, 0, X.base, X.panel_rows, 0, S * geo["Lp"], 4,
+                                       128, 128, None, dW.data_ptr(), ws.data_ptr(), nws, st), "tensor", L1_FLOP_PER_SPEC * S),
+        # reads dy, z (fp32) and the argmax code, writes the 4x unpooled fp16 panel: 1152 + 1024 B per pooled row
+        "bn_relu_unpool_bwd1": (lambda: L.call("dcue_bn_relu_unpool_bwd", dyn.data_ptr(), 128, None, 0, z.data_ptr(), code.data_ptr(),
+                                               bn[0].data_ptr(), bn[2].data_ptr(), bn[3].data_ptr(), sums.data_ptr(), float(rows), S,
+                                               geo["P"], 128, 4, geo["Lp"], dY.base, dY.panel_rows, 0, gsc.data_ptr(), None,
+                                               bsum.data_ptr(), None, ws.data_ptr(), nws, st), "hbm", (1152 + 1024) * rows),
     }
     res = {}
-    for name, fn in calls.items():
+    for name, (fn, bound, work) in calls.items():
         for _ in range(3):
             fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -178,7 +203,8 @@ def kernel_roofline(pkg, S, dev):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        res[name] = {"ms": ms, "tflops": L1_FLOP_PER_SPEC * S / (ms * 1e-3) / 1e12}
+        res[name] = {"ms": ms, "bound": bound, "achieved": work / (ms * 1e-3) / (1e12 if bound == "tensor" else 1e9),
+                     "unit": "TFLOP/s" if bound == "tensor" else "GB/s"}
     return res
 
 
@@ -290,13 +316,17 @@ def run_ours(args):
         tf_peak, hbm_peak, which = peaks()
         kern = kernel_roofline(pkg, B * (1 + N), dev)
         top = max(kern, key=lambda k: kern[k]["ms"])
+        peak = tf_peak if kern[top]["bound"] == "tensor" else hbm_peak
+        traffic = NCU_TRAFFIC_S21504.get(top)
+        traffic = None if traffic is None else traffic * (B * (1 + N)) / 21504.0
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f16", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps},
                "gpu_launches": int(launches), "final_loss": final_loss,
-               "roofline": {"bound": "tensor", "kernel": top, "achieved": kern[top]["tflops"], "peak": tf_peak, "unit": "TFLOP/s",
-                            "frac": kern[top]["tflops"] / tf_peak, "traffic": None, "peak_source": which + " (burst bf16 cuBLAS)",
+               "roofline": {"bound": kern[top]["bound"], "kernel": top, "achieved": kern[top]["achieved"], "peak": peak,
+                            "unit": kern[top]["unit"], "frac": kern[top]["achieved"] / peak, "traffic": traffic,
+                            "peak_source": which + (" (burst bf16 cuBLAS)" if kern[top]["bound"] == "tensor" else " (copy)"),
                             "kernels": kern}}
     if world > 1:
         dist.barrier()

@@ -168,7 +168,9 @@ int dcue_affine_pack(const float* z, int S, int P, int C, const float* scale, co
  * average, added as dtp/P to every row. */
 int dcue_bn_bwd_reduce(const float* dy, int lddy, const float* dtp, int lddtp, const float* z, const float* mean,
                        const float* rstd, int S, int P, int C, double* sums,
-                       float* absmax /* nullable: max |dy (+dtp/P)| */, void* ws, size_t ws_bytes, void* stream);
+                       float* absmax /* nullable: max |dy (+dtp/P)| */,
+                       float* dbeta /* nullable: fp32 copy of sums[0:C] */, float* dgamma /* nullable: sums[C:2C] */,
+                       void* ws, size_t ws_bytes, void* stream);
 /* Power-of-two scale for the 16-bit conv-backward operand (tcgen05 kind::f16 needs both operands in
  * one format, and unscaled fp16 gradients would underflow): out = {s, 1/s}, s the largest power of two
  * with s*bound <= 2^14, bound = max_c|scale_c| * absmax * (count > 0 ? 2 + sqrt(count) : 1) >= max|dz|. */
@@ -186,7 +188,8 @@ int dcue_bn_relu_unpool_bwd(const float* dy, int lddy, const float* dtp, int ldd
                             const double* sums, double count, int S, int P, int C, int pool, int Lp,
                             void* dy_panel, long panel_rows, int fmt,
                             const float* gscale /* panel values are multiplied by gscale[0]; nullable */,
-                            float* dz_out, double* bias_sums, void* ws, size_t ws_bytes, void* stream);
+                            float* dz_out, double* bias_sums, float* bias_out /* nullable: fp32 copy of bias_sums */,
+                            void* ws, size_t ws_bytes, void* stream);
 
 /* bn0 backward reductions (truedcuemel1dbn.py:79): dx = channels-last [S*L, C] gradient of the
  * normalised input (layer1 dgrad), pos/neg = the NCL fp32 input; sums = double[2*C] as above.

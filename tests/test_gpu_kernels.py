@@ -225,11 +225,11 @@ def test_conv_backward_kernels(impl, gi, S):
     gsc = torch.zeros(2, device=DEV)
     zero, one = torch.zeros(128, device=DEV), torch.ones(128, device=DEV)
     L.call("dcue_bn_bwd_reduce", dyn_d.data_ptr(), 128, None, 0, z.data_ptr(), zero.data_ptr(), one.data_ptr(), S, geo["P"], 128,
-           sums.data_ptr(), amax.data_ptr(), ws.data_ptr(), nws, st)
+           sums.data_ptr(), amax.data_ptr(), None, None, ws.data_ptr(), nws, st)
     L.call("dcue_grad_scale", amax.data_ptr(), None, 128, 0.0, gsc.data_ptr(), st)
     L.call("dcue_bn_relu_unpool_bwd", dyn_d.data_ptr(), 128, None, 0, z.data_ptr(), code.data_ptr(), None, None, None,
            None, 1.0, S, geo["P"], 128, geo["pool"], geo["Lp"], dY.base, dY.panel_rows, L.FMT_F16, gsc.data_ptr(), None,
-           bsum.data_ptr(), ws.data_ptr(), nws, st)
+           bsum.data_ptr(), None, ws.data_ptr(), nws, st)
     assert abs(amax.item() - dyn.abs().max().item()) < 1e-12
     sc = gsc.cpu()
     import math
