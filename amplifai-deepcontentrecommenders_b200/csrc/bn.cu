@@ -7,21 +7,43 @@
 
 namespace {
 
+// Where spectrogram s lives: either the s-th row of `pos` / `neg` (dense API, row stride L) or a crop of a
+// resident song pool, pool[idx[s], :, off[s] : off[s]+L] (index API, row stride T).  Out-of-range entries
+// raise the error flag and read song 0 / offset 0.
+struct SpecSrc {
+    const float* pos; const float* neg; int S_pos;
+    const int64_t* idx; const int32_t* off; long T; long n_songs; int* err;
+    __device__ __forceinline__ const float* base(long s, int C, int L, long& row_stride) const {
+        if (idx) {
+            long i = idx[s];
+            long o = off ? off[s] : 0;
+            if (i < 0 || i >= n_songs || o < 0 || o + L > T) {
+                if (err) atomicExch(err, 1);
+                i = 0;
+                o = 0;
+            }
+            row_stride = T;
+            return pos + i * (long)C * T + o;
+        }
+        row_stride = L;
+        return s < S_pos ? pos + s * (long)C * L : neg + (s - S_pos) * (long)C * L;
+    }
+};
+
 // ------------------------------------------------------------------ NCL input statistics
 // block = 8 warps; warp w owns channels w, w+8, ... (<=16 per warp for C=128); lanes stride
 // the L frames of one (s,c) row; per-lane fp32 partials, reduced across lanes/blocks in fp64.
 constexpr int STAT_MAXC_PER_WARP = 16;
 
 __global__ void __launch_bounds__(256)
-ncl_stats_kernel(const float* __restrict__ pos, int S_pos, const float* __restrict__ neg, int S_neg, int C, int L,
-                 double* __restrict__ partial /* [grid][2][C] */) {
+ncl_stats_kernel(SpecSrc src, int S, int C, int L, double* __restrict__ partial /* [grid][2][C] */) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float s1[STAT_MAXC_PER_WARP], s2[STAT_MAXC_PER_WARP];
 #pragma unroll
     for (int i = 0; i < STAT_MAXC_PER_WARP; ++i) s1[i] = s2[i] = 0.f;
-    const int S = S_pos + S_neg;
     for (int s = blockIdx.x; s < S; s += gridDim.x) {
-        const float* base = s < S_pos ? pos + (long)s * C * L : neg + (long)(s - S_pos) * C * L;
+        long rs;
+        const float* base = src.base(s, C, L, rs);
         if (L <= 160) {
             // 4 channel rows x 5 strided frames = 20 independent loads in flight per lane
 #pragma unroll
@@ -30,7 +52,7 @@ ncl_stats_kernel(const float* __restrict__ pos, int S_pos, const float* __restri
 #pragma unroll
                 for (int ii = 0; ii < 4; ++ii) {
                     const int c = w + 8 * (i0 + ii);
-                    const float* row = base + (long)c * L;
+                    const float* row = base + (long)c * rs;
 #pragma unroll
                     for (int k = 0; k < 5; ++k) {
                         const int t = lane + 32 * k;
@@ -51,7 +73,7 @@ ncl_stats_kernel(const float* __restrict__ pos, int S_pos, const float* __restri
             for (int i = 0; i < STAT_MAXC_PER_WARP; ++i) {
                 const int c = w + 8 * i;
                 if (c < C) {
-                    const float* row = base + (long)c * L;
+                    const float* row = base + (long)c * rs;
                     float a = 0.f, b = 0.f;
                     for (int t = lane; t < L; t += 32) {
                         const float v = __ldg(row + t);
@@ -75,22 +97,22 @@ ncl_stats_kernel(const float* __restrict__ pos, int S_pos, const float* __restri
     }
 }
 
-// out[j] = sum_b partial[b][j]; block = 32 columns x 8 row lanes, fixed summation order
+// out[j] = sum_b partial[b][j]; block = 8 columns x 32 row lanes, fixed summation order (deterministic)
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const double* __restrict__ partial, int nblk, int n, double* __restrict__ out,
                        float* __restrict__ fout0 = nullptr, float* __restrict__ fout1 = nullptr, int half = 0) {
-    __shared__ double red[8][33];
-    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int j = blockIdx.x * 32 + cl;
+    __shared__ double red[32][9];
+    const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    const int j = blockIdx.x * 8 + cl;
     double s = 0.0;
     if (j < n)
-        for (int b = rl; b < nblk; b += 8) s += partial[(long)b * n + j];
+        for (int b = rl; b < nblk; b += 32) s += partial[(long)b * n + j];
     red[rl][cl] = s;
     __syncthreads();
     if (rl == 0 && j < n) {
         double t = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += red[k][cl];
+        for (int k = 0; k < 32; ++k) t += red[k][cl];
         out[j] = t;
         // optional fp32 copies of the two halves (e.g. dbeta = sums[0:C], dgamma = sums[C:2C])
         if (fout0 && j < half) fout0[j] = (float)t;
@@ -132,19 +154,19 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 // thread <-> (spectrogram s, panel q, frame t): 8 coalesced loads (one per channel of the
 // panel), one 16-byte store; consecutive threads walk t so both sides are coalesced.
 __global__ void __launch_bounds__(256)
-ncl_pack_kernel(const float* __restrict__ pos, int S_pos, const float* __restrict__ neg, int S_neg, int C, int L,
-                const float* __restrict__ scale, const float* __restrict__ shift, uint4* __restrict__ panel,
-                long panel_rows, int Lp, int pad, int fmt) {
-    const long total = (long)(S_pos + S_neg) * (C / 8) * L;
+ncl_pack_kernel(SpecSrc src, int S, int C, int L, const float* __restrict__ scale, const float* __restrict__ shift,
+                uint4* __restrict__ panel, long panel_rows, int Lp, int pad, int fmt) {
+    const long total = (long)S * (C / 8) * L;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int t = (int)(i % L);
         const long sq = i / L;
         const int q = (int)(sq % (C / 8));
         const long s = sq / (C / 8);
-        const float* base = (s < S_pos ? pos + s * (long)C * L : neg + (s - S_pos) * (long)C * L) + (long)(q * 8) * L + t;
+        long rs;
+        const float* base = src.base(s, C, L, rs) + (long)(q * 8) * rs + t;
         float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldg(base + (long)j * L);
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(base + (long)j * rs);
         unsigned short h[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -515,20 +537,31 @@ extern "C" size_t dcue_ncl_stats_ws_bytes(int C) {
     return (size_t)dcue_num_sms() * STAT_BLOCKS_PER_SM * 2 * (size_t)C * sizeof(double) + 256;
 }
 
+static int ncl_stats_impl(const SpecSrc& src, int S, int C, int L, double* sums, void* ws, size_t ws_bytes, cudaStream_t st) {
+    int grid = dcue_num_sms() * STAT_BLOCKS_PER_SM;
+    if (grid > S) grid = S > 0 ? S : 1;
+    if (ws_bytes < (size_t)grid * 2 * C * sizeof(double)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_ncl_stats: workspace too small");
+    ncl_stats_kernel<<<grid, 256, 0, st>>>(src, S, C, L, (double*)ws);
+    DCUE_LAUNCH_CHECK();
+    reduce_partials_kernel<<<ceil_div_i(2 * C, 8), 256, 0, st>>>((const double*)ws, grid, 2 * C, sums);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int dcue_ncl_stats(const float* pos, int S_pos, const float* neg, int S_neg, int C, int L, double* sums,
                               void* ws, size_t ws_bytes, void* stream) {
     DCUE_CHECK_ARG(sums && ws && S_pos >= 0 && S_neg >= 0 && (pos || S_pos == 0) && (neg || S_neg == 0) && L > 0);
     DCUE_CHECK_ARG(C > 0 && C <= 8 * STAT_MAXC_PER_WARP);
-    cudaStream_t st = (cudaStream_t)stream;
-    const int S = S_pos + S_neg;
-    int grid = dcue_num_sms() * STAT_BLOCKS_PER_SM;
-    if (grid > S) grid = S > 0 ? S : 1;
-    if (ws_bytes < (size_t)grid * 2 * C * sizeof(double)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_ncl_stats: workspace too small");
-    ncl_stats_kernel<<<grid, 256, 0, st>>>(pos, S_pos, neg, S_neg, C, L, (double*)ws);
-    DCUE_LAUNCH_CHECK();
-    reduce_partials_kernel<<<ceil_div_i(2 * C, 32), 256, 0, st>>>((const double*)ws, grid, 2 * C, sums);
-    DCUE_LAUNCH_CHECK();
-    return 0;
+    SpecSrc src{pos, neg, S_pos, nullptr, nullptr, 0, 0, nullptr};
+    return ncl_stats_impl(src, S_pos + S_neg, C, L, sums, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dcue_ncl_stats_indexed(const float* pool, long n_songs, long T, const int64_t* idx, const int32_t* off, int S,
+                                      int C, int L, int* err_flag, double* sums, void* ws, size_t ws_bytes, void* stream) {
+    DCUE_CHECK_ARG(pool && idx && sums && ws && err_flag && S >= 0 && n_songs > 0 && L > 0 && T >= L);
+    DCUE_CHECK_ARG(C > 0 && C <= 8 * STAT_MAXC_PER_WARP);
+    SpecSrc src{pool, nullptr, 0, idx, off, T, n_songs, err_flag};
+    return ncl_stats_impl(src, S, C, L, sums, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int dcue_bn_finalize(const double* sums, double count, int C, const float* gamma, const float* beta,
@@ -544,20 +577,35 @@ extern "C" int dcue_bn_finalize(const double* sums, double count, int C, const f
     return 0;
 }
 
+static int ncl_pack_impl(const SpecSrc& src, int S, int C, int L, const float* scale, const float* shift, void* panel,
+                         long panel_rows, int Lp, int pad, int fmt, cudaStream_t st) {
+    const long total = (long)S * (C / 8) * L;
+    if (total == 0) return 0;
+    long blocks = (total + 255) / 256;
+    const long cap = (long)dcue_num_sms() * 32;
+    if (blocks > cap) blocks = cap;
+    ncl_pack_kernel<<<(int)blocks, 256, 0, st>>>(src, S, C, L, scale, shift, (uint4*)panel, panel_rows, Lp, pad, fmt);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int dcue_ncl_pack(const float* pos, int S_pos, const float* neg, int S_neg, int C, int L, const float* scale,
                              const float* shift, void* panel, long panel_rows, int Lp, int pad, int fmt, void* stream) {
     DCUE_CHECK_ARG(panel && S_pos >= 0 && S_neg >= 0 && (pos || S_pos == 0) && (neg || S_neg == 0));
     DCUE_CHECK_ARG(C > 0 && C % 8 == 0 && L > 0 && Lp >= L + pad && pad >= 0 && (!scale == !shift));
     DCUE_CHECK_ARG(panel_rows >= (long)(S_pos + S_neg) * Lp);
-    const long total = (long)(S_pos + S_neg) * (C / 8) * L;
-    if (total == 0) return 0;
-    long blocks = (total + 255) / 256;
-    const long cap = (long)dcue_num_sms() * 32;
-    if (blocks > cap) blocks = cap;
-    ncl_pack_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pos, S_pos, neg, S_neg, C, L, scale, shift,
-                                                                   (uint4*)panel, panel_rows, Lp, pad, fmt);
-    DCUE_LAUNCH_CHECK();
-    return 0;
+    SpecSrc src{pos, neg, S_pos, nullptr, nullptr, 0, 0, nullptr};
+    return ncl_pack_impl(src, S_pos + S_neg, C, L, scale, shift, panel, panel_rows, Lp, pad, fmt, (cudaStream_t)stream);
+}
+
+extern "C" int dcue_ncl_pack_indexed(const float* pool, long n_songs, long T, const int64_t* idx, const int32_t* off, int S,
+                                     int C, int L, int* err_flag, const float* scale, const float* shift, void* panel,
+                                     long panel_rows, int Lp, int pad, int fmt, void* stream) {
+    DCUE_CHECK_ARG(pool && idx && panel && err_flag && S >= 0 && n_songs > 0 && T >= L);
+    DCUE_CHECK_ARG(C > 0 && C % 8 == 0 && L > 0 && Lp >= L + pad && pad >= 0 && (!scale == !shift));
+    DCUE_CHECK_ARG(panel_rows >= (long)S * Lp);
+    SpecSrc src{pool, nullptr, 0, idx, off, T, n_songs, err_flag};
+    return ncl_pack_impl(src, S, C, L, scale, shift, panel, panel_rows, Lp, pad, fmt, (cudaStream_t)stream);
 }
 
 extern "C" int dcue_affine_pack(const float* z, int S, int P, int C, const float* scale, const float* shift, void* panel,
@@ -597,7 +645,7 @@ extern "C" int dcue_bn_bwd_reduce(const float* dy, int lddy, const float* dtp, i
     if (ws_bytes < (size_t)grid * (2 * C + 1) * sizeof(double)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_bn_bwd_reduce: workspace too small");
     bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, lddy, dtp, lddtp, z, mean, rstd, rows, P, C, (double*)ws);
     DCUE_LAUNCH_CHECK();
-    reduce_partials_kernel<<<ceil_div_i(2 * C, 32), 256, 0, st>>>((const double*)ws, grid, 2 * C, sums, dbeta, dgamma, C);
+    reduce_partials_kernel<<<ceil_div_i(2 * C, 8), 256, 0, st>>>((const double*)ws, grid, 2 * C, sums, dbeta, dgamma, C);
     DCUE_LAUNCH_CHECK();
     if (absmax) {
         reduce_max_kernel<<<1, 256, 0, st>>>((const double*)ws + (size_t)grid * 2 * C, grid, absmax);
@@ -626,7 +674,7 @@ extern "C" int dcue_bn_relu_unpool_bwd(const float* dy, int lddy, const float* d
                                                     panel_rows, fmt, gscale, dz_out, bias_sums ? (double*)ws : nullptr);
     DCUE_LAUNCH_CHECK();
     if (bias_sums) {
-        reduce_partials_kernel<<<ceil_div_i(C, 32), 256, 0, st>>>((const double*)ws, grid, C, bias_sums, bias_out, nullptr, C);
+        reduce_partials_kernel<<<ceil_div_i(C, 8), 256, 0, st>>>((const double*)ws, grid, C, bias_sums, bias_out, nullptr, C);
         DCUE_LAUNCH_CHECK();
     }
     return 0;
@@ -645,7 +693,7 @@ extern "C" int dcue_ncl_bn_bwd_reduce(const float* dx, const float* pos, int S_p
     if (ws_bytes < (size_t)G * 2 * C * sizeof(double)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_ncl_bn_bwd_reduce: workspace too small");
     ncl_bn_bwd_reduce_kernel<<<G * (C / 8), 128, 0, st>>>(dx, pos, S_pos, neg, S_neg, C, L, mean, rstd, (double*)ws);
     DCUE_LAUNCH_CHECK();
-    reduce_partials_kernel<<<ceil_div_i(2 * C, 32), 256, 0, st>>>((const double*)ws, G, 2 * C, sums);
+    reduce_partials_kernel<<<ceil_div_i(2 * C, 8), 256, 0, st>>>((const double*)ws, G, 2 * C, sums);
     DCUE_LAUNCH_CHECK();
     return 0;
 }

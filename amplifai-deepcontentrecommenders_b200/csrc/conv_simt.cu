@@ -188,18 +188,18 @@ __global__ void dcue_wgrad_reduce_kernel(const float* __restrict__ part, int npa
 
 __global__ void __launch_bounds__(256)
 dcue_reduce_partials_d(const double* __restrict__ partial, int nblk, int n, double* __restrict__ out) {
-    __shared__ double red[8][33];
-    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int j = blockIdx.x * 32 + cl;
+    __shared__ double red[32][9];
+    const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    const int j = blockIdx.x * 8 + cl;
     double s = 0.0;
     if (j < n)
-        for (int b = rl; b < nblk; b += 8) s += partial[(long)b * n + j];
+        for (int b = rl; b < nblk; b += 32) s += partial[(long)b * n + j];
     red[rl][cl] = s;
     __syncthreads();
     if (rl == 0 && j < n) {
         double t = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += red[k][cl];
+        for (int k = 0; k < 32; ++k) t += red[k][cl];
         out[j] = t;
     }
 }
@@ -233,7 +233,7 @@ int dcue_simt_conv_fwd(const void* panel, long panel_rows, int fmt, const void* 
                                                  g, z, code, sums ? (double*)ws : nullptr, nullptr, tap_bias);
     DCUE_LAUNCH_CHECK();
     if (sums) {
-        dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 32), 256, 0, st>>>((const double*)ws, grid, 2 * g.Cout, sums);
+        dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 8), 256, 0, st>>>((const double*)ws, grid, 2 * g.Cout, sums);
         DCUE_LAUNCH_CHECK();
     }
     return 0;

@@ -538,7 +538,7 @@ int dcue_tc_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_
     else e = launch_rows_t<0, 1>(panel, panel_rows, fmt, w_packed, fmt, bias, g, z, code, part, nullptr, tap_bias, dummy, grid, st);
     if (e) return e;
     if (sums) {
-        dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 32), 256, 0, st>>>((const double*)ws, grid * 4, 2 * g.Cout, sums);
+        dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 8), 256, 0, st>>>((const double*)ws, grid * 4, 2 * g.Cout, sums);
         DCUE_LAUNCH_CHECK();
     }
     return 0;

@@ -41,25 +41,60 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
 
     const bool a_r_contig = (p.sAr == 1);
     const bool b_j_contig = (p.sBj == 1);
+    // 16-byte loads need every row start 16-byte aligned: base pointer and the non-unit stride
+    const bool a_vec = ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) && (((a_r_contig ? p.sAi : p.sAr) & 3) == 0) &&
+                       (a_r_contig || p.sAi == 1) && ((rbeg & 3) == 0);
+    const bool b_vec = ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0) && (((b_j_contig ? p.sBr : p.sBj) & 3) == 0) &&
+                       (b_j_contig || p.sBr == 1) && ((rbeg & 3) == 0);
 
     for (int r0 = rbeg; r0 < rend; r0 += TK) {
-        // ---- load A tile (TM x TK)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        // ---- load A tile (TM x TK): one 16-byte load per thread when 4 consecutive elements are contiguous
+        {
             int li, lr;
-            if (a_r_contig) { li = tid >> 2; lr = (tid & 3) * 4 + q; }
-            else            { lr = tid >> 4; li = (tid & 15) * 4 + q; }
+            if (a_r_contig) { li = tid >> 2; lr = (tid & 3) * 4; }
+            else            { lr = tid >> 4; li = (tid & 15) * 4; }
             const int gi = i0 + li, gr = r0 + lr;
-            As[lr][li] = (gi < p.I && gr < rend) ? __ldg(p.A + gi * p.sAi + gr * p.sAr) : 0.f;
+            const float* src = p.A + gi * p.sAi + gr * p.sAr;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            const bool full = a_r_contig ? (gi < p.I && gr + 3 < rend) : (gr < rend && gi + 3 < p.I);
+            if (full && a_vec) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int gi2 = a_r_contig ? gi : gi + q, gr2 = a_r_contig ? gr + q : gr;
+                    if (gi2 < p.I && gr2 < rend) v[q] = __ldg(p.A + gi2 * p.sAi + gr2 * p.sAr);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (a_r_contig) As[lr + q][li] = v[q]; else As[lr][li + q] = v[q];
+            }
         }
         // ---- load B tile (TK x TN)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        {
             int lj, lr;
-            if (b_j_contig) { lr = tid >> 4; lj = (tid & 15) * 4 + q; }
-            else            { lj = tid >> 2; lr = (tid & 3) * 4 + q; }
+            if (b_j_contig) { lr = tid >> 4; lj = (tid & 15) * 4; }
+            else            { lj = tid >> 2; lr = (tid & 3) * 4; }
             const int gj = j0 + lj, gr = r0 + lr;
-            Bs[lr][lj] = (gj < p.J && gr < rend) ? __ldg(p.B + gr * p.sBr + gj * p.sBj) : 0.f;
+            const float* src = p.B + gr * p.sBr + gj * p.sBj;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            const bool full = b_j_contig ? (gr < rend && gj + 3 < p.J) : (gj < p.J && gr + 3 < rend);
+            if (full && b_vec) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int gj2 = b_j_contig ? gj + q : gj, gr2 = b_j_contig ? gr : gr + q;
+                    if (gj2 < p.J && gr2 < rend) v[q] = __ldg(p.B + gr2 * p.sBr + gj2 * p.sBj);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (b_j_contig) Bs[lr][lj + q] = v[q]; else Bs[lr + q][lj] = v[q];
+            }
         }
         __syncthreads();
 #pragma unroll

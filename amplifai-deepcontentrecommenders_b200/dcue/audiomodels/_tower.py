@@ -54,10 +54,12 @@ class TowerBase(nn.Module):
         names += ["fc.weight", "fc.bias"]
         self._param_names = tuple(names)
         self._dp = None  # set by parallel.DataParallelDCUE (BatchNorm statistics all-reduce)
+        self._err = None  # device flag: out-of-range song index / crop offset in the index feed
 
     def __getstate__(self):
         d = self.__dict__.copy()
         d["_dp"] = None  # process-group handles do not pickle (DCUE.save pickles the trainer)
+        d["_err"] = None
         return d
 
     def _params(self):
@@ -66,7 +68,22 @@ class TowerBase(nn.Module):
     def forward_posneg(self, pos, neg=None):
         """Tower over the rows of `pos` [B,128,L] followed by `neg` [B,N,128,L] (or [M,128,L]),
         equal to self(torch.cat([pos, neg.view(-1,128,L)])) without the copy -> [S, F]."""
-        return ops.SongTowerFn.apply(pos, neg, self, self.training, *self._params())
+        return ops.SongTowerFn.apply(pos, neg, None, self, self.training, *self._params())
+
+    def forward_indexed(self, pool, idx, off=None, frames=131):
+        """Tower over crops of a RESIDENT song pool: spectrogram s = pool[idx[s], :, off[s]:off[s]+frames]
+        (pool fp32 [n_songs,128,T] on the device, idx int64, off int32 or None = 0) -> [S, F].
+        Equals self(torch.stack([pool[i, :, o:o+frames] ...])) without materialising that batch or copying
+        it from the host."""
+        dev = self.fc.weight.device
+        if self._err is None or self._err.device != dev:
+            self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+        return ops.SongTowerFn.apply(pool, None, (idx, off, frames, self._err), self, self.training, *self._params())
+
+    def raise_if_index_error(self):
+        if self._err is not None and int(self._err.item()):
+            self._err.zero_()
+            raise IndexError("song index or crop offset out of range")
 
     def forward(self, x):
         """x [S,128,L] -> [S,F]; like the reference's trailing .squeeze(), S == 1 gives [F]."""

@@ -67,6 +67,39 @@ class DCUENet(nn.Module):
         scores = self.sim(u_featvects, pos_featvects).view(B, 1)
         return scores, u_featvects, pos_featvects, None
 
+    def _indexed_feats(self, pool, pos_idx, neg_idx, pos_off, neg_off, frames):
+        B, N = neg_idx.shape
+        idx = torch.cat([pos_idx.reshape(-1), neg_idx.reshape(-1)])
+        off = None
+        if pos_off is not None or neg_off is not None:
+            po = torch.zeros(B, dtype=torch.int32, device=idx.device) if pos_off is None else pos_off.reshape(-1).to(torch.int32)
+            no = torch.zeros(B * N, dtype=torch.int32, device=idx.device) if neg_off is None else neg_off.reshape(-1).to(torch.int32)
+            off = torch.cat([po.to(idx.device), no.to(idx.device)])
+        return self.conv.forward_indexed(pool, idx, off, frames)
+
+    def forward_indexed(self, u, pool, pos_idx, neg_idx, pos_off=None, neg_off=None, frames=131):
+        """forward(u, pos, neg) with pos = pool[pos_idx, :, off:off+frames], neg = pool[neg_idx, ...] taken
+        from a resident device pool by index: same outputs, no dense [B,N,128,L] tensor, no H2D copy."""
+        u_featvects = self.user_embd(u)
+        B, N = neg_idx.shape
+        feats = self._indexed_feats(pool, pos_idx.to(pool.device), neg_idx.to(pool.device), pos_off, neg_off, frames)
+        scores = ops.ScoreFn.apply(u_featvects, feats, B, N)
+        return scores, u_featvects, feats[:B], feats[B:].view(B, N, self.feature_dim)
+
+    def hinge_loss_step_indexed(self, u, pool, pos_idx, neg_idx, margin, pos_off=None, neg_off=None, frames=131,
+                                batch_total=None):
+        """hinge_loss_step on the index feed."""
+        u_featvects = self.user_embd(u)
+        B, N = neg_idx.shape
+        feats = self._indexed_feats(pool, pos_idx.to(pool.device), neg_idx.to(pool.device), pos_off, neg_off, frames)
+        total = B if batch_total is None else batch_total
+        loss_rows, _ = ops.HingeScoreFn.apply(u_featvects, feats, B, N, margin, total)
+        return loss_rows.sum() / total
+
+    def raise_if_index_error(self):
+        self.user_embd.raise_if_index_error()
+        self.conv.raise_if_index_error()
+
     def hinge_loss_step(self, u, pos, neg, margin, batch_total=None, return_all=False):
         """forward + DCUE._loss_func (max(0, margin - scores).sum(1).mean()) with the scoring, the
         loss and their backward fused in one kernel.  batch_total = global batch size under data

@@ -143,7 +143,9 @@ class SongTowerFn(torch.autograd.Function):
     """feats[S,F] = tower(cat(pos, neg))  without materialising the concatenation."""
 
     @staticmethod
-    def forward(ctx, pos, neg, mod, training, *params):
+    def forward(ctx, pos, neg, src, mod, training, *params):
+        """Dense feed: pos [B,128,L] (+ neg [.., 128, L]).  Index feed: pos = resident pool [n_songs,128,T],
+        neg = None, src = (idx int64 [S], off int32 [S] or None, frames, err_flag int32 [1])."""
         has_bn, res = mod._has_bn, mod._res
         H, F = mod.hidden_size, mod.output_size
         if H != 128:
@@ -154,9 +156,18 @@ class SongTowerFn(torch.autograd.Function):
         S_pos, C, frames = pos.shape
         if C != N_MELS:
             raise ValueError("expected %d mel bins, got %d" % (N_MELS, C))
-        if neg is not None:
-            neg = _check_input(neg, "neg").view(-1, C, frames)
-        S_neg = 0 if neg is None else neg.shape[0]
+        if src is not None:
+            idx, off, frames, err = src
+            n_songs, _, T = pos.shape
+            if idx.dtype != torch.int64 or (off is not None and off.dtype != torch.int32):
+                raise TypeError("song indices must be int64 and crop offsets int32")
+            idx = idx.to(pos.device).contiguous().view(-1)
+            off = None if off is None else off.to(pos.device).contiguous().view(-1)
+            S_pos, S_neg, neg = idx.numel(), 0, None
+        else:
+            if neg is not None:
+                neg = _check_input(neg, "neg").view(-1, C, frames)
+            S_neg = 0 if neg is None else neg.shape[0]
         S = S_pos + S_neg
         dev = pos.device
         st = L.stream()
@@ -186,7 +197,10 @@ class SongTowerFn(torch.autograd.Function):
         # border-aware bias (dcue_conv_tap_bias), which lets the backward skip layer1's data gradient.
         g0 = geo[0]
         if has_bn:
-            if training:
+            if training and src is not None:
+                L.call("dcue_ncl_stats_indexed", pos_p, n_songs, T, idx.data_ptr(), None if off is None else off.data_ptr(), S, C,
+                       frames, err.data_ptr(), ws.sums[0].data_ptr(), scratch, nscr, st)
+            elif training:
                 L.call("dcue_ncl_stats", pos_p, S_pos, neg_p, S_neg, C, frames, ws.sums[0].data_ptr(), scratch, nscr, st)
             bn_finalize(0, S * frames, C, affine=False)
             sc, sh = ws.bnp[0, 0].data_ptr(), ws.bnp[0, 1].data_ptr()
@@ -194,8 +208,12 @@ class SongTowerFn(torch.autograd.Function):
                    ws.tapb.data_ptr(), st)
         else:
             sc = sh = None
-        L.call("dcue_ncl_pack", pos_p, S_pos, neg_p, S_neg, C, frames, sc, sh, ws.X[0].base, ws.X[0].panel_rows,
-               g0["Lp"], g0["pad"], fmt, st)
+        if src is not None:
+            L.call("dcue_ncl_pack_indexed", pos_p, n_songs, T, idx.data_ptr(), None if off is None else off.data_ptr(), S, C, frames,
+                   err.data_ptr(), sc, sh, ws.X[0].base, ws.X[0].panel_rows, g0["Lp"], g0["pad"], fmt, st)
+        else:
+            L.call("dcue_ncl_pack", pos_p, S_pos, neg_p, S_neg, C, frames, sc, sh, ws.X[0].base, ws.X[0].panel_rows,
+                   g0["Lp"], g0["pad"], fmt, st)
         # ---- layer1..4: conv + pool + relu (+ BN statistics) -> affine -> next operand panel
         for i, g in enumerate(geo, start=1):
             Wt, bt = P["layer%d.weight" % i], P["layer%d.bias" % i]
@@ -363,7 +381,7 @@ class SongTowerFn(torch.autograd.Function):
                 dy = dx
         ctx.ws = None
         _release(ws)
-        return (None, None, None, None) + tuple(grads.get(n) for n in mod._param_names)
+        return (None, None, None, None, None) + tuple(grads.get(n) for n in mod._param_names)
 
 
 class UserTowerFn(torch.autograd.Function):

@@ -53,6 +53,11 @@ class DataParallelDCUE:
         gradient.  Returns the local partial loss (sum over ranks == reference loss)."""
         return self.model.hinge_loss_step(u, pos, neg, margin, batch_total=pos.shape[0] * self.world_size)
 
+    def loss_step_indexed(self, u, pool, pos_idx, neg_idx, margin, pos_off=None, neg_off=None, frames=131):
+        """loss_step on the index feed (resident song pool)."""
+        return self.model.hinge_loss_step_indexed(u, pool, pos_idx, neg_idx, margin, pos_off, neg_off, frames,
+                                                  batch_total=pos_idx.shape[0] * self.world_size)
+
     def reduce_gradients(self):
         """One flat SUM all-reduce over all non-BatchNorm gradients."""
         if self.world_size == 1:

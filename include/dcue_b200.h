@@ -94,6 +94,16 @@ int dcue_ncl_stats(const float* pos, int S_pos, const float* neg, int S_neg, int
                    double* sums, void* ws, size_t ws_bytes, void* stream);
 size_t dcue_ncl_stats_ws_bytes(int C);
 
+/* Index-based feed (replaces the per-sample torch.load + default_collate of
+ * dcrecommend/datasets/dcuedataset.py:235-256 and the 1.4 GB/step H2D copy, nn/dcue.py:195-199):
+ * spectrogram s = pool[idx[s], :, off[s] : off[s]+L] of a resident fp32 pool [n_songs, C, T] (off NULL = 0).
+ * err_flag (device int) is set if an index / offset is out of range. */
+int dcue_ncl_stats_indexed(const float* pool, long n_songs, long T, const int64_t* idx, const int32_t* off, int S,
+                           int C, int L, int* err_flag, double* sums, void* ws, size_t ws_bytes, void* stream);
+int dcue_ncl_pack_indexed(const float* pool, long n_songs, long T, const int64_t* idx, const int32_t* off, int S,
+                          int C, int L, int* err_flag, const float* scale, const float* shift, void* panel,
+                          long panel_rows, int Lp, int pad, int fmt, void* stream);
+
 /* BatchNorm finalize (truedcuemel1dbn.py:24,30,38,46,54,61): from sums/count produce
  * scale = gamma*rstd, shift = beta - mean*scale, mean, rstd; training!=0 uses batch statistics
  * and updates running_mean/var (momentum, unbiased var) and num_batches_tracked; otherwise the

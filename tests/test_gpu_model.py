@@ -168,3 +168,36 @@ def test_ten_adam_steps_track_oracle():
         assert abs(loss.item() - r["loss"].item()) <= 2e-3 * max(abs(r["loss"].item()), first), step
     for p, k in zip(qp, names):
         assert l2err(net.get_parameter(k), p) < 5e-3, k
+
+
+@pytest.mark.parametrize("mt", ["truedcuemel1dbn", "truedcuemel1dres"])
+def test_index_feed_equals_dense_feed(mt):
+    """forward_indexed on a resident pool == forward on the gathered crops, bit for bit (same kernels,
+    same operands), including gradients; bad indices raise."""
+    B, N, U, P, T = 5, 3, 30, 12, 150
+    params = fixtures.make_params(mt, seed=0, user_count=U)
+    g = torch.Generator().manual_seed(7)
+    pool = torch.randn(P, 128, T, generator=g)
+    u = torch.randint(0, U, (B,), generator=g)
+    pi, ni = torch.randint(0, P, (B,), generator=g), torch.randint(0, P, (B, N), generator=g)
+    po, no = torch.randint(0, T - 131, (B,), generator=g).int(), torch.randint(0, T - 131, (B, N), generator=g).int()
+    pos = torch.stack([pool[pi[b], :, po[b]:po[b] + 131] for b in range(B)])
+    neg = torch.stack([torch.stack([pool[ni[b, n], :, no[b, n]:no[b, n] + 131] for n in range(N)]) for b in range(B)])
+    a, b_ = _build(mt, U, params).train(), _build(mt, U, params).train()
+    la = a.hinge_loss_step(u.to(DEV), pos.to(DEV), neg.to(DEV), 0.2)
+    la.backward()
+    pool_d = pool.to(DEV)
+    lb = b_.hinge_loss_step_indexed(u.to(DEV), pool_d, pi.to(DEV), ni.to(DEV), 0.2, po.to(DEV), no.to(DEV))
+    lb.backward()
+    b_.raise_if_index_error()
+    assert la.item() == lb.item()
+    for (k, p), (_, q) in zip(a.named_parameters(), b_.named_parameters()):
+        assert torch.equal(p.grad, q.grad), k
+    s1, *_ = a(u.to(DEV), pos.to(DEV), neg.to(DEV))
+    s2, *_ = b_.forward_indexed(u.to(DEV), pool_d, pi.to(DEV), ni.to(DEV), po.to(DEV), no.to(DEV))
+    assert torch.equal(s1, s2)
+    ni_bad = ni.clone()
+    ni_bad[0, 0] = P
+    b_.forward_indexed(u.to(DEV), pool_d, pi.to(DEV), ni_bad.to(DEV), po.to(DEV), no.to(DEV))
+    with pytest.raises(IndexError):
+        b_.raise_if_index_error()
