@@ -438,6 +438,81 @@ class UserTowerFn(torch.autograd.Function):
         return None, gtable, gw1, gb1, gw2, gb2, None
 
 
+class UserMLPFn(torch.autograd.Function):
+    """u_f = linear2(relu(linear1(relu(rows)))) on pre-gathered raw table rows [B,E] (row-sharded table path:
+    the gather happened on the owning ranks).  Gradient w.r.t. rows is already ReLU-masked."""
+
+    @staticmethod
+    def forward(ctx, rows, w1, b1, w2, b2):
+        rows = rows.contiguous()
+        B, E = rows.shape
+        F = w2.shape[0]
+        dev, st = rows.device, L.stream()
+        f32 = dict(dtype=torch.float32, device=dev)
+        h0, h1, out = torch.empty(B, E, **f32), torch.empty(B, E, **f32), torch.empty(B, F, **f32)
+        iota = torch.arange(B, dtype=torch.int64, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.call("dcue_gather_relu_fwd", rows.data_ptr(), iota.data_ptr(), B, B, E, h0.data_ptr(), None, err.data_ptr(), st)
+        L.call("dcue_linear_fwd", h0.data_ptr(), E, w1.data_ptr(), b1.data_ptr(), B, E, E, 1, h1.data_ptr(), E, st)
+        L.call("dcue_linear_fwd", h1.data_ptr(), E, w2.data_ptr(), b2.data_ptr(), B, E, F, 0, out.data_ptr(), F, st)
+        ctx.save_for_backward(w1, w2, h0, h1)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        w1, w2, h0, h1 = ctx.saved_tensors
+        B, E = h0.shape
+        F = w2.shape[0]
+        dev, st = h0.device, L.stream()
+        f32 = dict(dtype=torch.float32, device=dev)
+        gout = gout.contiguous()
+        nscr = max(L.query("dcue_linear_wgrad_ws_bytes", B, E, F), L.query("dcue_linear_wgrad_ws_bytes", B, E, E))
+        scratch = torch.empty(nscr, dtype=torch.uint8, device=dev)
+        gw2, gb2 = torch.empty(F, E, **f32), torch.empty(F, **f32)
+        L.call("dcue_linear_wgrad", gout.data_ptr(), F, h1.data_ptr(), E, B, E, F, gw2.data_ptr(), gb2.data_ptr(),
+               scratch.data_ptr(), nscr, st)
+        dh1 = torch.empty(B, E, **f32)
+        L.call("dcue_linear_dgrad", gout.data_ptr(), F, w2.data_ptr(), B, E, F, h1.data_ptr(), E, dh1.data_ptr(), E, st)
+        gw1, gb1 = torch.empty(E, E, **f32), torch.empty(E, **f32)
+        L.call("dcue_linear_wgrad", dh1.data_ptr(), E, h0.data_ptr(), E, B, E, E, gw1.data_ptr(), gb1.data_ptr(),
+               scratch.data_ptr(), nscr, st)
+        drows = torch.empty(B, E, **f32)  # masked by the gather's ReLU (h0 > 0)
+        L.call("dcue_linear_dgrad", dh1.data_ptr(), E, w1.data_ptr(), B, E, E, h0.data_ptr(), E, drows.data_ptr(), E, st)
+        return drows, gw1, gb1, gw2, gb2
+
+
+def gather_rows(table, idx):
+    """raw table rows [B,E] with the gather kernel (idx int64 within [0, table.shape[0]))."""
+    B, (U, E) = idx.numel(), table.shape
+    dev = table.device
+    relu_out = torch.empty(B, E, dtype=torch.float32, device=dev)
+    raw = torch.empty(B, E, dtype=torch.float32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.call("dcue_gather_relu_fwd", table.data_ptr(), idx.contiguous().data_ptr(), B, U, E, relu_out.data_ptr(), raw.data_ptr(),
+           err.data_ptr(), L.stream())
+    return raw
+
+
+def scatter_rows(idx, grad_rows, n_rows):
+    """Dense [n_rows,E] sum of grad_rows by idx (deterministic sorted segment sum); entries with idx == n_rows
+    (the 'not mine' sentinel) are dropped."""
+    B, E = grad_rows.shape
+    dev = grad_rows.device
+    out = torch.zeros(n_rows + 1, E, dtype=torch.float32, device=dev)   # last row collects the sentinel entries
+    if B == 0:
+        return out[:n_rows]
+    sidx = torch.empty(B, dtype=torch.int64, device=dev)
+    spos = torch.empty(B, dtype=torch.int32, device=dev)
+    nscr = L.query("dcue_sort_ws_bytes", B)
+    scratch = torch.empty(nscr, dtype=torch.uint8, device=dev)
+    st = L.stream()
+    L.call("dcue_sort_indices", idx.contiguous().data_ptr(), B, n_rows + 1, sidx.data_ptr(), spos.data_ptr(), scratch.data_ptr(), nscr, st)
+    ones = torch.ones_like(grad_rows)   # no ReLU mask here: grad_rows is already masked
+    L.call("dcue_scatter_add_bwd", grad_rows.contiguous().data_ptr(), ones.data_ptr(), sidx.data_ptr(), spos.data_ptr(), B,
+           n_rows + 1, E, out.data_ptr(), st)
+    return out[:n_rows]
+
+
 class ScoreFn(torch.autograd.Function):
     """scores[b,n] = cos(u_b, pos_b) - cos(u_b, neg_bn)  (dcue.py:93-106); feats = [pos; neg]."""
 

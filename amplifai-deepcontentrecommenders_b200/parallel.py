@@ -27,8 +27,9 @@ def shard_slice(n, rank, world):
 def flat_bucket_names(named_grads):
     """Names of the gradients that need the SUM all-reduce: everything except the affine parameters
     of bn1..bn5, whose gradients are already global (computed from all-reduced sums).  bn0 is folded
-    into layer1, so its gradients are local partial sums like any weight gradient."""
-    return [n for n, _ in named_grads if ".bn" not in n or ".bn0." in n]
+    into layer1, so its gradients are local partial sums like any weight gradient.  A row-sharded user
+    table's gradient is complete on its owner and is excluded as well."""
+    return [n for n, _ in named_grads if (".bn" not in n or ".bn0." in n) and not n.endswith("user_embd.shard")]
 
 
 class DataParallelDCUE:
@@ -74,6 +75,99 @@ class DataParallelDCUE:
             loss = loss.detach().clone()
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
         return loss
+
+
+# ------------------------------------------------------------------------------ row-sharded user table (cfg4)
+def shard_rows(n_rows, rank, world):
+    """Contiguous block of table rows owned by `rank`: [lo, hi)."""
+    return shard_slice(n_rows, rank, world)
+
+
+def local_row_index(all_idx, lo, hi):
+    """Map global row indices to this owner's local rows; rows owned by other ranks map to the sentinel
+    (hi - lo).  Returns (local_idx int64, owned bool)."""
+    owned = (all_idx >= lo) & (all_idx < hi)
+    local = torch.where(owned, all_idx - lo, torch.full_like(all_idx, hi - lo))
+    return local, owned
+
+
+class _ShardedRowsFn(torch.autograd.Function):
+    """rows[b] = table[u[b]] for a table whose rows are block-sharded over the ranks.
+    forward : all_gather(indices) -> every owner gathers the rows it holds (zeros elsewhere)
+              -> all_to_all of the gathered rows back to the requesting ranks -> sum over owners
+    backward: all_gather(indices, gradient rows) -> every owner segment-sums the rows it owns into its
+              dense shard gradient (already the GLOBAL sum: it must not be all-reduced again)."""
+
+    @staticmethod
+    def forward(ctx, u, shard, lo, hi, group):
+        from . import ops
+        world = dist.get_world_size(group)
+        B, E = u.numel(), shard.shape[1]
+        all_idx = torch.empty(world * B, dtype=torch.int64, device=u.device)
+        dist.all_gather_into_tensor(all_idx, u.contiguous().view(-1), group=group)
+        local, owned = local_row_index(all_idx, lo, hi)
+        safe = torch.where(owned, local, torch.zeros_like(local))
+        part = ops.gather_rows(shard, safe) * owned.unsqueeze(1).to(shard.dtype)      # [world*B, E]
+        recv = torch.empty(world, B, E, dtype=shard.dtype, device=u.device)
+        dist.all_to_all_single(recv.view(world * B, E), part, group=group)           # row exchange over NVLink
+        ctx.save_for_backward(all_idx)
+        ctx.meta = (lo, hi, group, B, E)
+        return recv.sum(dim=0)                                                        # exactly one owner contributes
+
+    @staticmethod
+    def backward(ctx, grows):
+        from . import ops
+        (all_idx,) = ctx.saved_tensors
+        lo, hi, group, B, E = ctx.meta
+        world = dist.get_world_size(group)
+        all_g = torch.empty(world * B, E, dtype=grows.dtype, device=grows.device)
+        dist.all_gather_into_tensor(all_g, grows.contiguous(), group=group)
+        local, _ = local_row_index(all_idx, lo, hi)
+        gshard = ops.scatter_rows(local, all_g, hi - lo)
+        return None, gshard, None, None, None
+
+
+class ShardedUserTable(torch.nn.Module):
+    """Row-sharded replacement for UserEmbeddings' lookup table (BASELINE cfg4: 1M users x 300 over 8 GPUs).
+    Each rank owns rows [lo, hi) (+ its optimizer state); the MLP stays replicated / data parallel."""
+
+    def __init__(self, user_embd, group=None):
+        super().__init__()
+        from . import ops
+        self._ops = ops
+        self.group = group
+        self.world_size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        full = user_embd.embeddings.weight.detach()
+        self.user_count = full.shape[0]
+        self.lo, self.hi = shard_rows(self.user_count, self.rank, self.world_size)
+        self.shard = torch.nn.Parameter(full[self.lo:self.hi].clone())
+        self.linear1, self.linear2 = user_embd.linear1, user_embd.linear2
+
+    def forward(self, user_idx):
+        shape = user_idx.shape
+        rows = _ShardedRowsFn.apply(user_idx.reshape(-1).to(self.shard.device), self.shard, self.lo, self.hi, self.group)
+        out = self._ops.UserMLPFn.apply(rows, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias)
+        return out.view(*shape, -1)
+
+    def raise_if_index_error(self):
+        pass
+
+    def gather_full_table(self):
+        """[U,E] table on every rank (for checkpoints in the reference's state_dict layout)."""
+        sizes = [shard_rows(self.user_count, r, self.world_size) for r in range(self.world_size)]
+        m = max(h - l for l, h in sizes)
+        pad = torch.zeros(m, self.shard.shape[1], dtype=self.shard.dtype, device=self.shard.device)
+        pad[: self.hi - self.lo] = self.shard.detach()
+        out = [torch.empty_like(pad) for _ in range(self.world_size)]
+        dist.all_gather(out, pad, group=self.group)
+        return torch.cat([o[: h - l] for o, (l, h) in zip(out, sizes)])
+
+
+def shard_user_table(model, group=None):
+    """Replace model.user_embd by its row-sharded version (call before building the optimizer)."""
+    model.user_embd = ShardedUserTable(model.user_embd, group)
+    return model
 
 
 def sharded_topk(user_factors, item_factors_local, k, item_offset, group=None):

@@ -26,6 +26,19 @@ def test_bucket_excludes_batchnorm_affine():
                                             "conv.fc.bias"]
 
 
+def test_sharded_table_index_bookkeeping():
+    U, W = 1000, 8
+    spans = [par.shard_rows(U, r, W) for r in range(W)]
+    idx = torch.tensor([0, 124, 125, 999, 500, 125])
+    owners = torch.zeros_like(idx)
+    for r, (lo, hi) in enumerate(spans):
+        local, owned = par.local_row_index(idx, lo, hi)
+        assert (local[owned] == idx[owned] - lo).all() and (local[~owned] == hi - lo).all()   # sentinel = shard size
+        owners += owned.long()
+    assert (owners == 1).all()                                     # every index has exactly one owner
+    assert par.flat_bucket_names([("user_embd.shard", 0), ("user_embd.linear1.weight", 0)]) == ["user_embd.linear1.weight"]
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
