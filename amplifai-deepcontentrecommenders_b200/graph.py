@@ -1,0 +1,56 @@
+"""CUDA-graph capture of the fixed-shape part of a DCUE training step (forward + fused score/hinge loss +
+backward: ~100 kernel launches) so that a step costs one graph launch instead of ~100 launch gaps.
+The optimizer / scheduler stay outside the graph (the reference's Python-float learning-rate schedule keeps
+working unchanged).  Single-process only: under data parallelism the BatchNorm all-reduces sit between the
+kernels, so the eager path is used there.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class GraphedTrainStep:
+    """step = GraphedTrainStep(model, margin, u, pos, neg)   # example batch fixes the shapes
+       loss = step(u, pos, neg); optimizer.step()            # gradients are in model.parameters()[i].grad
+
+    With `pool` given, (pos, neg) are int64 song-index tensors into the resident pool (index feed)."""
+
+    def __init__(self, model, margin, u, pos, neg, pool=None, warmup=3):
+        self.model, self.margin, self.pool = model, margin, pool
+        self.u, self.pos, self.neg = u.clone(), pos.clone(), neg.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):           # warm-up off the default stream: allocators, workspaces, cub temp
+            for _ in range(warmup):
+                model.zero_grad(set_to_none=True)
+                self._loss().backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        # The graph zeroes the EXISTING .grad tensors and the backward accumulates into them in place, so the
+        # optimizer (and any other GraphedTrainStep of the same model) keeps seeing the same gradient storage.
+        # Do not call zero_grad(set_to_none=True) on the model afterwards.
+        params = [p for p in model.parameters() if p.requires_grad]
+        for p in params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        self._grads = [p.grad for p in params]
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            torch._foreach_zero_(self._grads)
+            self.loss = self._loss()
+            self.loss.backward()
+
+    def _loss(self):
+        if self.pool is not None:
+            return self.model.hinge_loss_step_indexed(self.u, self.pool, self.pos, self.neg, self.margin)
+        return self.model.hinge_loss_step(self.u, self.pos, self.neg, self.margin)
+
+    def __call__(self, u=None, pos=None, neg=None):
+        """Replay on a new batch of the captured shapes (pass nothing to reuse the static inputs).
+        Returns the loss tensor (static: read it before the next call)."""
+        if u is not None:
+            self.u.copy_(u, non_blocking=True)
+            self.pos.copy_(pos, non_blocking=True)
+            self.neg.copy_(neg, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -238,7 +238,7 @@ def run_ours(args):
     loss_acc = torch.zeros((), device=dev)
 
     def step(u_, pos_, neg_):
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad(set_to_none=False)
         loss = dp.loss_step(u_, pos_, neg_, CFG["margin"])
         loss.backward()
         dp.reduce_gradients()
@@ -250,6 +250,23 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    use_graph = world == 1 and not args.no_graph
+    graph_launches = 0
+    if use_graph:
+        c0 = L.lib().dcue_launch_count()
+        gstep = pkg.GraphedTrainStep(model, CFG["margin"], u, pos, neg, warmup=3)
+        graph_launches = (L.lib().dcue_launch_count() - c0) // 4       # 3 warm-up passes + the captured one
+
+        step_eager = step
+
+        def step(u_, pos_, neg_):  # noqa: F811  (same step: forward+loss+backward replayed as one CUDA graph)
+            if u_ is not u:
+                return step_eager(u_, pos_, neg_)      # other buffers (dense e2e double buffering): eager launches
+            loss = gstep()
+            opt.step()
+            sched.batch_step()
+            return loss.detach().clone()
 
     # ---------------- device-resident timing ("value")
     for _ in range(args.warmup):
@@ -264,6 +281,8 @@ def run_ours(args):
     e1.record()
     barrier()
     launches = L.lib().dcue_launch_count() - launches0
+    # under graph replay the library's launch counter does not tick: use the per-step count seen at capture
+    launches_per_step = launches / args.steps if not use_graph else graph_launches
     clocks = sampler.stop() if sampler else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
@@ -321,13 +340,21 @@ def run_ours(args):
     hidx = [(torch.randint(0, U, (B,), generator=gi).pin_memory(), torch.randint(0, pool_songs, (B,), generator=gi).pin_memory(),
              torch.randint(0, pool_songs, (B, N), generator=gi).pin_memory()) for _ in range(n_idx_batches)]
 
+    gidx = None
+    if use_graph:
+        u0_, p0_, n0_ = (t.to(dev) for t in hidx[0])
+        gidx = pkg.GraphedTrainStep(model, CFG["margin"], u0_, p0_, n0_, pool=pool)
+
     def idx_step(i):
         hu_, hp_, hn_ = hidx[i % n_idx_batches]
-        u_, p_, n_ = hu_.to(dev, non_blocking=True), hp_.to(dev, non_blocking=True), hn_.to(dev, non_blocking=True)
-        opt.zero_grad(set_to_none=True)
-        loss = dp.loss_step_indexed(u_, pool, p_, n_, CFG["margin"])
-        loss.backward()
-        dp.reduce_gradients()
+        if gidx is not None:
+            loss = gidx(hu_, hp_, hn_)           # pinned host -> static device index buffers, then one graph launch
+        else:
+            u_, p_, n_ = hu_.to(dev, non_blocking=True), hp_.to(dev, non_blocking=True), hn_.to(dev, non_blocking=True)
+            opt.zero_grad(set_to_none=False)
+            loss = dp.loss_step_indexed(u_, pool, p_, n_, CFG["margin"])
+            loss.backward()
+            dp.reduce_gradients()
         opt.step()
         sched.batch_step()
         return loss.detach().item()      # device -> host read of the step's result
@@ -364,7 +391,7 @@ def run_ours(args):
                "e2e_indexed": {"value": e2e_idx_value, "unit": UNIT, "h2d_bytes_per_step": h2d_idx, "d2h_bytes_per_step": 4,
                                "steps": idx_steps,
                                "api": "hinge_loss_step_indexed: resident pool of %d songs on the device, host sends u + song indices" % pool_songs},
-               "gpu_launches": int(launches), "final_loss": final_loss,
+               "gpu_launches": int(launches_per_step * args.steps), "final_loss": final_loss, "cuda_graph": bool(use_graph),
                "roofline": {"bound": kern[top]["bound"], "kernel": top, "achieved": kern[top]["achieved"], "peak": peak,
                             "unit": kern[top]["unit"], "frac": kern[top]["achieved"] / peak, "traffic": traffic,
                             "peak_source": which + (" (burst bf16 cuBLAS)" if kern[top]["bound"] == "tensor" else " (copy)"),
@@ -391,6 +418,7 @@ def main():
     ap.add_argument("--negs", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

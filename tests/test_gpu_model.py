@@ -201,3 +201,31 @@ def test_index_feed_equals_dense_feed(mt):
     b_.forward_indexed(u.to(DEV), pool_d, pi.to(DEV), ni_bad.to(DEV), po.to(DEV), no.to(DEV))
     with pytest.raises(IndexError):
         b_.raise_if_index_error()
+
+
+def test_cuda_graph_step_equals_eager():
+    """GraphedTrainStep (one graph launch per step) reproduces the eager step bit for bit, over several
+    replays with changing inputs and an optimizer stepping in between."""
+    mt, B, N, U = "truedcuemel1dbn", 6, 3, 40
+    params = fixtures.make_params(mt, seed=0, user_count=U)
+    batches = [fixtures.make_inputs(B, N, U, seed=10 + i) for i in range(3)]
+    eager, graphed = _build(mt, U, params).train(), _build(mt, U, params).train()
+    oe = torch.optim.Adam(eager.parameters(), 1e-3)
+    og = torch.optim.Adam(graphed.parameters(), 1e-3)
+    u0, p0, n0 = (t.to(DEV) for t in batches[0])
+    sd = {k: v.clone() for k, v in graphed.state_dict().items()}
+    step = pkg.GraphedTrainStep(graphed, 0.2, u0, p0, n0)
+    graphed.load_state_dict(sd)                   # warm-up + capture ran forward passes: restore BatchNorm buffers
+    for u, pos, neg in batches:
+        u, pos, neg = u.to(DEV), pos.to(DEV), neg.to(DEV)
+        eager.zero_grad(set_to_none=True)
+        le = eager.hinge_loss_step(u, pos, neg, 0.2)
+        le.backward()
+        oe.step()
+        lg = step(u, pos, neg)
+        og.step()
+        assert le.item() == lg.item()
+    for (k, p), (_, q) in zip(eager.named_parameters(), graphed.named_parameters()):
+        assert torch.equal(p, q), k
+    for (k, p), (_, q) in zip(eager.named_buffers(), graphed.named_buffers()):
+        assert torch.equal(p, q), k
