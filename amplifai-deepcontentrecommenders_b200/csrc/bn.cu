@@ -123,11 +123,14 @@ reduce_partials_kernel(const double* __restrict__ partial, int nblk, int n, doub
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
                                    int64_t* __restrict__ nbt, float momentum, float eps, int training,
-                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_o,
-                                   float* __restrict__ rstd_o) {
+                                   const float* __restrict__ center, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_o, float* __restrict__ rstd_o) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && training && nbt) *nbt += 1;
     if (c >= C) return;
+    // `center` (nullable): the statistics in `sums` are those of x - center[c] and the returned mean / shift
+    // refer to that centred operand; running_mean is still updated with the mean of x itself.
+    const double ctr = center ? (double)center[c] : 0.0;   // read before running_mean is updated (may alias)
     double mean, var;
     if (training) {
         mean = sums[c] / count;
@@ -135,11 +138,11 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
         if (var < 0.0) var = 0.0;
         if (rmean) {
             const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
-            rmean[c] = (float)((1.0 - momentum) * (double)rmean[c] + momentum * mean);
+            rmean[c] = (float)((1.0 - momentum) * (double)rmean[c] + momentum * (mean + ctr));
             rvar[c] = (float)((1.0 - momentum) * (double)rvar[c] + momentum * unb);
         }
     } else {
-        mean = rmean[c];
+        mean = (double)rmean[c] - ctr;
         var = rvar[c];
     }
     const double rstd = 1.0 / sqrt(var + (double)eps);
@@ -180,6 +183,68 @@ ncl_pack_kernel(SpecSrc src, int S, int C, int L, const float* __restrict__ scal
         o.z = h[4] | ((unsigned)h[5] << 16);
         o.w = h[6] | ((unsigned)h[7] << 16);
         panel[(long)q * panel_rows + s * Lp + pad + t] = o;
+    }
+}
+
+// ------------------------------------------------------------------ single-pass input kernel
+// u = x - center[c] (fp32) -> 16-bit panel, and per-channel sum / sum of squares of u in the same pass.
+// block (q, g): panel q (8 channels), spectrograms g, g+G, ...; warps split the spectrograms, lanes walk
+// the frames, so every lane keeps private partial sums for its panel's 8 channels (no atomics).
+__global__ void __launch_bounds__(256)
+ncl_center_pack_stats_kernel(SpecSrc src, int S, int C, int L, const float* __restrict__ center, uint4* __restrict__ panel,
+                             long panel_rows, int Lp, int pad, int fmt, double* __restrict__ partial /* [G][2][C] */) {
+    __shared__ double red[8][16];
+    const int npan = C / 8;
+    const int q = blockIdx.x % npan, gi = blockIdx.x / npan, G = gridDim.x / npan;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float ctr[8], a1[8], a2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ctr[j] = center ? center[q * 8 + j] : 0.f; a1[j] = a2[j] = 0.f; }
+    for (int s = gi + w * G; s < S; s += 8 * G) {
+        long rs;
+        const float* base = src.base(s, C, L, rs) + (long)(q * 8) * rs;
+        uint4* prow = panel + (long)q * panel_rows + (long)s * Lp + pad;
+        for (int t0 = 0; t0 < L; t0 += 64) {   // two frames per lane in flight: 16 independent loads
+            float v[2][8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = t0 + h * 32 + lane;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[h][j] = t < L ? __ldg(base + (long)j * rs + t) : 0.f;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = t0 + h * 32 + lane;
+                if (t >= L) continue;
+                unsigned short hh[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float u = v[h][j] - ctr[j];
+                    a1[j] += u;
+                    a2[j] = fmaf(u, u, a2[j]);
+                    hh[j] = cvt_f32_to16(u, fmt);
+                }
+                uint4 o;
+                o.x = hh[0] | ((unsigned)hh[1] << 16);
+                o.y = hh[2] | ((unsigned)hh[3] << 16);
+                o.z = hh[4] | ((unsigned)hh[5] << 16);
+                o.w = hh[6] | ((unsigned)hh[7] << 16);
+                prow[t] = o;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double s1 = warp_sum_d((double)a1[j]), s2 = warp_sum_d((double)a2[j]);
+        if (lane == 0) { red[w][j] = s1; red[w][8 + j] = s2; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        const int which = threadIdx.x >> 3, j = threadIdx.x & 7;
+        partial[((long)gi * 2 + which) * C + q * 8 + j] = t;
     }
 }
 
@@ -564,15 +629,50 @@ extern "C" int dcue_ncl_stats_indexed(const float* pool, long n_songs, long T, c
     return ncl_stats_impl(src, S, C, L, sums, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+static int center_pack_impl(const SpecSrc& src, int S, int C, int L, const float* center, void* panel, long panel_rows,
+                            int Lp, int pad, int fmt, double* sums, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const int npan = C / 8;
+    int G = dcue_num_sms() * 4 / npan;
+    if (G > (S + 7) / 8) G = (S + 7) / 8;
+    if (G < 1) G = 1;
+    if (ws_bytes < (size_t)G * 2 * C * sizeof(double)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_ncl_center_pack_stats: workspace too small");
+    ncl_center_pack_stats_kernel<<<G * npan, 256, 0, st>>>(src, S, C, L, center, (uint4*)panel, panel_rows, Lp, pad, fmt,
+                                                           (double*)ws);
+    DCUE_LAUNCH_CHECK();
+    reduce_partials_kernel<<<ceil_div_i(2 * C, 8), 256, 0, st>>>((const double*)ws, G, 2 * C, sums);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcue_ncl_center_pack_stats(const float* pos, int S_pos, const float* neg, int S_neg, int C, int L,
+                                          const float* center, void* panel, long panel_rows, int Lp, int pad, int fmt,
+                                          double* sums, void* ws, size_t ws_bytes, void* stream) {
+    DCUE_CHECK_ARG(panel && sums && ws && S_pos >= 0 && S_neg >= 0 && (pos || S_pos == 0) && (neg || S_neg == 0));
+    DCUE_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 128 && L > 0 && Lp >= L + pad && pad >= 0 && panel_rows >= (long)(S_pos + S_neg) * Lp);
+    SpecSrc src{pos, neg, S_pos, nullptr, nullptr, 0, 0, nullptr};
+    return center_pack_impl(src, S_pos + S_neg, C, L, center, panel, panel_rows, Lp, pad, fmt, sums, ws, ws_bytes,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int dcue_ncl_center_pack_stats_indexed(const float* pool, long n_songs, long T, const int64_t* idx,
+                                                  const int32_t* off, int S, int C, int L, int* err_flag, const float* center,
+                                                  void* panel, long panel_rows, int Lp, int pad, int fmt, double* sums,
+                                                  void* ws, size_t ws_bytes, void* stream) {
+    DCUE_CHECK_ARG(pool && idx && panel && sums && ws && err_flag && S >= 0 && n_songs > 0 && T >= L);
+    DCUE_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 128 && L > 0 && Lp >= L + pad && pad >= 0 && panel_rows >= (long)S * Lp);
+    SpecSrc src{pool, nullptr, 0, idx, off, T, n_songs, err_flag};
+    return center_pack_impl(src, S, C, L, center, panel, panel_rows, Lp, pad, fmt, sums, ws, ws_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int dcue_bn_finalize(const double* sums, double count, int C, const float* gamma, const float* beta,
                                 float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
-                                float eps, int training, float* scale, float* shift, float* mean, float* rstd,
-                                void* stream) {
+                                float eps, int training, const float* center, float* scale, float* shift, float* mean,
+                                float* rstd, void* stream) {
     DCUE_CHECK_ARG(C > 0 && scale && shift && mean && rstd);
     DCUE_CHECK_ARG(training ? (sums != nullptr && count > 0) : (running_mean && running_var));
     bn_finalize_kernel<<<ceil_div_i(C, 128), 128, 0, (cudaStream_t)stream>>>(
-        sums, count, C, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, training, scale,
-        shift, mean, rstd);
+        sums, count, C, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, training, center,
+        scale, shift, mean, rstd);
     DCUE_LAUNCH_CHECK();
     return 0;
 }

@@ -205,7 +205,8 @@ dcue_reduce_partials_d(const double* __restrict__ partial, int nblk, int n, doub
 }
 
 __global__ void pack_conv_weight_kernel(const float* __restrict__ W, int Cout, int Cin, int k, int mode, int fmt,
-                                        const float* __restrict__ col_scale, unsigned short* __restrict__ out) {
+                                        const float* __restrict__ col_scale, const float* __restrict__ col_scale2,
+                                        unsigned short* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int K = k * 128;
     if (i >= 128 * K) return;
@@ -213,7 +214,8 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ W, int Cout, i
     const int j = kk / 128, c = kk % 128;
     float v = 0.f;
     if (mode == 0) {  // A[co=m][j*128+ci=c] = W[co][ci][j]
-        if (m < Cout && c < Cin) v = W[((long)m * Cin + c) * k + j] * (col_scale ? col_scale[c] : 1.f);
+        if (m < Cout && c < Cin)
+            v = W[((long)m * Cin + c) * k + j] * (col_scale ? col_scale[c] : 1.f) * (col_scale2 ? col_scale2[c] : 1.f);
     } else {          // A[ci=m][jj*128+co=c] = W[co][ci][k-1-jj]
         if (m < Cin && c < Cout) v = W[((long)c * Cin + m) * k + (k - 1 - j)];
     }
@@ -268,30 +270,35 @@ int dcue_simt_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const v
 }
 
 extern "C" int dcue_pack_conv_weight(const float* W, int Cout, int Cin, int k, int mode, int fmt, const float* col_scale,
-                                     void* out, void* stream) {
+                                     const float* col_scale2, void* out, void* stream) {
     DCUE_CHECK_ARG(W && out && Cout > 0 && Cout <= 128 && Cin > 0 && Cin <= 128 && k >= 1 && k <= 4 &&
                    (mode == 0 || mode == 1));
     pack_conv_weight_kernel<<<ceil_div_i(128L * k * 128, 256), 256, 0, (cudaStream_t)stream>>>(
-        W, Cout, Cin, k, mode, fmt, col_scale, (unsigned short*)out);
+        W, Cout, Cin, k, mode, fmt, col_scale, col_scale2, (unsigned short*)out);
     DCUE_LAUNCH_CHECK();
     return 0;
 }
 
 
 // tapB[j][co] = sum_ci W[co][ci][j] * beta[ci]   (input-BatchNorm shift folded into the conv bias)
+// the constant each input channel carries is beta[c] + gamma[c]*shift[c] (shift: x-hat = rstd*u + shift)
 __global__ void tap_bias_kernel(const float* __restrict__ W, int Cout, int Cin, int k, const float* __restrict__ beta,
-                                float* __restrict__ out) {
+                                const float* __restrict__ gamma, const float* __restrict__ shift, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= k * Cout) return;
     const int j = i / Cout, co = i % Cout;
     float s = 0.f;
-    for (int c = 0; c < Cin; ++c) s = fmaf(W[((long)co * Cin + c) * k + j], beta[c], s);
+    for (int c = 0; c < Cin; ++c) {
+        const float b = beta[c] + (shift ? (gamma ? gamma[c] : 1.f) * shift[c] : 0.f);
+        s = fmaf(W[((long)co * Cin + c) * k + j], b, s);
+    }
     out[i] = s;
 }
 
-extern "C" int dcue_conv_tap_bias(const float* W, int Cout, int Cin, int k, const float* beta, float* tap_bias, void* stream) {
+extern "C" int dcue_conv_tap_bias(const float* W, int Cout, int Cin, int k, const float* beta, const float* gamma,
+                                  const float* shift, float* tap_bias, void* stream) {
     DCUE_CHECK_ARG(W && beta && tap_bias && Cout > 0 && Cin > 0 && k >= 1 && k <= 4);
-    tap_bias_kernel<<<ceil_div_i(k * Cout, 128), 128, 0, (cudaStream_t)stream>>>(W, Cout, Cin, k, beta, tap_bias);
+    tap_bias_kernel<<<ceil_div_i(k * Cout, 128), 128, 0, (cudaStream_t)stream>>>(W, Cout, Cin, k, beta, gamma, shift, tap_bias);
     DCUE_LAUNCH_CHECK();
     return 0;
 }
@@ -346,7 +353,8 @@ extern "C" int dcue_panel_row_sums(const void* panel, long panel_rows, int fmt, 
 //           = Tall[co] - sum_{border rows t with tap j outside} E[t][co]
 __global__ void __launch_bounds__(128)
 bn_fold_grads_kernel(const float* __restrict__ G, const float* __restrict__ W, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, const float* __restrict__ Tall, const float* __restrict__ E /* [4][128] */,
+                     const float* __restrict__ beta, const float* __restrict__ xs_scale, const float* __restrict__ xs_shift,
+                     const float* __restrict__ Tall, const float* __restrict__ E /* [4][128] */,
                      int4 erows, int Cout, int Cin, int k, int pad, int Lin, float* __restrict__ dW,
                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
     __shared__ float r1[128], r2[128];
@@ -355,6 +363,8 @@ bn_fold_grads_kernel(const float* __restrict__ G, const float* __restrict__ W, c
     if (co < Cout) {
         const int er[4] = {erows.x, erows.y, erows.z, erows.w};
         const float ga = gamma[ci], be = beta[ci];
+        // the operand was u with x-hat = xs_scale*u + xs_shift: G(x-hat) = xs_scale*G(u) + xs_shift*T
+        const float xr = xs_scale ? xs_scale[ci] : 1.f, xsft = xs_shift ? xs_shift[ci] : 0.f;
         for (int j = 0; j < k; ++j) {
             float T = Tall[co];
             for (int e = 0; e < 4; ++e) {
@@ -363,7 +373,7 @@ bn_fold_grads_kernel(const float* __restrict__ G, const float* __restrict__ W, c
                 if (tt < 0 || tt >= Lin) T -= E[e * 128 + co];
             }
             const long o = ((long)co * Cin + ci) * k + j;
-            const float g = G[o], w = W[o];
+            const float g = xr * G[o] + xsft * T, w = W[o];
             dW[o] = ga * g + be * T;
             sg = fmaf(w, g, sg);
             sb = fmaf(w, T, sb);
@@ -379,12 +389,12 @@ bn_fold_grads_kernel(const float* __restrict__ G, const float* __restrict__ W, c
     if (co == 0) { dgamma[ci] = r1[0]; dbeta[ci] = r2[0]; }
 }
 
-extern "C" int dcue_bn_fold_grads(const float* G, const float* W, const float* gamma, const float* beta, const float* Tall,
-                                  const float* E, int r0, int r1, int r2, int r3, int Cout, int Cin, int k, int pad, int Lin,
+extern "C" int dcue_bn_fold_grads(const float* G, const float* W, const float* gamma, const float* beta,
+                                  const float* xs_scale, const float* xs_shift, const float* Tall, const float* E, int r0, int r1, int r2, int r3, int Cout, int Cin, int k, int pad, int Lin,
                                   float* dW, float* dgamma, float* dbeta, void* stream) {
     DCUE_CHECK_ARG(G && W && gamma && beta && Tall && E && dW && dgamma && dbeta && Cout > 0 && Cout <= 128 && Cin > 0 &&
                    k >= 1 && k <= 4);
-    bn_fold_grads_kernel<<<Cin, 128, 0, (cudaStream_t)stream>>>(G, W, gamma, beta, Tall, E, make_int4(r0, r1, r2, r3), Cout,
+    bn_fold_grads_kernel<<<Cin, 128, 0, (cudaStream_t)stream>>>(G, W, gamma, beta, xs_scale, xs_shift, Tall, E, make_int4(r0, r1, r2, r3), Cout,
                                                                 Cin, k, pad, Lin, dW, dgamma, dbeta);
     DCUE_LAUNCH_CHECK();
     return 0;

@@ -179,9 +179,10 @@ class SongTowerFn(torch.autograd.Function):
         dp = mod._dp
         world = 1 if dp is None else dp.world_size
 
-        def bn_finalize(i, count, C_, affine=True):
+        def bn_finalize(i, count, C_, affine=True, centered=False):
             """sums[i] -> scale/shift/mean/rstd of BN layer i (batch or running statistics).
-            affine=False gives the plain normalisation (scale = rstd, shift = -mean*rstd)."""
+            affine=False gives the plain normalisation (scale = rstd, shift = -mean*rstd); centered=True means the
+            statistics were taken on x - running_mean (the single-pass input kernel)."""
             bnm = getattr(mod, "bn%d" % i)
             if training and dp is not None:
                 dp.all_reduce_sum(ws.sums[i])
@@ -189,37 +190,40 @@ class SongTowerFn(torch.autograd.Function):
                    P["bn%d.weight" % i].data_ptr() if affine else None,
                    P["bn%d.bias" % i].data_ptr() if affine else None, bnm.running_mean.data_ptr(), bnm.running_var.data_ptr(),
                    bnm.num_batches_tracked.data_ptr(), BN_MOMENTUM, BN_EPS, int(training),
+                   bnm.running_mean.data_ptr() if centered else None,
                    ws.bnp[i, 0].data_ptr(), ws.bnp[i, 1].data_ptr(), ws.bnp[i, 2].data_ptr(), ws.bnp[i, 3].data_ptr(), st)
 
         pos_p, neg_p = pos.data_ptr(), (None if neg is None else neg.data_ptr())
-        # ---- bn0 + transpose/convert into the layer1 operand panel.  The panel holds the plain
-        # normalised input xhat; bn0's gamma is folded into layer1's packed weights and its beta into a
-        # border-aware bias (dcue_conv_tap_bias), which lets the backward skip layer1's data gradient.
+        # ---- input -> layer1 operand panel.  BatchNorm towers: ONE pass over the fp32 input writes
+        # u = x - bn0.running_mean as the fp16 panel and accumulates the batch statistics of u; the exact
+        # normalisation x-hat = rstd*u + shift, bn0's gamma and beta are all folded into layer1 (packed weights
+        # W*gamma*rstd, border-aware bias), which also lets the backward skip layer1's data gradient.
         g0 = geo[0]
+        off_p = None if (src is None or off is None) else off.data_ptr()
         if has_bn:
-            if training and src is not None:
-                L.call("dcue_ncl_stats_indexed", pos_p, n_songs, T, idx.data_ptr(), None if off is None else off.data_ptr(), S, C,
-                       frames, err.data_ptr(), ws.sums[0].data_ptr(), scratch, nscr, st)
-            elif training:
-                L.call("dcue_ncl_stats", pos_p, S_pos, neg_p, S_neg, C, frames, ws.sums[0].data_ptr(), scratch, nscr, st)
-            bn_finalize(0, S * frames, C, affine=False)
-            sc, sh = ws.bnp[0, 0].data_ptr(), ws.bnp[0, 1].data_ptr()
+            rm0 = mod.bn0.running_mean.data_ptr()
+            if src is not None:
+                L.call("dcue_ncl_center_pack_stats_indexed", pos_p, n_songs, T, idx.data_ptr(), off_p, S, C, frames, err.data_ptr(),
+                       rm0, ws.X[0].base, ws.X[0].panel_rows, g0["Lp"], g0["pad"], fmt, ws.sums[0].data_ptr(), scratch, nscr, st)
+            else:
+                L.call("dcue_ncl_center_pack_stats", pos_p, S_pos, neg_p, S_neg, C, frames, rm0, ws.X[0].base, ws.X[0].panel_rows,
+                       g0["Lp"], g0["pad"], fmt, ws.sums[0].data_ptr(), scratch, nscr, st)
+            bn_finalize(0, S * frames, C, affine=False, centered=True)   # bnp[0] = (rstd, shift, mean_u, rstd)
             L.call("dcue_conv_tap_bias", P["layer1.weight"].data_ptr(), H, 128, g0["k"], P["bn0.bias"].data_ptr(),
-                   ws.tapb.data_ptr(), st)
+                   P["bn0.weight"].data_ptr(), ws.bnp[0, 1].data_ptr(), ws.tapb.data_ptr(), st)
+        elif src is not None:
+            L.call("dcue_ncl_pack_indexed", pos_p, n_songs, T, idx.data_ptr(), off_p, S, C, frames, err.data_ptr(), None, None,
+                   ws.X[0].base, ws.X[0].panel_rows, g0["Lp"], g0["pad"], fmt, st)
         else:
-            sc = sh = None
-        if src is not None:
-            L.call("dcue_ncl_pack_indexed", pos_p, n_songs, T, idx.data_ptr(), None if off is None else off.data_ptr(), S, C, frames,
-                   err.data_ptr(), sc, sh, ws.X[0].base, ws.X[0].panel_rows, g0["Lp"], g0["pad"], fmt, st)
-        else:
-            L.call("dcue_ncl_pack", pos_p, S_pos, neg_p, S_neg, C, frames, sc, sh, ws.X[0].base, ws.X[0].panel_rows,
+            L.call("dcue_ncl_pack", pos_p, S_pos, neg_p, S_neg, C, frames, None, None, ws.X[0].base, ws.X[0].panel_rows,
                    g0["Lp"], g0["pad"], fmt, st)
         # ---- layer1..4: conv + pool + relu (+ BN statistics) -> affine -> next operand panel
         for i, g in enumerate(geo, start=1):
             Wt, bt = P["layer%d.weight" % i], P["layer%d.bias" % i]
             fold = has_bn and i == 1
             L.call("dcue_pack_conv_weight", Wt.data_ptr(), H, 128, g["k"], 0, fmt,
-                   P["bn0.weight"].data_ptr() if fold else None, ws.wp[i - 1].data_ptr(), st)
+                   P["bn0.weight"].data_ptr() if fold else None, ws.bnp[0, 0].data_ptr() if fold else None,
+                   ws.wp[i - 1].data_ptr(), st)
             want_stats = has_bn and training
             L.call("dcue_conv_pool_fwd", impl, ws.X[i - 1].base, ws.X[i - 1].panel_rows, fmt, ws.wp[i - 1].data_ptr(),
                    bt.data_ptr(), ws.tapb.data_ptr() if fold else None, S, g["Lp"], g["Lin"], g["pad"], g["P"], g["pool"],
@@ -367,13 +371,14 @@ class SongTowerFn(torch.autograd.Function):
                        gsc, b["E"].data_ptr(), st)
                 dW1, dg0, db0 = torch.empty(H, 128, k_, **f32), torch.empty(128, **f32), torch.empty(128, **f32)
                 L.call("dcue_bn_fold_grads", gW_i.data_ptr(), P["layer1.weight"].data_ptr(), P["bn0.weight"].data_ptr(),
-                       P["bn0.bias"].data_ptr(), gb_i.data_ptr(), b["E"].data_ptr(), brow[0], brow[1], brow[2], brow[3], H, 128,
+                       P["bn0.bias"].data_ptr(), ws.bnp[0, 0].data_ptr(), ws.bnp[0, 1].data_ptr(), gb_i.data_ptr(),
+                       b["E"].data_ptr(), brow[0], brow[1], brow[2], brow[3], H, 128,
                        k_, pad_, lin_, dW1.data_ptr(), dg0.data_ptr(), db0.data_ptr(), st)
                 gW_i = dW1
                 grads["bn0.weight"], grads["bn0.bias"] = dg0, db0
             grads["layer%d.weight" % i], grads["layer%d.bias" % i] = gW_i, gb_i
             if i > 1:
-                L.call("dcue_pack_conv_weight", P["layer%d.weight" % i].data_ptr(), H, 128, g["k"], 1, fmt, None,
+                L.call("dcue_pack_conv_weight", P["layer%d.weight" % i].data_ptr(), H, 128, g["k"], 1, fmt, None, None,
                        b["wpd"][i - 1].data_ptr(), st)
                 dx = b["dx"][i - 1]
                 L.call("dcue_conv_dgrad", impl, dYp.base, dYp.panel_rows, gfmt, b["wpd"][i - 1].data_ptr(), fmt, S, g["Lp"],

@@ -111,7 +111,20 @@ int dcue_ncl_pack_indexed(const float* pool, long n_songs, long T, const int64_t
 int dcue_bn_finalize(const double* sums, double count, int C, const float* gamma, const float* beta,
                      float* running_mean, float* running_var, int64_t* num_batches_tracked,
                      float momentum, float eps, int training,
+                     const float* center /* nullable: sums are statistics of x - center (may alias running_mean) */,
                      float* scale, float* shift, float* mean, float* rstd, void* stream);
+
+/* Single pass over the fp32 input (replaces dcue_ncl_stats + dcue_ncl_pack for the BatchNorm towers):
+ * u = x - center[c] is written as the 16-bit layer-1 operand panel and its per-channel sum / sum of squares
+ * are accumulated in the same sweep (sums = double[2*C]).  center = bn0.running_mean keeps u small whatever
+ * the data offset; the exact batch normalisation x-hat = rstd*u + shift is folded into layer 1. */
+int dcue_ncl_center_pack_stats(const float* pos, int S_pos, const float* neg, int S_neg, int C, int L,
+                               const float* center, void* panel, long panel_rows, int Lp, int pad, int fmt,
+                               double* sums, void* ws, size_t ws_bytes, void* stream);
+int dcue_ncl_center_pack_stats_indexed(const float* pool, long n_songs, long T, const int64_t* idx,
+                                       const int32_t* off, int S, int C, int L, int* err_flag, const float* center,
+                                       void* panel, long panel_rows, int Lp, int pad, int fmt, double* sums,
+                                       void* ws, size_t ws_bytes, void* stream);
 
 /* x[S,C,L] fp32 (pos rows then neg rows) -> scale*x+shift -> 16-bit panel rows
  * r = s*Lp + pad + t  (fused transpose + convert; scale/shift NULL = identity). */
@@ -123,22 +136,25 @@ int dcue_ncl_pack(const float* pos, int S_pos, const float* neg, int S_neg, int 
  * mode 0 (forward): A[co][j*Cin+ci] = W[co][ci][j];
  * mode 1 (dgrad):   A[ci][jj*Cout+co] = W[co][ci][k-1-jj].   Rows/cols beyond C are zero. */
 int dcue_pack_conv_weight(const float* W, int Cout, int Cin, int k, int mode, int fmt,
-                          const float* col_scale /* mode 0: W[co][ci][j] *= col_scale[ci]; nullable */, void* out,
-                          void* stream);
+                          const float* col_scale /* mode 0: W[co][ci][j] *= col_scale[ci]; nullable */,
+                          const float* col_scale2 /* second per-ci factor; nullable */, void* out, void* stream);
 
 /* Folding an input-side BatchNorm (gamma, beta) into the conv that consumes it, so that the conv
  * operand is the plain normalised input xhat (truedcuemel1dbn.py:79-80):
  *   conv(gamma*xhat + beta) = conv_{W*gamma}(xhat) + sum over taps j that hit a data row of tapB[j],
  * tapB[j][co] = sum_ci W[co][ci][j]*beta[ci].  tap_bias out = float[k][Cout]. */
-int dcue_conv_tap_bias(const float* W, int Cout, int Cin, int k, const float* beta, float* tap_bias, void* stream);
+int dcue_conv_tap_bias(const float* W, int Cout, int Cin, int k, const float* beta,
+                       const float* gamma /* nullable */, const float* shift /* nullable: constant = beta + gamma*shift */,
+                       float* tap_bias, void* stream);
 /* out[i][c] = gscale[1] * sum_s panel[s*Lp + r_i][c], i < 4 (r_i < 0 = unused): border row sums of dY. out = float[4][128] */
 int dcue_panel_row_sums(const void* panel, long panel_rows, int fmt, int S, int Lp, int r0, int r1, int r2, int r3,
                         const float* gscale, float* out, void* stream);
 /* Backward of the folded pair from G = wgrad(dY, xhat):  dW = gamma*G + beta*T, dgamma = sum W*G,
  * dbeta = sum W*T, with T[co][j] = Tall[co] - sum of the border row sums E whose tap j is padding.
  * This replaces the layer-1 data gradient and the BatchNorm-backward pass over the input batch. */
-int dcue_bn_fold_grads(const float* G, const float* W, const float* gamma, const float* beta, const float* Tall,
-                       const float* E, int r0, int r1, int r2, int r3, int Cout, int Cin, int k, int pad, int Lin,
+int dcue_bn_fold_grads(const float* G, const float* W, const float* gamma, const float* beta,
+                       const float* xs_scale, const float* xs_shift /* operand u with x-hat = xs_scale*u + xs_shift; nullable */,
+                       const float* Tall, const float* E, int r0, int r1, int r2, int r3, int Cout, int Cin, int k, int pad, int Lin,
                        float* dW, float* dgamma, float* dbeta, void* stream);
 
 /* Conv1d + bias + MaxPool1d(pool) + ReLU with BatchNorm partial sums, implicit GEMM over

@@ -72,37 +72,39 @@ class _RoundedConv(torch.autograd.Function):
 
 
 class _FoldedBNConv(torch.autograd.Function):
-    """layer1(bn0(x)) as the B200 path evaluates it: the conv operand is the plain normalised input
-    xhat, bn0.weight is folded into the weights and bn0.bias into a border-aware bias; backward gets
-    dW, dgamma, dbeta from G = sum dY*xhat (no data gradient).  Same function, different roundings."""
+    """layer1(bn0(x)) as the B200 path evaluates it.  The conv operand is u = x - running_mean (rounded to
+    the operand dtype); the exact normalisation x-hat = r*u + shift, bn0.weight and bn0.bias are folded into
+    the weights (W*gamma*r, rounded) and a border-aware bias; backward gets dW, dgamma, dbeta from
+    G = sum dY*u (no data gradient).  Same function as the reference, different roundings."""
 
     @staticmethod
-    def forward(ctx, xhat, w, b, gamma, beta, padding, op_dt, g_dt):
-        xr = _round(xhat, op_dt)
-        wg = _round(w * gamma[None, :, None], op_dt)
-        S, C, L = xhat.shape
-        beta_img = beta.view(1, C, 1).expand(1, C, L)
-        y = F.conv1d(xr, wg, None, padding=padding) + F.conv1d(beta_img, w, None, padding=padding) + b.view(1, -1, 1)
-        ctx.save_for_backward(xr, w, gamma, beta)
+    def forward(ctx, u, w, b, gamma, beta, r, shift, padding, op_dt, g_dt):
+        ur = _round(u, op_dt)
+        wg = _round(w * (gamma * r)[None, :, None], op_dt)
+        S, C, L = u.shape
+        const_img = (beta + gamma * shift).view(1, C, 1).expand(1, C, L)
+        y = F.conv1d(ur, wg, None, padding=padding) + F.conv1d(const_img, w, None, padding=padding) + b.view(1, -1, 1)
+        ctx.save_for_backward(ur, w, gamma, beta, r, shift)
         ctx.padding, ctx.g_dt = padding, g_dt
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        xr, w, gamma, beta = ctx.saved_tensors
-        pad, k, L = ctx.padding, w.shape[2], xr.shape[2]
+        ur, w, gamma, beta, r, shift = ctx.saved_tensors
+        pad, k, L = ctx.padding, w.shape[2], ur.shape[2]
         gr = _round(gy, ctx.g_dt)
-        G = torch.nn.grad.conv1d_weight(xr, w.shape, gr, padding=pad)
+        Gu = torch.nn.grad.conv1d_weight(ur, w.shape, gr, padding=pad)
         tall = gy.sum(dim=(0, 2))
         T = tall[:, None].repeat(1, k)
         for j in range(k):
             for t in range(gy.shape[2]):
                 if not 0 <= t + j - pad < L:
                     T[:, j] = T[:, j] - gr[:, :, t].sum(0)
+        G = r[None, :, None] * Gu + shift[None, :, None] * T[:, None, :]      # sum dY * x-hat
         dW = gamma[None, :, None] * G + beta[None, :, None] * T[:, None, :]
         dgamma = (w * G).sum(dim=(0, 2))
         dbeta = (w * T[:, None, :]).sum(dim=(0, 2))
-        return None, dW, tall, dgamma, dbeta, None, None, None
+        return None, dW, tall, dgamma, dbeta, None, None, None, None, None
 
 
 def _conv(x, w, b, padding, op_dt, g_dt):
@@ -149,13 +151,24 @@ def tower_forward(p, x, model_type, training=True, prefix="conv.", operand_dtype
     if new_stats is not None:
         stats = {}
     fold = bn and (operand_dtype is not None or grad_dtype is not None)
-    if bn:
-        x = _bn(x, q, "bn0", training, stats, affine=not fold)
+    if bn and not fold:
+        x = _bn(x, q, "bn0", training, stats)
+    elif bn:
+        # B200 evaluation order: operand u = x - running_mean, statistics of the batch folded into layer1
+        center = q["bn0.running_mean"].to(x.dtype)
+        _bn(x, q, "bn0", training, stats, affine=False)          # running-statistics update only
+        if training:
+            mean_x, var = x.mean(dim=(0, 2)).detach(), x.var(dim=(0, 2), unbiased=False).detach()
+        else:
+            mean_x, var = center, q["bn0.running_var"].to(x.dtype)
+        r0 = torch.rsqrt(var + BN_EPS)
+        shift0 = -(mean_x - center) * r0
+        x = x - center[None, :, None]
     tps = []
     for i, (pad, pool) in enumerate(((2, 4), (2, 4), (2, 4), (1, 2)), start=1):
         if fold and i == 1:
-            x = _FoldedBNConv.apply(x, q["layer1.weight"], q["layer1.bias"], q["bn0.weight"], q["bn0.bias"], pad,
-                                    operand_dtype, grad_dtype)
+            x = _FoldedBNConv.apply(x, q["layer1.weight"], q["layer1.bias"], q["bn0.weight"], q["bn0.bias"], r0, shift0,
+                                    pad, operand_dtype, grad_dtype)
         else:
             x = _conv(x, q["layer%d.weight" % i], q["layer%d.bias" % i], pad, operand_dtype, grad_dtype)
         x = F.max_pool1d(x, pool)

@@ -156,7 +156,7 @@ def _conv_case(S, gi, seed):
     L.call("dcue_ncl_pack", xd.data_ptr(), S, None, 0, 128, geo["Lin"], None, None, X.base, X.panel_rows, geo["Lp"],
            geo["pad"], L.FMT_F16, st)
     wp = torch.empty(128 * geo["k"] * 128, dtype=torch.int16, device=DEV)
-    L.call("dcue_pack_conv_weight", wd.data_ptr(), 128, 128, geo["k"], 0, L.FMT_F16, None, wp.data_ptr(), st)
+    L.call("dcue_pack_conv_weight", wd.data_ptr(), 128, 128, geo["k"], 0, L.FMT_F16, None, None, wp.data_ptr(), st)
     torch.cuda.synchronize()
     return dict(geo=geo, x=x, w=w, b=b, X=X, wp=wp, S=S, wd=wd, bd=bd)
 
@@ -256,7 +256,7 @@ def test_conv_backward_kernels(impl, gi, S):
            S * geo["Lp"], geo["k"], 128, 128, gsc.data_ptr(), dW.data_ptr(), ws.data_ptr(), nws, st)
     assert relerr(dW, wr.grad) < 5e-5
     wpd = torch.empty(128 * geo["k"] * 128, dtype=torch.int16, device=DEV)
-    L.call("dcue_pack_conv_weight", c["wd"].data_ptr(), 128, 128, geo["k"], 1, L.FMT_F16, None, wpd.data_ptr(), st)
+    L.call("dcue_pack_conv_weight", c["wd"].data_ptr(), 128, 128, geo["k"], 1, L.FMT_F16, None, None, wpd.data_ptr(), st)
     dx = torch.full((S * geo["Lin"], 128), float("nan"), device=DEV)
     L.call("dcue_conv_dgrad", impl, dY.base, dY.panel_rows, L.FMT_F16, wpd.data_ptr(), L.FMT_F16, S, geo["Lp"], geo["Lin"],
            geo["pad"], geo["k"], 128, 128, gsc.data_ptr(), dx.data_ptr(), ws.data_ptr(), nws, st)
@@ -282,7 +282,7 @@ def test_ncl_stats_and_bn_finalize():
     out = torch.empty(4, 128, device=DEV)
     n = 14 * 131
     L.call("dcue_bn_finalize", sums.data_ptr(), float(n), 128, gam_d.data_ptr(), bet_d.data_ptr(), rmd.data_ptr(),
-           rvd.data_ptr(), nbt.data_ptr(), 0.1, 1e-5, 1, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), st)
+           rvd.data_ptr(), nbt.data_ptr(), 0.1, 1e-5, 1, None, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), st)
     mean, var = x.mean((0, 2)), x.var((0, 2), unbiased=False)
     rstd = 1 / torch.sqrt(var + 1e-5)
     assert relerr(out[2], mean) < 1e-5 and relerr(out[3], rstd) < 1e-5
@@ -321,3 +321,41 @@ def test_topk_scores(nu, ni, k):
     # and against the pure fp32 oracle (reference semantics): scores within fp16 operand rounding
     v32, i32 = O.topk_scores(uf, itf, kk)
     assert (ts[:, :kk].cpu() - v32).abs().max() < 2e-3
+
+
+def test_single_pass_center_pack_stats():
+    """u = x - center as the fp16 panel + statistics of u in one sweep; finalize with the centre reproduces
+    the BatchNorm statistics of x (running_mean updated with the mean of x, not of u)."""
+    g = torch.Generator().manual_seed(11)
+    pos, neg = torch.randn(3, 128, 131, generator=g) * 2 + 1, torch.randn(10, 128, 131, generator=g) - 0.5
+    x = torch.cat([pos, neg])
+    rm, rv = torch.randn(128, generator=g) * 0.3, torch.rand(128, generator=g) + 0.5
+    geo = ops.tower_geometry(131)[0]
+    S = 13
+    X = ops.Panel(S, geo["Lp"], DEV)
+    pos_d, neg_d, rmd, rvd = pos.to(DEV), neg.to(DEV), rm.to(DEV), rv.to(DEV)
+    sums = torch.zeros(256, dtype=torch.float64, device=DEV)
+    nws = max(L.query("dcue_ncl_stats_ws_bytes", 128), 1 << 20)
+    ws = torch.empty(nws, dtype=torch.uint8, device=DEV)
+    st = L.stream()
+    L.call("dcue_ncl_center_pack_stats", pos_d.data_ptr(), 3, neg_d.data_ptr(), 10, 128, 131, rmd.data_ptr(), X.base, X.panel_rows,
+           geo["Lp"], geo["pad"], L.FMT_F16, sums.data_ptr(), ws.data_ptr(), nws, st)
+    u = (x - rm[None, :, None])
+    got = _unpack_panel(X, S * geo["Lp"], L.FMT_F16).view(S, geo["Lp"], 128)
+    assert torch.equal(got[:, geo["pad"]:geo["pad"] + 131].cpu(), u.half().float().permute(0, 2, 1))
+    assert got[:, :geo["pad"]].abs().sum() == 0 and got[:, geo["pad"] + 131:].abs().sum() == 0
+    ud = u.double()
+    assert relerr(sums[:128], ud.sum((0, 2))) < 1e-6 and relerr(sums[128:], (ud * ud).sum((0, 2))) < 1e-6
+    nbt = torch.tensor(0, device=DEV)
+    out = torch.empty(4, 128, device=DEV)
+    n = S * 131
+    L.call("dcue_bn_finalize", sums.data_ptr(), float(n), 128, None, None, rmd.data_ptr(), rvd.data_ptr(), nbt.data_ptr(), 0.1, 1e-5,
+           1, rmd.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), st)
+    xd = x.double()
+    mean, var = xd.mean((0, 2)), xd.var((0, 2), unbiased=False)
+    rstd = 1 / torch.sqrt(var + 1e-5)
+    assert relerr(out[3], rstd) < 1e-5 and relerr(out[0], rstd) < 1e-5
+    assert relerr(out[2], mean - rm.double()) < 1e-5                       # mean of the centred operand
+    assert relerr(out[1], -(mean - rm.double()) * rstd) < 1e-5
+    assert relerr(rmd, 0.9 * rm.double() + 0.1 * mean) < 1e-6              # running_mean tracks the mean of x
+    assert relerr(rvd, 0.9 * rv.double() + 0.1 * var * n / (n - 1)) < 1e-6

@@ -38,7 +38,7 @@ def one(op, fmt_dy, fmt_o, gi=0, S=5):
                    None, o.data_ptr(), ws.data_ptr(), nws, st)
         else:
             wpd = torch.empty(128 * geo["k"] * 128, dtype=torch.int16, device=dev)
-            L.call("dcue_pack_conv_weight", w.data_ptr(), 128, 128, geo["k"], 1, fmt_o, None, wpd.data_ptr(), st)
+            L.call("dcue_pack_conv_weight", w.data_ptr(), 128, 128, geo["k"], 1, fmt_o, None, None, wpd.data_ptr(), st)
             o = torch.zeros(S * geo["Lin"], 128, device=dev)
             L.call("dcue_conv_dgrad", impl, dY.base, dY.panel_rows, fmt_dy, wpd.data_ptr(), fmt_o, S, geo["Lp"], geo["Lin"], geo["pad"], geo["k"],
                    128, 128, None, o.data_ptr(), ws.data_ptr(), nws, st)
