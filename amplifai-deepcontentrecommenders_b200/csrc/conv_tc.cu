@@ -388,9 +388,10 @@ tc_wgrad_kernel(const uint4* __restrict__ dyp, long dy_rows, int fmt_dy, const u
     const uint32_t DONE = bar0 + 8u * (2 * WG_NSTAGE);
 
     const long ntiles = (rows_total + BN - 1) / BN;
-    const long per = (ntiles + gridDim.x - 1) / gridDim.x;
-    const long tbeg = blockIdx.x * per;
-    const long tend = tbeg + per < ntiles ? tbeg + per : ntiles;
+    // balanced contiguous ranges: grid <= ntiles (tc_grid), so every CTA owns >= 1 tile and its TMEM
+    // accumulators are always written before the epilogue reads them
+    const long tbeg = ntiles * blockIdx.x / gridDim.x;
+    const long tend = ntiles * (blockIdx.x + 1) / gridDim.x;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < WG_NSTAGE; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
@@ -458,6 +459,10 @@ tc_wgrad_kernel(const uint4* __restrict__ dyp, long dy_rows, int fmt_dy, const u
             for (int ch = 0; ch < 4; ++ch) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * 128 + ch * 32), v);
+                if (tend <= tbeg) {  // rows_total == 0: nothing was accumulated
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                }
                 float4* d4 = reinterpret_cast<float4*>(dst + j * 128 + ch * 32);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);

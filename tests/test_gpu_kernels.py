@@ -186,7 +186,7 @@ def _oracle_conv_fwd(c):
 
 
 @pytest.mark.parametrize("impl", [L.IMPL_SIMT, L.IMPL_TC])
-@pytest.mark.parametrize("gi,S", [(0, 5), (1, 9), (2, 33), (3, 70), (0, 31)])
+@pytest.mark.parametrize("gi,S", [(0, 5), (1, 9), (2, 33), (3, 70), (0, 31), (0, 160), (1, 1100)])
 def test_conv_pool_fwd(impl, gi, S):
     c = _conv_case(S, gi, 100 + gi)
     # the packed operand is exactly the fp16 rounding of the input, zero elsewhere
@@ -205,9 +205,11 @@ def test_conv_pool_fwd(impl, gi, S):
 
 
 @pytest.mark.parametrize("impl", [L.IMPL_SIMT, L.IMPL_TC])
-@pytest.mark.parametrize("gi,S", [(0, 5), (1, 9), (2, 33), (3, 70)])
+@pytest.mark.parametrize("gi,S", [(0, 5), (1, 9), (2, 33), (3, 70), (0, 160), (0, 300), (1, 1100)])
 def test_conv_backward_kernels(impl, gi, S):
-    """unpool -> dY panel (bf16) -> wgrad / dgrad, against autograd of the rounded-operand conv."""
+    """unpool -> dY panel (bf16) -> wgrad / dgrad, against autograd of the rounded-operand conv.
+    The larger S give more 128-row tiles than SMs with an uneven remainder (170, 319, 310 tiles on 148 CTAs):
+    every persistent CTA must own at least one tile."""
     c = _conv_case(S, gi, 200 + gi)
     geo = c["geo"]
     z, code, _ = _run_conv_fwd(c, L.IMPL_SIMT)

@@ -43,10 +43,13 @@ def main():
         loss.backward()
         dp.reduce_gradients()
         total = dp.reduce_loss(loss)
-        worst = 0.0
+        worst, errs = 0.0, []
         for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
             e = ((p.grad - q.grad).norm() / q.grad.norm().clamp_min(1e-30)).item()
+            errs.append((e, k, q.grad.norm().item()))
             worst = max(worst, e)
+        if rank == 0 and worst > 1e-3:
+            print("DP_PARITY_DETAIL", mt, sorted(errs, reverse=True)[:6], flush=True)
         berr = max(((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)).item()
                    for (_, a), (_, b) in zip(net.named_buffers(), ref.named_buffers())) if list(net.named_buffers()) else 0.0
         lerr = abs(total.item() - loss_ref.item()) / abs(loss_ref.item())
