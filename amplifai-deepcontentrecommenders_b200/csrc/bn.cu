@@ -589,6 +589,153 @@ ncl_bn_bwd_reduce_kernel(const float* __restrict__ dx, const float* __restrict__
     }
 }
 
+// ------------------------------------------------------------------ row-lane kernels (C == 128, panel output)
+// lane = row, warp = 8-channel group (panel): a lane reads its 32-byte sector of the [rows,128] fp32 row and
+// writes 16-byte panel chunks; consecutive lanes hold consecutive rows, so every warp store is one contiguous
+// run of the panel and no shared-memory transpose is needed (the tiled kernels above were l1tex/smem bound:
+// ncu 47 % l1tex, 37 % DRAM at layer-1 size).
+constexpr int RL_THREADS = 512;     // 16 warps = the 16 panels of a 128-channel row
+
+__device__ __forceinline__ uint4 pack8_16(const float (&v)[8], int fmt) {
+    unsigned short h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = cvt_f32_to16(v[j], fmt);
+    uint4 o;
+    o.x = h[0] | ((unsigned)h[1] << 16);
+    o.y = h[2] | ((unsigned)h[3] << 16);
+    o.z = h[4] | ((unsigned)h[5] << 16);
+    o.w = h[6] | ((unsigned)h[7] << 16);
+    return o;
+}
+
+// y = scale*z + shift -> panel rows (s*Lp + pad + p)
+template <int UNROLL>
+__global__ void __launch_bounds__(RL_THREADS)
+affine_pack_rows_kernel(const float* __restrict__ z, long rows, int P, const float* __restrict__ scale,
+                        const float* __restrict__ shift, uint4* __restrict__ panel, long panel_rows, int Lp, int pad, int fmt) {
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = scale ? scale[q * 8 + j] : 1.f; sh[j] = shift ? shift[q * 8 + j] : 0.f; }
+    uint4* dst = panel + (long)q * panel_rows + pad;
+    for (long r0 = (long)blockIdx.x * (32 * UNROLL); r0 < rows; r0 += (long)gridDim.x * (32 * UNROLL)) {
+        float4 a[UNROLL], b[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long r = r0 + u * 32 + lane;
+            a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < rows) {
+                const float4* src = reinterpret_cast<const float4*>(z + r * 128 + q * 8);
+                a[u] = __ldg(src);
+                b[u] = __ldg(src + 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long r = r0 + u * 32 + lane;
+            if (r >= rows) continue;
+            const float x[8] = {a[u].x, a[u].y, a[u].z, a[u].w, b[u].x, b[u].y, b[u].z, b[u].w};
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(x[j], sc[j], sh[j]);
+            const long s = (long)((unsigned)r / (unsigned)P);   // rows < 2^31 (checked by the host wrapper)
+            dst[s * Lp + (r - s * P)] = pack8_16(v, fmt);
+        }
+    }
+}
+
+// dz = relu'(z) * scale * (dy - s1/n - xhat*s2/n) as one FMA pair per element (a*dy + b*z + c with per-channel
+// a = scale, b = -scale*rstd*s2/n, c = scale*(rstd*s2/n*mean - s1/n)); the POOL rows of each window are written
+// as POOL 16-byte chunks (value where the argmax code matches, zero elsewhere) = 16*POOL contiguous bytes per lane.
+template <int POOL, int UNROLL>
+__global__ void __launch_bounds__(RL_THREADS)
+bn_relu_unpool_rows_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ dtp, int lddtp,
+                           const float* __restrict__ z, const uint8_t* __restrict__ code, const float* __restrict__ scale,
+                           const float* __restrict__ mean, const float* __restrict__ rstd, const double* __restrict__ sums,
+                           double count, long rows, int P, int Lp, uint4* __restrict__ panel, long panel_rows, int fmt,
+                           const float* __restrict__ gscale, double* __restrict__ bias_partial) {
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float gs = gscale ? gscale[0] : 1.f;
+    float ka[8], kb[8], kc[8], acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = q * 8 + j;
+        const float sc = scale ? scale[c] : 1.f;
+        ka[j] = sc; kb[j] = 0.f; kc[j] = 0.f; acc[j] = 0.f;
+        if (sums) {
+            const double inv_n = 1.0 / count;
+            const double rs2 = (double)rstd[c] * sums[128 + c] * inv_n;
+            kb[j] = (float)(-(double)sc * rs2);
+            kc[j] = (float)((double)sc * (rs2 * (double)mean[c] - sums[c] * inv_n));
+        }
+    }
+    const float invP = 1.f / (float)P;
+    uint4* dst = panel + (long)q * panel_rows;
+    for (long r0 = (long)blockIdx.x * (32 * UNROLL); r0 < rows; r0 += (long)gridDim.x * (32 * UNROLL)) {
+        float4 g0[UNROLL], g1[UNROLL], z0[UNROLL], z1[UNROLL];
+        uint2 cd[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {   // every load of the iteration is issued before any is consumed
+            const long r = r0 + u * 32 + lane;
+            g0[u] = g1[u] = z0[u] = z1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            cd[u] = make_uint2(0u, 0u);
+            if (r < rows) {
+                const float4* gp = reinterpret_cast<const float4*>(dy + r * lddy + q * 8);
+                const float4* zp = reinterpret_cast<const float4*>(z + r * 128 + q * 8);
+                g0[u] = __ldg(gp); g1[u] = __ldg(gp + 1);
+                z0[u] = __ldg(zp); z1[u] = __ldg(zp + 1);
+                cd[u] = __ldg(reinterpret_cast<const uint2*>(code + r * 128 + q * 8));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long r = r0 + u * 32 + lane;
+            if (r >= rows) continue;
+            float g[8] = {g0[u].x, g0[u].y, g0[u].z, g0[u].w, g1[u].x, g1[u].y, g1[u].z, g1[u].w};
+            const float zz[8] = {z0[u].x, z0[u].y, z0[u].z, z0[u].w, z1[u].x, z1[u].y, z1[u].z, z1[u].w};
+            const long s = (long)((unsigned)r / (unsigned)P);   // rows < 2^31 (checked by the host wrapper)
+            if (dtp) {
+                const float4* tp = reinterpret_cast<const float4*>(dtp + s * lddtp + q * 8);
+                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+                g[0] = fmaf(t0.x, invP, g[0]); g[1] = fmaf(t0.y, invP, g[1]); g[2] = fmaf(t0.z, invP, g[2]); g[3] = fmaf(t0.w, invP, g[3]);
+                g[4] = fmaf(t1.x, invP, g[4]); g[5] = fmaf(t1.y, invP, g[5]); g[6] = fmaf(t1.z, invP, g[6]); g[7] = fmaf(t1.w, invP, g[7]);
+            }
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gg = fmaf(ka[j], g[j], fmaf(kb[j], zz[j], kc[j]));
+                v[j] = zz[j] > 0.f ? gg : 0.f;
+                acc[j] += v[j];
+            }
+            unsigned short h[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = cvt_f32_to16(v[j] * gs, fmt);
+            const unsigned cw[2] = {cd[u].x, cd[u].y};
+            uint4* o = dst + s * Lp + (r - s * P) * POOL;
+#pragma unroll
+            for (int pi = 0; pi < POOL; ++pi) {
+                unsigned w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = ((cw[j >> 2] >> (8 * (j & 3))) & 0xffu) == (unsigned)pi ? (unsigned)h[j] : 0u;
+                o[pi] = make_uint4(w[0] | (w[1] << 16), w[2] | (w[3] << 16), w[4] | (w[5] << 16), w[6] | (w[7] << 16));
+            }
+        }
+    }
+    if (bias_partial) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float t = warp_sum(acc[j]);
+            if (lane == 0) bias_partial[(long)blockIdx.x * 128 + q * 8 + j] = (double)t;
+        }
+    }
+}
+
+int rows_grid(long rows, int rows_per_block, int blocks_per_sm) {
+    const long tiles = (rows + rows_per_block - 1) / rows_per_block;
+    const long cap = (long)dcue_num_sms() * blocks_per_sm;
+    return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+}
+
 int tile_grid(long rows) {
     long tiles = (rows + TR - 1) / TR;
     long cap = (long)dcue_num_sms() * 6;
@@ -715,7 +862,11 @@ extern "C" int dcue_affine_pack(const float* z, int S, int P, int C, const float
     cudaStream_t st = (cudaStream_t)stream;
     const long rows = (long)S * P;
     if (rows == 0) return 0;
-    if (panel || y) {
+    if (panel && !y && C == 128 && ((uintptr_t)z & 15) == 0 && rows < (1L << 31)) {
+        affine_pack_rows_kernel<2><<<rows_grid(rows, 64, 2), RL_THREADS, 0, st>>>(z, rows, P, scale, shift, (uint4*)panel,
+                                                                                  panel_rows, Lp, pad, fmt);
+        DCUE_LAUNCH_CHECK();
+    } else if (panel || y) {
         affine_pack_kernel<<<tile_grid(rows), 256, 0, st>>>(z, rows, P, C, scale, shift, (uint4*)panel, panel_rows, Lp,
                                                             pad, fmt, y);
         DCUE_LAUNCH_CHECK();
@@ -766,12 +917,25 @@ extern "C" int dcue_bn_relu_unpool_bwd(const float* dy, int lddy, const float* d
     cudaStream_t st = (cudaStream_t)stream;
     const long rows = (long)S * P;
     if (rows == 0) return 0;
-    const int grid = tile_grid(rows);
+    const bool fast = dy_panel && !dz_out && C == 128 && (pool == 2 || pool == 4) && ((uintptr_t)z & 15) == 0 && rows < (1L << 31) &&
+                      ((uintptr_t)code & 7) == 0 && (!dtp || (lddtp % 4 == 0 && ((uintptr_t)dtp & 15) == 0));
+    const int grid = fast ? rows_grid(rows, 64, 1) : tile_grid(rows);
     if (bias_sums && (!ws || ws_bytes < (size_t)grid * C * sizeof(double)))
         DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_bn_relu_unpool_bwd: workspace too small");
-    bn_relu_unpool_bwd_kernel<<<grid, 256, 0, st>>>(dy, lddy, dtp, lddtp, z, code, scale, mean, rstd, sums,
-                                                    count > 0 ? count : 1.0, rows, P, C, pool, Lp, (uint4*)dy_panel,
-                                                    panel_rows, fmt, gscale, dz_out, bias_sums ? (double*)ws : nullptr);
+    if (fast) {
+        double* bp = bias_sums ? (double*)ws : nullptr;
+        const double cnt = count > 0 ? count : 1.0;
+        if (pool == 4)
+            bn_relu_unpool_rows_kernel<4, 2><<<grid, RL_THREADS, 0, st>>>(dy, lddy, dtp, lddtp, z, code, scale, mean, rstd, sums, cnt,
+                                                                         rows, P, Lp, (uint4*)dy_panel, panel_rows, fmt, gscale, bp);
+        else
+            bn_relu_unpool_rows_kernel<2, 2><<<grid, RL_THREADS, 0, st>>>(dy, lddy, dtp, lddtp, z, code, scale, mean, rstd, sums, cnt,
+                                                                         rows, P, Lp, (uint4*)dy_panel, panel_rows, fmt, gscale, bp);
+    } else {
+        bn_relu_unpool_bwd_kernel<<<grid, 256, 0, st>>>(dy, lddy, dtp, lddtp, z, code, scale, mean, rstd, sums,
+                                                        count > 0 ? count : 1.0, rows, P, C, pool, Lp, (uint4*)dy_panel,
+                                                        panel_rows, fmt, gscale, dz_out, bias_sums ? (double*)ws : nullptr);
+    }
     DCUE_LAUNCH_CHECK();
     if (bias_sums) {
         reduce_partials_kernel<<<ceil_div_i(C, 8), 256, 0, st>>>((const double*)ws, grid, C, bias_sums, bias_out, nullptr, C);

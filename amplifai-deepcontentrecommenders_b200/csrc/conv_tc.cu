@@ -129,6 +129,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// predicated global stores: dead lanes issue nothing.  (They used to write one shared scratch word instead; ncu
+// showed every SM serialising on that single L2 sector -- the layer-2 dgrad spent its whole 270 us there.)
+__device__ __forceinline__ void st_pred_f32(float* p, float v, bool ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %2, 0;\n\t"
+        "@p st.global.f32 [%0], %1;\n\t"
+        "}" ::"l"(p), "f"(v), "r"((int)ok) : "memory");
+}
+__device__ __forceinline__ void st_pred_u8(uint8_t* p, uint32_t v, bool ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %2, 0;\n\t"
+        "@p st.global.u8 [%0], %1;\n\t"
+        "}" ::"l"(p), "r"(v), "r"((int)ok) : "memory");
+}
+
 // shared-memory matrix descriptor, SWIZZLE_NONE (cute::UMMA::SmemDescriptor):
 //   [0,14) start>>4 | [16,30) leading byte offset>>4 | [32,46) stride byte offset>>4 | [46,48) version=1
 // K-major : LBO = distance between the two 8-element K chunks of one MMA, SBO = between 8-row groups
@@ -324,11 +343,8 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
                     const bool ok = chan_ok && s < g.S && p < g.P;
                     const float val = ok ? fmaxf(best + bv, 0.f) : 0.f;
                     const long o = ((long)s * g.P + p) * g.Cout + m;
-                    // branch-free stores: dead lanes write to a scratch word instead of diverging
-                    float* zp = ok ? out + o : dummy;
-                    uint8_t* cp = ok ? code + o : reinterpret_cast<uint8_t*>(dummy);
-                    *zp = val;
-                    *cp = (uint8_t)bi;
+                    st_pred_f32(out + o, val, ok);
+                    st_pred_u8(code + o, (uint32_t)bi, ok);
                     ts1 += val;
                     ts2 = fmaf(val, val, ts2);
                     q += POOL;
@@ -343,8 +359,7 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
                 for (int t = 0; t < 32; ++t) {
                     const int tt = q - g.pad;
                     const bool ok = chan_ok && s < g.S && tt >= 0 && tt < g.Lin;
-                    float* dp = ok ? out + ((long)s * g.Lin + tt) * g.Cout + m : dummy;
-                    *dp = v[t] * bv;
+                    st_pred_f32(out + ((long)s * g.Lin + tt) * g.Cout + m, v[t] * bv, ok);
                     ++q;
                     const bool wrap = q == g.Lp;
                     q = wrap ? 0 : q;

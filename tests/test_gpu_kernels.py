@@ -265,6 +265,62 @@ def test_conv_backward_kernels(impl, gi, S):
     assert relerr(dx.view(S, geo["Lin"], 128), xr.grad.permute(0, 2, 1)) < 5e-5
 
 
+@pytest.mark.parametrize("gi,S,with_tp", [(0, 7, False), (1, 40, True), (3, 300, True), (0, 70, False)])
+def test_bn_backward_unpool_and_affine_pack(gi, S, with_tp):
+    """BatchNorm-backward + ReLU mask + max-unpool into the 16-bit dY panel (truedcuemel1dbn.py:80-95 autograd) and
+    the BatchNorm-apply -> next operand panel, both against fp64 formulas on the same inputs.  Panel values are
+    one fp16 rounding of the fp32 result: <= 2^-11 relative + the fp32 evaluation noise."""
+    geo = ops.tower_geometry(131)[gi]
+    P, pool, Lp = geo["P"], geo["pool"], geo["Lp"]
+    rows = S * P
+    g = torch.Generator().manual_seed(900 + gi)
+    z = torch.relu(torch.randn(rows, 128, generator=g) + 0.3)
+    dy = torch.randn(rows, 128, generator=g) * 1e-3
+    dtp = torch.randn(S, 640, generator=g) * 1e-3 if with_tp else None     # a column slice of a wider matrix (res towers)
+    code = torch.randint(0, pool, (rows, 128), generator=g, dtype=torch.uint8)
+    gamma = torch.rand(128, generator=g) + 0.5
+    mean, var = z.double().mean(0), z.double().var(0, unbiased=False)
+    rstd = 1 / torch.sqrt(var + 1e-5)
+    scale = gamma.double() * rstd
+    geff = dy.double() + (dtp[:, 128:256].double().repeat_interleave(P, 0) / P if with_tp else 0)
+    xhat = (z.double() - mean) * rstd
+    s1, s2 = geff.sum(0), (geff * xhat).sum(0)
+    dz_ref = (z > 0) * scale * (geff - s1 / rows - xhat * s2 / rows)
+    gs = 2.0 ** 12
+    st = L.stream()
+    d = lambda t: None if t is None else t.to(DEV)
+    zd, dyd, dtpd, coded = d(z), d(dy), d(dtp), d(code)
+    scd, meand, rstdd = d(scale.float()), d(mean.float()), d(rstd.float())
+    sums = torch.cat([s1, s2]).to(DEV)
+    gsc = torch.tensor([gs, 1 / gs], device=DEV)
+    dY = ops.Panel(S, Lp, DEV)
+    bsum = torch.zeros(128, dtype=torch.float64, device=DEV)
+    bout = torch.empty(128, device=DEV)
+    nws = L.query("dcue_bn_bwd_ws_bytes", 128)
+    ws = torch.empty(nws, dtype=torch.uint8, device=DEV)
+    L.call("dcue_bn_relu_unpool_bwd", dyd.data_ptr(), 128, None if dtp is None else dtpd[:, 128:].data_ptr(), 640, zd.data_ptr(),
+           coded.data_ptr(), scd.data_ptr(), meand.data_ptr(), rstdd.data_ptr(), sums.data_ptr(), float(rows), S, P, 128, pool, Lp,
+           dY.base, dY.panel_rows, L.FMT_F16, gsc.data_ptr(), None, bsum.data_ptr(), bout.data_ptr(), ws.data_ptr(), nws, st)
+    got = _unpack_panel(dY, S * Lp, L.FMT_F16).view(S, Lp, 128).cpu().double() / gs
+    ref = torch.zeros(S, Lp, 128, dtype=torch.float64)
+    win = torch.arange(P).view(1, -1, 1) * pool + code.long().view(S, P, 128)
+    ref.scatter_(1, win, dz_ref.view(S, P, 128))
+    assert (got != 0).sum() <= (ref != 0).sum()                  # exactly one slot per window, the rest stays zero
+    assert ((got != 0) & (ref == 0)).sum() == 0
+    assert relerr(got, ref) < 1e-3 and l2err(got, ref) < 5e-4   # fp16 panel: 2^-11 per element
+    assert relerr(bsum, dz_ref.sum(0)) < 1e-4 and relerr(bout, dz_ref.sum(0)) < 1e-4
+    # BatchNorm apply -> operand panel of the next stage (rows s*Lp2 + pad2 + p)
+    Lp2, pad2 = P + 5, 2
+    X = ops.Panel(S, Lp2, DEV)
+    shift = (torch.randn(128, generator=g)).to(DEV)
+    L.call("dcue_affine_pack", zd.data_ptr(), S, P, 128, scd.data_ptr(), shift.data_ptr(), X.base, X.panel_rows, Lp2, pad2,
+           L.FMT_F16, None, None, 0, st)
+    gotx = _unpack_panel(X, S * Lp2, L.FMT_F16).view(S, Lp2, 128).cpu()
+    refx = (z * scale.float() + shift.cpu()).half().float().view(S, P, 128)
+    assert gotx[:, :pad2].abs().sum() == 0 and gotx[:, pad2 + P:].abs().sum() == 0
+    assert (gotx[:, pad2:pad2 + P] - refx).abs().max() <= 2e-3 * refx.abs().max()   # 1 fp16 ulp (fma vs mul+add)
+
+
 # ------------------------------------------------------------------ BatchNorm kernels
 def test_ncl_stats_and_bn_finalize():
     g = torch.Generator().manual_seed(7)

@@ -22,7 +22,8 @@ def main(path):
         lines = [l for l in f if not l.startswith("==")]
     rows = [(r["Kernel Name"], float(r["Metric Value"].replace(",", ""))) for r in csv.DictReader(lines)]
     starts = [i for i, (n, _) in enumerate(rows) if "gather_relu" in n]
-    step = rows[starts[0]:starts[1]]
+    which = int(sys.argv[2]) if len(sys.argv) > 2 else min(2, len(starts) - 2)   # skip the allocating first steps
+    step = rows[starts[which]:starts[which + 1]]
     tot = sum(t for _, t in step)
     agg = collections.OrderedDict()
     for n, t in step:
