@@ -166,7 +166,8 @@ ncl_pack_kernel(SpecSrc src, int S, int C, int L, const float* __restrict__ scal
         const int q = (int)(sq % (C / 8));
         const long s = sq / (C / 8);
         long rs;
-        const float* base = src.base(s, C, L, rs) + (long)(q * 8) * rs + t;
+        const float* base = src.base(s, C, L, rs);   // sets rs: keep it a separate statement
+        base += (long)(q * 8) * rs + t;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = __ldg(base + (long)j * rs);
@@ -202,7 +203,8 @@ ncl_center_pack_stats_kernel(SpecSrc src, int S, int C, int L, const float* __re
     for (int j = 0; j < 8; ++j) { ctr[j] = center ? center[q * 8 + j] : 0.f; a1[j] = a2[j] = 0.f; }
     for (int s = gi + w * G; s < S; s += 8 * G) {
         long rs;
-        const float* base = src.base(s, C, L, rs) + (long)(q * 8) * rs;
+        const float* base = src.base(s, C, L, rs);   // sets rs: keep it a separate statement
+        base += (long)(q * 8) * rs;
         uint4* prow = panel + (long)q * panel_rows + (long)s * Lp + pad;
         for (int t0 = 0; t0 < L; t0 += 64) {   // two frames per lane in flight: 16 independent loads
             float v[2][8];

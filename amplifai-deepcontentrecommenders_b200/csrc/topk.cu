@@ -1,35 +1,16 @@
 // Eval scorer: all-pairs cosine score GEMM (tcgen05, fp32 accumulate in TMEM) with a fused
-// streaming top-k kept in shared memory — the score matrix is never materialised.
+// streaming top-k -- the score matrix is never materialised.
 //
 // Generalises DCUE.predict (dcrecommend/nn/dcue.py:495-513: model.sim of one user's factor row
-// against every candidate song's factor row) to all users x all songs.
-//
-//   users on the MMA M axis (one TMEM lane = one user), songs on N.  CTA = 128 users x one
-//   contiguous range of songs; the user tile lives in TMEM (TS-mode MMA), song tiles stream through a
-//   3-stage cp.async.bulk ring; accumulators are double buffered so the filter overlaps the next MMA.
-//   Filter: one TMEM lane = one user, so each epilogue thread owns one user: its threshold (the k-th
-//   best score at the last compaction) and its list length live in registers.  A chunk of 32 fresh scores
-//   is first reduced with a max tree; only if some lane beats its threshold are the columns scanned,
-//   and a passing score is APPENDED to that user's unsorted list in shared memory by its own lane (plain
-//   predicated stores, all 32 users in parallel).  When a list reaches CAP entries the warp sorts it
-//   cooperatively (bitonic network, 4 entries per lane, 15 shuffle steps), keeps the k best and raises the
-//   threshold: one ~400-instruction compaction per CAP-k appends instead of a dependent
-//   shuffle/LDS/STS chain per insert (ncu of the first version: 3 % tensor pipe, 780 cycles per insert).
-//   Finish: one last sort per user, write the k best (descending, ties by lower song index).
+// against every candidate song's factor row) to all users x all songs (BASELINE cfg5).
+// Design notes are at topk_stream_kernel below.
 #include "common.cuh"
 #include <stdlib.h>
 
 namespace {
 
-constexpr int TU = 128;        // users per CTA (MMA M)
-constexpr int TI = 128;        // songs per tile (MMA N)
-constexpr int SLOTS = 128;     // kept candidates per user (k <= SLOTS)
 constexpr int ROWB = 16;
-constexpr int PANEL_BYTES = 128 * ROWB;  // 2048: one 8-wide K chunk of a 128-row tile
-constexpr int NSTAGE = 3;
-constexpr int NTHREADS = 192;
-constexpr int ACC0 = 64;         // accumulator columns start (the user tile occupies TMEM columns [0, Kp/2 <= 64))
-constexpr int NACC = 3;          // accumulator stages: absorbs the jitter of rare compactions / slow scans
+constexpr int PANEL_BYTES = 128 * ROWB;  // 2048: one 8-wide K chunk of a 128-row operand tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -72,26 +53,6 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
 }
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
 // asynchronous TMEM load: the registers are valid only after tmem_ld_fence() on the same array
 __device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -115,21 +76,19 @@ __device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[32]) {
                       "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                  :: "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_fence16(uint32_t (&r)[16]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
 }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
@@ -140,8 +99,34 @@ __device__ __forceinline__ uint32_t make_idesc(int a_fmt, int b_fmt, int M, int 
            ((uint32_t)(M >> 4) << 24);
 }
 
-constexpr int CAP = SLOTS;      // list capacity per user
-constexpr int LD = SLOTS + 1;   // row stride (floats): (user + slot) % 32 banks -> lane-parallel appends do not collide
+// ----------------------------------------------------------------------------- streaming top-k scorer
+// Transposed formulation: SONGS on the MMA M axis (one TMEM lane = one song of the 128-song tile), 256 USERS on N
+// (one accumulator column = one user).  An epilogue ("appender") thread therefore sees one song against many users
+// and the per-user state is addressed by the (compile-time) column: the hot loop is one predicate-accumulating
+// compare per score against the user's threshold in shared memory and one warp vote per 4 columns -- no per-lane
+// lists, no shuffles, no divergence unless some song beats some user's threshold (a few 1e-4 of the scores).
+//   * passing scores are APPENDED to the user's candidate list in an L2-resident global scratch (CAPH slots per
+//     user, slot index from a shared-memory counter, warp-aggregated atomics);
+//   * a list that has grown beyond LIMIT is FROZEN at a tile boundary ([0, n) no longer changes; appends continue
+//     behind it) and queued; dedicated compactor warps pop the queue, radix-select the k best of the frozen part
+//     in place (exact k-th largest key, 16 entries per lane, one REDUX per key bit) and publish the new threshold;
+//     the owner warp installs it at a later tile boundary (surviving tail entries move down behind the k kept);
+//     the appenders never wait for a compaction unless a list is about to overflow, and then they help;
+//   * at the end of the song range every list is reduced to <= k entries, sorted (descending, ties by lower song
+//     index) and written out.
+// History (ncu, 500k songs, k=100): users-on-lanes version 1 600 instructions per warp and tile, 4 % tensor pipe;
+// transposed with synchronous bitonic compaction: hot loop 21 % of the instructions, sorts 48 %, 28 % of the samples
+// stalled at the epilogue barrier behind one sorting warp -> asynchronous compactors + selection instead of sorting.
+constexpr int NU = 256;          // users per CTA (MMA N)
+constexpr int TS = 128;          // songs per tile (MMA M)
+constexpr int CAPH = 1024;       // candidate slots per user in the global scratch
+constexpr int LIMIT = 384;       // freeze + compact a list longer than this (frozen part <= LIMIT + TS = 512)
+constexpr int HARD = CAPH - TS;  // a list longer than this could overflow in the next tile: wait for its compaction
+constexpr int NST = 4;           // song-tile stages
+constexpr int NEPI = 8;          // appender warps: (TMEM lane quarter) x (column half)
+constexpr int NCOMP = 4;         // compactor warps
+constexpr int NTHREADS2 = 64 + (NEPI + NCOMP) * 32;
+constexpr int UPANEL = NU * ROWB;   // 4096: one 8-wide K chunk of the 256-user operand
 
 struct Cand {
     float s;
@@ -152,19 +137,86 @@ __device__ __forceinline__ bool before(const Cand& a, const Cand& b) {
     return a.s > b.s || (a.s == b.s && (unsigned)a.i < (unsigned)b.i);
 }
 
-// Warp-cooperative bitonic sort (descending) of 128 candidates, element g = lane*4 + e.
-__device__ __forceinline__ void bitonic_sort128(Cand (&c)[4], int lane) {
+// order-preserving map float bits -> unsigned (larger float = larger key) and back
+__device__ __forceinline__ unsigned f2key(int bits) { return (unsigned)bits ^ ((bits < 0) ? 0xffffffffu : 0x80000000u); }
+__device__ __forceinline__ int key2f(unsigned key) { return (int)(key ^ ((key & 0x80000000u) ? 0x80000000u : 0xffffffffu)); }
+
+// Keep the k best of lst[0, n) (k <= n <= 512) in lst[0, k), unordered; returns the k-th best score.  Warp
+// cooperative, entry g = e*32 + lane (coalesced); exact radix select over the key bits that actually vary.
+__device__ __noinline__ float select_topk_inplace(int2* __restrict__ lst, int n, int k, int lane) {
+    unsigned key[16];
+    int idx[16];
+    unsigned vmask = 0, aand = 0xffffffffu, oor = 0u;
 #pragma unroll
-    for (int size = 2; size <= 128; size <<= 1) {
+    for (int e = 0; e < 16; ++e) {
+        const int g = e * 32 + lane;
+        key[e] = 0u;
+        idx[e] = -1;
+        if (g < n) {
+            const int2 v = __ldcg(lst + g);      // appended by other warps of this CTA: read through L2
+            key[e] = f2key(v.x);
+            idx[e] = v.y;
+            vmask |= 1u << e;
+            aand &= key[e];
+            oor |= key[e];
+        }
+    }
+    aand = __reduce_and_sync(0xffffffffu, aand);
+    oor = __reduce_or_sync(0xffffffffu, oor);
+    const unsigned diff = aand ^ oor;            // key bits on which the entries differ
+    unsigned prefix = aand;                      // bits common to all entries (varying bits are 0 here)
+    unsigned decided = ~diff;                    // mask of the bits of `prefix` that are final
+    int rem = k;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const unsigned b = 1u << bit;
+        if (!(diff & b)) continue;
+        // candidates agree with prefix on every decided bit (the common bits and the varying bits above) and have this bit set
+        const unsigned m = decided | b;
+        const unsigned want = prefix | b;
+        int c = 0;
 #pragma unroll
+        for (int e = 0; e < 16; ++e) c += (((vmask >> e) & 1u) && ((key[e] & m) == want)) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= rem) prefix |= b; else rem -= c;
+        decided |= b;
+    }
+    const unsigned T = prefix;                   // key of the k-th best; `rem` entries equal to T are still needed
+    __syncwarp();                                // every lane has loaded its entries: the front of the list may be overwritten
+    const unsigned lt = (1u << lane) - 1u;
+    int base = 0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        const bool kp = ((vmask >> e) & 1u) && key[e] > T;
+        const unsigned bm = __ballot_sync(0xffffffffu, kp);
+        if (kp) __stcg(lst + base + __popc(bm & lt), make_int2(key2f(key[e]), idx[e]));
+        base += __popc(bm);
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        const bool eq = ((vmask >> e) & 1u) && key[e] == T;
+        const unsigned bm = __ballot_sync(0xffffffffu, eq);
+        const int pos = base + __popc(bm & lt);
+        if (eq && pos < k) __stcg(lst + pos, make_int2(key2f(key[e]), idx[e]));
+        base += __popc(bm);
+    }
+    __syncwarp();
+    return __int_as_float(key2f(T));
+}
+
+// Warp-cooperative bitonic sort (descending) of 256 candidates, element g = lane*8 + e (final output only).
+__device__ __forceinline__ void bitonic_sort256(Cand (&c)[8], int lane) {
+#pragma unroll 1
+    for (int size = 2; size <= 256; size <<= 1) {
+#pragma unroll 1
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            if (stride >= 4) {
-                const int lx = stride >> 2;
+            if (stride >= 8) {
+                const int lx = stride >> 3;
                 const bool lower = (lane & lx) == 0;                    // g < partner
-                const bool desc = ((lane * 4) & size) == 0;             // size >= 8: uniform over e
+                const bool desc = ((lane * 8) & size) == 0;             // size >= 16: uniform over e
                 const bool keep_first = lower == desc;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
+                for (int e = 0; e < 8; ++e) {
                     Cand o;
                     o.s = __shfl_xor_sync(0xffffffffu, c[e].s, lx);
                     o.i = __shfl_xor_sync(0xffffffffu, c[e].i, lx);
@@ -172,116 +224,122 @@ __device__ __forceinline__ void bitonic_sort128(Cand (&c)[4], int lane) {
                     if (mine_first != keep_first) c[e] = o;
                 }
             } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int pe = e ^ stride;
-                    if (pe > e) {
-                        const bool desc = ((lane * 4 + e) & size) == 0;
-                        const bool in_order = before(c[e], c[pe]);
-                        if (in_order != desc) { const Cand t = c[e]; c[e] = c[pe]; c[pe] = t; }
-                    }
-                }
+#define DCUE_INTRA(ST)                                                                           \
+    _Pragma("unroll") for (int e = 0; e < 8; ++e) {                                               \
+        const int pe = e ^ (ST);                                                                 \
+        if (pe > e) {                                                                            \
+            const bool desc = ((lane * 8 + e) & size) == 0;                                      \
+            const bool in_order = before(c[e], c[pe]);                                           \
+            if (in_order != desc) { const Cand t = c[e]; c[e] = c[pe]; c[pe] = t; }              \
+        }                                                                                        \
+    }
+                if (stride == 4) { DCUE_INTRA(4) }
+                else if (stride == 2) { DCUE_INTRA(2) }
+                else { DCUE_INTRA(1) }
+#undef DCUE_INTRA
             }
         }
     }
 }
 
-// Sort user `u`'s list (entries >= n are empty), write it back sorted; returns the k-th best score.
-__device__ __forceinline__ float compact_user(float* __restrict__ cs, int* __restrict__ ci, int u, int n, int k, int lane) {
-    Cand c[4];
+// Final output of one user: lst[0, n) with n <= 256 -> the k best, sorted, to out_s / out_i (missing: -inf / -1).
+__device__ __noinline__ void sort_and_write(const int2* __restrict__ lst, int n, int k, long item_offset,
+                                            float* __restrict__ os, int64_t* __restrict__ oi, int lane) {
+    Cand c[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int g = lane * 4 + e;
-        c[e].s = g < n ? cs[u * LD + g] : -INFINITY;
-        c[e].i = g < n ? ci[u * LD + g] : -1;
+    for (int e = 0; e < 8; ++e) {
+        const int g = lane * 8 + e;
+        int2 v = make_int2(__float_as_int(-INFINITY), -1);
+        if (g < n) v = __ldcg(lst + g);
+        c[e].s = __int_as_float(v.x);
+        c[e].i = v.y;
     }
-    bitonic_sort128(c, lane);
+    bitonic_sort256(c, lane);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        cs[u * LD + lane * 4 + e] = c[e].s;
-        ci[u * LD + lane * 4 + e] = c[e].i;
+    for (int e = 0; e < 8; ++e) {
+        const int g = lane * 8 + e;
+        if (g < k) {
+            os[g] = c[e].s;
+            oi[g] = c[e].i < 0 ? -1 : (int64_t)c[e].i + item_offset;
+        }
     }
-    // k-th best = element k-1 = lane (k-1)/4, e = (k-1)%4
-    const int ke = (k - 1) & 3;
-    const float mine = ke == 0 ? c[0].s : ke == 1 ? c[1].s : ke == 2 ? c[2].s : c[3].s;
-    const float kth = __shfl_sync(0xffffffffu, mine, (k - 1) >> 2);
-    __syncwarp();
-    return kth;
 }
 
-struct UserState {   // per-lane (= per-user) filter state, kept in registers
-    float thr;       // k-th best score at the last compaction
-    int cnt;         // entries in this user's list
+struct TopkShared {          // per-user state and the compaction queue (shared memory)
+    float thr[NU];           // score a candidate must beat
+    int cnt[NU];             // entries in the user's list (frozen part included)
+    int pend_n[NU];          // > 0: [0, pend_n) is frozen and queued / being compacted
+    float newthr[NU];        // published by the compactor
+    int done[NU];            // compaction finished, waiting for the owner to install it
+    int qbuf[NU];            // ring of queued users (a user is queued at most once at a time)
+    int q_res, q_tail, q_head, over, exit_flag, pad[3];
 };
 
-// Rare path, ONE non-inlined copy (keeps the hot loop small enough for the instruction cache): re-read a
-// 32-column chunk of the accumulator from TMEM, append every score that beats its user's threshold (each
-// lane appends to its own user's list), and compact any list that fills up.
-__device__ __noinline__ UserState scan_chunk(uint32_t taddr, long ib, long iend, UserState st, bool enable,
-                                             float* __restrict__ cs, int* __restrict__ ci, int ubase, int k, int lane) {
-    float v[32];
-    tmem_ld32(taddr, v);
-    const int u = ubase + lane;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        if (enable && v[j] > st.thr && ib + j < iend) {
-            cs[u * LD + st.cnt] = v[j];
-            ci[u * LD + st.cnt] = (int)(ib + j);
-            ++st.cnt;
-        }
-        unsigned full = __ballot_sync(0xffffffffu, st.cnt == CAP);
-        while (full) {
-            const int l = __ffs(full) - 1;
-            full &= full - 1;
-            const float kth = compact_user(cs, ci, ubase + l, CAP, k, lane);
-            if (lane == l) { st.thr = kth; st.cnt = k; }
+// pop one queued user (lane 0 decides), compact it, publish.  Returns false if the queue was empty.
+__device__ __forceinline__ bool compact_one(TopkShared* sh, int2* __restrict__ mylists, int k, int lane, bool block,
+                                            bool* exiting) {
+    int slot = -1;
+    if (lane == 0) {
+        for (;;) {
+            const int h = *(volatile int*)&sh->q_head;
+            const int t = *(volatile int*)&sh->q_tail;
+            if (h < t) {
+                if (atomicCAS(&sh->q_head, h, h + 1) == h) { slot = h; break; }
+            } else if (!block) {
+                break;
+            } else if (*(volatile int*)&sh->exit_flag) {
+                slot = -2;
+                break;
+            } else {
+                __nanosleep(200);
+            }
         }
     }
-    return st;
-}
-
-// compaction of every user whose list is full (state by value: keeps thr/cnt in registers)
-__device__ __noinline__ UserState compact_full(unsigned full, UserState st, float* __restrict__ cs, int* __restrict__ ci,
-                                               int ubase, int k, int lane) {
-    while (full) {
-        const int l = __ffs(full) - 1;
-        full &= full - 1;
-        const float kth = compact_user(cs, ci, ubase + l, CAP, k, lane);
-        if (lane == l) { st.thr = kth; st.cnt = k; }
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot == -2 && exiting) *exiting = true;
+    if (slot < 0) return false;
+    __threadfence_block();
+    const int u = *(volatile int*)&sh->qbuf[slot & (NU - 1)];
+    const int n = *(volatile int*)&sh->pend_n[u];
+    const float t = select_topk_inplace(mylists + (size_t)u * CAPH, n, k, lane);
+    if (lane == 0) {
+        sh->newthr[u] = t;
+        __threadfence_block();
+        *(volatile int*)&sh->done[u] = 1;
     }
-    return st;
+    __syncwarp();
+    return true;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
-topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long n_users, const uint4* __restrict__ items,
-            long i_rows, long n_items, int Kp, int fmt, int k, long item_offset, long items_per_split, int dbg,
-            float* __restrict__ out_s, int64_t* __restrict__ out_i /* [splits][n_users][k] */) {
+__global__ void __launch_bounds__(NTHREADS2, 1)
+topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_users, const uint4* __restrict__ items,
+                   long n_items, int Kp, int fmt, int k, long item_offset, long items_per_split, int splits,
+                   long n_work, int2* __restrict__ lists /* [grid][NU][CAPH] */, float* __restrict__ out_s,
+                   int64_t* __restrict__ out_i /* [splits][n_users][k] */) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int npan = Kp / 8;
     const int tile_bytes = npan * PANEL_BYTES;
-    uint8_t* sB = smem;
-    float* cs = reinterpret_cast<float*>(sB + NSTAGE * tile_bytes);
-    int* ci = reinterpret_cast<int*>(cs + TU * LD);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uintptr_t>(ci + TU * LD + 1) & ~(uintptr_t)7);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1 + 2 * NACC);
+    uint8_t* sU = smem;                                   // [npan][256 users][16 B]
+    uint8_t* sA = sU + npan * UPANEL;                     // NST song tiles, [npan][128 songs][16 B] each
+    TopkShared* sh = reinterpret_cast<TopkShared*>(sA + NST * tile_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sh + 1);
+    // bars: [0..NST) full, [NST..2NST) empty, UFULL, UEMPTY, TFULL[2], TEMPTY[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 6);
     const uint32_t bar0 = smem_u32(bars);
     auto FULL = [&](int s) { return bar0 + 8u * s; };
-    auto EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
-    const uint32_t AFULL = bar0 + 8u * (2 * NSTAGE);
-    auto TFULL = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 1 + a); };
-    auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 1 + NACC + a); };
-
-    const long u0 = (long)blockIdx.x * TU;
-    const long ibeg = (long)blockIdx.y * items_per_split;
-    const long iend = ibeg + items_per_split < n_items ? ibeg + items_per_split : n_items;
-    const long ntiles = iend > ibeg ? (iend - ibeg + TI - 1) / TI : 0;
+    auto EMPTY = [&](int s) { return bar0 + 8u * (NST + s); };
+    const uint32_t UFULL = bar0 + 8u * (2 * NST), UEMPTY = bar0 + 8u * (2 * NST + 1);
+    auto TFULL = [&](int a) { return bar0 + 8u * (2 * NST + 2 + a); };
+    auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * NST + 4 + a); };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-        mbar_init(AFULL, 4);
-        for (int a = 0; a < NACC; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 4); }
+        for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        mbar_init(UFULL, 1);
+        mbar_init(UEMPTY, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), NEPI); }
         fence_barrier_init();
+        sh->q_res = sh->q_tail = sh->q_head = sh->over = sh->exit_flag = 0;
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -291,157 +349,236 @@ topk_kernel(const uint4* __restrict__ users, long u_rows /* panel rows */, long 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    int2* mylists = lists + (size_t)blockIdx.x * NU * CAPH;
+
+    // every role walks the same work list: item w = (256-user tile, song split)
+    auto song_range = [&](long w, long& ibeg, long& iend) {
+        const int sp = (int)(w % splits);
+        ibeg = (long)sp * items_per_split;
+        iend = ibeg + items_per_split < n_items ? ibeg + items_per_split : n_items;
+        if (iend < ibeg) iend = ibeg;
+    };
 
     if (warp == 0) {
+        // ===== producer: the user tile once per work item, then the song tiles of its range =====
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0;
-            for (long t = 0; t < ntiles; ++t) {
-                mbar_wait(EMPTY(stage), phase ^ 1);
-                mbar_expect_tx(FULL(stage), (uint32_t)tile_bytes);
-                const long r0 = ibeg + t * TI;   // multiple of 128: tile index r0 >> 7
-                bulk_g2s(smem_u32(sB + stage * tile_bytes), items + (r0 >> 7) * (long)npan * 128, (uint32_t)tile_bytes, FULL(stage));
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            uint32_t phase = 0, uphase = 0;
+            for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const long ut = w / splits;
+                long ibeg, iend;
+                song_range(w, ibeg, iend);
+                mbar_wait(UEMPTY, uphase ^ 1);       // the previous item's MMAs have finished reading sU
+                const int halves = (ut * 2 + 1 < n_utiles128) ? 2 : 1;
+                mbar_expect_tx(UFULL, (uint32_t)(halves * tile_bytes));
+                for (int h = 0; h < halves; ++h)
+                    for (int q = 0; q < npan; ++q)
+                        bulk_g2s(smem_u32(sU + q * UPANEL + h * PANEL_BYTES), users + ((ut * 2 + h) * (long)npan + q) * 128,
+                                 PANEL_BYTES, UFULL);
+                uphase ^= 1;
+                const long ntiles = (iend - ibeg + TS - 1) / TS;
+                for (long t = 0; t < ntiles; ++t) {
+                    mbar_wait(EMPTY(stage), phase ^ 1);
+                    mbar_expect_tx(FULL(stage), (uint32_t)tile_bytes);
+                    const long r0 = ibeg + t * TS;   // multiple of 128: tile index r0 >> 7
+                    bulk_g2s(smem_u32(sA + stage * tile_bytes), items + (r0 >> 7) * (long)npan * 128, (uint32_t)tile_bytes,
+                             FULL(stage));
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
+        // ===== MMA issuer: D[song, user] (128 x 256, fp32) = A (songs, K-major) x B (users, K-major)^T =====
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(fmt, fmt, TU, TI);
-            mbar_wait(AFULL, 0);   // the four epilogue warps have copied the user tile into TMEM
-            tc_fence_after();
+            const uint32_t idesc = make_idesc(fmt, fmt, TS, NU);
             int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (long t = 0; t < ntiles; ++t) {
-                mbar_wait(TEMPTY(acc), acc_phase ^ 1);
-                mbar_wait(FULL(stage), phase);
+            uint32_t phase = 0, acc_phase = 0, uphase = 0;
+            for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+                long ibeg, iend;
+                song_range(w, ibeg, iend);
+                const long ntiles = (iend - ibeg + TS - 1) / TS;
+                mbar_wait(UFULL, uphase);
+                uphase ^= 1;
                 tc_fence_after();
-                const uint32_t b0 = smem_u32(sB + stage * tile_bytes);
-                for (int c = 0; c < Kp / 16; ++c) {
-                    const uint64_t bd = make_desc(b0 + (uint32_t)(2 * c * PANEL_BYTES), PANEL_BYTES, 128);
-                    umma_f16_ts(tmem_base + (uint32_t)(ACC0 + acc * TI), tmem_base + (uint32_t)(c * 8), bd, idesc, c != 0);
+                const uint32_t u0s = smem_u32(sU);
+                for (long t = 0; t < ntiles; ++t) {
+                    mbar_wait(TEMPTY(acc), acc_phase ^ 1);
+                    mbar_wait(FULL(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA + stage * tile_bytes);
+                    for (int c = 0; c < Kp / 16; ++c) {
+                        const uint64_t ad = make_desc(a0 + (uint32_t)(2 * c * PANEL_BYTES), PANEL_BYTES, 128);
+                        const uint64_t bd = make_desc(u0s + (uint32_t)(2 * c * UPANEL), UPANEL, 128);
+                        umma_f16(tmem_base + (uint32_t)(acc * NU), ad, bd, idesc, c != 0);
+                    }
+                    umma_commit(EMPTY(stage));
+                    umma_commit(TFULL(acc));
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                umma_commit(EMPTY(stage));
-                umma_commit(TFULL(acc));
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+                umma_commit(UEMPTY);   // arrives once every MMA of this item has retired
             }
         }
         __syncwarp();
+    } else if (warp >= 2 + NEPI) {
+        // ===== compactors: pop frozen lists, select the k best in place, publish the new threshold =====
+        bool exiting = false;
+        while (!exiting) compact_one(sh, mylists, k, lane, true, &exiting);
     } else {
-        const int quarter = warp & 3;
-        const int ubase = quarter * 32;
-        const int u = ubase + lane;          // this lane's user within the tile == TMEM lane
-        {   // user tile -> TMEM (TS-mode A operand): row m, K chunk kk8 = one uint4 = columns 4*kk8..4*kk8+3
-            for (int c0 = 0; c0 < 16; c0 += 8) {
-                uint32_t r[32];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    uint4 w = make_uint4(0u, 0u, 0u, 0u);
-                    if (c0 + i < npan) w = __ldg(users + ((u0 >> 7) * (long)npan + (c0 + i)) * 128 + u);
-                    r[4 * i] = w.x; r[4 * i + 1] = w.y; r[4 * i + 2] = w.z; r[4 * i + 3] = w.w;
-                }
-                tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c0 * 4), r);
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(AFULL);
-        }
-        UserState st;
-        st.thr = -INFINITY;
-        st.cnt = 0;
+        // ===== appenders: 8 warps = 4 TMEM lane quarters (songs) x 2 column halves (users) =====
+        const int e = warp - 2;
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+        const int half = e >> 2;                 // users [half*128, half*128+128)
+        const int et = threadIdx.x - 64;         // 0..255
+        const unsigned lt = (1u << lane) - 1u;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (long t = 0; t < ntiles; ++t) {
-            mbar_wait(TFULL(acc), acc_phase);
-            tc_fence_after();
-            const long it0 = ibeg + t * TI;
-            // hot path: all four 32-column loads in flight, one wait, a max tree per chunk
-            uint32_t r0[32], r1[32], r2[32], r3[32];
-            const uint32_t tb = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ACC0 + acc * TI);
-            if (dbg >= 3) {  // timing experiment: no TMEM reads at all
+        auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory"); };
+
+        // Tile-boundary bookkeeping of the users owned by this warp (u = e*32 + lane): install finished compactions,
+        // freeze + queue lists that grew beyond LIMIT.  With finishing == false the appenders only wait (and help)
+        // while some list could overflow in the next tile; with finishing == true until nothing is pending.
+        auto boundary = [&](bool finishing) {
+            for (;;) {
+                epi_sync();                                   // all appends of the tile are visible
+                const int u = e * 32 + lane;
+                // (a) install finished compactions: survivors of the tail move down behind the k kept entries
+                unsigned inst = __ballot_sync(0xffffffffu, *(volatile int*)&sh->done[u] != 0);
+                while (inst) {
+                    const int l = __ffs(inst) - 1;
+                    inst &= inst - 1;
+                    const int uu = e * 32 + l;
+                    __threadfence_block();
+                    const float nt = *(volatile float*)&sh->newthr[uu];
+                    const int n0 = sh->pend_n[uu], c = sh->cnt[uu];
+                    int2* lst = mylists + (size_t)uu * CAPH;
+                    int w = k;
+                    for (int j0 = n0; j0 < c; j0 += 32) {      // destinations are always below the sources
+                        const int j = j0 + lane;
+                        int2 v = make_int2(0, 0);
+                        bool keep = false;
+                        if (j < c) { v = __ldcg(lst + j); keep = __int_as_float(v.x) > nt; }
+                        const unsigned bm = __ballot_sync(0xffffffffu, keep);
+                        if (keep) __stcg(lst + w + __popc(bm & lt), v);
+                        w += __popc(bm);
+                        __syncwarp();
+                    }
+                    if (lane == 0) {
+                        sh->cnt[uu] = w;
+                        sh->thr[uu] = nt;
+                        sh->pend_n[uu] = 0;
+                        *(volatile int*)&sh->done[uu] = 0;
+                    }
+                    __syncwarp();
+                }
+                // (b) freeze + queue
+                const int cu = sh->cnt[u];
+                const bool pending = sh->pend_n[u] != 0;
+                const bool fr = !pending && cu > (finishing ? (k > LIMIT ? k : LIMIT) : LIMIT);
+                const unsigned fm = __ballot_sync(0xffffffffu, fr);
+                if (fm) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&sh->q_res, __popc(fm));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (fr) {
+                        sh->pend_n[u] = cu < 512 ? cu : 512;
+                        sh->qbuf[(base + __popc(fm & lt)) & (NU - 1)] = u;
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        __threadfence_block();
+                        while (atomicCAS(&sh->q_tail, base, base + __popc(fm)) != base) {}   // publish in order
+                    }
+                }
+                const bool wait_for = finishing ? (pending || fr) : (sh->cnt[u] > HARD);
+                if (__any_sync(0xffffffffu, wait_for) && lane == 0) *(volatile int*)&sh->over = 1;
+                epi_sync();
+                const bool over = *(volatile int*)&sh->over != 0;
+                if (!over) break;
+                if (!compact_one(sh, mylists, k, lane, false, nullptr)) __nanosleep(200);   // help instead of idling
+                epi_sync();
+                if (et == 0) *(volatile int*)&sh->over = 0;
+            }
+        };
+
+        for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const long ut = w / splits;
+            const int sp = (int)(w % splits);
+            long ibeg, iend;
+            song_range(w, ibeg, iend);
+            const long ntiles = (iend - ibeg + TS - 1) / TS;
+            // per-user state: users beyond n_users never accept a candidate
+            sh->thr[et] = (ut * NU + et < n_users) ? -INFINITY : INFINITY;
+            sh->cnt[et] = 0;
+            sh->pend_n[et] = 0;
+            sh->done[et] = 0;
+            epi_sync();
+            for (long t = 0; t < ntiles; ++t) {
+                mbar_wait(TFULL(acc), acc_phase);
+                tc_fence_after();
+                const long song = ibeg + t * TS + quarter * 32 + lane;     // this lane's song
+                const bool song_ok = song < iend;
+                const int song_i = (int)song;
+                const uint32_t tb = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * NU + half * 128);
+                // 128 user columns in 8 steps of 16 (a run-time loop: the fully unrolled version was 70 KB of SASS and
+                // "no instruction" was the top stall in ncu); the next 16 columns are in flight while these are compared
+                auto process16 = [&](const uint32_t (&r)[16], int ucol) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 th = *reinterpret_cast<const float4*>(sh->thr + ucol + j);
+                        const float vv[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                             __uint_as_float(r[j + 3])};
+                        const float tt[4] = {th.x, th.y, th.z, th.w};
+                        const bool p = song_ok && (vv[0] > tt[0] || vv[1] > tt[1] || vv[2] > tt[2] || vv[3] > tt[3]);
+                        if (__any_sync(0xffffffffu, p)) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (song_ok && vv[q] > tt[q]) {   // lanes rarely collide outside the first few tiles
+                                    const int u = ucol + j + q;
+                                    const int pos = atomicAdd(&sh->cnt[u], 1);
+                                    if (pos < CAPH)   // cannot fail: cnt <= HARD at tile start, <= TS appends per tile
+                                        __stcg(mylists + (size_t)u * CAPH + pos, make_int2(__float_as_int(vv[q]), song_i));
+                                }
+                            }
+                        }
+                    }
+                };
+                uint32_t ra[16], rb[16];
+                tmem_ld16_async(tb, ra);
+#pragma unroll 1
+                for (int it = 0; it < 8; it += 2) {
+                    tmem_wait_ld();
+                    tmem_ld_fence16(ra);
+                    tmem_ld16_async(tb + (uint32_t)((it + 1) * 16), rb);
+                    process16(ra, half * 128 + it * 16);
+                    tmem_wait_ld();
+                    tmem_ld_fence16(rb);
+                    if (it + 2 < 8) tmem_ld16_async(tb + (uint32_t)((it + 2) * 16), ra);
+                    process16(rb, half * 128 + it * 16 + 16);
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(TEMPTY(acc));
-                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
-                continue;
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                boundary(false);
             }
-            tmem_ld32_async(tb, r0);
-            tmem_ld32_async(tb + 32, r1);
-            tmem_ld32_async(tb + 64, r2);
-            tmem_ld32_async(tb + 96, r3);
-            tmem_wait_ld();
-            tmem_ld_fence(r0); tmem_ld_fence(r1); tmem_ld_fence(r2); tmem_ld_fence(r3);
-            float mx[4];
-#define DCUE_CHUNK_MAX(R, C)                                                                              \
-            {                                                                                             \
-                float m0 = __uint_as_float(R[0]), m1 = __uint_as_float(R[1]), m2 = __uint_as_float(R[2]),  \
-                      m3 = __uint_as_float(R[3]);                                                         \
-                _Pragma("unroll") for (int j = 4; j < 32; j += 4) {                                         \
-                    m0 = fmaxf(m0, __uint_as_float(R[j])); m1 = fmaxf(m1, __uint_as_float(R[j + 1]));     \
-                    m2 = fmaxf(m2, __uint_as_float(R[j + 2])); m3 = fmaxf(m3, __uint_as_float(R[j + 3])); \
-                }                                                                                         \
-                mx[C] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));                                              \
+            // ---- finish: every list down to <= max(k, LIMIT) entries with nothing pending, then the k best, sorted
+            boundary(true);
+            for (int uu = 0; uu < 32; ++uu) {
+                const int u = e * 32 + uu;
+                const long gu = ut * NU + u;
+                if (gu >= n_users) break;
+                int n = sh->cnt[u];
+                int2* lst = mylists + (size_t)u * CAPH;
+                if (n > k) { select_topk_inplace(lst, n, k, lane); n = k; }
+                const long ob = ((long)sp * n_users + gu) * k;
+                sort_and_write(lst, n, k, item_offset, out_s + ob, out_i + ob, lane);
             }
-            DCUE_CHUNK_MAX(r0, 0)
-            DCUE_CHUNK_MAX(r1, 1)
-            DCUE_CHUNK_MAX(r2, 2)
-            DCUE_CHUNK_MAX(r3, 3)
-#undef DCUE_CHUNK_MAX
-            if (it0 + TI > iend) {
-                // last tile: the slow path masks the columns beyond the song range
-                for (int c = 0; c < 4; ++c)
-                    st = scan_chunk(tb + (uint32_t)(c * 32), it0 + c * 32, iend, st, true, cs, ci, ubase, k, lane);
-            } else if (dbg < 1) {
-                // A chunk is examined only if some user of this warp beat its threshold there.  Each lane then
-                // builds the mask of its passing columns; with exactly one (the common case) the value is the
-                // chunk maximum it already holds, so it appends directly -- all 32 users in parallel.  Lanes with
-                // several candidates (warm-up) take the slow path that re-reads the chunk from TMEM.
-#define DCUE_CHUNK_SCAN(R, C)                                                                                   \
-                if (__any_sync(0xffffffffu, mx[C] > st.thr)) {                                                  \
-                    unsigned bits = 0;                                                                          \
-                    _Pragma("unroll") for (int j = 0; j < 32; ++j)                                                \
-                        bits |= (__uint_as_float(R[j]) > st.thr) ? (1u << j) : 0u;                              \
-                    const int pc = __popc(bits);                                                                \
-                    if (pc == 1) {                                                                              \
-                        cs[u * LD + st.cnt] = mx[C];                                                            \
-                        ci[u * LD + st.cnt] = (int)(it0 + (C) * 32 + __ffs(bits) - 1);                          \
-                        ++st.cnt;                                                                               \
-                    }                                                                                           \
-                    const unsigned full = __ballot_sync(0xffffffffu, st.cnt == CAP);                            \
-                    if (full) st = compact_full(full, st, cs, ci, ubase, k, lane);                              \
-                    if (__any_sync(0xffffffffu, pc > 1))                                                        \
-                        st = scan_chunk(tb + (uint32_t)((C) * 32), it0 + (C) * 32, iend, st, pc > 1, cs, ci, ubase, k, lane); \
-                }
-                DCUE_CHUNK_SCAN(r0, 0)
-                DCUE_CHUNK_SCAN(r1, 1)
-                DCUE_CHUNK_SCAN(r2, 2)
-                DCUE_CHUNK_SCAN(r3, 3)
-#undef DCUE_CHUNK_SCAN
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(TEMPTY(acc));
-            if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+            epi_sync();   // nobody resets the per-user state while another warp still reads it
         }
-        // ---- finish: final sort of every user's list; lane L writes slots 4L..4L+3
-        __syncwarp();
-        for (int uu = 0; uu < 32; ++uu) {
-            const int usr = ubase + uu;
-            const long gu = u0 + usr;
-            if (gu >= n_users) break;
-            const int n = __shfl_sync(0xffffffffu, st.cnt, uu);
-            compact_user(cs, ci, usr, n, k, lane);
-            const long ob = ((long)blockIdx.y * n_users + gu) * k;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int slot = lane * 4 + e;
-                if (slot < k) {
-                    const int it = ci[usr * LD + slot];
-                    out_s[ob + slot] = cs[usr * LD + slot];
-                    out_i[ob + slot] = it < 0 ? -1 : (int64_t)it + item_offset;
-                }
-            }
+        if (et == 0) {
+            __threadfence_block();
+            *(volatile int*)&sh->exit_flag = 1;
         }
     }
     tc_fence_before();
@@ -507,14 +644,20 @@ __global__ void topk_merge_kernel(const float* __restrict__ s, const int64_t* __
 }
 
 int topk_splits(long n_users, long n_items) {
-    const long ublocks = (n_users + TU - 1) / TU;
+    const long ublocks = (n_users + NU - 1) / NU;
     long want = (2L * dcue_num_sms() + ublocks - 1) / ublocks;
-    const long maxs = (n_items + 4 * TI - 1) / (4 * TI);
+    const long maxs = (n_items + 8 * TS - 1) / (8 * TS);
     if (want > maxs) want = maxs;
     if (want > 16) want = 16;
     if (want < 1) want = 1;
     return (int)want;
 }
+int topk_grid(long n_users, int splits) {
+    const long work = ((n_users + NU - 1) / NU) * splits;
+    const long sms = dcue_num_sms();
+    return (int)(work < sms ? (work > 0 ? work : 1) : sms);
+}
+size_t topk_list_bytes(int grid) { return (size_t)grid * NU * CAPH * sizeof(int2); }
 
 }  // namespace
 
@@ -530,38 +673,39 @@ extern "C" int dcue_normalize_rows(const float* x, long rows, int F, float eps, 
 extern "C" size_t dcue_topk_ws_bytes(int impl, long n_users, long n_items, int k) {
     (void)impl;
     const int splits = topk_splits(n_users, n_items);
-    return splits > 1 ? (size_t)splits * n_users * k * (sizeof(float) + sizeof(int64_t)) + 256 : 256;
+    const size_t parts = splits > 1 ? (size_t)splits * n_users * k * (sizeof(float) + sizeof(int64_t)) : 0;
+    return topk_list_bytes(topk_grid(n_users, splits)) + parts + 512;
 }
 
 extern "C" int dcue_topk_scores(int impl, const void* users_n, long n_users, const void* items_n, long n_items, int Kp,
                                 int fmt, int k, long item_offset, float* top_scores, int64_t* top_idx, void* ws,
                                 size_t ws_bytes, void* stream) {
-    DCUE_CHECK_ARG(users_n && items_n && top_scores && top_idx && n_users >= 0 && n_items >= 0 && k > 0 &&
-                   k <= SLOTS - 8);  // a compaction must free at least 8 slots
-    DCUE_CHECK_ARG(Kp % 16 == 0 && Kp >= 16 && Kp <= 128);
+    DCUE_CHECK_ARG(users_n && items_n && top_scores && top_idx && n_users >= 0 && n_items >= 0 && k > 0 && k <= 256);
+    DCUE_CHECK_ARG(Kp % 16 == 0 && Kp >= 16 && Kp <= 128 && n_items < (1L << 31));
     if (impl != DCUE_IMPL_TC) DCUE_FAIL(DCUE_E_UNSUPPORTED, "dcue_topk_scores: only the tcgen05 implementation exists");
     if (n_users == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int splits = topk_splits(n_users, n_items);
+    const int grid = topk_grid(n_users, splits);
     long per = (n_items + splits - 1) / splits;
-    per = round_up_l(per > 0 ? per : 1, TI);
+    per = round_up_l(per > 0 ? per : 1, TS);
+    const size_t list_bytes = topk_list_bytes(grid);
+    const size_t part_bytes = splits > 1 ? (size_t)splits * n_users * k * (sizeof(float) + sizeof(int64_t)) : 0;
+    if (!ws || ws_bytes < list_bytes + part_bytes)
+        DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_topk_scores: workspace %zu < %zu", ws_bytes, list_bytes + part_bytes);
     float* os = top_scores;
     int64_t* oi = top_idx;
     if (splits > 1) {
-        const size_t need = (size_t)splits * n_users * k * (sizeof(float) + sizeof(int64_t));
-        if (!ws || ws_bytes < need) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_topk_scores: workspace %zu < %zu", ws_bytes, need);
-        oi = (int64_t*)ws;
-        os = (float*)((char*)ws + (size_t)splits * n_users * k * sizeof(int64_t));
+        oi = (int64_t*)((char*)ws + list_bytes);
+        os = (float*)((char*)oi + (size_t)splits * n_users * k * sizeof(int64_t));
     }
-    // slots that are never filled (fewer than k songs in a split) must read as "missing"
-    DCUE_CUDA(cudaMemsetAsync(oi, 0xff, (size_t)splits * n_users * k * sizeof(int64_t), st));
-    const size_t smem = (size_t)NSTAGE * (Kp / 8) * PANEL_BYTES + (size_t)TU * (SLOTS + 1) * 8 + 16 +
-                        8 * (2 * NSTAGE + 1 + 2 * NACC) + 16;
-    DCUE_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((n_users + TU - 1) / TU), splits);
-    topk_kernel<<<grid, NTHREADS, smem, st>>>((const uint4*)users_n, round_up_l(n_users, 128), n_users,
-                                              (const uint4*)items_n, round_up_l(n_items, 128), n_items, Kp, fmt, k,
-                                              item_offset, per, getenv("DCUE_TOPK_DEBUG") ? atoi(getenv("DCUE_TOPK_DEBUG")) : 0, os, oi);
+    const int npan = Kp / 8;
+    const size_t smem = (size_t)npan * UPANEL + (size_t)NST * npan * PANEL_BYTES + sizeof(TopkShared) + 8 * (2 * NST + 6) + 16;
+    DCUE_CUDA(cudaFuncSetAttribute(topk_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long n_work = ((n_users + NU - 1) / NU) * splits;
+    topk_stream_kernel<<<grid, NTHREADS2, smem, st>>>((const uint4*)users_n, round_up_l(n_users, 128) / 128, n_users,
+                                                      (const uint4*)items_n, n_items, Kp, fmt, k, item_offset, per, splits, n_work,
+                                                      (int2*)ws, os, oi);
     DCUE_LAUNCH_CHECK();
     if (splits > 1) {
         topk_merge_kernel<<<ceil_div_i(n_users, 128), 128, 0, st>>>(os, oi, splits, n_users, k, top_scores, top_idx);

@@ -249,7 +249,8 @@ int dcue_normalize_rows(const float* x, long rows, int F, float eps, int Kp, int
                         void* stream);
 /* All-pairs cosine score GEMM + fused top-k (generalises DCUE.predict, nn/dcue.py:495-513):
  * for each user row the k best (score, item index + item_offset) among `items` rows, sorted
- * descending (k <= 120).  users_n/items_n: outputs of dcue_normalize_rows. */
+ * descending (k <= 256; missing slots: score -inf, index -1).  users_n/items_n: outputs of
+ * dcue_normalize_rows.  ws: dcue_topk_ws_bytes() bytes (per-CTA candidate lists + split partials). */
 int dcue_topk_scores(int impl, const void* users_n, long n_users, const void* items_n, long n_items,
                      int Kp, int fmt, int k, long item_offset, float* top_scores, int64_t* top_idx,
                      void* ws, size_t ws_bytes, void* stream);

@@ -351,7 +351,8 @@ def test_ncl_stats_and_bn_finalize():
 
 
 # ------------------------------------------------------------------ eval scorer
-@pytest.mark.parametrize("nu,ni,k", [(300, 1000, 100), (128, 257, 10), (5, 90, 100), (1000, 5000, 100)])
+@pytest.mark.parametrize("nu,ni,k", [(300, 1000, 100), (128, 257, 10), (5, 90, 100), (1000, 5000, 100), (600, 30000, 100),
+                                     (40, 3000, 256), (257, 70000, 1)])
 def test_topk_scores(nu, ni, k):
     g = torch.Generator().manual_seed(nu + ni)
     uf, itf = torch.randn(nu, 100, generator=g), torch.randn(ni, 100, generator=g)
