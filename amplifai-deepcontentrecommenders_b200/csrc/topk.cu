@@ -119,9 +119,10 @@ __device__ __forceinline__ uint32_t make_idesc(int a_fmt, int b_fmt, int M, int 
 // stalled at the epilogue barrier behind one sorting warp -> asynchronous compactors + selection instead of sorting.
 constexpr int NU = 256;          // users per CTA (MMA N)
 constexpr int TS = 128;          // songs per tile (MMA M)
-constexpr int CAPH = 1024;       // candidate slots per user in the global scratch
-constexpr int LIMIT = 384;       // freeze + compact a list longer than this (frozen part <= LIMIT + TS = 512)
-constexpr int HARD = CAPH - TS;  // a list longer than this could overflow in the next tile: wait for its compaction
+constexpr int CAPH = 2048;       // candidate slots per user in the global scratch
+constexpr int BSTEP = 4;         // tiles between two boundary checks of the appenders
+constexpr int LIMIT = 384;       // freeze + compact a list longer than this (the frozen part is capped at 512 entries)
+constexpr int HARD = CAPH - BSTEP * TS;  // a list longer than this could overflow before the next check: wait for its compaction
 constexpr int NST = 4;           // song-tile stages
 constexpr int NEPI = 8;          // appender warps: (TMEM lane quarter) x (column half)
 constexpr int NCOMP = 4;         // compactor warps
@@ -291,7 +292,7 @@ __device__ __forceinline__ bool compact_one(TopkShared* sh, int2* __restrict__ m
                 slot = -2;
                 break;
             } else {
-                __nanosleep(200);
+                __nanosleep(1000);
             }
         }
     }
@@ -523,21 +524,32 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                 // 128 user columns in 8 steps of 16 (a run-time loop: the fully unrolled version was 70 KB of SASS and
                 // "no instruction" was the top stall in ncu); the next 16 columns are in flight while these are compared
                 auto process16 = [&](const uint32_t (&r)[16], int ucol) {
+                    // one vote per 16 users: all 16 compares are independent (the per-4-column votes were a chain of
+                    // LDS -> FSETP -> VOTE -> BRA latencies, ncu: 0.3 IPC with "wait"/"branch resolving" on top)
+                    float tt[16];
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const float4 th = *reinterpret_cast<const float4*>(sh->thr + ucol + j);
-                        const float vv[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                             __uint_as_float(r[j + 3])};
-                        const float tt[4] = {th.x, th.y, th.z, th.w};
-                        const bool p = song_ok && (vv[0] > tt[0] || vv[1] > tt[1] || vv[2] > tt[2] || vv[3] > tt[3]);
-                        if (__any_sync(0xffffffffu, p)) {
+                        tt[j] = th.x; tt[j + 1] = th.y; tt[j + 2] = th.z; tt[j + 3] = th.w;
+                    }
+                    unsigned bits = 0;
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                if (song_ok && vv[q] > tt[q]) {   // lanes rarely collide outside the first few tiles
-                                    const int u = ucol + j + q;
-                                    const int pos = atomicAdd(&sh->cnt[u], 1);
-                                    if (pos < CAPH)   // cannot fail: cnt <= HARD at tile start, <= TS appends per tile
-                                        __stcg(mylists + (size_t)u * CAPH + pos, make_int2(__float_as_int(vv[q]), song_i));
+                    for (int j = 0; j < 16; ++j) bits |= (__uint_as_float(r[j]) > tt[j]) ? (1u << j) : 0u;
+                    bits = song_ok ? bits : 0u;
+                    const unsigned any = __reduce_or_sync(0xffffffffu, bits);
+                    if (any) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (any & (0xfu << (4 * g))) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const int j = 4 * g + q;
+                                    if (bits & (1u << j)) {   // lanes rarely collide outside the first few tiles
+                                        const int u = ucol + j;
+                                        const int pos = atomicAdd(&sh->cnt[u], 1);
+                                        if (pos < CAPH)   // cannot fail: cnt <= HARD at the last boundary
+                                            __stcg(mylists + (size_t)u * CAPH + pos, make_int2((int)r[j], song_i));
+                                    }
                                 }
                             }
                         }
@@ -560,7 +572,7 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                 __syncwarp();
                 if (lane == 0) mbar_arrive(TEMPTY(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                boundary(false);
+                if ((t & (BSTEP - 1)) == BSTEP - 1) boundary(false);
             }
             // ---- finish: every list down to <= max(k, LIMIT) entries with nothing pending, then the k best, sorted
             boundary(true);
