@@ -26,11 +26,24 @@ gather_relu_kernel(const float* __restrict__ table, const int64_t* __restrict__ 
         const float4* s4 = reinterpret_cast<const float4*>(src);
         float4* d4 = reinterpret_cast<float4*>(dst);
         float4* r4 = reinterpret_cast<float4*>(rdst);
-        for (int i = lane; i < E / 4; i += 32) {
-            float4 v = __ldg(s4 + i);
-            if (r4) r4[i] = v;
-            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-            d4[i] = v;
+        const int n4 = E / 4;
+        for (int i0 = 0; i0 < n4; i0 += 128) {   // 4 independent 16-byte loads per lane in flight before any store
+            float4 v[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = i0 + t * 32 + lane;
+                if (i < n4) v[t] = __ldg(s4 + i);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = i0 + t * 32 + lane;
+                if (i < n4) {
+                    float4 w = v[t];
+                    if (r4) r4[i] = w;
+                    w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f);
+                    d4[i] = w;
+                }
+            }
         }
     } else {
         for (int i = lane; i < E; i += 32) {
@@ -59,6 +72,21 @@ segment_scatter_kernel(const float* __restrict__ gout, const float* __restrict__
     int end = i + 1;
     while (end < B && sidx[end] == row) ++end;
     float* dst = gtable + row * (long)E;
+    if ((E & 3) == 0 && ((reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(fwd) | reinterpret_cast<uintptr_t>(gtable)) & 15) == 0) {
+        // 16-byte loads/stores: every row starts 16-byte aligned
+        for (int e0 = lane * 4; e0 < E; e0 += 128) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = i; j < end; ++j) {
+                const long p = (long)spos[j] * E + e0;
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gout + p));
+                const float4 f = __ldg(reinterpret_cast<const float4*>(fwd + p));
+                a.x += f.x > 0.f ? g.x : 0.f; a.y += f.y > 0.f ? g.y : 0.f;
+                a.z += f.z > 0.f ? g.z : 0.f; a.w += f.w > 0.f ? g.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(dst + e0) = a;
+        }
+        return;
+    }
     for (int e0 = lane * 4; e0 < E; e0 += 128) {
         float a[4] = {0.f, 0.f, 0.f, 0.f};
         for (int j = i; j < end; ++j) {

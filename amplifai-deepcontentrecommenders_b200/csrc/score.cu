@@ -120,12 +120,164 @@ score_kernel(const float* __restrict__ u, const float* __restrict__ feats, const
     if (MODE == 2 && lane == 0) loss_rows[b] = loss;
 }
 
+// ---- F % 4 == 0, F <= 128: 8 lanes per feature row, 16-byte accesses, FOUR negatives of the triplet in flight per
+// warp (the one-row-at-a-time kernel above is a chain of load -> two 5-step warp reductions -> store per negative:
+// 2.6 TB/s at N = 20; rows of 100 floats also leave a quarter of its lanes idle).
+__device__ __forceinline__ float group8_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+struct Row4 {
+    float4 v[4];
+};
+__device__ __forceinline__ void load_row4(Row4& r, const float* __restrict__ p, int n4, int sub, bool on) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int e = sub + 8 * i;
+        r.v[i] = (on && e < n4) ? __ldg(reinterpret_cast<const float4*>(p) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+__device__ __forceinline__ void store_row4(const Row4& r, float* __restrict__ p, int n4, int sub, bool on) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int e = sub + 8 * i;
+        if (on && e < n4) reinterpret_cast<float4*>(p)[e] = r.v[i];
+    }
+}
+__device__ __forceinline__ float dot4(const Row4& a, const Row4& b) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        s = fmaf(a.v[i].x, b.v[i].x, s); s = fmaf(a.v[i].y, b.v[i].y, s);
+        s = fmaf(a.v[i].z, b.v[i].z, s); s = fmaf(a.v[i].w, b.v[i].w, s);
+    }
+    return group8_sum(s);
+}
+__device__ __forceinline__ void scale4(Row4& o, const Row4& a, float k) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o.v[i] = make_float4(a.v[i].x * k, a.v[i].y * k, a.v[i].z * k, a.v[i].w * k);
+}
+
+// d cos / dx with the reciprocal norms hoisted out of the element loop (the division per element made the kernel
+// instruction-bound): k = 1/|x| if |x| >= eps (and c kept), else k = 1/eps with c = 0
+__device__ __forceinline__ float dcos_k(float yh, float xh, float c_eff, float k) { return (yh - c_eff * xh) * k; }
+
+template <int MODE>
+__global__ void __launch_bounds__(WARPS * 32, 4)
+score_kernel_g8(const float* __restrict__ u, const float* __restrict__ feats, const float* __restrict__ gscores,
+                int B, int N, int F, float eps, float margin, float inv_batch, float* __restrict__ scores,
+                float* __restrict__ loss_rows, float* __restrict__ du, float* __restrict__ dfeats) {
+    const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+    const int b = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int n4 = F >> 2;
+    const float inv_eps = 1.f / eps;
+    Row4 uh;
+    float nu, np, cpos;
+    {
+        Row4 ur, pr;
+        load_row4(ur, u + (long)b * F, n4, sub, true);      // every 8-lane group holds the user row
+        load_row4(pr, feats + (long)b * F, n4, sub, true);
+        nu = sqrtf(dot4(ur, ur));
+        np = sqrtf(dot4(pr, pr));
+        scale4(uh, ur, 1.f / fmaxf(nu, eps));
+        scale4(pr, pr, 1.f / fmaxf(np, eps));
+        cpos = dot4(uh, pr);
+    }
+    const float ku = nu >= eps ? 1.f / nu : inv_eps;        // d/du factors
+    const bool u_ok = nu >= eps;
+
+    Row4 acc;   // this group's share of sum_n dL/dc_n * dc_n/du
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float G = 0.f, loss = 0.f;
+    const float* negp = feats + ((long)B + (long)b * N) * F;
+    float* dnegp = MODE ? dfeats + ((long)B + (long)b * N) * F : nullptr;
+    Row4 nxt;
+    load_row4(nxt, negp + (long)grp * F, n4, sub, grp < N);
+    for (int n0 = 0; n0 < N; n0 += 4) {
+        const int n = n0 + grp;
+        const bool on = n < N;
+        Row4 nh = nxt;
+        load_row4(nxt, negp + (long)(n + 4) * F, n4, sub, n + 4 < N);   // the next four rows are in flight
+        const float nn = sqrtf(dot4(nh, nh));
+        scale4(nh, nh, 1.f / fmaxf(nn, eps));
+        const float cn = dot4(uh, nh);
+        const float s = cpos - cn;
+        if (MODE != 1 && on && sub == 0) scores[(long)b * N + n] = s;
+        if (MODE == 0) continue;
+        float g = 0.f;  // dL/ds_n
+        if (MODE == 2) {
+            const float h = margin - s;
+            if (on) {
+                loss += fmaxf(h, 0.f);
+                g = -(h > 0.f ? 1.f : (h == 0.f ? 0.5f : 0.f)) * inv_batch;
+            }
+        } else if (on) {
+            g = gscores[(long)b * N + n];
+        }
+        G += g;
+        // dL/dc_n = -g
+        const float kn = -g * (nn >= eps ? 1.f / nn : inv_eps), cn_n = nn >= eps ? cn : 0.f;
+        const float kun = -g * ku, cn_u = u_ok ? cn : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 uu = uh.v[i], hh = nh.v[i];
+            acc.v[i].x += dcos_k(hh.x, uu.x, cn_u, kun); acc.v[i].y += dcos_k(hh.y, uu.y, cn_u, kun);
+            acc.v[i].z += dcos_k(hh.z, uu.z, cn_u, kun); acc.v[i].w += dcos_k(hh.w, uu.w, cn_u, kun);
+            nh.v[i] = make_float4(dcos_k(uu.x, hh.x, cn_n, kn), dcos_k(uu.y, hh.y, cn_n, kn), dcos_k(uu.z, hh.z, cn_n, kn),
+                                  dcos_k(uu.w, hh.w, cn_n, kn));
+        }
+        store_row4(nh, dnegp + (long)n * F, n4, sub, on);
+    }
+    if (MODE == 0) return;
+    // combine the four groups (fixed order: deterministic)
+    G += __shfl_xor_sync(0xffffffffu, G, 8);
+    G += __shfl_xor_sync(0xffffffffu, G, 16);
+    loss += __shfl_xor_sync(0xffffffffu, loss, 8);
+    loss += __shfl_xor_sync(0xffffffffu, loss, 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float a[4] = {acc.v[i].x, acc.v[i].y, acc.v[i].z, acc.v[i].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            a[t] += __shfl_xor_sync(0xffffffffu, a[t], 8);
+            a[t] += __shfl_xor_sync(0xffffffffu, a[t], 16);
+        }
+        acc.v[i] = make_float4(a[0], a[1], a[2], a[3]);
+    }
+    // positive row: dL/dc_pos = +G (re-read: keeping its normalised copy live across the loop costs 16 registers)
+    Row4 ph;
+    load_row4(ph, feats + (long)b * F, n4, sub, true);
+    scale4(ph, ph, 1.f / fmaxf(np, eps));
+    const float kp = G * (np >= eps ? 1.f / np : inv_eps), cp_p = np >= eps ? cpos : 0.f;
+    const float kup = G * ku, cp_u = u_ok ? cpos : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 uu = uh.v[i], hh = ph.v[i];
+        acc.v[i].x += dcos_k(hh.x, uu.x, cp_u, kup); acc.v[i].y += dcos_k(hh.y, uu.y, cp_u, kup);
+        acc.v[i].z += dcos_k(hh.z, uu.z, cp_u, kup); acc.v[i].w += dcos_k(hh.w, uu.w, cp_u, kup);
+        ph.v[i] = make_float4(dcos_k(uu.x, hh.x, cp_p, kp), dcos_k(uu.y, hh.y, cp_p, kp), dcos_k(uu.z, hh.z, cp_p, kp),
+                              dcos_k(uu.w, hh.w, cp_p, kp));
+    }
+    store_row4(ph, dfeats + (long)b * F, n4, sub, grp == 0);
+    store_row4(acc, du + (long)b * F, n4, sub, grp == 0);
+    if (MODE == 2 && lane == 0) loss_rows[b] = loss;
+}
+
 template <int MODE>
 int launch(const float* u, const float* feats, const float* gs, int B, int N, int F, float eps, float margin,
            float inv_batch, float* scores, float* loss_rows, float* du, float* dfeats, cudaStream_t st) {
     if (B == 0) return 0;
     dim3 grid(ceil_div_i(B, WARPS)), block(WARPS * 32);
-    if (F <= 128)
+    const bool al16 = ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(feats) | reinterpret_cast<uintptr_t>(du) |
+                        reinterpret_cast<uintptr_t>(dfeats)) & 15) == 0;
+    if (F <= 128 && (F & 3) == 0 && al16 && N > 0)
+        score_kernel_g8<MODE><<<grid, block, 0, st>>>(u, feats, gs, B, N, F, eps, margin, inv_batch, scores, loss_rows, du,
+                                                      dfeats);
+    else if (F <= 128)
         score_kernel<4, MODE><<<grid, block, 0, st>>>(u, feats, gs, B, N, F, eps, margin, inv_batch, scores,
                                                       loss_rows, du, dfeats);
     else

@@ -375,6 +375,31 @@ def run_ours(args):
     h2d_idx = B * 8 * 2 + B * N * 8
     del pool
 
+    # ---------------- eval scorer (second half of BASELINE.json's metric): cfg5 = all-pairs cosine scores of user
+    # factors against 500k song factors with the fused top-100; songs sharded over the ranks, per-rank lists merged.
+    # A bounded sample of the 1M users (the kernel's cost is linear in users) keeps the default run short.
+    ev_users, ev_items, ev_k = args.eval_users, 500000, 100
+    ge = torch.Generator(device=dev).manual_seed(3)
+    ufac = torch.randn(ev_users, CFG["feat"], generator=ge, device=dev)
+    lo_i, hi_i = par.shard_slice(ev_items, rank, world)
+    ifac = torch.randn(ev_items, CFG["feat"], generator=ge, device=dev)[lo_i:hi_i].contiguous()   # same factors on every rank
+    par.sharded_topk(ufac[:4096], ifac, ev_k, lo_i)
+    barrier()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record()
+    ev_s, ev_i = par.sharded_topk(ufac, ifac, ev_k, lo_i)
+    ee1.record()
+    barrier()
+    ems = torch.tensor([ee0.elapsed_time(ee1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    eval_out = {"metric": "eval scored users/sec (top-%d)" % ev_k, "value": ev_users / (ems.item() * 1e-3), "unit": "users/s",
+                "ms": ems.item(), "users": ev_users, "songs": ev_items, "songs_per_gpu": hi_i - lo_i, "k": ev_k,
+                "tflops_algorithmic": 2.0 * CFG["feat"] * ev_users * ev_items / (ems.item() * 1e-3) / 1e12,
+                "workload": "cfg5 on a %d-user sample: fp16 factors, fp32 accumulate, songs sharded over %d GPU(s), merged top-k"
+                            % (ev_users, world)}
+    del ufac, ifac, ev_s, ev_i
+
     out = None
     if rank == 0:
         tf_peak, hbm_peak, which = peaks()
@@ -392,6 +417,7 @@ def run_ours(args):
                                "steps": idx_steps,
                                "api": "hinge_loss_step_indexed: resident pool of %d songs on the device, host sends u + song indices" % pool_songs},
                "gpu_launches": int(launches_per_step * args.steps), "final_loss": final_loss, "cuda_graph": bool(use_graph),
+               "eval": eval_out,
                "roofline": {"bound": kern[top]["bound"], "kernel": top, "achieved": kern[top]["achieved"], "peak": peak,
                             "unit": kern[top]["unit"], "frac": kern[top]["achieved"] / peak, "traffic": traffic,
                             "peak_source": which + (" (burst bf16 cuBLAS)" if kern[top]["bound"] == "tensor" else " (copy)"),
@@ -417,6 +443,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="triplets per GPU")
     ap.add_argument("--negs", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--eval-users", type=int, default=131072, help="users scored in the eval leg (sample of cfg5's 1M)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph step")
     args = ap.parse_args()
