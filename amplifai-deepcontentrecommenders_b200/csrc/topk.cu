@@ -124,7 +124,9 @@ constexpr int BSTEP = 4;         // tiles between two boundary checks of the app
 constexpr int LIMIT = 384;       // freeze + compact a list longer than this (the frozen part is capped at 512 entries)
 constexpr int HARD = CAPH - BSTEP * TS;  // a list longer than this could overflow before the next check: wait for its compaction
 constexpr int NST = 4;           // song-tile stages
-constexpr int NEPI = 8;          // appender warps: (TMEM lane quarter) x (column half)
+constexpr int NEPI = 16;         // appender warps: (TMEM lane quarter) x (column quarter)
+constexpr int UPW = NU / NEPI;   // users owned (bookkeeping, final output) per appender warp
+constexpr int CPW = 4 * NU / NEPI;   // user columns compared per appender warp
 constexpr int NCOMP = 4;         // compactor warps
 constexpr int NTHREADS2 = 64 + (NEPI + NCOMP) * 32;
 constexpr int UPANEL = NU * ROWB;   // 4096: one 8-wide K chunk of the 256-user operand
@@ -429,8 +431,9 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
         // ===== appenders: 8 warps = 4 TMEM lane quarters (songs) x 2 column halves (users) =====
         const int e = warp - 2;
         const int quarter = warp & 3;            // TMEM lane quarter this warp may read
-        const int half = e >> 2;                 // users [half*128, half*128+128)
-        const int et = threadIdx.x - 64;         // 0..255
+        const int half = e >> 2;                 // users [half*CPW, half*CPW + CPW)
+        const int et = threadIdx.x - 64;         // 0..NEPI*32-1
+        const bool owner_lane = lane < UPW;      // lanes that own a user in the boundary bookkeeping
         const unsigned lt = (1u << lane) - 1u;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -442,13 +445,13 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
         auto boundary = [&](bool finishing) {
             for (;;) {
                 epi_sync();                                   // all appends of the tile are visible
-                const int u = e * 32 + lane;
+                const int u = e * UPW + (lane % UPW);
                 // (a) install finished compactions: survivors of the tail move down behind the k kept entries
-                unsigned inst = __ballot_sync(0xffffffffu, *(volatile int*)&sh->done[u] != 0);
+                unsigned inst = __ballot_sync(0xffffffffu, owner_lane && *(volatile int*)&sh->done[u] != 0);
                 while (inst) {
                     const int l = __ffs(inst) - 1;
                     inst &= inst - 1;
-                    const int uu = e * 32 + l;
+                    const int uu = e * UPW + l;
                     __threadfence_block();
                     const float nt = *(volatile float*)&sh->newthr[uu];
                     const int n0 = sh->pend_n[uu], c = sh->cnt[uu];
@@ -475,7 +478,7 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                 // (b) freeze + queue
                 const int cu = sh->cnt[u];
                 const bool pending = sh->pend_n[u] != 0;
-                const bool fr = !pending && cu > (finishing ? (k > LIMIT ? k : LIMIT) : LIMIT);
+                const bool fr = owner_lane && !pending && cu > (finishing ? (k > LIMIT ? k : LIMIT) : LIMIT);
                 const unsigned fm = __ballot_sync(0xffffffffu, fr);
                 if (fm) {
                     int base = 0;
@@ -491,7 +494,7 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                         while (atomicCAS(&sh->q_tail, base, base + __popc(fm)) != base) {}   // publish in order
                     }
                 }
-                const bool wait_for = finishing ? (pending || fr) : (sh->cnt[u] > HARD);
+                const bool wait_for = owner_lane && (finishing ? (pending || fr) : (sh->cnt[u] > HARD));
                 if (__any_sync(0xffffffffu, wait_for) && lane == 0) *(volatile int*)&sh->over = 1;
                 epi_sync();
                 const bool over = *(volatile int*)&sh->over != 0;
@@ -509,10 +512,12 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
             song_range(w, ibeg, iend);
             const long ntiles = (iend - ibeg + TS - 1) / TS;
             // per-user state: users beyond n_users never accept a candidate
-            sh->thr[et] = (ut * NU + et < n_users) ? -INFINITY : INFINITY;
-            sh->cnt[et] = 0;
-            sh->pend_n[et] = 0;
-            sh->done[et] = 0;
+            if (et < NU) {
+                sh->thr[et] = (ut * NU + et < n_users) ? -INFINITY : INFINITY;
+                sh->cnt[et] = 0;
+                sh->pend_n[et] = 0;
+                sh->done[et] = 0;
+            }
             epi_sync();
             for (long t = 0; t < ntiles; ++t) {
                 mbar_wait(TFULL(acc), acc_phase);
@@ -520,7 +525,7 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                 const long song = ibeg + t * TS + quarter * 32 + lane;     // this lane's song
                 const bool song_ok = song < iend;
                 const int song_i = (int)song;
-                const uint32_t tb = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * NU + half * 128);
+                const uint32_t tb = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * NU + half * CPW);
                 // 128 user columns in 8 steps of 16 (a run-time loop: the fully unrolled version was 70 KB of SASS and
                 // "no instruction" was the top stall in ncu); the next 16 columns are in flight while these are compared
                 auto process16 = [&](const uint32_t (&r)[16], int ucol) {
@@ -558,15 +563,15 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                 uint32_t ra[16], rb[16];
                 tmem_ld16_async(tb, ra);
 #pragma unroll 1
-                for (int it = 0; it < 8; it += 2) {
+                for (int it = 0; it < CPW / 16; it += 2) {
                     tmem_wait_ld();
                     tmem_ld_fence16(ra);
                     tmem_ld16_async(tb + (uint32_t)((it + 1) * 16), rb);
-                    process16(ra, half * 128 + it * 16);
+                    process16(ra, half * CPW + it * 16);
                     tmem_wait_ld();
                     tmem_ld_fence16(rb);
-                    if (it + 2 < 8) tmem_ld16_async(tb + (uint32_t)((it + 2) * 16), ra);
-                    process16(rb, half * 128 + it * 16 + 16);
+                    if (it + 2 < CPW / 16) tmem_ld16_async(tb + (uint32_t)((it + 2) * 16), ra);
+                    process16(rb, half * CPW + it * 16 + 16);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -576,8 +581,8 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
             }
             // ---- finish: every list down to <= max(k, LIMIT) entries with nothing pending, then the k best, sorted
             boundary(true);
-            for (int uu = 0; uu < 32; ++uu) {
-                const int u = e * 32 + uu;
+            for (int uu = 0; uu < UPW; ++uu) {
+                const int u = e * UPW + uu;
                 const long gu = ut * NU + u;
                 if (gu >= n_users) break;
                 int n = sh->cnt[u];
