@@ -71,3 +71,28 @@ extern "C" int dcue_conv_wgrad(int impl, const void* dy_panel, long dy_panel_row
     return dcue_simt_conv_wgrad(dy_panel, dy_panel_rows, fmt_dy, x_panel, x_panel_rows, fmt_x, rows_total, k, Cin, Cout,
                                 gscale, dW, ws, ws_bytes, (cudaStream_t)stream);
 }
+
+extern "C" size_t dcue_conv_wgrad_unpool_ws_bytes(int k) { return dcue_tc_wgrad_unpool_ws_bytes(k); }
+
+extern "C" int dcue_conv_wgrad_unpool(const float* dy, int lddy, const float* dtp, int lddtp, const float* z, const uint8_t* code,
+                                      const float* scale, const float* mean, const float* rstd, const double* sums, double count,
+                                      int S, int P, int pool, int Lp, const void* x_panel, long x_panel_rows, int fmt, int k,
+                                      int Cin, int Cout, const float* gscale, float* dW, double* bias_sums, float* bias_out,
+                                      void* ws, size_t ws_bytes, void* stream) {
+    DCUE_CHECK_ARG(dy && z && code && x_panel && dW && S >= 0 && P > 0 && lddy >= 128 && lddy % 4 == 0);
+    DCUE_CHECK_ARG(((uintptr_t)dy & 15) == 0 && ((uintptr_t)z & 15) == 0 && ((uintptr_t)code & 15) == 0);
+    DCUE_CHECK_ARG(!dtp || (lddtp % 4 == 0 && ((uintptr_t)dtp & 15) == 0));
+    DCUE_CHECK_ARG(!sums || (mean && rstd && count > 0));
+    if (pool != 4 || k != 4 || Cin != 128 || Cout != 128)
+        DCUE_FAIL(DCUE_E_UNSUPPORTED, "dcue_conv_wgrad_unpool: built for pool 4, k 4, 128 channels");
+    DCUE_CHECK_ARG(Lp % 4 == 0 && P * pool <= Lp && (long)S * Lp < (1L << 31) - 4096);
+    DCUE_CHECK_ARG(x_panel_rows >= round_up_l((long)S * Lp, 128) + 16);
+    if (S == 0) {
+        DCUE_CUDA(cudaMemsetAsync(dW, 0, (size_t)Cout * Cin * k * sizeof(float), (cudaStream_t)stream));
+        if (bias_sums) DCUE_CUDA(cudaMemsetAsync(bias_sums, 0, 128 * sizeof(double), (cudaStream_t)stream));
+        if (bias_out) DCUE_CUDA(cudaMemsetAsync(bias_out, 0, 128 * sizeof(float), (cudaStream_t)stream));
+        return 0;
+    }
+    return dcue_tc_conv_wgrad_unpool(dy, lddy, dtp, lddtp, z, code, scale, mean, rstd, sums, count, S, P, Lp, x_panel,
+                                     x_panel_rows, fmt, k, gscale, dW, bias_sums, bias_out, ws, ws_bytes, (cudaStream_t)stream);
+}

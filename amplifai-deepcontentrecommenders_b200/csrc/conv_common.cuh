@@ -47,6 +47,11 @@ int dcue_tc_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const voi
                        long rows_total, int k, int Cin, int Cout, const float* gscale, float* dW, void* ws,
                        size_t ws_bytes, cudaStream_t st);
 size_t dcue_tc_ws_bytes(int k);
+size_t dcue_tc_wgrad_unpool_ws_bytes(int k);
+int dcue_tc_conv_wgrad_unpool(const float* dy, int lddy, const float* dtp, int lddtp, const float* z, const uint8_t* code,
+                              const float* scale, const float* mean, const float* rstd, const double* sums, double count, int S,
+                              int P, int Lp, const void* x_panel, long x_rows, int fmt, int k, const float* gscale, float* dW,
+                              double* bias_sums, float* bias_out, void* ws, size_t ws_bytes, cudaStream_t st);
 
 __global__ void dcue_wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int Cout, int Cin, int k,
                                          const float* __restrict__ gscale, float* __restrict__ dW);

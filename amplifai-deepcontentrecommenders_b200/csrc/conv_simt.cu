@@ -282,37 +282,51 @@ extern "C" int dcue_pack_conv_weight(const float* W, int Cout, int Cin, int k, i
 
 // tapB[j][co] = sum_ci W[co][ci][j] * beta[ci]   (input-BatchNorm shift folded into the conv bias)
 // the constant each input channel carries is beta[c] + gamma[c]*shift[c] (shift: x-hat = rstd*u + shift)
-__global__ void tap_bias_kernel(const float* __restrict__ W, int Cout, int Cin, int k, const float* __restrict__ beta,
-                                const float* __restrict__ gamma, const float* __restrict__ shift, float* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= k * Cout) return;
-    const int j = i / Cout, co = i % Cout;
-    float s = 0.f;
-    for (int c = 0; c < Cin; ++c) {
+// one warp per output channel: lanes stride the contiguous [Cin][k] weight row (coalesced), shuffle reduction
+__global__ void __launch_bounds__(128)
+tap_bias_kernel(const float* __restrict__ W, int Cout, int Cin, int k, const float* __restrict__ beta,
+                const float* __restrict__ gamma, const float* __restrict__ shift, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int co = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (co >= Cout) return;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* w = W + (long)co * Cin * k;
+    for (int c = lane; c < Cin; c += 32) {
         const float b = beta[c] + (shift ? (gamma ? gamma[c] : 1.f) * shift[c] : 0.f);
-        s = fmaf(W[((long)co * Cin + c) * k + j], b, s);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < k) s[j] = fmaf(w[c * k + j], b, s[j]);
     }
-    out[i] = s;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float t = warp_sum(s[j]);
+        if (lane == 0 && j < k) out[j * Cout + co] = t;
+    }
 }
 
 extern "C" int dcue_conv_tap_bias(const float* W, int Cout, int Cin, int k, const float* beta, const float* gamma,
                                   const float* shift, float* tap_bias, void* stream) {
     DCUE_CHECK_ARG(W && beta && tap_bias && Cout > 0 && Cin > 0 && k >= 1 && k <= 4);
-    tap_bias_kernel<<<ceil_div_i(k * Cout, 128), 128, 0, (cudaStream_t)stream>>>(W, Cout, Cin, k, beta, gamma, shift, tap_bias);
+    tap_bias_kernel<<<ceil_div_i(Cout, 4), 128, 0, (cudaStream_t)stream>>>(W, Cout, Cin, k, beta, gamma, shift, tap_bias);
     DCUE_LAUNCH_CHECK();
     return 0;
 }
 
-// out[i][c] = inv_scale * sum_s panel[s*Lp + rows[i]][c]  for up to 4 rows per spectrogram
+// out[z][i][c] = inv_scale * (sum over the z-th slice of the spectrograms) panel[s*Lp + rows[i]][c] for up to 4 rows per
+// spectrogram; the PRS_SLICES partial sums are added in fixed order by the consumer (dcue_bn_fold_grads).
+// (The one-block-per-(panel,row) version ran 64 blocks of 84 strided loads each: 60 us for 22 MB.)
+constexpr int PRS_SLICES = 64;
 __global__ void __launch_bounds__(256)
 panel_row_sums_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt, int S, int Lp, int4 rows,
-                      const float* __restrict__ gscale, float* __restrict__ out /* [4][128] */) {
-    __shared__ float red[8][8][33];
-    const int q = blockIdx.x, ri = blockIdx.y;
+                      const float* __restrict__ gscale, float* __restrict__ out /* [PRS_SLICES][4][128] */) {
+    __shared__ float red[8][8];
+    const int q = blockIdx.x, ri = blockIdx.y, z = blockIdx.z;
     const int row = ri == 0 ? rows.x : ri == 1 ? rows.y : ri == 2 ? rows.z : rows.w;
+    const int per = (S + PRS_SLICES - 1) / PRS_SLICES;
+    const int s0 = z * per, s1 = min(S, s0 + per);
     float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (row >= 0)
-        for (int s = threadIdx.x; s < S; s += 256) {
+        for (int s = s0 + threadIdx.x; s < s1; s += 256) {
             const uint4 v = __ldg(panel + (long)q * panel_rows + (long)s * Lp + row);
             const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -325,23 +339,80 @@ panel_row_sums_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt,
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float v = warp_sum(a[j]);
-        if (lane == 0) red[wp][j][0] = v;
+        if (lane == 0) red[wp][j] = v;
     }
     __syncthreads();
     if (threadIdx.x < 8) {
         float t = 0.f;
 #pragma unroll
-        for (int w2 = 0; w2 < 8; ++w2) t += red[w2][threadIdx.x][0];
-        out[ri * 128 + q * 8 + threadIdx.x] = t * (gscale ? gscale[1] : 1.f);
+        for (int w2 = 0; w2 < 8; ++w2) t += red[w2][threadIdx.x];
+        out[(z * 4 + ri) * 128 + q * 8 + threadIdx.x] = t * (gscale ? gscale[1] : 1.f);
     }
 }
+
+extern "C" int dcue_panel_row_sums_parts(void) { return PRS_SLICES; }
 
 extern "C" int dcue_panel_row_sums(const void* panel, long panel_rows, int fmt, int S, int Lp, int r0, int r1, int r2, int r3,
                                    const float* gscale, float* out, void* stream) {
     DCUE_CHECK_ARG(panel && out && S >= 0 && Lp > 0 && r0 < Lp && r1 < Lp && r2 < Lp && r3 < Lp);
-    dim3 grid(16, 4);
+    dim3 grid(16, 4, PRS_SLICES);
     panel_row_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)panel, panel_rows, fmt, S, Lp,
                                                                   make_int4(r0, r1, r2, r3), gscale, out);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+// The same border row sums taken from the POOLED inputs (no dY panel exists on the fused unpool+wgrad path):
+// out[z][e][c] = sum over slice z of [code[s*P+p_e][c] == c_e] * dz(s*P+p_e, c),  flat border row r_e = p_e*pool + c_e,
+// dz = relu'(z) * (a*dy + b*z + c) as in bn_relu_unpool_rows_kernel (unscaled: true gradient units).
+__global__ void __launch_bounds__(512)
+border_row_sums_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ dtp, int lddtp,
+                       const float* __restrict__ z, const uint8_t* __restrict__ code, const float* __restrict__ scale,
+                       const float* __restrict__ mean, const float* __restrict__ rstd, const double* __restrict__ sums,
+                       double count, int S, int P, int pool, int4 rows, float* __restrict__ out /* [PRS_SLICES][4][128] */) {
+    __shared__ float red[4][128];
+    const int c = threadIdx.x & 127, ph = threadIdx.x >> 7;
+    const int ri = blockIdx.x, zs = blockIdx.y;
+    const int row = ri == 0 ? rows.x : ri == 1 ? rows.y : ri == 2 ? rows.z : rows.w;
+    float a = 0.f;
+    if (row >= 0 && row / pool < P) {
+        const int pe = row / pool;
+        const unsigned ce = (unsigned)(row - pe * pool);
+        const float sc = scale ? scale[c] : 1.f;
+        float kb = 0.f, kc = 0.f;
+        if (sums) {
+            const double inv_n = 1.0 / count;
+            const double rs2 = (double)rstd[c] * sums[128 + c] * inv_n;
+            kb = (float)(-(double)sc * rs2);
+            kc = (float)((double)sc * (rs2 * (double)mean[c] - sums[c] * inv_n));
+        }
+        const float invP = 1.f / (float)P;
+        const int per = (S + PRS_SLICES - 1) / PRS_SLICES;
+        const int s0 = zs * per, s1 = min(S, s0 + per);
+#pragma unroll 4
+        for (int sp = s0 + ph; sp < s1; sp += 4) {
+            const long r = (long)sp * P + pe;
+            float g = dy[r * lddy + c];
+            const float zz = z[r * 128 + c];
+            const unsigned cd = code[r * 128 + c];
+            if (dtp) g = fmaf(dtp[(long)sp * lddtp + c], invP, g);
+            const float v = fmaf(sc, g, fmaf(kb, zz, kc));
+            a += (zz > 0.f && cd == ce) ? v : 0.f;
+        }
+    }
+    red[ph][c] = a;
+    __syncthreads();
+    if (ph == 0) out[(zs * 4 + ri) * 128 + c] = (red[0][c] + red[1][c]) + (red[2][c] + red[3][c]);
+}
+
+extern "C" int dcue_border_row_sums(const float* dy, int lddy, const float* dtp, int lddtp, const float* z, const uint8_t* code,
+                                    const float* scale, const float* mean, const float* rstd, const double* sums, double count,
+                                    int S, int P, int C, int pool, int r0, int r1, int r2, int r3, float* out, void* stream) {
+    DCUE_CHECK_ARG(dy && z && code && out && S >= 0 && P > 0 && C == 128 && pool >= 1 && lddy >= C);
+    DCUE_CHECK_ARG(!sums || (mean && rstd && count > 0));
+    dim3 grid(4, PRS_SLICES);
+    border_row_sums_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(dy, lddy, dtp, lddtp, z, code, scale, mean, rstd, sums,
+                                                                   count > 0 ? count : 1.0, S, P, pool, make_int4(r0, r1, r2, r3), out);
     DCUE_LAUNCH_CHECK();
     return 0;
 }
@@ -354,7 +425,7 @@ extern "C" int dcue_panel_row_sums(const void* panel, long panel_rows, int fmt, 
 __global__ void __launch_bounds__(128)
 bn_fold_grads_kernel(const float* __restrict__ G, const float* __restrict__ W, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ xs_scale, const float* __restrict__ xs_shift,
-                     const float* __restrict__ Tall, const float* __restrict__ E /* [4][128] */,
+                     const float* __restrict__ Tall, const float* __restrict__ E /* [PRS_SLICES][4][128] */,
                      int4 erows, int Cout, int Cin, int k, int pad, int Lin, float* __restrict__ dW,
                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
     __shared__ float r1[128], r2[128];
@@ -362,6 +433,13 @@ bn_fold_grads_kernel(const float* __restrict__ G, const float* __restrict__ W, c
     float sg = 0.f, sb = 0.f;
     if (co < Cout) {
         const int er[4] = {erows.x, erows.y, erows.z, erows.w};
+        float Esum[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {   // fixed-order sum of the row-sum slices
+            float t = 0.f;
+            for (int z = 0; z < PRS_SLICES; ++z) t += E[(z * 4 + e) * 128 + co];
+            Esum[e] = t;
+        }
         const float ga = gamma[ci], be = beta[ci];
         // the operand was u with x-hat = xs_scale*u + xs_shift: G(x-hat) = xs_scale*G(u) + xs_shift*T
         const float xr = xs_scale ? xs_scale[ci] : 1.f, xsft = xs_shift ? xs_shift[ci] : 0.f;
@@ -370,7 +448,7 @@ bn_fold_grads_kernel(const float* __restrict__ G, const float* __restrict__ W, c
             for (int e = 0; e < 4; ++e) {
                 if (er[e] < 0) continue;
                 const int tt = er[e] + j - pad;
-                if (tt < 0 || tt >= Lin) T -= E[e * 128 + co];
+                if (tt < 0 || tt >= Lin) T -= Esum[e];
             }
             const long o = ((long)co * Cin + ci) * k + j;
             const float g = xr * G[o] + xsft * T, w = W[o];

@@ -492,6 +492,263 @@ tc_wgrad_kernel(const uint4* __restrict__ dyp, long dy_rows, int fmt_dy, const u
     }
 }
 
+// ----------------------------------------------------------------------------- fused unpool + wgrad
+// dW[co,ci,j] = sum_r dY[r,co] X[r+j,ci] where dY is never materialised: the 16-bit gradient operand tile is built in
+// shared memory by 8 "expander" warps straight from the pooled fp32 inputs (gradient dy, pre-BatchNorm activation z,
+// argmax code): BatchNorm backward (a*dy + b*z + c per channel), ReLU mask, scale, fp16, and the value is placed on
+// the row of its pooling window that won the max (the other POOL-1 rows are zero).  Versus unpool -> panel -> wgrad
+// this removes one write and one read of the 4x-unpooled panel (2 x 749 MB at layer 1) and a launch.
+// lane = pooling window of the 128-row tile (32 windows x POOL 4), warp e = channel panels 2e, 2e+1.  Global loads go
+// straight to registers (32-byte sector per lane, as in bn_relu_unpool_rows_kernel) one tile ahead; the smem stores
+// rotate the row order per lane pair so that a warp store instruction touches every bank once.
+constexpr int WGU_EXP = 8;                          // expander warps
+constexpr int WGU_DY_PANEL = WG_DY_PANEL;           // dY operand panel stride of the fused kernel
+constexpr int WGU_STAGE_BYTES = PANELS * WGU_DY_PANEL + B_STAGE_BYTES;
+constexpr int WGU_THREADS = 64 + WGU_EXP * 32;
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct UnpoolSrc {
+    const float* dy; int lddy;
+    const float* dtp; int lddtp;
+    const float* z; const uint8_t* code;
+    const float* scale; const float* mean; const float* rstd; const double* sums; double count;
+    int S, P, Lp;
+    const float* gscale;
+};
+
+template <int KTAPS>
+__global__ void __launch_bounds__(WGU_THREADS, 1)
+tc_wgrad_unpool_kernel(UnpoolSrc src, int fmt, const uint4* __restrict__ xp, long x_rows, long rows_total,
+                       float* __restrict__ part /* [grid][128][KTAPS][128] */, double* __restrict__ bias_partial /* [grid][128] */) {
+    constexpr int TCOLS = KTAPS * 128 <= 128 ? 128 : (KTAPS * 128 <= 256 ? 256 : 512);
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(16) float kconst[3][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_NSTAGE * WGU_STAGE_BYTES);
+    // bars: [0..N) full (X tile by bulk copy), [N..2N) empty, [2N..3N) dyfull (expanders), 3N: done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * WG_NSTAGE + 1);
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int st) { return bar0 + 8u * st; };
+    auto EMPTY = [&](int st) { return bar0 + 8u * (WG_NSTAGE + st); };
+    auto DYFULL = [&](int st) { return bar0 + 8u * (2 * WG_NSTAGE + st); };
+    const uint32_t DONE = bar0 + 8u * (3 * WG_NSTAGE);
+
+    const long ntiles = (rows_total + BN - 1) / BN;
+    const long tbeg = ntiles * blockIdx.x / gridDim.x;          // balanced: every CTA owns >= 1 tile (grid <= ntiles)
+    const long tend = ntiles * (blockIdx.x + 1) / gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < WG_NSTAGE; ++st) { mbar_init(FULL(st), 1); mbar_init(EMPTY(st), 1); mbar_init(DYFULL(st), WGU_EXP); }
+        mbar_init(DONE, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TCOLS>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            Pipe pp;
+            for (long tile = tbeg; tile < tend; ++tile) {
+                mbar_wait(EMPTY(pp.stage), pp.phase ^ 1);
+                mbar_expect_tx(FULL(pp.stage), B_STAGE_BYTES);
+                const long r0 = tile * BN;
+                uint8_t* x_dst = smem + pp.stage * WGU_STAGE_BYTES + PANELS * WGU_DY_PANEL;
+#pragma unroll 4
+                for (int q = 0; q < PANELS; ++q)
+                    bulk_g2s(smem_u32(x_dst + q * B_PANEL_BYTES), xp + (long)q * x_rows + r0, B_PANEL_BYTES, FULL(pp.stage));
+                pp.advance(WG_NSTAGE);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(fmt, fmt, 1, 1, 128, 128);
+            Pipe pp;
+            bool first = true;
+            for (long tile = tbeg; tile < tend; ++tile) {
+                mbar_wait(FULL(pp.stage), pp.phase);
+                mbar_wait(DYFULL(pp.stage), pp.phase);
+                tc_fence_after();
+                const uint32_t dy0 = smem_u32(smem + pp.stage * WGU_STAGE_BYTES);
+                const uint32_t x0 = dy0 + PANELS * WGU_DY_PANEL;
+#pragma unroll
+                for (int kk = 0; kk < BN / 16; ++kk) {  // 16 rows (MMA K) per instruction
+                    const uint64_t ad = make_desc(dy0 + (uint32_t)(kk * 16 * ROWB), 128, WGU_DY_PANEL);
+#pragma unroll
+                    for (int j = 0; j < KTAPS; ++j) {
+                        const uint64_t bd = make_desc(x0 + (uint32_t)((kk * 16 + j) * ROWB), 128, B_PANEL_BYTES);
+                        umma_f16(tmem_base + (uint32_t)(j * 128), ad, bd, idesc, !(first && kk == 0));
+                    }
+                }
+                first = false;
+                umma_commit(EMPTY(pp.stage));
+                pp.advance(WG_NSTAGE);
+            }
+            umma_commit(DONE);
+        }
+        __syncwarp();
+    } else {
+        // ===== expanders: pooled fp32 inputs -> the 16-bit dY operand tile of every stage =====
+        // lane = pooling window of the 128-row tile, warp e = channel panels 2e, 2e+1 (a 64-byte run of every input row
+        // per lane).  A variant with fully coalesced row loads and a lane-pair exchange was tried and was slower
+        // (525 vs 448 us at layer-1 size: 40 % more instructions, the kernel is issue/latency bound in the expanders).
+        const int e = warp - 2;
+        const float gs = src.gscale ? src.gscale[0] : 1.f;
+        // per-channel BatchNorm-backward constants live in shared memory (broadcast reads): as registers they pushed the
+        // two prefetch sets into spills
+        float acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+        if (lane < 16) {
+            const int c = e * 16 + lane;
+            const float sc = src.scale ? src.scale[c] : 1.f;
+            float b0 = 0.f, c0 = 0.f;
+            if (src.sums) {
+                const double inv_n = 1.0 / src.count;
+                const double rs2 = (double)src.rstd[c] * src.sums[128 + c] * inv_n;
+                b0 = (float)(-(double)sc * rs2);
+                c0 = (float)((double)sc * (rs2 * (double)src.mean[c] - src.sums[c] * inv_n));
+            }
+            kconst[0][c] = sc; kconst[1][c] = b0; kconst[2][c] = c0;
+        }
+        __syncwarp();
+        const float invP = 1.f / (float)src.P;
+        // raw inputs of this lane's pooling window, TWO tiles ahead (two register sets: one tile of prefetch left
+        // ~1 us of global-load latency exposed per tile)
+        struct Raw {
+            float4 g4[4], z4[4];
+            uint2 cd[2];
+            bool valid;
+            long srow;
+        };
+        auto fetch = [&](Raw& w, long tile) {   // 16 channels of dy, z, code -> registers
+            const unsigned r = (unsigned)(tile * BN) + 4u * (unsigned)lane;
+            const unsigned sp = r / (unsigned)src.Lp;
+            const unsigned pw = (r - sp * (unsigned)src.Lp) >> 2;
+            w.valid = tile < tend && (int)sp < src.S && (int)pw < src.P;
+            w.srow = (long)sp;
+            if (w.valid) {
+                const long crow = (long)sp * src.P + pw;
+                const float4* gp = reinterpret_cast<const float4*>(src.dy + crow * src.lddy + e * 16);
+                const float4* zp = reinterpret_cast<const float4*>(src.z + crow * 128 + e * 16);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { w.g4[i] = __ldg(gp + i); w.z4[i] = __ldg(zp + i); }
+                const uint2* cp = reinterpret_cast<const uint2*>(src.code + crow * 128 + e * 16);
+                w.cd[0] = __ldg(cp);
+                w.cd[1] = __ldg(cp + 1);
+            }
+        };
+        Pipe pp;
+        auto expand = [&](Raw& w, long tile) {
+            unsigned short h[16];
+            unsigned cw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) h[i] = 0;
+            if (w.valid) {
+                float g[16] = {w.g4[0].x, w.g4[0].y, w.g4[0].z, w.g4[0].w, w.g4[1].x, w.g4[1].y, w.g4[1].z, w.g4[1].w,
+                               w.g4[2].x, w.g4[2].y, w.g4[2].z, w.g4[2].w, w.g4[3].x, w.g4[3].y, w.g4[3].z, w.g4[3].w};
+                const float zz[16] = {w.z4[0].x, w.z4[0].y, w.z4[0].z, w.z4[0].w, w.z4[1].x, w.z4[1].y, w.z4[1].z, w.z4[1].w,
+                                      w.z4[2].x, w.z4[2].y, w.z4[2].z, w.z4[2].w, w.z4[3].x, w.z4[3].y, w.z4[3].z, w.z4[3].w};
+                if (src.dtp) {
+                    const float4* tp = reinterpret_cast<const float4*>(src.dtp + w.srow * src.lddtp + e * 16);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 t = __ldg(tp + i);
+                        g[4 * i] = fmaf(t.x, invP, g[4 * i]); g[4 * i + 1] = fmaf(t.y, invP, g[4 * i + 1]);
+                        g[4 * i + 2] = fmaf(t.z, invP, g[4 * i + 2]); g[4 * i + 3] = fmaf(t.w, invP, g[4 * i + 3]);
+                    }
+                }
+#pragma unroll
+                for (int i4 = 0; i4 < 16; i4 += 4) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(&kconst[0][e * 16 + i4]);
+                    const float4 b4 = *reinterpret_cast<const float4*>(&kconst[1][e * 16 + i4]);
+                    const float4 c4 = *reinterpret_cast<const float4*>(&kconst[2][e * 16 + i4]);
+                    const float ka[4] = {a4.x, a4.y, a4.z, a4.w}, kb[4] = {b4.x, b4.y, b4.z, b4.w}, kc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int i = i4 + t;
+                        const float gg = fmaf(ka[t], g[i], fmaf(kb[t], zz[i], kc[t]));
+                        const float v = zz[i] > 0.f ? gg : 0.f;
+                        acc[i] += v;
+                        h[i] = cvt_f32_to16(v * gs, fmt);
+                    }
+                }
+                cw[0] = w.cd[0].x; cw[1] = w.cd[0].y; cw[2] = w.cd[1].x; cw[3] = w.cd[1].y;
+            }
+            fetch(w, tile + 2);                       // refill this register set: two tiles of loads stay in flight
+            mbar_wait(EMPTY(pp.stage), pp.phase ^ 1); // the MMAs that read this stage (3 tiles ago) have retired
+            uint8_t* dy_dst = smem + pp.stage * WGU_STAGE_BYTES;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint8_t* base = dy_dst + (e * 2 + half) * WGU_DY_PANEL + lane * (4 * ROWB);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = (jj + (lane >> 1)) & 3;   // lane pairs start on different rows: conflict-free 16-byte stores
+                    unsigned wd[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int ch = half * 8 + c;
+                        const unsigned code_c = (cw[ch >> 2] >> (8 * (ch & 3))) & 0xffu;
+                        wd[c] = code_c == (unsigned)j ? (unsigned)h[ch] : 0u;
+                    }
+                    *reinterpret_cast<uint4*>(base + j * ROWB) =
+                        make_uint4(wd[0] | (wd[1] << 16), wd[2] | (wd[3] << 16), wd[4] | (wd[5] << 16), wd[6] | (wd[7] << 16));
+                }
+            }
+            fence_proxy_async();                      // generic-proxy stores -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(DYFULL(pp.stage));
+            pp.advance(WG_NSTAGE);
+        };
+        Raw ra, rb;
+        fetch(ra, tbeg);
+        fetch(rb, tbeg + 1);
+        for (long tile = tbeg; tile < tend; tile += 2) {
+            expand(ra, tile);
+            if (tile + 1 < tend) expand(rb, tile + 1);
+        }
+        if (bias_partial) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float t = warp_sum(acc[i]);
+                if (lane == 0) bias_partial[(long)blockIdx.x * 128 + e * 16 + i] = (double)t;
+            }
+        }
+        if (e < 4) {
+            // ===== epilogue: the four warps covering the four TMEM lane quarters write the CTA's partial =====
+            const int quarter = warp & 3;
+            const int co = quarter * 32 + lane;
+            mbar_wait(DONE, 0);
+            tc_fence_after();
+            float* dst = part + ((long)blockIdx.x * 128 + co) * KTAPS * 128;
+#pragma unroll 1
+            for (int j = 0; j < KTAPS; ++j) {
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * 128 + ch * 32), v);
+                    if (tend <= tbeg) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                    }
+                    float4* d4 = reinterpret_cast<float4*>(dst + j * 128 + ch * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TCOLS>(tmem_base);
+    }
+}
+
 size_t rows_smem_bytes(int k, bool atmem) {
     if (atmem) return (size_t)6 * B_STAGE_BYTES + 8 * (2 * 6 + 5) + 16;
     return (size_t)k * PANELS * A_PANEL_BYTES + NSTAGE * B_STAGE_BYTES + 8 * (2 * NSTAGE + 5) + 16;
@@ -534,6 +791,11 @@ int launch_rows_t(const void* panel, long panel_rows, int fmt_in, const void* w_
 }
 
 }  // namespace
+
+__global__ void dcue_cvt_d2f_kernel(const double* __restrict__ in, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
 
 size_t dcue_tc_ws_bytes(int k) {
     // [grid*4][2][128] stat partials + one scratch line for dead-lane stores
@@ -598,5 +860,38 @@ int dcue_tc_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const voi
     DCUE_LAUNCH_CHECK();
     dcue_wgrad_reduce_kernel<<<ceil_div_i((long)Cout * Cin * k, 256), 256, 0, st>>>((const float*)ws, grid, Cout, Cin, k, gscale, dW);
     DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+size_t dcue_tc_wgrad_unpool_ws_bytes(int k) {
+    return (size_t)dcue_num_sms() * 128 * k * 128 * sizeof(float) + (size_t)dcue_num_sms() * 128 * sizeof(double) + 256;
+}
+
+int dcue_tc_conv_wgrad_unpool(const float* dy, int lddy, const float* dtp, int lddtp, const float* z, const uint8_t* code,
+                              const float* scale, const float* mean, const float* rstd, const double* sums, double count, int S,
+                              int P, int Lp, const void* x_panel, long x_rows, int fmt, int k, const float* gscale, float* dW,
+                              double* bias_sums, float* bias_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (k != 4) DCUE_FAIL(DCUE_E_UNSUPPORTED, "fused unpool+wgrad is built for k == 4 (got %d)", k);
+    const long rows_total = (long)S * Lp;
+    const int grid = tc_grid(rows_total);
+    const size_t part_bytes = (size_t)grid * 128 * k * 128 * sizeof(float);
+    if (!ws || ws_bytes < part_bytes + (size_t)grid * 128 * sizeof(double))
+        DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_wgrad_unpool: workspace too small");
+    double* bpart = bias_sums ? (double*)((char*)ws + part_bytes) : nullptr;
+    UnpoolSrc src{dy, lddy, dtp, lddtp, z, code, scale, mean, rstd, sums, count > 0 ? count : 1.0, S, P, Lp, gscale};
+    constexpr size_t SMEM = (size_t)WG_NSTAGE * WGU_STAGE_BYTES + 8 * (3 * WG_NSTAGE + 1) + 16;
+    DCUE_CUDA(cudaFuncSetAttribute(tc_wgrad_unpool_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    tc_wgrad_unpool_kernel<4><<<grid, WGU_THREADS, SMEM, st>>>(src, fmt, (const uint4*)x_panel, x_rows, rows_total, (float*)ws, bpart);
+    DCUE_LAUNCH_CHECK();
+    dcue_wgrad_reduce_kernel<<<ceil_div_i((long)128 * 128 * k, 256), 256, 0, st>>>((const float*)ws, grid, 128, 128, k, gscale, dW);
+    DCUE_LAUNCH_CHECK();
+    if (bias_sums) {
+        dcue_reduce_partials_d<<<ceil_div_i(128, 8), 256, 0, st>>>(bpart, grid, 128, bias_sums);
+        DCUE_LAUNCH_CHECK();
+        if (bias_out) {
+            dcue_cvt_d2f_kernel<<<1, 128, 0, st>>>(bias_sums, 128, bias_out);
+            DCUE_LAUNCH_CHECK();
+        }
+    }
     return 0;
 }

@@ -33,6 +33,12 @@ def conv_impl():
     return L.IMPL_SIMT if os.environ.get("DCUE_CONV_IMPL", "tc").lower() == "simt" else L.IMPL_TC
 
 
+def fused_wgrad():
+    """Layer 1 backward as ONE tcgen05 kernel (BatchNorm-backward + unpool + weight gradient, no dY panel in HBM)
+    unless DCUE_FUSED_WGRAD=0 selects the separate unpool -> panel -> wgrad kernels."""
+    return os.environ.get("DCUE_FUSED_WGRAD", "1") != "0"
+
+
 def operand_fmt():
     """16-bit format of the forward conv operands: fp16 (default) or bf16 (DCUE_OPERAND=bf16)."""
     return L.FMT_BF16 if os.environ.get("DCUE_OPERAND", "f16").lower() == "bf16" else L.FMT_F16
@@ -89,10 +95,18 @@ class TowerWorkspace:
         self.wp = [torch.empty(128 * g["k"] * 128, dtype=torch.int16, device=device) for g in self.geo]
         nbytes = max(L.query("dcue_conv_ws_bytes", L.IMPL_TC, S, g["Lp"], 4, 128, 128) for g in self.geo)
         nbytes = max(nbytes, L.query("dcue_ncl_stats_ws_bytes", 128), L.query("dcue_bn_bwd_ws_bytes", 128),
+                     L.query("dcue_conv_wgrad_unpool_ws_bytes", 4),
                      L.query("dcue_linear_wgrad_ws_bytes", S, 4 * H + F, F),
                      L.query("dcue_linear_wgrad_ws_bytes", S, H, F))
         self.scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
         self._bwd = None
+
+    def dy_panel(self, i):
+        """Gradient operand panel of stage i (0-based); layer 1's is never needed on the fused wgrad path (749 MB at cfg2)."""
+        b = self.bwd()
+        if b["dY"][i] is None:
+            b["dY"][i] = Panel(self.S, self.geo[i]["Lp"], self.device)
+        return b["dY"][i]
 
     def bwd(self):
         """Backward-only buffers, created on first use."""
@@ -100,12 +114,12 @@ class TowerWorkspace:
             S, dev = self.S, self.device
             f32 = dict(dtype=torch.float32, device=dev)
             b = {}
-            b["dY"] = [Panel(S, g["Lp"], dev) for g in self.geo]
+            b["dY"] = [None] * len(self.geo)       # 16-bit gradient operand panels, created on first use (dy_panel)
             b["dx"] = [torch.empty(S * g["Lin"], 128, **f32) for g in self.geo]
             b["wpd"] = [torch.empty(128 * g["k"] * 128, dtype=torch.int16, device=dev) for g in self.geo]
             b["bsum"] = torch.zeros(2 * 128, dtype=torch.float64, device=dev)
             b["dsums"] = torch.zeros(6, 2 * 128, dtype=torch.float64, device=dev)
-            b["E"] = torch.zeros(4, 128, **f32)
+            b["E"] = torch.zeros(L.lib().dcue_panel_row_sums_parts(), 4, 128, **f32)   # border row sums, per slice
             b["amax"] = torch.zeros(6, **f32)
             b["gscale"] = torch.ones(6, 2, **f32)
             self._bwd = b
@@ -351,24 +365,36 @@ class SongTowerFn(torch.autograd.Function):
             dtp = dfc[:, (i - 1) * H:].data_ptr() if res else None
             bn_sums(i, dy.data_ptr(), H, dtp, Kfc, ws.z[i - 1], g["P"], H)
             gsc = b["gscale"][i].data_ptr()
-            dYp = b["dY"][i - 1]
             gb_i = torch.empty(H, **f32)
-            L.call("dcue_bn_relu_unpool_bwd", dy.data_ptr(), H, dtp, Kfc, ws.z[i - 1].data_ptr(), ws.code[i - 1].data_ptr(),
-                   ws.bnp[i, 0].data_ptr() if has_bn else None, ws.bnp[i, 2].data_ptr() if has_bn else None,
-                   ws.bnp[i, 3].data_ptr() if has_bn else None, b["dsums"][i].data_ptr() if bn_train else None,
-                   float(S * g["P"] * world), S, g["P"], H, g["pool"], g["Lp"], dYp.base, dYp.panel_rows, gfmt, gsc, None,
-                   b["bsum"].data_ptr(), gb_i.data_ptr(), scratch, nscr, st)
             gW_i = torch.empty(H, 128, g["k"], **f32)
-            L.call("dcue_conv_wgrad", impl, dYp.base, dYp.panel_rows, gfmt, ws.X[i - 1].base, ws.X[i - 1].panel_rows, fmt,
-                   S * g["Lp"], g["k"], 128, H, gsc, gW_i.data_ptr(), scratch, nscr, st)
+            bn_args = (ws.bnp[i, 0].data_ptr() if has_bn else None, ws.bnp[i, 2].data_ptr() if has_bn else None,
+                       ws.bnp[i, 3].data_ptr() if has_bn else None, b["dsums"][i].data_ptr() if bn_train else None,
+                       float(S * g["P"] * world))
+            # layer 1 needs no data gradient: its dY operand is built inside the weight-gradient kernel
+            fused = i == 1 and impl == L.IMPL_TC and g["pool"] == 4 and g["k"] == 4 and fused_wgrad()
+            dYp = None if fused else ws.dy_panel(i - 1)
+            if fused:
+                L.call("dcue_conv_wgrad_unpool", dy.data_ptr(), H, dtp, Kfc, ws.z[i - 1].data_ptr(), ws.code[i - 1].data_ptr(),
+                       *bn_args, S, g["P"], g["pool"], g["Lp"], ws.X[i - 1].base, ws.X[i - 1].panel_rows, fmt, g["k"], 128, H,
+                       gsc, gW_i.data_ptr(), b["bsum"].data_ptr(), gb_i.data_ptr(), scratch, nscr, st)
+            else:
+                L.call("dcue_bn_relu_unpool_bwd", dy.data_ptr(), H, dtp, Kfc, ws.z[i - 1].data_ptr(), ws.code[i - 1].data_ptr(),
+                       *bn_args, S, g["P"], H, g["pool"], g["Lp"], dYp.base, dYp.panel_rows, gfmt, gsc, None,
+                       b["bsum"].data_ptr(), gb_i.data_ptr(), scratch, nscr, st)
+                L.call("dcue_conv_wgrad", impl, dYp.base, dYp.panel_rows, gfmt, ws.X[i - 1].base, ws.X[i - 1].panel_rows, fmt,
+                       S * g["Lp"], g["k"], 128, H, gsc, gW_i.data_ptr(), scratch, nscr, st)
             if i == 1 and has_bn:
                 # gW_i is G = sum dY * xhat.  bn0 was folded into this conv: its gradients and the true
                 # weight gradient follow from G and a few border row sums -- no data gradient needed.
                 k_, pad_, lin_ = g["k"], g["pad"], g["Lin"]
                 brow = list(range(pad_)) + list(range(lin_ + pad_ - k_ + 1, lin_ + 2 * pad_ - k_ + 1))
                 brow = (brow + [-1, -1, -1, -1])[:4]
-                L.call("dcue_panel_row_sums", dYp.base, dYp.panel_rows, gfmt, S, g["Lp"], brow[0], brow[1], brow[2], brow[3],
-                       gsc, b["E"].data_ptr(), st)
+                if fused:
+                    L.call("dcue_border_row_sums", dy.data_ptr(), H, dtp, Kfc, ws.z[0].data_ptr(), ws.code[0].data_ptr(), *bn_args,
+                           S, g["P"], H, g["pool"], brow[0], brow[1], brow[2], brow[3], b["E"].data_ptr(), st)
+                else:
+                    L.call("dcue_panel_row_sums", dYp.base, dYp.panel_rows, gfmt, S, g["Lp"], brow[0], brow[1], brow[2], brow[3],
+                           gsc, b["E"].data_ptr(), st)
                 dW1, dg0, db0 = torch.empty(H, 128, k_, **f32), torch.empty(128, **f32), torch.empty(128, **f32)
                 L.call("dcue_bn_fold_grads", gW_i.data_ptr(), P["layer1.weight"].data_ptr(), P["bn0.weight"].data_ptr(),
                        P["bn0.bias"].data_ptr(), ws.bnp[0, 0].data_ptr(), ws.bnp[0, 1].data_ptr(), gb_i.data_ptr(),

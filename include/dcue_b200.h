@@ -146,7 +146,10 @@ int dcue_pack_conv_weight(const float* W, int Cout, int Cin, int k, int mode, in
 int dcue_conv_tap_bias(const float* W, int Cout, int Cin, int k, const float* beta,
                        const float* gamma /* nullable */, const float* shift /* nullable: constant = beta + gamma*shift */,
                        float* tap_bias, void* stream);
-/* out[i][c] = gscale[1] * sum_s panel[s*Lp + r_i][c], i < 4 (r_i < 0 = unused): border row sums of dY. out = float[4][128] */
+/* out[z][i][c] = gscale[1] * (sum over the z-th slice of the spectrograms) panel[s*Lp + r_i][c], i < 4 (r_i < 0 = unused):
+ * border row sums of dY as dcue_panel_row_sums_parts() partial sums, out = float[parts][4][128]; dcue_bn_fold_grads adds
+ * the parts in fixed order (deterministic). */
+int dcue_panel_row_sums_parts(void);
 int dcue_panel_row_sums(const void* panel, long panel_rows, int fmt, int S, int Lp, int r0, int r1, int r2, int r3,
                         const float* gscale, float* out, void* stream);
 /* Backward of the folded pair from G = wgrad(dY, xhat):  dW = gamma*G + beta*T, dgamma = sum W*G,
@@ -181,6 +184,22 @@ int dcue_conv_wgrad(int impl, const void* dy_panel, long dy_panel_rows, int fmt_
                     const float* gscale /* {s, 1/s}, nullable */, float* dW, void* ws, size_t ws_bytes,
                     void* stream);
 size_t dcue_conv_ws_bytes(int impl, int S, int Lp, int k, int Cin, int Cout);
+
+/* Fused BatchNorm-backward + ReLU mask + MaxPool unpooling + conv weight gradient (tcgen05 only): the 16-bit dY operand
+ * is built in shared memory from the pooled inputs (arguments as dcue_bn_relu_unpool_bwd) and never written to HBM.
+ * Used where no data gradient is needed afterwards (layer 1).  dW as dcue_conv_wgrad; bias_sums[128] (fp64) /
+ * bias_out[128] (fp32, nullable) get the conv bias gradient.  pool == 4, k == 4, 128 channels. */
+int dcue_conv_wgrad_unpool(const float* dy, int lddy, const float* dtp /* nullable */, int lddtp, const float* z,
+                           const uint8_t* code, const float* scale, const float* mean, const float* rstd,
+                           const double* sums /* nullable: no batch-statistics terms */, double count, int S, int P, int pool,
+                           int Lp, const void* x_panel, long x_panel_rows, int fmt, int k, int Cin, int Cout,
+                           const float* gscale, float* dW, double* bias_sums, float* bias_out, void* ws, size_t ws_bytes,
+                           void* stream);
+size_t dcue_conv_wgrad_unpool_ws_bytes(int k);
+/* Border row sums of the (never materialised) dY taken from the pooled inputs; out as dcue_panel_row_sums. */
+int dcue_border_row_sums(const float* dy, int lddy, const float* dtp, int lddtp, const float* z, const uint8_t* code,
+                         const float* scale, const float* mean, const float* rstd, const double* sums, double count,
+                         int S, int P, int C, int pool, int r0, int r1, int r2, int r3, float* out, void* stream);
 
 /* y = scale*z+shift written (a) as the next layer's 16-bit panel rows s*Lp+pad+p (panel nullable)
  * and/or (b) as fp32 [S*P, C] (y nullable); tp (nullable) [S, ldtp] gets the time average of y

@@ -321,6 +321,58 @@ def test_bn_backward_unpool_and_affine_pack(gi, S, with_tp):
     assert (gotx[:, pad2:pad2 + P] - refx).abs().max() <= 2e-3 * refx.abs().max()   # 1 fp16 ulp (fma vs mul+add)
 
 
+@pytest.mark.parametrize("gi,S,with_tp,with_bn", [(0, 7, False, True), (0, 160, True, True), (1, 700, False, False), (0, 301, False, True)])
+def test_fused_unpool_wgrad_matches_unfused(gi, S, with_tp, with_bn):
+    """dcue_conv_wgrad_unpool (the dY operand built in shared memory by the weight-gradient kernel) against the separate
+    unpool -> dY panel -> wgrad kernels on the same inputs: same fp16 operand values, same tile partition -> the weight
+    gradient agrees to fp32 summation noise; bias gradient and border row sums likewise."""
+    geo = ops.tower_geometry(131)[gi]
+    P, pool, Lp, k = geo["P"], geo["pool"], geo["Lp"], geo["k"]
+    rows = S * P
+    g = torch.Generator().manual_seed(1200 + gi + S)
+    c = _conv_case(S, gi, 77 + S)                      # X panel of the stage
+    z = torch.relu(torch.randn(rows, 128, generator=g) + 0.3).to(DEV)
+    dy = (torch.randn(rows, 128, generator=g) * 1e-3).to(DEV)
+    dtp = (torch.randn(S, 640, generator=g) * 1e-3).to(DEV) if with_tp else None
+    code = torch.randint(0, pool, (rows, 128), generator=g, dtype=torch.uint8).to(DEV)
+    scale = (torch.rand(128, generator=g) + 0.5).to(DEV)
+    mean, rstd = (torch.rand(128, generator=g) * 0.5).to(DEV), (torch.rand(128, generator=g) + 0.5).to(DEV)
+    sums = (torch.randn(256, generator=g).double() * rows * 1e-4).to(DEV)
+    gsc = torch.tensor([4096.0, 1 / 4096.0], device=DEV)
+    st = L.stream()
+    nws = max(L.query("dcue_conv_ws_bytes", L.IMPL_TC, S, Lp, k, 128, 128), L.query("dcue_bn_bwd_ws_bytes", 128),
+              L.query("dcue_conv_wgrad_unpool_ws_bytes", k))
+    ws = torch.empty(nws, dtype=torch.uint8, device=DEV)
+    bn = (scale.data_ptr(), mean.data_ptr(), rstd.data_ptr(), sums.data_ptr(), float(rows)) if with_bn else (None, None, None, None, 1.0)
+    tp_ptr = None if dtp is None else dtp[:, 256:].data_ptr()
+    # reference: separate kernels
+    dY = ops.Panel(S, Lp, DEV)
+    bsum0, bout0 = torch.zeros(128, dtype=torch.float64, device=DEV), torch.empty(128, device=DEV)
+    L.call("dcue_bn_relu_unpool_bwd", dy.data_ptr(), 128, tp_ptr, 640, z.data_ptr(), code.data_ptr(), *bn, S, P, 128, pool, Lp,
+           dY.base, dY.panel_rows, L.FMT_F16, gsc.data_ptr(), None, bsum0.data_ptr(), bout0.data_ptr(), ws.data_ptr(), nws, st)
+    dW0 = torch.empty(128, 128, k, device=DEV)
+    L.call("dcue_conv_wgrad", L.IMPL_TC, dY.base, dY.panel_rows, L.FMT_F16, c["X"].base, c["X"].panel_rows, L.FMT_F16, S * Lp, k,
+           128, 128, gsc.data_ptr(), dW0.data_ptr(), ws.data_ptr(), nws, st)
+    parts = L.lib().dcue_panel_row_sums_parts()
+    brow = [0, 1, geo["Lin"] + geo["pad"] - k + 1, geo["Lin"] + geo["pad"] - k + 2]
+    E0 = torch.zeros(parts, 4, 128, device=DEV)
+    L.call("dcue_panel_row_sums", dY.base, dY.panel_rows, L.FMT_F16, S, Lp, *brow, gsc.data_ptr(), E0.data_ptr(), st)
+    # fused
+    dW1 = torch.full((128, 128, k), float("nan"), device=DEV)
+    bsum1, bout1 = torch.zeros(128, dtype=torch.float64, device=DEV), torch.empty(128, device=DEV)
+    L.call("dcue_conv_wgrad_unpool", dy.data_ptr(), 128, tp_ptr, 640, z.data_ptr(), code.data_ptr(), *bn, S, P, pool, Lp,
+           c["X"].base, c["X"].panel_rows, L.FMT_F16, k, 128, 128, gsc.data_ptr(), dW1.data_ptr(), bsum1.data_ptr(), bout1.data_ptr(),
+           ws.data_ptr(), nws, st)
+    E1 = torch.zeros(parts, 4, 128, device=DEV)
+    L.call("dcue_border_row_sums", dy.data_ptr(), 128, tp_ptr, 640, z.data_ptr(), code.data_ptr(), *bn, S, P, 128, pool, *brow,
+           E1.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert relerr(dW1, dW0) < 2e-6
+    assert relerr(bsum1, bsum0) < 1e-6 and relerr(bout1, bout0) < 1e-6
+    # the panel's row sums carry the fp16 rounding of each entry, the pooled inputs do not: 2^-11 per element
+    assert relerr(E1.sum(0), E0.sum(0)) < 2e-3
+
+
 # ------------------------------------------------------------------ BatchNorm kernels
 def test_ncl_stats_and_bn_finalize():
     g = torch.Generator().manual_seed(7)
