@@ -22,10 +22,12 @@ class UserEmbeddings(nn.Module):
         self.linear2 = nn.Linear(self.user_embdim, self.feature_dim)
 
         self._err = None  # device flag set by the gather kernel on an out-of-range index
+        self._dp = None   # set by parallel.DataParallelDCUE: exchange gradient rows instead of the dense table gradient
 
     def __getstate__(self):
         d = self.__dict__.copy()
         d["_err"] = None
+        d["_dp"] = None
         return d
 
     def _err_flag(self):
@@ -39,7 +41,7 @@ class UserEmbeddings(nn.Module):
         nn.Embedding raises IndexError) yields NaN rows and sets a device flag without a host sync;
         call raise_if_index_error() -- the trainer does, whenever it reads the loss."""
         return ops.UserTowerFn.apply(user_idx, self.embeddings.weight, self.linear1.weight, self.linear1.bias,
-                                     self.linear2.weight, self.linear2.bias, self._err_flag())
+                                     self.linear2.weight, self.linear2.bias, self._err_flag(), getattr(self, "_dp", None))
 
     def raise_if_index_error(self):
         if self._err is not None and int(self._err.item()):

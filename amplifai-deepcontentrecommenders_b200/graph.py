@@ -1,8 +1,9 @@
 """CUDA-graph capture of the fixed-shape part of a DCUE training step (forward + fused score/hinge loss +
 backward: ~100 kernel launches) so that a step costs one graph launch instead of ~100 launch gaps.
 The optimizer / scheduler stay outside the graph (the reference's Python-float learning-rate schedule keeps
-working unchanged).  Single-process only: under data parallelism the BatchNorm all-reduces sit between the
-kernels, so the eager path is used there.
+working unchanged).  Under data parallelism (`dp=DataParallelDCUE(model)`) the NCCL collectives -- the per-layer
+BatchNorm statistic all-reduces and the flat gradient all-reduce -- are captured into the same graph, so a
+multi-GPU step is one graph launch as well.
 """
 from __future__ import annotations
 
@@ -15,8 +16,8 @@ class GraphedTrainStep:
 
     With `pool` given, (pos, neg) are int64 song-index tensors into the resident pool (index feed)."""
 
-    def __init__(self, model, margin, u, pos, neg, pool=None, warmup=3):
-        self.model, self.margin, self.pool = model, margin, pool
+    def __init__(self, model, margin, u, pos, neg, pool=None, warmup=3, dp=None):
+        self.model, self.margin, self.pool, self.dp = model, margin, pool, dp
         self.u, self.pos, self.neg = u.clone(), pos.clone(), neg.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -24,6 +25,8 @@ class GraphedTrainStep:
             for _ in range(warmup):
                 model.zero_grad(set_to_none=True)
                 self._loss().backward()
+                if dp is not None:
+                    dp.reduce_gradients()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         # The graph zeroes the EXISTING .grad tensors and the backward accumulates into them in place, so the
@@ -39,8 +42,14 @@ class GraphedTrainStep:
             torch._foreach_zero_(self._grads)
             self.loss = self._loss()
             self.loss.backward()
+            if dp is not None:
+                dp.reduce_gradients()
 
     def _loss(self):
+        if self.dp is not None:
+            if self.pool is not None:
+                return self.dp.loss_step_indexed(self.u, self.pool, self.pos, self.neg, self.margin)
+            return self.dp.loss_step(self.u, self.pos, self.neg, self.margin)
         if self.pool is not None:
             return self.model.hinge_loss_step_indexed(self.u, self.pool, self.pos, self.neg, self.margin)
         return self.model.hinge_loss_step(self.u, self.pos, self.neg, self.margin)

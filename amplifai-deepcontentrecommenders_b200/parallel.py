@@ -12,6 +12,8 @@ Eval (BASELINE cfg5) shards songs across ranks and merges per-rank top-k lists.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -24,12 +26,20 @@ def shard_slice(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def row_exchange():
+    """Replicated user table under DP: exchange gradient rows (default) or all-reduce the dense gradient
+    (DCUE_DP_DENSE_TABLE=1, the A/B switch)."""
+    return os.environ.get("DCUE_DP_DENSE_TABLE", "0") != "1"
+
+
 def flat_bucket_names(named_grads):
     """Names of the gradients that need the SUM all-reduce: everything except the affine parameters
     of bn1..bn5, whose gradients are already global (computed from all-reduced sums).  bn0 is folded
     into layer1, so its gradients are local partial sums like any weight gradient.  A row-sharded user
-    table's gradient is complete on its owner and is excluded as well."""
-    return [n for n, _ in named_grads if (".bn" not in n or ".bn0." in n) and not n.endswith("user_embd.shard")]
+    table's gradient is complete on its owner and is excluded as well; so is the replicated table's dense gradient,
+    which UserTowerFn builds from the all-gathered gradient rows of every rank (already the global sum)."""
+    return [n for n, _ in named_grads if (".bn" not in n or ".bn0." in n) and not n.endswith("user_embd.shard")
+            and not (n.endswith("user_embd.embeddings.weight") and row_exchange())]
 
 
 class DataParallelDCUE:
@@ -40,6 +50,8 @@ class DataParallelDCUE:
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         model.conv._dp = self if self.world_size > 1 else None
+        if hasattr(model.user_embd, "embeddings"):      # replicated table: row exchange instead of a dense all-reduce
+            model.user_embd._dp = self if (self.world_size > 1 and row_exchange()) else None
         if broadcast and self.world_size > 1:
             for t in list(model.parameters()) + list(model.buffers()):
                 dist.broadcast(t.data, 0, group=group)
@@ -48,6 +60,13 @@ class DataParallelDCUE:
     def all_reduce_sum(self, t):
         if self.world_size > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def all_gather_rows(self, t):
+        """[n, ...] on every rank -> [world*n, ...] in rank order."""
+        t = t.contiguous()
+        out = torch.empty((self.world_size * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        return out
 
     def loss_step(self, u, pos, neg, margin):
         """Local slice of the global batch -> loss contribution whose gradients sum to the global

@@ -251,11 +251,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    use_graph = world == 1 and not args.no_graph
+    use_graph = not args.no_graph      # under DP the NCCL collectives are captured into the graph as well
     graph_launches = 0
     if use_graph:
         c0 = L.lib().dcue_launch_count()
-        gstep = pkg.GraphedTrainStep(model, CFG["margin"], u, pos, neg, warmup=3)
+        gstep = pkg.GraphedTrainStep(model, CFG["margin"], u, pos, neg, warmup=3, dp=dp if world > 1 else None)
         graph_launches = (L.lib().dcue_launch_count() - c0) // 4       # 3 warm-up passes + the captured one
 
         step_eager = step
@@ -343,7 +343,7 @@ def run_ours(args):
     gidx = None
     if use_graph:
         u0_, p0_, n0_ = (t.to(dev) for t in hidx[0])
-        gidx = pkg.GraphedTrainStep(model, CFG["margin"], u0_, p0_, n0_, pool=pool)
+        gidx = pkg.GraphedTrainStep(model, CFG["margin"], u0_, p0_, n0_, pool=pool, dp=dp if world > 1 else None)
 
     def idx_step(i):
         hu_, hp_, hn_ = hidx[i % n_idx_batches]
@@ -431,7 +431,12 @@ def run_ours(args):
                                    "sample": "oracle port of the reference train step (cfg1: batch 64 x %d negs), %d steps, %.1f s/step" % (N, n, sps)}
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that captured NCCL collectives keep the communicator busy: tearing the process group down with
+        # them alive hung the ranks at exit.  Everything is printed; leave without the collective teardown.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

@@ -22,8 +22,9 @@ def test_shard_slice_covers_everything():
 def test_bucket_excludes_batchnorm_affine():
     names = [("conv.bn0.weight", 0), ("conv.layer1.weight", 0), ("conv.bn3.bias", 0), ("user_embd.embeddings.weight", 0),
              ("conv.fc.bias", 0)]
-    assert par.flat_bucket_names(names) == ["conv.bn0.weight", "conv.layer1.weight", "user_embd.embeddings.weight",
-                                            "conv.fc.bias"]
+    # bn1..bn5 affine gradients come from all-reduced sums; the replicated table's dense gradient is built from the
+    # all-gathered gradient rows of every rank (ops.UserTowerFn): neither goes through the flat SUM all-reduce
+    assert par.flat_bucket_names(names) == ["conv.bn0.weight", "conv.layer1.weight", "conv.fc.bias"]
 
 
 def test_sharded_table_index_bookkeeping():
@@ -55,9 +56,10 @@ def _worker(rank, world, port, out):
     stats = torch.tensor([1.0 + rank, 2.0], dtype=torch.float64)
     dp.all_reduce_sum(stats)
     loss = dp.reduce_loss(torch.tensor(0.25 * (rank + 1)))
+    rows = dp.all_gather_rows(torch.full((2, 3), float(rank)))
     res = dict(w=w, g_conv=net.conv.layer1.weight.grad[0, 0, 0].item(), g_bn=net.conv.bn1.weight.grad[0].item(),
                g_tab=net.user_embd.embeddings.weight.grad[3, 7].item(), stats=stats, loss=loss.item(),
-               hooked=net.conv._dp is dp)
+               hooked=net.conv._dp is dp and net.user_embd._dp is dp, rows=rows)
     torch.save(res, out % rank)
     dist.destroy_process_group()
 
@@ -69,7 +71,8 @@ def test_data_parallel_plumbing_world2(tmp_path):
     r0, r1 = torch.load(out % 0), torch.load(out % 1)
     assert torch.equal(r0["w"], r1["w"])                      # parameters broadcast from rank 0
     assert r0["g_conv"] == r1["g_conv"] == 3.0                # 1 + 2 summed
-    assert r0["g_tab"] == r1["g_tab"] == 3.0                  # dense table gradient is in the bucket
+    assert r0["g_tab"] == 1.0 and r1["g_tab"] == 2.0          # table gradient: exchanged as rows in the backward, not here
+    assert torch.equal(r0["rows"], torch.tensor([[0.0] * 3] * 2 + [[1.0] * 3] * 2)) and torch.equal(r0["rows"], r1["rows"])
     assert r0["g_bn"] == 1.0 and r1["g_bn"] == 2.0            # BN affine grads are already global: untouched
     assert torch.equal(r0["stats"], torch.tensor([3.0, 4.0], dtype=torch.float64))
     assert abs(r0["loss"] - 0.75) < 1e-12 and r0["hooked"] and r1["hooked"]

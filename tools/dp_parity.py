@@ -23,7 +23,7 @@ def main():
     par = importlib.import_module("amplifai-deepcontentrecommenders_b200.parallel")
     ok = True
     for mt in ("truedcuemel1dbn", "truedcuemel1dres"):
-        B, N, U = 8 * world, 4, 60
+        B, N, U = 16 * world, 4, 60   # reference S = B*(1+N) >= 160: more 128-row tiles than SMs at layer 1
         params = fixtures.make_params(mt, seed=0, user_count=U)
         u, pos, neg = fixtures.make_inputs(B, N, U, seed=1)
         cfg = {"feature_dim": 100, "conv_hidden": 128, "user_embdim": 300, "user_count": U, "model_type": mt}
