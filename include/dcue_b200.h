@@ -261,6 +261,17 @@ int dcue_score_hinge_fwdbwd(const float* u, const float* feats, int B, int N, in
                             float margin, int batch_total, float* scores, float* loss_rows, float* du,
                             float* dfeats, void* stream);
 
+/* ---------------------------------------------------------------- multi-GPU ---------------- */
+
+/* One-shot SUM all-reduce of inout[n] (fp64, n <= dcue_peer_allreduce_slot_doubles()) over NVLink peer memory: replaces
+ * the 13 latency-bound NCCL all-reduces per data-parallel step (SyncBN statistics; the reference has no multi-GPU path,
+ * BASELINE cfg3).  peer_bufs_dev / peer_signals_dev: DEVICE arrays of `world` pointers to every rank's symmetric buffer
+ * (2 slots of slot_doubles fp64) and zero-initialised signal pad (>= world uint32); counter: one zero-initialised device
+ * uint32 of the calling rank.  Every rank must issue the same sequence of calls.  Result bit-identical on all ranks. */
+int dcue_peer_allreduce_f64(const void* peer_bufs_dev, const void* peer_signals_dev, void* counter, int rank, int world,
+                            double* inout, int n, void* stream);
+int dcue_peer_allreduce_slot_doubles(void);
+
 /* ---------------------------------------------------------------- eval scorer ------------ */
 
 /* row-normalise factors (x / max(||x||,eps)) into 16-bit K-major rows padded to Kp (mult of 16). */
