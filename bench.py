@@ -152,7 +152,8 @@ def workload_config(args, extra=None):
 
 # ------------------------------------------------------------------------------------- GPU arm
 # DRAM bytes per launch at S = 21504 from the ncu --set full captures in profiles/ (scaled linearly with S)
-NCU_TRAFFIC_S21504 = {"conv1_fwd_pool": 749.1e6 + 419.6e6}
+NCU_TRAFFIC_S21504 = {"conv1_fwd_pool": 751.0e6 + 422.0e6, "conv1_wgrad_unpool": 1566.6e6 + 8.5e6, "conv1_wgrad": 1500.0e6 + 4.4e6,
+                      "bn_relu_unpool_bwd1": 818.0e6 + 689.0e6}
 
 
 def kernel_roofline(pkg, S, dev):
@@ -176,7 +177,8 @@ def kernel_roofline(pkg, S, dev):
     bn = torch.ones(4, 128, device=dev)
     gsc = torch.ones(2, device=dev)
     dW = torch.empty(128, 128, 4, device=dev)
-    nws = max(L.query("dcue_conv_ws_bytes", L.IMPL_TC, S, geo["Lp"], 4, 128, 128), L.query("dcue_bn_bwd_ws_bytes", 128))
+    nws = max(L.query("dcue_conv_ws_bytes", L.IMPL_TC, S, geo["Lp"], 4, 128, 128), L.query("dcue_bn_bwd_ws_bytes", 128),
+              L.query("dcue_conv_wgrad_unpool_ws_bytes", 4))
     ws = torch.empty(nws, dtype=torch.uint8, device=dev)
     calls = {
         "conv1_fwd_pool": (lambda: L.call("dcue_conv_pool_fwd", L.IMPL_TC, X.base, X.panel_rows, 0, wp.data_ptr(), bias.data_ptr(), None, S,
@@ -184,6 +186,11 @@ def kernel_roofline(pkg, S, dev):
                                           sums.data_ptr(), ws.data_ptr(), nws, st), "tensor", L1_FLOP_PER_SPEC * S),
         "conv1_wgrad": (lambda: L.call("dcue_conv_wgrad", L.IMPL_TC, dY.base, dY.panel_rows, 0, X.base, X.panel_rows, 0, S * geo["Lp"], 4,
                                        128, 128, None, dW.data_ptr(), ws.data_ptr(), nws, st), "tensor", L1_FLOP_PER_SPEC * S),
+        # fused layer-1 backward (the step's longest kernel): BatchNorm-backward + unpool built in smem + weight gradient
+        "conv1_wgrad_unpool": (lambda: L.call("dcue_conv_wgrad_unpool", dyn.data_ptr(), 128, None, 0, z.data_ptr(), code.data_ptr(),
+                                              bn[0].data_ptr(), bn[2].data_ptr(), bn[3].data_ptr(), sums.data_ptr(), float(rows), S,
+                                              geo["P"], 4, geo["Lp"], X.base, X.panel_rows, 0, 4, 128, 128, gsc.data_ptr(),
+                                              dW.data_ptr(), bsum.data_ptr(), None, ws.data_ptr(), nws, st), "tensor", L1_FLOP_PER_SPEC * S),
         # reads dy, z (fp32) and the argmax code, writes the 4x unpooled fp16 panel: 1152 + 1024 B per pooled row
         "bn_relu_unpool_bwd1": (lambda: L.call("dcue_bn_relu_unpool_bwd", dyn.data_ptr(), 128, None, 0, z.data_ptr(), code.data_ptr(),
                                                bn[0].data_ptr(), bn[2].data_ptr(), bn[3].data_ptr(), sums.data_ptr(), float(rows), S,
@@ -278,6 +285,8 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         loss_acc += step(u, pos, neg)
+        if os.environ.get("DCUE_BENCH_SYNC_EACH_STEP") == "1":   # diagnostic only
+            torch.cuda.synchronize()
     e1.record()
     barrier()
     launches = L.lib().dcue_launch_count() - launches0

@@ -402,6 +402,24 @@ def test_ncl_stats_and_bn_finalize():
     assert int(nbt) == 4
 
 
+def test_peer_allreduce_single_rank_plumbing():
+    """dcue_peer_allreduce_f64 with world = 1 (own buffer as the only peer): identity, the call counter advances and the
+    two slots alternate -- the multi-rank behaviour is covered on real GPUs by tools/dp_parity.py (torchrun)."""
+    slot = L.lib().dcue_peer_allreduce_slot_doubles()
+    buf = torch.zeros(2 * slot, dtype=torch.float64, device=DEV)
+    sig = torch.zeros(64, dtype=torch.int32, device=DEV)
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    bufs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=DEV)
+    sigs = torch.tensor([sig.data_ptr()], dtype=torch.int64, device=DEV)
+    for call in range(1, 4):
+        x = torch.arange(256, dtype=torch.float64, device=DEV) * call
+        ref = x.clone()
+        L.call("dcue_peer_allreduce_f64", bufs.data_ptr(), sigs.data_ptr(), counter.data_ptr(), 0, 1, x.data_ptr(), 256, L.stream())
+        torch.cuda.synchronize()
+        assert torch.equal(x, ref) and counter.item() == call and sig[0].item() == call
+        assert torch.equal(buf[(call & 1) * slot:(call & 1) * slot + 256], ref)
+
+
 # ------------------------------------------------------------------ eval scorer
 @pytest.mark.parametrize("nu,ni,k", [(300, 1000, 100), (128, 257, 10), (5, 90, 100), (1000, 5000, 100), (600, 30000, 100),
                                      (40, 3000, 256), (257, 70000, 1)])
