@@ -317,7 +317,10 @@ __device__ __forceinline__ bool compact_one(TopkShared* sh, int2* __restrict__ m
 __global__ void __launch_bounds__(NTHREADS2, 1)
 topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_users, const uint4* __restrict__ items,
                    long n_items, int Kp, int fmt, int k, long item_offset, long items_per_split, int splits,
-                   long n_work, int2* __restrict__ lists /* [grid][NU][CAPH] */, float* __restrict__ out_s,
+                   long n_work, int tile_stride /* score every tile_stride-th 128-song tile (threshold pre-pass) */,
+                   const float* __restrict__ init_thr /* nullable: per-user starting threshold, stride thr_ld */, long thr_ld,
+                   int* __restrict__ n_failed, int thr_only /* write only the k-th best score per user to out_s[user] */,
+                   int2* __restrict__ lists /* [grid][NU][CAPH] */, float* __restrict__ out_s,
                    int64_t* __restrict__ out_i /* [splits][n_users][k] */) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -379,11 +382,11 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                         bulk_g2s(smem_u32(sU + q * UPANEL + h * PANEL_BYTES), users + ((ut * 2 + h) * (long)npan + q) * 128,
                                  PANEL_BYTES, UFULL);
                 uphase ^= 1;
-                const long ntiles = (iend - ibeg + TS - 1) / TS;
+                const long ntiles = ((iend - ibeg + TS - 1) / TS + tile_stride - 1) / tile_stride;
                 for (long t = 0; t < ntiles; ++t) {
                     mbar_wait(EMPTY(stage), phase ^ 1);
                     mbar_expect_tx(FULL(stage), (uint32_t)tile_bytes);
-                    const long r0 = ibeg + t * TS;   // multiple of 128: tile index r0 >> 7
+                    const long r0 = ibeg + t * tile_stride * TS;   // multiple of 128: tile index r0 >> 7
                     bulk_g2s(smem_u32(sA + stage * tile_bytes), items + (r0 >> 7) * (long)npan * 128, (uint32_t)tile_bytes,
                              FULL(stage));
                     if (++stage == NST) { stage = 0; phase ^= 1; }
@@ -399,7 +402,7 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
             for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
                 long ibeg, iend;
                 song_range(w, ibeg, iend);
-                const long ntiles = (iend - ibeg + TS - 1) / TS;
+                const long ntiles = ((iend - ibeg + TS - 1) / TS + tile_stride - 1) / tile_stride;
                 mbar_wait(UFULL, uphase);
                 uphase ^= 1;
                 tc_fence_after();
@@ -495,7 +498,10 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                     }
                 }
                 const bool wait_for = owner_lane && (finishing ? (pending || fr) : (sh->cnt[u] > HARD));
-                if (__any_sync(0xffffffffu, wait_for) && lane == 0) *(volatile int*)&sh->over = 1;
+                // a long queue means many users are streaming against stale thresholds (the start of an unseeded stream
+                // freezes all 256 lists at once): every appender warp helps the 4 compactors until it is short again
+                const bool backlog = *(volatile int*)&sh->q_tail - *(volatile int*)&sh->q_head > 16;
+                if ((__any_sync(0xffffffffu, wait_for) || backlog) && lane == 0) *(volatile int*)&sh->over = 1;
                 epi_sync();
                 const bool over = *(volatile int*)&sh->over != 0;
                 if (!over) break;
@@ -510,10 +516,12 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
             const int sp = (int)(w % splits);
             long ibeg, iend;
             song_range(w, ibeg, iend);
-            const long ntiles = (iend - ibeg + TS - 1) / TS;
-            // per-user state: users beyond n_users never accept a candidate
+            const long ntiles = ((iend - ibeg + TS - 1) / TS + tile_stride - 1) / tile_stride;
+            // per-user state: users beyond n_users never accept a candidate; a seeded threshold (two-pass mode) is a guess
+            // below which nothing is kept -- a user left with fewer than k candidates is reported as failed
             if (et < NU) {
-                sh->thr[et] = (ut * NU + et < n_users) ? -INFINITY : INFINITY;
+                const long gu0 = ut * NU + et;
+                sh->thr[et] = gu0 < n_users ? (init_thr ? init_thr[gu0 * thr_ld] : -INFINITY) : INFINITY;
                 sh->cnt[et] = 0;
                 sh->pend_n[et] = 0;
                 sh->done[et] = 0;
@@ -522,7 +530,7 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
             for (long t = 0; t < ntiles; ++t) {
                 mbar_wait(TFULL(acc), acc_phase);
                 tc_fence_after();
-                const long song = ibeg + t * TS + quarter * 32 + lane;     // this lane's song
+                const long song = ibeg + t * tile_stride * TS + quarter * 32 + lane;     // this lane's song
                 const bool song_ok = song < iend;
                 const int song_i = (int)song;
                 const uint32_t tb = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * NU + half * CPW);
@@ -587,8 +595,20 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                 if (gu >= n_users) break;
                 int n = sh->cnt[u];
                 int2* lst = mylists + (size_t)u * CAPH;
-                if (n > k) { select_topk_inplace(lst, n, k, lane); n = k; }
+                if (thr_only) {   // threshold pre-pass: the k-th best sampled score seeds the next pass (-inf: too few sampled)
+                    const float kth = n >= k ? select_topk_inplace(lst, n, k, lane) : -INFINITY;
+                    if (lane == 0) out_s[gu] = kth;
+                    continue;
+                }
                 const long ob = ((long)sp * n_users + gu) * k;
+                const long avail = iend - ibeg;
+                if (init_thr && n < (avail < k ? (int)avail : k)) {
+                    // the seeded threshold was too high for this user: mark the row, the caller re-scores it exactly
+                    for (int g = lane; g < k; g += 32) { out_s[ob + g] = -INFINITY; out_i[ob + g] = -2; }
+                    if (lane == 0) atomicAdd(n_failed, 1);
+                    continue;
+                }
+                if (n > k) { select_topk_inplace(lst, n, k, lane); n = k; }
                 sort_and_write(lst, n, k, item_offset, out_s + ob, out_i + ob, lane);
             }
             epi_sync();   // nobody resets the per-user state while another warp still reads it
@@ -694,15 +714,12 @@ extern "C" size_t dcue_topk_ws_bytes(int impl, long n_users, long n_items, int k
     return topk_list_bytes(topk_grid(n_users, splits)) + parts + 512;
 }
 
-extern "C" int dcue_topk_scores(int impl, const void* users_n, long n_users, const void* items_n, long n_items, int Kp,
-                                int fmt, int k, long item_offset, float* top_scores, int64_t* top_idx, void* ws,
-                                size_t ws_bytes, void* stream) {
-    DCUE_CHECK_ARG(users_n && items_n && top_scores && top_idx && n_users >= 0 && n_items >= 0 && k > 0 && k <= 256);
-    DCUE_CHECK_ARG(Kp % 16 == 0 && Kp >= 16 && Kp <= 128 && n_items < (1L << 31));
-    if (impl != DCUE_IMPL_TC) DCUE_FAIL(DCUE_E_UNSUPPORTED, "dcue_topk_scores: only the tcgen05 implementation exists");
-    if (n_users == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int splits = topk_splits(n_users, n_items);
+namespace {
+// one launch of the streaming scorer (+ the split merge); ws = [candidate lists][split partials]
+int launch_topk(const void* users_n, long n_users, const void* items_n, long n_items, int Kp, int fmt, int k, long item_offset,
+                int tile_stride, const float* init_thr, long thr_ld, int* n_failed, int thr_only, float* top_scores,
+                int64_t* top_idx, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const int splits = init_thr || tile_stride > 1 ? 1 : topk_splits(n_users, n_items);
     const int grid = topk_grid(n_users, splits);
     long per = (n_items + splits - 1) / splits;
     per = round_up_l(per > 0 ? per : 1, TS);
@@ -722,13 +739,80 @@ extern "C" int dcue_topk_scores(int impl, const void* users_n, long n_users, con
     const long n_work = ((n_users + NU - 1) / NU) * splits;
     topk_stream_kernel<<<grid, NTHREADS2, smem, st>>>((const uint4*)users_n, round_up_l(n_users, 128) / 128, n_users,
                                                       (const uint4*)items_n, n_items, Kp, fmt, k, item_offset, per, splits, n_work,
-                                                      (int2*)ws, os, oi);
+                                                      tile_stride, init_thr, thr_ld, n_failed, thr_only, (int2*)ws, os, oi);
     DCUE_LAUNCH_CHECK();
     if (splits > 1) {
         topk_merge_kernel<<<ceil_div_i(n_users, 128), 128, 0, st>>>(os, oi, splits, n_users, k, top_scores, top_idx);
         DCUE_LAUNCH_CHECK();
     }
     return 0;
+}
+
+// two-pass plan: sample every s-th song tile, seed each user's threshold with the r-th best sampled score, so that about
+// 4k scores of the full stream pass it (k is then reached with probability ~1 - 1e-4 per user; the rest is re-scored)
+bool topk_2pass_plan(long n_users, long n_items, int k, int* stride, int* r) {
+    if (topk_splits(n_users, n_items) != 1 || n_items < 32768 || k > 128) return false;
+    const int C = 4 * k;
+    int s = C / 20;
+    if (s > 16) s = 16;
+    if (s < 2) return false;
+    *stride = s;
+    *r = (C + s - 1) / s;
+    return true;
+}
+}  // namespace
+
+extern "C" int dcue_topk_scores(int impl, const void* users_n, long n_users, const void* items_n, long n_items, int Kp,
+                                int fmt, int k, long item_offset, float* top_scores, int64_t* top_idx, void* ws,
+                                size_t ws_bytes, void* stream) {
+    DCUE_CHECK_ARG(users_n && items_n && top_scores && top_idx && n_users >= 0 && n_items >= 0 && k > 0 && k <= 256);
+    DCUE_CHECK_ARG(Kp % 16 == 0 && Kp >= 16 && Kp <= 128 && n_items < (1L << 31));
+    if (impl != DCUE_IMPL_TC) DCUE_FAIL(DCUE_E_UNSUPPORTED, "dcue_topk_scores: only the tcgen05 implementation exists");
+    if (n_users == 0) return 0;
+    return launch_topk(users_n, n_users, items_n, n_items, Kp, fmt, k, item_offset, 1, nullptr, 0, nullptr, 0, top_scores, top_idx, ws,
+                       ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" size_t dcue_topk_2pass_ws_bytes(int impl, long n_users, long n_items, int k) {
+    int s = 0, r = 0;
+    const size_t base = dcue_topk_ws_bytes(impl, n_users, n_items, k);
+    if (!topk_2pass_plan(n_users, n_items, k, &s, &r)) return base;
+    return base + 2 * (size_t)n_users * sizeof(float) + 512;
+}
+
+extern "C" int dcue_topk_scores_2pass(int impl, const void* users_n, long n_users, const void* items_n, long n_items, int Kp,
+                                      int fmt, int k, long item_offset, float* top_scores, int64_t* top_idx, int* n_failed,
+                                      void* ws, size_t ws_bytes, void* stream) {
+    DCUE_CHECK_ARG(users_n && items_n && top_scores && top_idx && n_failed && n_users >= 0 && n_items >= 0 && k > 0 && k <= 256);
+    DCUE_CHECK_ARG(Kp % 16 == 0 && Kp >= 16 && Kp <= 128 && n_items < (1L << 31));
+    if (impl != DCUE_IMPL_TC) DCUE_FAIL(DCUE_E_UNSUPPORTED, "dcue_topk_scores: only the tcgen05 implementation exists");
+    cudaStream_t st = (cudaStream_t)stream;
+    DCUE_CUDA(cudaMemsetAsync(n_failed, 0, sizeof(int), st));
+    if (n_users == 0) return 0;
+    int s = 0, r = 0;
+    if (!topk_2pass_plan(n_users, n_items, k, &s, &r))
+        return launch_topk(users_n, n_users, items_n, n_items, Kp, fmt, k, item_offset, 1, nullptr, 0, nullptr, 0, top_scores, top_idx,
+                           ws, ws_bytes, st);
+    const size_t base = topk_list_bytes(topk_grid(n_users, 1));
+    if (!ws || ws_bytes < base + 2 * (size_t)n_users * sizeof(float))
+        DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_topk_scores_2pass: workspace too small");
+    float* thrA = (float*)((char*)ws + base);
+    float* thrB = thrA + n_users;
+    // level A (only when the stream is long enough to pay for it): every (16 s)-th tile, unseeded, 20th best -> seeds level B.
+    // An unseeded stream is expensive at its START (thresholds at -inf flood the lists), so the unseeded level is kept tiny.
+    const long tiles = (n_items + TS - 1) / TS;
+    const float* seedB = nullptr;
+    if (tiles / (16L * s) >= 12) {
+        if (int e = launch_topk(users_n, n_users, items_n, n_items, Kp, fmt, 20, 0, 16 * s, nullptr, 0, nullptr, 1, thrA, nullptr, ws, base, st))
+            return e;
+        seedB = thrA;
+    }
+    // level B: every s-th tile from level A's seeds (a user level A left short simply starts at -inf), r-th best -> seeds the
+    // full stream; level C: all songs.  A seed that turns out too high only costs that user an exact re-score by the caller.
+    if (int e = launch_topk(users_n, n_users, items_n, n_items, Kp, fmt, r, 0, s, seedB, 1, n_failed, 1, thrB, nullptr, ws, base, st))
+        return e;
+    return launch_topk(users_n, n_users, items_n, n_items, Kp, fmt, k, item_offset, 1, thrB, 1, n_failed, 0, top_scores, top_idx, ws,
+                       base, st);
 }
 
 extern "C" int dcue_topk_merge(const float* scores, const int64_t* idx, int parts, long n_users, int k, float* out_scores,

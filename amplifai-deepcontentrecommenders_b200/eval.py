@@ -4,6 +4,8 @@ from __future__ import annotations
 
 import torch
 
+import os
+
 from . import _lib as L
 
 COS_EPS = 1e-8
@@ -35,6 +37,33 @@ def topk_scores(user_factors, item_factors, k, item_offset=0, normalized_items=N
     un, Kp = normalize_factors(user_factors)
     inn, Kp2 = normalized_items if normalized_items is not None else normalize_factors(item_factors)
     assert Kp == Kp2
+    scores = torch.empty(n_users, k, dtype=torch.float32, device=dev)
+    idx = torch.empty(n_users, k, dtype=torch.int64, device=dev)
+    if os.environ.get("DCUE_TOPK_2PASS", "1") != "0":
+        # threshold pre-pass on a song sample + full pass from the seeded thresholds; the few users whose seed was too
+        # high are re-scored exactly below, so the result is the same top-k
+        nws = L.query("dcue_topk_2pass_ws_bytes", L.IMPL_TC, n_users, n_items, k)
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        n_failed = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.call("dcue_topk_scores_2pass", L.IMPL_TC, un.data_ptr(), n_users, inn.data_ptr(), n_items, Kp, L.FMT_F16, k, item_offset,
+               scores.data_ptr(), idx.data_ptr(), n_failed.data_ptr(), ws.data_ptr(), nws, L.stream())
+        if int(n_failed.item()):
+            rows = torch.nonzero(idx[:, 0] == -2).flatten()
+            s2, i2 = _topk_exact(user_factors[rows], inn, Kp, n_items, k, item_offset)
+            scores[rows], idx[rows] = s2, i2
+        return scores, idx
+    nws = L.query("dcue_topk_ws_bytes", L.IMPL_TC, n_users, n_items, k)
+    ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+    L.call("dcue_topk_scores", L.IMPL_TC, un.data_ptr(), n_users, inn.data_ptr(), n_items, Kp, L.FMT_F16, k, item_offset,
+           scores.data_ptr(), idx.data_ptr(), ws.data_ptr(), nws, L.stream())
+    return scores, idx
+
+
+def _topk_exact(user_factors, inn, Kp, n_items, k, item_offset):
+    """single-pass scorer (thresholds start at -inf) for a few users."""
+    n_users = user_factors.shape[0]
+    dev = user_factors.device
+    un, _ = normalize_factors(user_factors)
     scores = torch.empty(n_users, k, dtype=torch.float32, device=dev)
     idx = torch.empty(n_users, k, dtype=torch.int64, device=dev)
     nws = L.query("dcue_topk_ws_bytes", L.IMPL_TC, n_users, n_items, k)

@@ -285,6 +285,15 @@ int dcue_topk_scores(int impl, const void* users_n, long n_users, const void* it
                      int Kp, int fmt, int k, long item_offset, float* top_scores, int64_t* top_idx,
                      void* ws, size_t ws_bytes, void* stream);
 size_t dcue_topk_ws_bytes(int impl, long n_users, long n_items, int k);
+/* Same result in two passes: pass 1 scores every s-th 128-song tile and seeds each user's threshold with the r-th best
+ * sampled score (s*r ~ 4k), pass 2 streams all songs from those thresholds (4x fewer candidates, no list compaction).
+ * A user whose seed was too high (fewer than k candidates, probability ~1e-4) gets index -2 in every slot and is counted
+ * in *n_failed (device int): the caller re-scores those rows with dcue_topk_scores.  Falls back to the single pass for
+ * small inputs. */
+int dcue_topk_scores_2pass(int impl, const void* users_n, long n_users, const void* items_n, long n_items,
+                           int Kp, int fmt, int k, long item_offset, float* top_scores, int64_t* top_idx,
+                           int* n_failed, void* ws, size_t ws_bytes, void* stream);
+size_t dcue_topk_2pass_ws_bytes(int impl, long n_users, long n_items, int k);
 /* merge `parts` per-shard top-k lists [parts][n_users][k] into one (song-sharded eval). */
 int dcue_topk_merge(const float* scores, const int64_t* idx, int parts, long n_users, int k,
                     float* out_scores, int64_t* out_idx, void* stream);

@@ -452,6 +452,32 @@ def test_topk_scores(nu, ni, k):
     assert (ts[:, :kk].cpu() - v32).abs().max() < 2e-3
 
 
+@pytest.mark.parametrize("adversarial", [False, True])
+def test_topk_two_pass_equals_single_pass(adversarial, monkeypatch):
+    """Two-pass scorer (thresholds seeded from a song sample) == the single-pass scorer, row for row.  The adversarial
+    case plants 30 near-duplicates of the users' common direction in the sampled tile, so every seed is far too high and
+    every user goes through the exact re-scoring path."""
+    nu, ni, k = 76000, 40000, 100          # >= 296 user tiles: one song split, the two-pass plan applies
+    g = torch.Generator(device=DEV).manual_seed(5)
+    itf = torch.randn(ni, 100, generator=g, device=DEV)
+    uf = torch.randn(nu, 100, generator=g, device=DEV)
+    if adversarial:
+        v = torch.randn(100, generator=g, device=DEV)
+        uf = v + 0.3 * uf
+        itf[:30] = v + 0.01 * itf[:30]
+    monkeypatch.setenv("DCUE_TOPK_2PASS", "0")
+    s1, i1 = pkg.eval.topk_scores(uf, itf, k)
+    monkeypatch.setenv("DCUE_TOPK_2PASS", "1")
+    s2, i2 = pkg.eval.topk_scores(uf, itf, k)
+    assert (i2 >= 0).all()
+    assert torch.equal(s1, s2)
+    same = (i1 == i2).all(dim=1)
+    # equal scores may come out in either order only if the songs tie exactly: compare as sets there
+    for r in torch.nonzero(~same).flatten().tolist()[:50]:
+        assert set(i1[r].tolist()) == set(i2[r].tolist())
+    assert (~same).float().mean().item() < 1e-3
+
+
 def test_single_pass_center_pack_stats():
     """u = x - center as the fp16 panel + statistics of u in one sweep; finalize with the centre reproduces
     the BatchNorm statistics of x (running_mean updated with the mean of x, not of u)."""
