@@ -481,7 +481,8 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                 // (b) freeze + queue
                 const int cu = sh->cnt[u];
                 const bool pending = sh->pend_n[u] != 0;
-                const bool fr = owner_lane && !pending && cu > (finishing ? (k > LIMIT ? k : LIMIT) : LIMIT);
+                // a seeded stream expects ~4k candidates per user in total: do not compact them mid-stream
+                const bool fr = owner_lane && !pending && cu > (finishing ? (k > LIMIT ? k : LIMIT) : (init_thr ? 1024 : LIMIT));
                 const unsigned fm = __ballot_sync(0xffffffffu, fr);
                 if (fm) {
                     int base = 0;
