@@ -681,21 +681,27 @@ tc_wgrad_unpool_kernel(UnpoolSrc src, int fmt, const uint4* __restrict__ xp, lon
             fetch(w, tile + 2);                       // refill this register set: two tiles of loads stay in flight
             mbar_wait(EMPTY(pp.stage), pp.phase ^ 1); // the MMAs that read this stage (3 tiles ago) have retired
             uint8_t* dy_dst = smem + pp.stage * WGU_STAGE_BYTES;
+            // halves packed two per register once; per row the four code bytes of a word become two 16-bit-lane masks with
+            // word-wide logic (exact zero-byte test + byte permutes) instead of a compare and select per channel
+            unsigned hp[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) hp[c] = (unsigned)h[2 * c] | ((unsigned)h[2 * c + 1] << 16);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint8_t* base = dy_dst + (e * 2 + half) * WGU_DY_PANEL + lane * (4 * ROWB);
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
-                    const int j = (jj + (lane >> 1)) & 3;   // lane pairs start on different rows: conflict-free 16-byte stores
-                    unsigned wd[8];
+                    const unsigned j = (unsigned)((jj + (lane >> 1)) & 3);   // lane pairs start on different rows: conflict-free stores
+                    unsigned out[4];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const int ch = half * 8 + c;
-                        const unsigned code_c = (cw[ch >> 2] >> (8 * (ch & 3))) & 0xffu;
-                        wd[c] = code_c == (unsigned)j ? (unsigned)h[ch] : 0u;
+                    for (int wq = 0; wq < 2; ++wq) {
+                        const unsigned t = cw[half * 2 + wq] ^ (j * 0x01010101u);              // byte == 0 where code == j
+                        const unsigned nz = ((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t;             // bit 7 set where the byte is non-zero
+                        const unsigned m8 = ((~nz & 0x80808080u) >> 7) * 0xffu;                // 0xff in the matching bytes
+                        out[2 * wq] = hp[half * 4 + 2 * wq] & __byte_perm(m8, 0u, 0x1100);     // channels 0,1 of the word
+                        out[2 * wq + 1] = hp[half * 4 + 2 * wq + 1] & __byte_perm(m8, 0u, 0x3322);   // channels 2,3
                     }
-                    *reinterpret_cast<uint4*>(base + j * ROWB) =
-                        make_uint4(wd[0] | (wd[1] << 16), wd[2] | (wd[3] << 16), wd[4] | (wd[5] << 16), wd[6] | (wd[7] << 16));
+                    *reinterpret_cast<uint4*>(base + j * ROWB) = make_uint4(out[0], out[1], out[2], out[3]);
                 }
             }
             fence_proxy_async();                      // generic-proxy stores -> visible to the tensor core's async proxy
