@@ -7,6 +7,8 @@ multi-GPU step is one graph launch as well.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 
@@ -18,6 +20,10 @@ class GraphedTrainStep:
 
     def __init__(self, model, margin, u, pos, neg, pool=None, warmup=3, dp=None):
         self.model, self.margin, self.pool, self.dp = model, margin, pool, dp
+        # Under data parallelism the host is kept at most `max_inflight` graph launches ahead of the device: with an
+        # unbounded launch queue the ranks measured 0.4 ms per step slower (8 x B200: graph launches carrying NCCL work).
+        self.max_inflight = int(os.environ.get("DCUE_DP_MAX_INFLIGHT", "3")) if dp is not None else 0
+        self._events, self._launches = [], 0
         self.u, self.pos, self.neg = u.clone(), pos.clone(), neg.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -61,5 +67,15 @@ class GraphedTrainStep:
             self.u.copy_(u, non_blocking=True)
             self.pos.copy_(pos, non_blocking=True)
             self.neg.copy_(neg, non_blocking=True)
-        self.graph.replay()
+        if self.max_inflight > 0:
+            if len(self._events) < self.max_inflight:
+                self._events.append(torch.cuda.Event())
+            ev = self._events[self._launches % self.max_inflight]
+            if self._launches >= self.max_inflight:
+                ev.synchronize()          # the launch issued max_inflight steps ago has finished
+            self.graph.replay()
+            ev.record()
+            self._launches += 1
+        else:
+            self.graph.replay()
         return self.loss
