@@ -482,7 +482,8 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                 const int cu = sh->cnt[u];
                 const bool pending = sh->pend_n[u] != 0;
                 // a seeded stream expects ~4k candidates per user in total: do not compact them mid-stream
-                const bool fr = owner_lane && !pending && cu > (finishing ? (k > LIMIT ? k : LIMIT) : (init_thr ? 1024 : LIMIT));
+                // at the end of the stream only lists beyond the selection capacity (512) need a compaction first
+                const bool fr = owner_lane && !pending && cu > (finishing ? 512 : (init_thr ? 1024 : LIMIT));
                 const unsigned fm = __ballot_sync(0xffffffffu, fr);
                 if (fm) {
                     int base = 0;
@@ -588,7 +589,7 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 if ((t & (BSTEP - 1)) == BSTEP - 1) boundary(false);
             }
-            // ---- finish: every list down to <= max(k, LIMIT) entries with nothing pending, then the k best, sorted
+            // ---- finish: every list down to <= 512 entries with nothing pending, then the k best, sorted
             boundary(true);
             for (int uu = 0; uu < UPW; ++uu) {
                 const int u = e * UPW + uu;
