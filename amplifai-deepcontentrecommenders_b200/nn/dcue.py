@@ -21,6 +21,7 @@ from torch.utils.data import DataLoader, Subset
 from .. import eval as dcue_eval
 from ..dcue.dcue import DCUENet
 from ..optim.cyclic_scheduler import CyclicLRWithRestarts
+from ..optim.fused_adam import FusedAdam
 from ..optim.ranger import Ranger
 from .trainer import Trainer
 
@@ -96,8 +97,9 @@ class DCUE(Trainer):
         self.model = self.model.cuda()
 
         if self.optimize == 'adam':
-            self.optimizer = optim.Adam(self.model.parameters(), self.lr, (self.beta_one, self.beta_two), self.eps,
-                                        self.weight_decay)
+            # torch.optim.Adam semantics and state_dict layout, one multi-tensor launch per step (optim/fused_adam.py)
+            self.optimizer = FusedAdam(self.model.parameters(), self.lr, (self.beta_one, self.beta_two), self.eps,
+                                       self.weight_decay)
         elif self.optimize == 'sgd':
             self.optimizer = optim.SGD(self.model.parameters(), self.lr, self.beta_one, weight_decay=self.weight_decay,
                                        nesterov=True)

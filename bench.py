@@ -234,7 +234,11 @@ def run_ours(args):
     model = pkg.DCUENet({"feature_dim": CFG["feat"], "conv_hidden": CFG["hidden"], "user_embdim": CFG["emb"], "user_count": U,
                          "model_type": CFG["model_type"]}).to(dev).train()
     dp = par.DataParallelDCUE(model)
-    opt = torch.optim.Adam(model.parameters(), CFG["lr"], CFG["betas"], CFG["eps"], 0)
+    # torch.optim.Adam semantics in one multi-tensor launch (DCUE_BENCH_TORCH_ADAM=1: the library optimizer, for A/B)
+    if os.environ.get("DCUE_BENCH_TORCH_ADAM") == "1":
+        opt = torch.optim.Adam(model.parameters(), CFG["lr"], CFG["betas"], CFG["eps"], 0)
+    else:
+        opt = optim.FusedAdam(model.parameters(), CFG["lr"], CFG["betas"], CFG["eps"], 0)
     sched = optim.CyclicLRWithRestarts(opt, B * world, epoch_size=B * world * 100000, restart_period=30, t_mult=2, policy="cosine")
     sched.step()
 

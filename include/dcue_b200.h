@@ -261,6 +261,17 @@ int dcue_score_hinge_fwdbwd(const float* u, const float* feats, int B, int N, in
                             float margin, int batch_total, float* scores, float* loss_rows, float* du,
                             float* dfeats, void* stream);
 
+/* ---------------------------------------------------------------- optimizer ---------------- */
+
+/* torch.optim.Adam.step() for ALL parameter tensors in one launch (dcrecommend/nn/dcue.py:143-147, :209).
+ * table_dev: device array of n_tensors rows {float* p, const float* g, float* m, float* v, int64 n};
+ * blk_first_dev[i] = first block of tensor i when tensor j takes ceil(n_j / dcue_adam_elems_per_block()) blocks;
+ * total_blocks = their sum.  bias_correction{1,2} = 1 - beta{1,2}^step.  amsgrad = False, L2 weight decay. */
+int dcue_adam_multi_step(const void* table_dev, const int* blk_first_dev, int n_tensors, int total_blocks, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
+                         float bias_correction2, void* stream);
+int dcue_adam_elems_per_block(void);
+
 /* ---------------------------------------------------------------- multi-GPU ---------------- */
 
 /* One-shot SUM all-reduce of inout[n] (fp64, n <= dcue_peer_allreduce_slot_doubles()) over NVLink peer memory: replaces

@@ -420,6 +420,32 @@ def test_peer_allreduce_single_rank_plumbing():
         assert torch.equal(buf[(call & 1) * slot:(call & 1) * slot + 256], ref)
 
 
+def test_fused_adam_matches_torch_adam():
+    """optim.FusedAdam (one multi-tensor launch) against torch.optim.Adam: same trajectory over 6 steps with weight decay,
+    odd sizes (scalar tails, unaligned views) and a changing learning rate; state_dict keys interchange."""
+    g = torch.Generator().manual_seed(21)
+    shapes = [(1000, 300), (128, 128, 4), (100,), (7,), (33, 5), (4097,)]
+    ps_a = [torch.nn.Parameter(torch.randn(*sh, generator=g).to(DEV)) for sh in shapes]
+    ps_b = [torch.nn.Parameter(p.detach().clone()) for p in ps_a]
+    oa = pkg.optim.FusedAdam(ps_a, 1e-3, (0.9, 0.99), 1e-8, 0.01)
+    ob = torch.optim.Adam(ps_b, 1e-3, (0.9, 0.99), 1e-8, 0.01)
+    for step in range(6):
+        for pa, pb in zip(ps_a, ps_b):
+            gr = torch.randn(pa.shape, generator=g).to(DEV) * (10.0 ** (step - 3))
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        for o in (oa, ob):
+            o.param_groups[0]["lr"] = 1e-3 * (1 + step)
+            o.step()
+    for pa, pb in zip(ps_a, ps_b):
+        assert relerr(pa, pb) < 2e-6
+        sa, sb = oa.state[pa], ob.state[pb]
+        assert float(sa["step"]) == float(sb["step"]) == 6.0
+        assert relerr(sa["exp_avg"], sb["exp_avg"]) < 2e-6 and relerr(sa["exp_avg_sq"], sb["exp_avg_sq"]) < 2e-6
+    assert set(oa.state_dict()["state"][0].keys()) == set(ob.state_dict()["state"][0].keys())
+    ob2 = torch.optim.Adam(ps_b, 1e-3, (0.9, 0.99), 1e-8, 0.01)
+    ob2.load_state_dict(oa.state_dict())        # the reference's optimizer checkpoints load either way
+
+
 # ------------------------------------------------------------------ eval scorer
 @pytest.mark.parametrize("nu,ni,k", [(300, 1000, 100), (128, 257, 10), (5, 90, 100), (1000, 5000, 100), (600, 30000, 100),
                                      (40, 3000, 256), (257, 70000, 1)])
