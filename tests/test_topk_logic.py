@@ -87,3 +87,26 @@ def test_seeding_leaves_k_candidates_with_high_probability():
     # closed form tail of the dominant term (normal approximation): z = (mean - k) / (mean / sqrt(r))
     z = (r * s - k) / (r * s / math.sqrt(r))
     assert z > 3.5
+
+
+def test_unpool_row_mask_bit_trick():
+    """The fused layer-1 backward (conv_tc.cu: tc_wgrad_unpool_kernel) turns the four argmax-code bytes of a word into two
+    16-bit-lane masks with word-wide logic: XOR with the row, exact zero-byte test, byte -> 0xff, byte permutes.
+    Restated here for every byte value that can occur (codes 0..3 and the 'no window' filler 0xff) and every row."""
+    def prmt(x, sel):   # __byte_perm(x, 0, sel) for selector nibbles 0..3
+        by = [(x >> (8 * i)) & 0xFF for i in range(4)]
+        return sum(by[(sel >> (4 * i)) & 0x7] << (8 * i) for i in range(4))
+    vals = [0, 1, 2, 3, 0xFF]
+    for j in range(4):
+        for b0 in vals:
+            for b1 in vals:
+                for b2 in vals:
+                    for b3 in vals:
+                        cw = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24)
+                        t = cw ^ (j * 0x01010101)
+                        nz = (((t & 0x7F7F7F7F) + 0x7F7F7F7F) | t) & 0xFFFFFFFF
+                        m8 = ((((~nz) & 0x80808080) >> 7) * 0xFF) & 0xFFFFFFFF
+                        lo, hi = prmt(m8, 0x1100), prmt(m8, 0x3322)
+                        want_lo = (0xFFFF if b0 == j else 0) | (0xFFFF0000 if b1 == j else 0)
+                        want_hi = (0xFFFF if b2 == j else 0) | (0xFFFF0000 if b3 == j else 0)
+                        assert (lo, hi) == (want_lo, want_hi)
