@@ -1,4 +1,4 @@
-"""CPU restatement of the selection logic of the top-k scorer (csrc/topk.cu), checked against numpy:
+"""CPU restatements of two pieces of device-side logic, checked against numpy.  (1) The selection logic of the top-k scorer (csrc/topk.cu):
   * the order-preserving float -> uint32 key map and the bit-by-bit radix select of the k-th largest key
     (select_topk_inplace: common bits skipped, `rem` copies of the threshold key kept),
   * the seeding arithmetic of dcue_topk_scores_2pass (r-th best of every s-th tile => about 4k candidates, and how
