@@ -3,6 +3,7 @@
     (select_topk_inplace: common bits skipped, `rem` copies of the threshold key kept),
   * the seeding arithmetic of dcue_topk_scores_2pass (r-th best of every s-th tile => about 4k candidates, and how
     rarely fewer than k).
+(2) The word-wide row masks of the fused layer-1 backward (csrc/conv_tc.cu: tc_wgrad_unpool_kernel).
 The kernels themselves are checked on the GPU (tests/test_gpu_kernels.py); this pins the algorithm they implement."""
 import math
 
