@@ -38,7 +38,7 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled every 20 ms DURING the timed region (NVML in-process;
+    """SM clock and throttle reasons sampled every ~5 ms DURING the timed region (NVML in-process;
     falls back to `nvidia-smi -lms` when pynvml is unavailable)."""
     BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
@@ -69,7 +69,7 @@ class ClockSampler:
             except Exception as e:  # noqa: BLE001
                 self.err = str(e)
                 return
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def stop(self):
         self.stop_flag = True
@@ -455,7 +455,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="triplets per GPU")
