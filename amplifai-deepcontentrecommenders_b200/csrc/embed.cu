@@ -62,12 +62,13 @@ __global__ void iota_kernel(int32_t* p, int n) {
 // one warp per sorted entry; only segment heads work: they sum their run in position order
 __global__ void __launch_bounds__(256)
 segment_scatter_kernel(const float* __restrict__ gout, const float* __restrict__ fwd,
-                       const int64_t* __restrict__ sidx, const int32_t* __restrict__ spos, int B, int E,
+                       const int64_t* __restrict__ sidx, const int32_t* __restrict__ spos, int B, int U, int E,
                        float* __restrict__ gtable) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= B) return;
     const int64_t row = sidx[i];
+    if (row < 0 || row >= U) return;   // out-of-range index (flagged by the forward gather): never write outside the table
     if (i > 0 && sidx[i - 1] == row) return;
     int end = i + 1;
     while (end < B && sidx[end] == row) ++end;
@@ -102,6 +103,80 @@ segment_scatter_kernel(const float* __restrict__ gout, const float* __restrict__
 #pragma unroll
         for (int t = 0; t < 4; ++t)
             if (e0 + t < E) dst[e0 + t] = a[t];
+    }
+}
+
+
+// Sort-free deterministic segment sum for step-sized batches (B <= DCUE_SCATTER_DIRECT_MAX): one warp per batch row b
+// scans the whole index vector (L1/L2 resident, 8 B per entry).  A row with an EARLIER duplicate does nothing; the first
+// occurrence of a table row ("head") adds every later duplicate in position order, so the result equals the sorted
+// segment sum bit for bit -- without the sort, its workspace, or the two extra launches.
+constexpr int SCAT_CHUNK = 512;   // floats of a row handled per scan (4 x float4 per lane)
+__global__ void __launch_bounds__(256)
+dup_scan_scatter_kernel(const float* __restrict__ gout, const float* __restrict__ fwd, const int64_t* __restrict__ idx,
+                        int B, int U, int E, float* __restrict__ gtable) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int64_t row = idx[b];
+    if (row < 0 || row >= U) return;
+    const bool vec = (E & 3) == 0 && ((reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(fwd) |
+                                      reinterpret_cast<uintptr_t>(gtable)) & 15) == 0;
+    float* dst = gtable + row * (long)E;
+    for (int c0 = 0; c0 < E; c0 += SCAT_CHUNK) {
+        float4 a[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) a[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j0 = 0; j0 < B; j0 += 32) {
+            const int j = j0 + lane;
+            unsigned m = __ballot_sync(0xffffffffu, j < B && __ldg(idx + j) == row);
+            if (j0 + 32 <= b) {          // chunk entirely before b
+                if (m) return;           // an earlier duplicate is the head
+                continue;
+            }
+            if (j0 <= b) {               // chunk containing b
+                if (m & ((1u << (b - j0)) - 1u)) return;
+            }
+            while (m) {                  // b itself and later duplicates, ascending position
+                const int pj = j0 + __ffs(m) - 1;
+                m &= m - 1;
+                const long p = (long)pj * E;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int e0 = c0 + t * 128 + lane * 4;
+                    if (vec) {
+                        if (e0 < E) {
+                            const float4 g = __ldg(reinterpret_cast<const float4*>(gout + p + e0));
+                            float4 f = make_float4(1.f, 1.f, 1.f, 1.f);
+                            if (fwd) f = __ldg(reinterpret_cast<const float4*>(fwd + p + e0));
+                            a[t].x += f.x > 0.f ? g.x : 0.f; a[t].y += f.y > 0.f ? g.y : 0.f;
+                            a[t].z += f.z > 0.f ? g.z : 0.f; a[t].w += f.w > 0.f ? g.w : 0.f;
+                        }
+                    } else {
+                        float* av = &a[t].x;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (e0 + q < E) {
+                                const float g = __ldg(gout + p + e0 + q);
+                                const float f = fwd ? __ldg(fwd + p + e0 + q) : 1.f;
+                                av[q] += f > 0.f ? g : 0.f;
+                            }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int e0 = c0 + t * 128 + lane * 4;
+            if (vec) {
+                if (e0 < E) *reinterpret_cast<float4*>(dst + e0) = a[t];
+            } else {
+                const float* av = &a[t].x;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (e0 + q < E) dst[e0 + q] = av[q];
+            }
+        }
     }
 }
 
@@ -158,7 +233,21 @@ extern "C" int dcue_scatter_add_bwd(const float* grad_out, const float* fwd_out,
     DCUE_CHECK_ARG(grad_out && fwd_out && sorted_idx && sorted_pos && grad_table && B >= 0 && U > 0 && E > 0);
     if (B == 0) return 0;
     segment_scatter_kernel<<<ceil_div_i(B, 8), 256, 0, (cudaStream_t)stream>>>(grad_out, fwd_out, sorted_idx,
-                                                                                sorted_pos, B, E, grad_table);
+                                                                                sorted_pos, B, U, E, grad_table);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcue_scatter_direct_max(void) { return 16384; }
+
+extern "C" int dcue_scatter_add_rows(const float* grad_rows, const float* fwd_mask, const int64_t* idx, int B, int U, int E,
+                                     float* grad_table, void* stream) {
+    DCUE_CHECK_ARG(grad_rows && idx && grad_table && B >= 0 && U > 0 && E > 0);
+    if (B > dcue_scatter_direct_max())
+        DCUE_FAIL(DCUE_E_UNSUPPORTED, "dcue_scatter_add_rows: B = %d > %d, use dcue_sort_indices + dcue_scatter_add_bwd", B,
+                  dcue_scatter_direct_max());
+    if (B == 0) return 0;
+    dup_scan_scatter_kernel<<<ceil_div_i(B, 8), 256, 0, (cudaStream_t)stream>>>(grad_rows, fwd_mask, idx, B, U, E, grad_table);
     DCUE_LAUNCH_CHECK();
     return 0;
 }

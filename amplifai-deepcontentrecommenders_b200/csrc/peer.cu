@@ -13,6 +13,13 @@
 namespace {
 
 constexpr int PEER_SLOT_DOUBLES = 512;
+constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;   // 20 s
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -43,7 +50,18 @@ peer_allreduce_f64_kernel(double* const* __restrict__ bufs, unsigned* const* __r
     if ((int)threadIdx.x < world) {
         st_release_sys(sigs[threadIdx.x] + rank, e);                       // tell peer `threadIdx.x` that my slot is ready
         const unsigned* my_pad = sigs[rank] + threadIdx.x;
-        while ((int)(ld_acquire_sys(my_pad) - e) < 0) __nanosleep(20);   // peer's call e (or a later one) is published
+        // peer's call e (or a later one) is published.  The wait is bounded: a rank that died or raised would otherwise hang
+        // every other GPU inside this kernel; after PEER_TIMEOUT_NS the flag counter[1] is raised (the result is then invalid)
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        while ((int)(ld_acquire_sys(my_pad) - e) < 0) {
+            __nanosleep(20);
+            if ((++spins & 1023u) == 0) {
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > PEER_TIMEOUT_NS) { atomicExch(reinterpret_cast<int*>(counter) + 1, 1 + (int)threadIdx.x); break; }
+            }
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {

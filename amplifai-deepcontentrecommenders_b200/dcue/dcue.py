@@ -100,6 +100,17 @@ class DCUENet(nn.Module):
         self.user_embd.raise_if_index_error()
         self.conv.raise_if_index_error()
 
+    def error_flags(self):
+        """The device int32 flags raised by an out-of-range user index / song index (for FusedAdam.set_skip_flags: a
+        flagged step must not touch the parameters)."""
+        dev = self.conv.fc.weight.device
+        if self.conv._err is None or self.conv._err.device != dev:
+            self.conv._err = torch.zeros(1, dtype=torch.int32, device=dev)
+        flags = [self.conv._err]
+        if hasattr(self.user_embd, "_err_flag"):
+            flags.append(self.user_embd._err_flag())
+        return flags
+
     def hinge_loss_step(self, u, pos, neg, margin, batch_total=None, return_all=False):
         """forward + DCUE._loss_func (max(0, margin - scores).sum(1).mean()) with the scoring, the
         loss and their backward fused in one kernel.  batch_total = global batch size under data

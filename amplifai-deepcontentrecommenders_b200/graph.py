@@ -25,6 +25,9 @@ class GraphedTrainStep:
         self.max_inflight = int(os.environ.get("DCUE_DP_MAX_INFLIGHT", "3")) if dp is not None else 0
         self._events, self._launches = [], 0
         self.u, self.pos, self.neg = u.clone(), pos.clone(), neg.clone()
+        # warm-up and capture run training-mode forwards: BatchNorm running statistics / num_batches_tracked would advance
+        # by warmup + 1 steps behind the caller's back -> snapshot them here and restore after the capture
+        buffers = [(b, b.detach().clone()) for b in model.buffers()]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):           # warm-up off the default stream: allocators, workspaces, cub temp
@@ -50,6 +53,17 @@ class GraphedTrainStep:
             self.loss.backward()
             if dp is not None:
                 dp.reduce_gradients()
+        with torch.no_grad():
+            for b, saved in buffers:
+                b.copy_(saved)
+        torch.cuda.synchronize()
+
+    def release(self):
+        """Drop the captured graph (and the NCCL work it holds).  Call on every rank before
+        torch.distributed.destroy_process_group(): a live graph with captured collectives keeps the communicator busy."""
+        torch.cuda.synchronize()
+        self.graph = None
+        self.loss = None
 
     def _loss(self):
         if self.dp is not None:

@@ -7,17 +7,29 @@ What changed relative to the reference's loops (results are the same quantities)
   * _user_factors is one batched call, _item_factors accumulates with an index_add on the device;
   * predict() gathers factor rows with tensor indexing instead of Python lists;
   * recommend_topk() is new: all users x all songs cosine scores with a fused top-k (BASELINE cfg5);
+  * score()/score_song() keep every score on the device and compute AUC / mAP with one kernel over all sampled users
+    (csrc/metrics.cu) instead of Python lists + sklearn per user;
   * save() stores state_dicts (loadable under torch >= 2.6), load() also accepts the reference's
-    whole-object pickles.
+    whole-object pickles; factor matrices are stored as CPU tensors like the reference's;
+  * user_factors / item_factors live on the GPU while the trainer runs (the reference keeps CPU tensors): call
+    .cpu() before .numpy();
+  * an out-of-range user / song index does not synchronise every step: the fused optimizers skip the update of a flagged
+    step on the device (parameters stay intact) and IndexError is raised when the epoch's loss is read;
+  * under torchrun (torch.distributed initialised, world size > 1) _init_nn wraps the model in
+    parallel.DataParallelDCUE, every rank trains on its shard of each loader (DistributedSampler), only rank 0 writes
+    checkpoints; close() releases captured CUDA graphs before the process group.
 """
 import os
 
 import numpy as np
 import torch
+import torch.distributed as dist
 from torch import optim
 from torch.optim.lr_scheduler import StepLR
 from torch.utils.data import DataLoader, Subset
+from torch.utils.data.distributed import DistributedSampler
 
+from .. import _lib as L
 from .. import eval as dcue_eval
 from ..dcue.dcue import DCUENet
 from ..optim.cyclic_scheduler import CyclicLRWithRestarts
@@ -81,6 +93,29 @@ class DCUE(Trainer):
         self.num_workers = 8
 
         self.USE_CUDA = torch.cuda.is_available()
+        self._dp = None           # parallel.DataParallelDCUE under torchrun
+        self._graph_steps = []    # captured CUDA graphs (released by close())
+
+    # ------------------------------------------------------------------ multi-GPU plumbing
+    @staticmethod
+    def _world():
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    @staticmethod
+    def _rank():
+        return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+    def close(self):
+        """Release captured CUDA graphs (they hold NCCL work) BEFORE tearing the process group down, so a multi-GPU run
+        exits through the normal path."""
+        for g in self._graph_steps:
+            g.release()
+        self._graph_steps = []
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
 
     # ------------------------------------------------------------------ model / optimiser
     def _init_nn(self, audio_model=None):
@@ -109,7 +144,14 @@ class DCUE(Trainer):
                                     betas=(self.beta_one, self.beta_two), eps=1e-5, weight_decay=self.weight_decay)
         else:
             raise ValueError("unknown optimizer {!r}".format(self.optimize))
-        self.scheduler = CyclicLRWithRestarts(self.optimizer, self.batch_size, epoch_size=self.epoch_size,
+        if hasattr(self.optimizer, 'set_skip_flags'):
+            self.optimizer.set_skip_flags(self.model.error_flags())
+        self._dp = None
+        if self._world() > 1:
+            from ..parallel import DataParallelDCUE
+            self._dp = DataParallelDCUE(self.model)      # broadcasts rank 0's parameters, installs the SyncBN hooks
+        # the scheduler counts GLOBAL samples per batch (every rank consumes batch_size of them)
+        self.scheduler = CyclicLRWithRestarts(self.optimizer, self.batch_size * self._world(), epoch_size=self.epoch_size,
                                               restart_period=self.restart_period, t_mult=self.t_mult, policy='cosine')
 
     def _loss_func(self, preds):
@@ -126,20 +168,31 @@ class DCUE(Trainer):
 
     def _train_epoch(self, loader):
         """One pass over `loader`: zero_grad, forward, hinge loss, backward, optimizer.step,
-        scheduler.batch_step per batch.  Returns (samples_processed, mean train loss)."""
+        scheduler.batch_step per batch.  Returns (samples_processed, mean train loss).  Data parallel: every rank runs
+        its own batches, gradients are the global-batch gradients (parallel.DataParallelDCUE)."""
         self.model.train()
         loss_sum = torch.zeros((), device='cuda')
         samples_processed = 0
+        guarded = bool(getattr(self.optimizer, 'skip_flags', None))
         for batch_samples in loader:
             u, pos, neg = self._to_device(batch_samples)
             self.model.zero_grad(set_to_none=True)
-            loss = self.model.hinge_loss_step(u, pos, neg, self.margin)
-            loss.backward()
+            if self._dp is not None:
+                loss = self._dp.loss_step(u, pos, neg, self.margin)
+                loss.backward()
+                self._dp.reduce_gradients()
+                loss = self._dp.reduce_loss(loss)
+            else:
+                loss = self.model.hinge_loss_step(u, pos, neg, self.margin)
+                loss.backward()
+            if not guarded:
+                # optimizers without the on-device guard (SGD): a bad index must not reach the parameters
+                self.model.raise_if_index_error()
             self.optimizer.step()
             self.scheduler.batch_step()
-            samples_processed += pos.size()[0]
-            loss_sum += loss.detach() * pos.size()[0]
-        self.model.user_embd.raise_if_index_error()
+            samples_processed += pos.size()[0] * self._world()
+            loss_sum += loss.detach() * (pos.size()[0] * self._world())
+        self.model.raise_if_index_error()
         train_loss = loss_sum.item() / max(samples_processed, 1)
         return samples_processed, train_loss
 
@@ -204,15 +257,19 @@ class DCUE(Trainer):
                           train_loss, val_loss, train_auc, val_auc, train_map, val_map, val_user_auc, val_user_map),
                       flush=True)
                 self._update_best(val_map, val_auc, val_loss)
-                self.nn_epoch += 1
-                if self.nn_epoch >= self.num_epochs + 1:
-                    break
+                self.nn_epoch += 1          # like the reference, a started sweep over the 10 loaders always finishes
 
     def _batch_loaders(self, dataset, k=None):
         loaders = []
         for subset_batch_indexes in dataset.get_batches(k):
-            loaders += [DataLoader(Subset(dataset, subset_batch_indexes), batch_size=self.batch_size, shuffle=True,
-                                   num_workers=self.num_workers, drop_last=True, pin_memory=True)]
+            sub = Subset(dataset, subset_batch_indexes)
+            if self._world() > 1:   # every rank draws a disjoint shard of the sub-epoch
+                sampler = DistributedSampler(sub, self._world(), self._rank(), shuffle=True, seed=self.nn_epoch, drop_last=True)
+                loaders += [DataLoader(sub, batch_size=self.batch_size, sampler=sampler, num_workers=self.num_workers,
+                                       drop_last=True, pin_memory=True)]
+            else:
+                loaders += [DataLoader(sub, batch_size=self.batch_size, shuffle=True, num_workers=self.num_workers,
+                                       drop_last=True, pin_memory=True)]
         return loaders
 
     # ------------------------------------------------------------------ factors
@@ -284,52 +341,81 @@ class DCUE(Trainer):
         uf, itf = self.user_factors.cuda(), self.item_factors.cuda()
         return self._pair_scores(loader, 'u', 'song_idx', uf, itf)
 
+    def _pair_scores_device(self, loader, first_factors, second_factors):
+        """_pair_scores without leaving the device: -> (scores f32 [n], targets u8 [n]) or (None, None)."""
+        dev = first_factors.device
+        scores, targets = [], []
+        self.model.eval()
+        with torch.no_grad():
+            for batch_samples in loader:
+                a = first_factors[torch.as_tensor(batch_samples['u'], dtype=torch.int64, device=dev).view(-1)]
+                b = second_factors[torch.as_tensor(batch_samples['song_idx'], dtype=torch.int64, device=dev).view(-1)]
+                if b.size()[0] > 1:
+                    scores.append(self.model.sim(a.contiguous(), b.contiguous()))
+                    targets.append(torch.as_tensor(batch_samples['y']).view(-1).to(dev, non_blocking=True).ne(0).to(torch.uint8))
+        if not scores:
+            return torch.empty(0, device=dev), torch.empty(0, dtype=torch.uint8, device=dev)
+        return torch.cat(scores), torch.cat(targets)
+
+    @staticmethod
+    def ranking_metrics(scores, targets, seg_offsets, group=None):
+        """AUC / AP of every segment on the device (csrc/metrics.cu) -> double [n_seg, 8], see dcue_auc_ap_segments."""
+        n_seg = seg_offsets.numel() - 1
+        out = torch.zeros(n_seg, 8, dtype=torch.float64, device=scores.device)
+        if n_seg > 0:
+            L.call("dcue_auc_ap_segments", scores.contiguous().data_ptr(), targets.contiguous().data_ptr(),
+                   L.ptr(None if group is None else group.contiguous()), seg_offsets.contiguous().data_ptr(), n_seg,
+                   out.data_ptr(), L.stream())
+        return out
+
     def score(self, users, pred_loader, truth_loader, k=10000):
         """Mean weighted AUC and mAP over `users`, mixing each user's positives of one split with the
-        negatives of the other (the reference's estimator, nn/dcue.py:380-449)."""
-        from sklearn.metrics import average_precision_score, roc_auc_score
-        auc, mAP = [], []
+        negatives of the other (the reference's estimator, nn/dcue.py:380-449).  Every user's candidate scores stay on
+        the device; one kernel computes all users' AUCs (per half) and APs."""
+        uf, itf = self.user_factors.cuda(), self.item_factors.cuda()
+        sc, tg, gr, offs = [], [], [], [0]
         for user_id in users:
-            sp, tp = self.predict(user_id, pred_loader)
-            st, tt = self.predict(user_id, truth_loader)
-            if sp is None and tp is None:
-                break
-            sp, tp, st, tt = np.array(sp), np.array(tp), np.array(st), np.array(tt)
-            halves = [(list(sp[tp == 1]) + list(st[tt == 0]), list(tp[tp == 1]) + list(tt[tt == 0])),
-                      (list(sp[tp == 0]) + list(st[tt == 1]), list(tp[tp == 0]) + list(tt[tt == 1]))]
-            total = len(halves[0][0]) + len(halves[1][0])
-            weights = [len(halves[0][0]) / total, len(halves[1][0]) / total]
-            part, all_s, all_t = [], [], []
-            for s, t in halves:
-                all_s += s
-                all_t += t
-                if sum(t) == len(t):
-                    part += [1]
-                elif sum(t) == 0:
-                    part += [0]
-                else:
-                    part += [roc_auc_score(t, s)]
-            auc += [weights[0] * part[0] + weights[1] * part[1]]
-            mAP += [average_precision_score(all_t, all_s)]
-        return np.mean(auc), np.mean(mAP)
+            pred_loader.dataset.create_user_data(user_id)
+            if not pred_loader.dataset.user_has_songs:
+                break                                   # like the reference: predict() returned (None, None)
+            sp, tp = self._pair_scores_device(pred_loader, uf, itf)
+            truth_loader.dataset.create_user_data(user_id)
+            if truth_loader.dataset.user_has_songs:
+                st, tt = self._pair_scores_device(truth_loader, uf, itf)
+            else:
+                st, tt = sp[:0], tp[:0]
+            # half 0 = pred positives + truth negatives, half 1 = pred negatives + truth positives (nn/dcue.py:405-418)
+            sc += [sp, st]
+            tg += [tp, tt]
+            gr += [1 - tp, tt]
+            offs.append(offs[-1] + sp.numel() + st.numel())
+        if len(offs) == 1:
+            return np.nan, np.nan
+        seg = torch.tensor(offs, dtype=torch.int64, device=uf.device)
+        m = self.ranking_metrics(torch.cat(sc), torch.cat(tg), seg, torch.cat(gr))
+        total = (m[:, 2] + m[:, 3]).clamp_min(1.0)
+        auc = (m[:, 2] / total) * m[:, 0] + (m[:, 3] / total) * m[:, 1]
+        return auc.mean().item(), m[:, 6].mean().item()
 
     def score_song(self, songs, pred_loader, k=10000):
-        from sklearn.metrics import average_precision_score, roc_auc_score
-        auc, mAP = [], []
+        """Mean AUC / mAP over `songs` (each against its candidate users), nn/dcue.py:451-476, on the device."""
+        uf, itf = self.user_factors.cuda(), self.item_factors.cuda()
+        sc, tg, offs = [], [], [0]
         for song_id in songs:
-            s, t = self.predict_song(song_id, pred_loader)
-            if s is None or t is None:
+            pred_loader.dataset.create_song_data(song_id)
+            if not pred_loader.dataset.song_has_users:
                 continue
-            if sum(t) == len(t):
-                auc += [1]
-                mAP += [1]
-            elif sum(t) == 0:
-                auc += [0]
-                mAP += [0]
-            else:
-                auc += [roc_auc_score(t, s)]
-                mAP += [average_precision_score(t, s)]
-        return np.mean(auc), np.mean(mAP)
+            s, t = self._pair_scores_device(pred_loader, uf, itf)
+            sc.append(s)
+            tg.append(t)
+            offs.append(offs[-1] + s.numel())
+        if len(offs) == 1:
+            return np.nan, np.nan
+        seg = torch.tensor(offs, dtype=torch.int64, device=uf.device)
+        m = self.ranking_metrics(torch.cat(sc), torch.cat(tg), seg)
+        n, P = m[:, 2], m[:, 4]
+        ap = torch.where(P == n, torch.ones_like(n), torch.where(P == 0, torch.zeros_like(n), m[:, 6]))
+        return m[:, 0].mean().item(), ap.mean().item()
 
     def _compute_scores(self, split, pred_loader, truth_loader, train_data, val_data, test_data, pct=0.025):
         if split == 'train':
@@ -377,11 +463,14 @@ class DCUE(Trainer):
     def save(self, models_dir=None):
         """<models_dir>/<subdir>/epoch_<n>.pth with hyper-parameters, factor matrices and the
         state_dicts of model / optimizer / scheduler."""
-        if self.model is None or models_dir is None:
+        if self.model is None or models_dir is None or self._rank() != 0:
             return
         path = os.path.join(models_dir, self._format_model_subdir())
         os.makedirs(path, exist_ok=True)
-        ckpt = {k: v for k, v in self.__dict__.items() if k not in self._STATE_KEYS}
+        ckpt = {k: v for k, v in self.__dict__.items() if k not in self._STATE_KEYS and not k.startswith('_')}
+        for k in ('user_factors', 'item_factors', 'best_user_factors', 'best_item_factors'):
+            if torch.is_tensor(ckpt.get(k)):
+                ckpt[k] = ckpt[k].cpu()                      # the reference stores CPU factor matrices
         ckpt['format'] = 'dcue_b200.state_dict.v1'
         ckpt['model_state'] = self.model.state_dict()
         ckpt['optimizer_state'] = self.optimizer.state_dict()

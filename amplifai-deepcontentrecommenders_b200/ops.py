@@ -446,8 +446,7 @@ class UserTowerFn(torch.autograd.Function):
         dev, st = table.device, L.stream()
         f32 = dict(dtype=torch.float32, device=dev)
         gout = gout.contiguous().view(B, F)
-        nscr = max(L.query("dcue_linear_wgrad_ws_bytes", B, E, F), L.query("dcue_linear_wgrad_ws_bytes", B, E, E),
-                   L.query("dcue_sort_ws_bytes", B))
+        nscr = max(L.query("dcue_linear_wgrad_ws_bytes", B, E, F), L.query("dcue_linear_wgrad_ws_bytes", B, E, E))
         scratch = torch.empty(nscr, dtype=torch.uint8, device=dev)
         gw2, gb2 = torch.empty(F, E, **f32), torch.empty(F, **f32)
         L.call("dcue_linear_wgrad", gout.data_ptr(), F, h1.data_ptr(), E, B, E, F, gw2.data_ptr(), gb2.data_ptr(),
@@ -469,12 +468,7 @@ class UserTowerFn(torch.autograd.Function):
         elif ctx.needs_input_grad[1]:
             dh0 = torch.empty(B, E, **f32)  # ReLU mask of the gather is applied in the scatter kernel
             L.call("dcue_linear_dgrad", dh1.data_ptr(), E, w1.data_ptr(), B, E, E, None, 0, dh0.data_ptr(), E, st)
-            sidx = torch.empty(B, dtype=torch.int64, device=dev)
-            spos = torch.empty(B, dtype=torch.int32, device=dev)
-            L.call("dcue_sort_indices", idx.data_ptr(), B, U, sidx.data_ptr(), spos.data_ptr(), scratch.data_ptr(), nscr, st)
-            gtable = torch.zeros(U, E, **f32)  # dense gradient, like nn.Embedding(sparse=False)
-            L.call("dcue_scatter_add_bwd", dh0.data_ptr(), h0.data_ptr(), sidx.data_ptr(), spos.data_ptr(), B, U, E,
-                   gtable.data_ptr(), st)
+            gtable = scatter_rows(idx, dh0, U, mask=h0)     # dense gradient, like nn.Embedding(sparse=False)
         return None, gtable, gw1, gb1, gw2, gb2, None, None
 
 
@@ -533,24 +527,34 @@ def gather_rows(table, idx):
     return raw
 
 
-def scatter_rows(idx, grad_rows, n_rows):
-    """Dense [n_rows,E] sum of grad_rows by idx (deterministic sorted segment sum); entries with idx == n_rows
-    (the 'not mine' sentinel) are dropped."""
+def scatter_rows(idx, grad_rows, n_rows, mask=None):
+    """Dense [n_rows,E] sum of grad_rows by idx, deterministic (duplicates are added in position order); entries whose
+    index is outside [0, n_rows) -- the 'not mine' sentinel of the sharded table, or a bad user index already flagged by
+    the forward gather -- are dropped.  mask (optional, [B,E]): ReLU output of the gather, gradient passes where > 0.
+    Step-sized batches take the sort-free single-launch kernel; larger ones sort by row first."""
     B, E = grad_rows.shape
     dev = grad_rows.device
-    out = torch.zeros(n_rows + 1, E, dtype=torch.float32, device=dev)   # last row collects the sentinel entries
+    out = torch.zeros(n_rows, E, dtype=torch.float32, device=dev)
     if B == 0:
-        return out[:n_rows]
+        return out
+    st = L.stream()
+    idx, grad_rows = idx.contiguous(), grad_rows.contiguous()
+    mask = None if mask is None else mask.contiguous()
+    if B <= L.lib().dcue_scatter_direct_max():
+        L.call("dcue_scatter_add_rows", grad_rows.data_ptr(), L.ptr(mask), idx.data_ptr(), B, n_rows, E, out.data_ptr(), st)
+        return out
     sidx = torch.empty(B, dtype=torch.int64, device=dev)
     spos = torch.empty(B, dtype=torch.int32, device=dev)
     nscr = L.query("dcue_sort_ws_bytes", B)
     scratch = torch.empty(nscr, dtype=torch.uint8, device=dev)
-    st = L.stream()
-    L.call("dcue_sort_indices", idx.contiguous().data_ptr(), B, n_rows + 1, sidx.data_ptr(), spos.data_ptr(), scratch.data_ptr(), nscr, st)
-    ones = torch.ones_like(grad_rows)   # no ReLU mask here: grad_rows is already masked
-    L.call("dcue_scatter_add_bwd", grad_rows.contiguous().data_ptr(), ones.data_ptr(), sidx.data_ptr(), spos.data_ptr(), B,
-           n_rows + 1, E, out.data_ptr(), st)
-    return out[:n_rows]
+    # out-of-range keys: the sort orders by the low bits only, which is fine -- equal keys stay adjacent and the scatter
+    # kernel skips every row outside [0, n_rows)
+    L.call("dcue_sort_indices", idx.data_ptr(), B, n_rows + 1, sidx.data_ptr(), spos.data_ptr(), scratch.data_ptr(), nscr, st)
+    if mask is None:
+        mask = torch.ones_like(grad_rows)
+    L.call("dcue_scatter_add_bwd", grad_rows.data_ptr(), mask.data_ptr(), sidx.data_ptr(), spos.data_ptr(), B, n_rows, E,
+           out.data_ptr(), st)
+    return out
 
 
 class ScoreFn(torch.autograd.Function):

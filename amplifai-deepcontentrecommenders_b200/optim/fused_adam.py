@@ -8,6 +8,7 @@ import torch
 from torch.optim.optimizer import Optimizer
 
 from .. import _lib as L
+from ._multi_tensor import PointerTable
 
 
 class FusedAdam(Optimizer):
@@ -20,26 +21,37 @@ class FusedAdam(Optimizer):
         if not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0:
             raise ValueError(f"Invalid beta parameters: {betas}")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
-        self._tables = {}     # group index -> (key, table, blk_first, n_tensors, total_blocks)
+        self._tables = {}     # group index -> PointerTable
+        self.skip_flags = []  # up to two device int32 flags: a raised flag turns the step into a no-op (bad index in the batch)
+
+    def set_skip_flags(self, flags):
+        """Device error flags (e.g. DCUENet.error_flags()): when one is raised the kernel leaves every parameter and
+        moment untouched, so a NaN-poisoned step never reaches the weights and no host sync is needed per step."""
+        flags = [f for f in flags if f is not None]
+        if len(flags) > 2:
+            raise ValueError("at most two skip flags")
+        self.skip_flags = flags
+
+    def _invalidate(self):
+        self._tables = {}
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._invalidate()            # the state tensors were replaced: cached raw pointers are stale
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        if hasattr(self, "_tables"):
+            self._invalidate()
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._tables = {}
+        self.__dict__.setdefault("skip_flags", [])
 
     def _table(self, gi, params):
-        key = tuple((p.data_ptr(), p.grad.data_ptr(), p.numel()) for p in params)
-        hit = self._tables.get(gi)
-        if hit is not None and hit[0] == key:
-            return hit
-        per = L.lib().dcue_adam_elems_per_block()
-        rows, first, blocks = [], [], 0
-        for p in params:
-            st = self.state[p]
-            rows.append([p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()])
-            first.append(blocks)
-            blocks += (p.numel() + per - 1) // per
-        dev = params[0].device
-        table = torch.tensor(rows, dtype=torch.int64).to(dev)
-        blk_first = torch.tensor(first, dtype=torch.int32).to(dev)
-        hit = (key, table, blk_first, len(params), blocks)
-        self._tables[gi] = hit
-        return hit
+        tab = self._tables.setdefault(gi, PointerTable())
+        return tab.get(params, [(self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"]) for p in params])
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -67,7 +79,8 @@ class FusedAdam(Optimizer):
             if any(float(self.state[p]["step"]) != step for p in params):
                 raise RuntimeError("FusedAdam: parameters of one group must share the step count")
             b1, b2 = group["betas"]
-            _, table, blk_first, n, blocks = self._table(gi, params)
+            table, blk_first, n, blocks = self._table(gi, params)
+            fl = [f.data_ptr() for f in self.skip_flags] + [None, None]
             L.call("dcue_adam_multi_step", table.data_ptr(), blk_first.data_ptr(), n, blocks, float(group["lr"]), float(b1), float(b2),
-                   float(group["eps"]), float(group["weight_decay"]), 1.0 - b1 ** step, 1.0 - b2 ** step, L.stream())
+                   float(group["eps"]), float(group["weight_decay"]), 1.0 - b1 ** step, 1.0 - b2 ** step, fl[0], fl[1], L.stream())
         return loss

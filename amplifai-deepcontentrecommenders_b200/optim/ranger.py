@@ -1,12 +1,18 @@
 """Ranger = Rectified Adam (Liu et al. 2019) + Lookahead (Zhang et al. 2019), API-compatible with
 the reference's dcrecommend/optim/ranger.py (same constructor, hyper-parameters, state keys
-``step / exp_avg / exp_avg_sq / slow_buffer`` and update rule), written as multi-tensor
-(``torch._foreach``) updates: a handful of fused launches per step instead of ~12 per parameter.
+``step / exp_avg / exp_avg_sq / slow_buffer`` and update rule, ranger.py:82-165).
+
+CUDA parameters take ONE multi-tensor kernel launch per step (csrc/optim.cu ``dcue_ranger_multi_step``: moments,
+weight decay, rectified update and the lookahead interpolation fused, 1 read-modify-write pass over p/m/v(/slow)
+instead of ~12 elementwise passes per parameter).  Parameters that are not on a CUDA device (host-side unit tests of the
+update rule) take the same arithmetic as ``torch._foreach`` updates.
 """
 import math
 
 import torch
 from torch.optim.optimizer import Optimizer
+
+from ._multi_tensor import PointerTable
 
 
 class Ranger(Optimizer):
@@ -27,6 +33,31 @@ class Ranger(Optimizer):
         self.N_sma_threshhold = N_sma_threshhold
         self.alpha = alpha
         self.k = k
+        self._tables = {}
+        self.skip_flags = []
+
+    def set_skip_flags(self, flags):
+        """See FusedAdam.set_skip_flags."""
+        flags = [f for f in flags if f is not None]
+        if len(flags) > 2:
+            raise ValueError("at most two skip flags")
+        self.skip_flags = flags
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables = {}
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        self._tables = {}
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._tables = {}
+        self.__dict__.setdefault("skip_flags", [])
+        for name in ("N_sma_threshhold", "alpha", "k"):
+            if name not in self.__dict__:
+                setattr(self, name, self.defaults[name])
 
     @staticmethod
     def _rectification(step, beta1, beta2, threshold):
@@ -40,10 +71,27 @@ class Ranger(Optimizer):
             return True, r / bias1
         return False, 1.0 / bias1
 
+    def _fused(self, key, group, step, ps):
+        from .. import _lib as L
+        for p in ps:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("Ranger (fused): parameters must be contiguous fp32 CUDA tensors")
+            if p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
+                p.grad = p.grad.float().contiguous()
+        beta1, beta2 = group["betas"]
+        adaptive, step_size = self._rectification(step, beta1, beta2, self.N_sma_threshhold)
+        tab = self._tables.setdefault(key, PointerTable())
+        table, blk_first, n, blocks = tab.get(
+            ps, [(self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"], self.state[p]["slow_buffer"]) for p in ps])
+        fl = [f.data_ptr() for f in self.skip_flags] + [None, None]
+        L.call("dcue_ranger_multi_step", table.data_ptr(), blk_first.data_ptr(), n, blocks, float(step_size * group["lr"]),
+               float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"] * group["lr"]), int(adaptive),
+               int(step % group["k"] == 0), float(self.alpha), fl[0], fl[1], L.stream())
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             beta1, beta2 = group["betas"]
             # parameters of one group may be at different steps (e.g. late-added): bucket by step
             buckets = {}
@@ -59,8 +107,11 @@ class Ranger(Optimizer):
                     state["exp_avg_sq"] = torch.zeros_like(p, dtype=torch.float32)
                     state["slow_buffer"] = p.detach().clone()
                 state["step"] += 1
-                buckets.setdefault(state["step"], []).append(p)
-            for step, ps in buckets.items():
+                buckets.setdefault((state["step"], p.is_cuda), []).append(p)
+            for (step, on_gpu), ps in buckets.items():
+                if on_gpu:
+                    self._fused((gi, step % 2 if len(buckets) > 1 else 0), group, step, ps)
+                    continue
                 grads = [p.grad.float() for p in ps]
                 m = [self.state[p]["exp_avg"] for p in ps]
                 v = [self.state[p]["exp_avg_sq"] for p in ps]

@@ -69,6 +69,13 @@ int dcue_gather_relu_fwd(const float* table, const int64_t* idx, int B, int U, i
 int dcue_sort_indices(const int64_t* idx, int B, int U, int64_t* sorted_idx, int32_t* sorted_pos,
                       void* ws, size_t ws_bytes, void* stream);
 size_t dcue_sort_ws_bytes(int B);
+/* The same dense gradient WITHOUT a sort for step-sized batches (B <= dcue_scatter_direct_max()): one launch, no
+ * workspace; the first occurrence of a table row sums its duplicates in position order (bit-identical to the sorted
+ * segment sum).  fwd_mask (nullable) = ReLU output of the gather (gradient passes where > 0).  Rows whose index is
+ * outside [0,U) are skipped.  grad_table must be zeroed by the caller. */
+int dcue_scatter_add_rows(const float* grad_rows, const float* fwd_mask, const int64_t* idx, int B, int U, int E,
+                          float* grad_table, void* stream);
+int dcue_scatter_direct_max(void);
 int dcue_scatter_add_bwd(const float* grad_out, const float* fwd_out /* relu output, mask */,
                          const int64_t* sorted_idx, const int32_t* sorted_pos, int B, int U, int E,
                          float* grad_table, void* stream);
@@ -269,16 +276,27 @@ int dcue_score_hinge_fwdbwd(const float* u, const float* feats, int B, int N, in
  * total_blocks = their sum.  bias_correction{1,2} = 1 - beta{1,2}^step.  amsgrad = False, L2 weight decay. */
 int dcue_adam_multi_step(const void* table_dev, const int* blk_first_dev, int n_tensors, int total_blocks, float lr,
                          float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
-                         float bias_correction2, void* stream);
+                         float bias_correction2,
+                         const int* skip_flag_a /* nullable device flags: a non-zero flag makes the step a no-op */,
+                         const int* skip_flag_b, void* stream);
 int dcue_adam_elems_per_block(void);
+/* Ranger.step() = RAdam + Lookahead for ALL parameter tensors in one launch (dcrecommend/optim/ranger.py:82-165).
+ * table rows {float* p, const float* g, float* exp_avg, float* exp_avg_sq, float* slow_buffer, int64 n}; blocks as above.
+ * step_size_times_lr = RAdam step size (rectified when adaptive != 0) * lr; lookahead != 0 on every k-th step:
+ * slow += alpha*(p - slow); p = slow. */
+int dcue_ranger_multi_step(const void* table_dev, const int* blk_first_dev, int n_tensors, int total_blocks,
+                           float step_size_times_lr, float beta1, float beta2, float eps, float weight_decay_times_lr,
+                           int adaptive, int lookahead, float alpha, const int* skip_flag_a, const int* skip_flag_b,
+                           void* stream);
 
 /* ---------------------------------------------------------------- multi-GPU ---------------- */
 
 /* One-shot SUM all-reduce of inout[n] (fp64, n <= dcue_peer_allreduce_slot_doubles()) over NVLink peer memory: replaces
  * the 13 latency-bound NCCL all-reduces per data-parallel step (SyncBN statistics; the reference has no multi-GPU path,
  * BASELINE cfg3).  peer_bufs_dev / peer_signals_dev: DEVICE arrays of `world` pointers to every rank's symmetric buffer
- * (2 slots of slot_doubles fp64) and zero-initialised signal pad (>= world uint32); counter: one zero-initialised device
- * uint32 of the calling rank.  Every rank must issue the same sequence of calls.  Result bit-identical on all ranks. */
+ * (2 slots of slot_doubles fp64) and zero-initialised signal pad (>= world uint32); counter: TWO zero-initialised device
+ * uint32 of the calling rank (call counter; [1] is raised when a peer did not answer within 20 s -- the result is then
+ * invalid and the caller must abort).  Every rank must issue the same sequence of calls.  Result bit-identical on all ranks. */
 int dcue_peer_allreduce_f64(const void* peer_bufs_dev, const void* peer_signals_dev, void* counter, int rank, int world,
                             double* inout, int n, void* stream);
 int dcue_peer_allreduce_slot_doubles(void);
@@ -308,6 +326,17 @@ size_t dcue_topk_2pass_ws_bytes(int impl, long n_users, long n_items, int k);
 /* merge `parts` per-shard top-k lists [parts][n_users][k] into one (song-sharded eval). */
 int dcue_topk_merge(const float* scores, const int64_t* idx, int parts, long n_users, int k,
                     float* out_scores, int64_t* out_idx, void* stream);
+
+/* ---------------------------------------------------------------- ranking metrics -------- */
+
+/* ROC-AUC and average precision per segment on the device (replaces sklearn's roc_auc_score / average_precision_score
+ * over Python lists in DCUE.score / DCUE.score_song, dcrecommend/nn/dcue.py:380-476).  Segment i = elements
+ * [seg_offsets[i], seg_offsets[i+1]) of scores / targets (0/1) / group (0/1, nullable = all 0).  Ties are handled like
+ * sklearn (thresholds = distinct scores).  out[i] = double[8]: {AUC of half 0, AUC of half 1, elements in half 0 / 1,
+ * positives in half 0 / 1, AP over the whole segment, positives in the segment}; a half with only positives has AUC 1,
+ * one with no positive AUC 0 (the reference's conventions). */
+int dcue_auc_ap_segments(const float* scores, const uint8_t* targets, const uint8_t* group, const int64_t* seg_offsets,
+                         int n_segments, double* out, void* stream);
 
 #ifdef __cplusplus
 }
