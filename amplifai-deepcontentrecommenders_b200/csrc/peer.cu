@@ -85,3 +85,219 @@ extern "C" int dcue_peer_allreduce_f64(const void* peer_bufs_dev, const void* pe
     DCUE_LAUNCH_CHECK();
     return 0;
 }
+
+// ====================================================================================================================
+// Row-sharded / replicated user table over NVLink peer memory (BASELINE cfg4 and the table-gradient exchange of cfg3).
+//
+// Every rank owns one symmetric "exchange" buffer:  [flags: 2 channels x 64 uint32][pad to 1 KB][idx: cap int64][rows: cap x E f32]
+// and (row-sharded table) keeps its shard of the table itself in symmetric memory.  Then
+//   forward : rows[b] = shard_of_owner(u[b])[local(u[b])] is a plain gather whose loads go over NVLink -- no index
+//             all-to-all, no row all-to-all, no padding traffic (dcue_peer_gather_relu_fwd);
+//   backward: the user-MLP data gradient is written straight into the rank's `rows` slot; ONE single-CTA kernel publishes
+//             the rank's indices, raises a flag in every peer (release.sys), waits for theirs and copies all index lists
+//             (dcue_peer_exchange_i64); the owner then segment-sums the gradient rows it owns, reading them from the peers'
+//             slots in (rank, position) order -- deterministic, bit-identical wherever two ranks sum the same rows
+//             (dcue_peer_scatter_add_rows).
+// Single-slot safety: a rank rewrites its slot only after a barrier that every peer reaches after its previous read
+// (the forward barrier of the sharded table / the SyncBN all-reduces of the data-parallel step).
+// ====================================================================================================================
+namespace {
+
+constexpr int XCH_FLAG_BYTES = 1024;
+constexpr int XCH_CHANNELS = 2;
+
+__device__ __forceinline__ bool peer_wait(const unsigned* pad, unsigned e, unsigned* timeout_flag) {
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
+    while ((int)(ld_acquire_sys(pad) - e) < 0) {
+        __nanosleep(20);
+        if ((++spins & 1023u) == 0) {
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > PEER_TIMEOUT_NS) { atomicExch(timeout_flag, 1u + threadIdx.x); return false; }
+        }
+    }
+    return true;
+}
+
+// counter[0..1]: call counters of the two channels, counter[2]: timeout flag
+__global__ void __launch_bounds__(256)
+peer_exchange_i64_kernel(uint8_t* const* __restrict__ bufs, unsigned* __restrict__ counter, int channel, int rank, int world,
+                         const int64_t* __restrict__ mine, int n, int64_t* __restrict__ all_out) {
+    __shared__ unsigned ep;
+    if (threadIdx.x == 0) ep = ++counter[channel];
+    __syncthreads();
+    const unsigned e = ep;
+    int64_t* my_idx = reinterpret_cast<int64_t*>(bufs[rank] + XCH_FLAG_BYTES);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) my_idx[i] = mine[i];
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        unsigned* peer_flags = reinterpret_cast<unsigned*>(bufs[threadIdx.x]) + channel * 64;
+        st_release_sys(peer_flags + rank, e);
+        const unsigned* my_flags = reinterpret_cast<const unsigned*>(bufs[rank]) + channel * 64;
+        peer_wait(my_flags + threadIdx.x, e, counter + 2);
+    }
+    __syncthreads();
+    if (all_out)
+        for (int r = 0; r < world; ++r) {
+            const int64_t* src = reinterpret_cast<const int64_t*>(bufs[r] + XCH_FLAG_BYTES);
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                int64_t v;
+                asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(src + i) : "memory");
+                all_out[(long)r * n + i] = v;
+            }
+        }
+}
+
+// owner / local row of a global row under the contiguous block partition of parallel.shard_slice
+__device__ __forceinline__ void block_owner(long r, long base, long rem, int& owner, long& local) {
+    const long cut = (base + 1) * rem;
+    if (r < cut) { owner = (int)(r / (base + 1)); local = r - (long)owner * (base + 1); }
+    else { const long q = (r - cut) / base; owner = (int)(rem + q); local = r - cut - q * base; }
+}
+
+__global__ void __launch_bounds__(256)
+peer_gather_relu_kernel(const float* const* __restrict__ shards, long base, long rem, const int64_t* __restrict__ idx, int B, long U,
+                        int E, float* __restrict__ out, float* __restrict__ raw, int* __restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int64_t r = idx[b];
+    float* dst = out + (long)b * E;
+    if (r < 0 || r >= U) {
+        if (lane == 0) atomicExch(err, 1);
+        for (int i = lane; i < E; i += 32) dst[i] = __int_as_float(0x7fc00000);
+        return;
+    }
+    int owner;
+    long local;
+    block_owner(r, base, rem, owner, local);
+    const float* src = shards[owner] + local * (long)E;
+    float* rdst = raw ? raw + (long)b * E : nullptr;
+    if ((E & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        const int n4 = E / 4;
+        for (int i0 = 0; i0 < n4; i0 += 128) {
+            float4 v[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = i0 + t * 32 + lane;
+                if (i < n4) v[t] = __ldcg(s4 + i);          // peer memory: L2 of the owner, not this SM's L1
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = i0 + t * 32 + lane;
+                if (i < n4) {
+                    float4 w = v[t];
+                    if (rdst) reinterpret_cast<float4*>(rdst)[i] = w;
+                    w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f);
+                    reinterpret_cast<float4*>(dst)[i] = w;
+                }
+            }
+        }
+    } else {
+        for (int i = lane; i < E; i += 32) {
+            const float v = __ldcg(src + i);
+            if (rdst) rdst[i] = v;
+            dst[i] = fmaxf(v, 0.f);
+        }
+    }
+}
+
+// warp per entry j of the world*B exchanged (index, gradient row) pairs; see dup_scan_scatter_kernel (embed.cu)
+__global__ void __launch_bounds__(256)
+peer_scatter_add_rows_kernel(uint8_t* const* __restrict__ bufs, long rows_off_bytes, const int64_t* __restrict__ all_idx, int world, int B,
+                             long lo, long hi, int E, float* __restrict__ gshard) {
+    const int lane = threadIdx.x & 31;
+    const int n = world * B;
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (j >= n) return;
+    const int64_t row = all_idx[j];
+    if (row < lo || row >= hi) return;
+    float* dst = gshard + (row - lo) * (long)E;
+    for (int c0 = 0; c0 < E; c0 += 512) {
+        float4 a[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) a[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const int jj = j0 + lane;
+            unsigned m = __ballot_sync(0xffffffffu, jj < n && __ldg(all_idx + jj) == row);
+            if (j0 + 32 <= j) {
+                if (m) return;
+                continue;
+            }
+            if (j0 <= j && (m & ((1u << (j - j0)) - 1u))) return;
+            while (m) {
+                const int pj = j0 + __ffs(m) - 1;
+                m &= m - 1;
+                const int r = pj / B, pos = pj - r * B;
+                const float* src = reinterpret_cast<const float*>(bufs[r] + rows_off_bytes) + (long)pos * E;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int e0 = c0 + t * 128 + lane * 4;
+                    if ((E & 3) == 0) {
+                        if (e0 < E) {
+                            const float4 g = __ldcg(reinterpret_cast<const float4*>(src + e0));
+                            a[t].x += g.x; a[t].y += g.y; a[t].z += g.z; a[t].w += g.w;
+                        }
+                    } else {
+                        float* av = &a[t].x;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (e0 + q < E) av[q] += __ldcg(src + e0 + q);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int e0 = c0 + t * 128 + lane * 4;
+            if ((E & 3) == 0) {
+                if (e0 < E) *reinterpret_cast<float4*>(dst + e0) = a[t];
+            } else {
+                const float* av = &a[t].x;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (e0 + q < E) dst[e0 + q] = av[q];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" size_t dcue_peer_exchange_bytes(int capacity_rows, int E) {
+    return (size_t)XCH_FLAG_BYTES + (size_t)capacity_rows * 8 + (size_t)capacity_rows * E * 4;
+}
+extern "C" size_t dcue_peer_exchange_rows_offset(int capacity_rows) { return (size_t)XCH_FLAG_BYTES + (size_t)capacity_rows * 8; }
+
+extern "C" int dcue_peer_exchange_i64(const void* peer_bufs_dev, void* counter, int channel, int rank, int world, const int64_t* mine,
+                                      int n, int64_t* all_out, void* stream) {
+    DCUE_CHECK_ARG(peer_bufs_dev && counter && channel >= 0 && channel < XCH_CHANNELS && world >= 1 && world <= 64 && rank >= 0 &&
+                   rank < world && n >= 0 && (n == 0 || mine));
+    peer_exchange_i64_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((uint8_t* const*)peer_bufs_dev, (unsigned*)counter, channel, rank,
+                                                                  world, mine, n, all_out);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcue_peer_gather_relu_fwd(const void* peer_shards_dev, long U, int world, const int64_t* idx, int B, int E, float* out,
+                                         float* raw_out, int* err_flag, void* stream) {
+    DCUE_CHECK_ARG(peer_shards_dev && idx && out && err_flag && U > 0 && world >= 1 && B >= 0 && E > 0);
+    if (B == 0) return 0;
+    peer_gather_relu_kernel<<<ceil_div_i(B, 8), 256, 0, (cudaStream_t)stream>>>((const float* const*)peer_shards_dev, U / world,
+                                                                                 U % world, idx, B, U, E, out, raw_out, err_flag);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcue_peer_scatter_add_rows(const void* peer_bufs_dev, int capacity_rows, const int64_t* all_idx, int world, int B, long lo,
+                                          long hi, int E, float* grad_shard, void* stream) {
+    DCUE_CHECK_ARG(peer_bufs_dev && all_idx && grad_shard && world >= 1 && B >= 0 && B <= capacity_rows && hi >= lo && E > 0);
+    if (B == 0 || hi == lo) return 0;
+    peer_scatter_add_rows_kernel<<<ceil_div_i((long)world * B, 8), 256, 0, (cudaStream_t)stream>>>(
+        (uint8_t* const*)peer_bufs_dev, (long)dcue_peer_exchange_rows_offset(capacity_rows), all_idx, world, B, lo, hi, E, grad_shard);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}

@@ -73,6 +73,17 @@ def _topk_exact(user_factors, inn, Kp, n_items, k, item_offset):
     return scores, idx
 
 
+def merge_topk_parts(s, i):
+    """[parts, U, k] stacked per-shard lists (each descending) -> merged (scores [U,k], idx [U,k]); no staging copy."""
+    s, i = s.contiguous(), i.contiguous()
+    parts, n_users, k = s.shape
+    out_s = torch.empty(n_users, k, dtype=torch.float32, device=s.device)
+    out_i = torch.empty(n_users, k, dtype=torch.int64, device=s.device)
+    if n_users:
+        L.call("dcue_topk_merge", s.data_ptr(), i.data_ptr(), parts, n_users, k, out_s.data_ptr(), out_i.data_ptr(), L.stream())
+    return out_s, out_i
+
+
 def merge_topk(scores_parts, idx_parts):
     """Merge per-shard top-k lists ([parts][U,k], each descending) into the global top-k
     (song-sharded eval: one part per GPU)."""

@@ -462,9 +462,18 @@ class UserTowerFn(torch.autograd.Function):
             # data parallel: exchange the B ReLU-masked gradient rows (+ their indices) instead of all-reducing the
             # dense [U,E] gradient (1.2 MB per rank instead of 24 MB at cfg3); every rank then segment-sums the same
             # world*B rows in the same order, so the dense gradient is already the global sum and identical everywhere
-            drows = torch.empty(B, E, **f32)
-            L.call("dcue_linear_dgrad", dh1.data_ptr(), E, w1.data_ptr(), B, E, E, h0.data_ptr(), E, drows.data_ptr(), E, st)
-            gtable = scatter_rows(dp.all_gather_rows(idx), dp.all_gather_rows(drows), U)
+            xch = dp.table_exchange(B, E, dev) if hasattr(dp, "table_exchange") else None
+            if xch is not None:
+                # NVLink peer memory: the masked gradient rows are written straight into this rank's exchange slot, one
+                # single-CTA kernel publishes the indices + barriers, and every rank sums all world*B rows in (rank, position)
+                # order reading them from the peers' slots -- no NCCL all-gather, no staging copies
+                xch.barrier(0)          # every peer has finished reading the previous step's rows
+                L.call("dcue_linear_dgrad", dh1.data_ptr(), E, w1.data_ptr(), B, E, E, h0.data_ptr(), E, xch.rows.data_ptr(), E, st)
+                gtable = xch.scatter_add(xch.exchange_indices(idx), B, 0, U)
+            else:
+                drows = torch.empty(B, E, **f32)
+                L.call("dcue_linear_dgrad", dh1.data_ptr(), E, w1.data_ptr(), B, E, E, h0.data_ptr(), E, drows.data_ptr(), E, st)
+                gtable = scatter_rows(dp.all_gather_rows(idx), dp.all_gather_rows(drows), U)
         elif ctx.needs_input_grad[1]:
             dh0 = torch.empty(B, E, **f32)  # ReLU mask of the gather is applied in the scatter kernel
             L.call("dcue_linear_dgrad", dh1.data_ptr(), E, w1.data_ptr(), B, E, E, None, 0, dh0.data_ptr(), E, st)

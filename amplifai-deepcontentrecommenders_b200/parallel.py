@@ -53,7 +53,7 @@ class PeerAllReduce:
         pg = group if group is not None else dist.group.WORLD
         self.buf = symm.empty(2 * self.slot, dtype=torch.float64, device=device)
         self.hdl = symm.rendezvous(self.buf, pg.group_name)
-        self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self.counter = torch.zeros(2, dtype=torch.int32, device=device)     # [call counter, time-out flag]
         self.rank, self.world = self.hdl.rank, self.hdl.world_size
         if self.hdl.signal_pad_size < 4 * self.world:
             raise RuntimeError("signal pad too small")
@@ -61,6 +61,61 @@ class PeerAllReduce:
     def __call__(self, t):
         self.L.call("dcue_peer_allreduce_f64", self.hdl.buffer_ptrs_dev, self.hdl.signal_pad_ptrs_dev, self.counter.data_ptr(),
                     self.rank, self.world, t.data_ptr(), t.numel(), self.L.stream())
+
+    def check(self):
+        """Raise if a peer did not answer within the kernel's time-out (a rank died or raised): host sync."""
+        if int(self.counter[1].item()):
+            raise RuntimeError("peer all-reduce timed out waiting for another rank")
+
+
+class PeerExchange:
+    """Symmetric exchange buffer for (user index, gradient row) pairs over NVLink peer memory (csrc/peer.cu): every rank
+    writes its rows into its own slot, one single-CTA kernel publishes the indices + barriers + collects all index lists,
+    and the owner reads the rows it needs straight from the peers' slots."""
+
+    def __init__(self, group, device, capacity, E):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib as L
+        self.L = L
+        pg = group if group is not None else dist.group.WORLD
+        capacity = (capacity + 1) // 2 * 2
+        self.capacity, self.E = capacity, E
+        nbytes = L.query("dcue_peer_exchange_bytes", capacity, E)
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, pg.group_name)
+        self.rank, self.world = self.hdl.rank, self.hdl.world_size
+        off = L.query("dcue_peer_exchange_rows_offset", capacity)
+        self.rows = self.buf[off: off + capacity * E * 4].view(torch.float32).view(capacity, E)   # this rank's rows slot
+        self.counter = torch.zeros(3, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)          # every rank's flags are zero before the first exchange
+
+    def barrier(self, channel=0):
+        self.L.call("dcue_peer_exchange_i64", self.hdl.buffer_ptrs_dev, self.counter.data_ptr(), channel, self.rank, self.world,
+                    None, 0, None, self.L.stream())
+
+    def exchange_indices(self, idx, channel=1):
+        """Publish idx [B] int64, barrier, -> all ranks' indices [world*B] in rank order."""
+        idx = idx.contiguous()
+        B = idx.numel()
+        if B > self.capacity:
+            raise ValueError("exchange capacity %d < batch %d" % (self.capacity, B))
+        out = torch.empty(self.world * B, dtype=torch.int64, device=idx.device)
+        self.L.call("dcue_peer_exchange_i64", self.hdl.buffer_ptrs_dev, self.counter.data_ptr(), channel, self.rank, self.world,
+                    idx.data_ptr(), B, out.data_ptr(), self.L.stream())
+        return out
+
+    def scatter_add(self, all_idx, B, lo, hi):
+        """Dense [hi-lo, E] sum of every rank's rows slot entries whose index falls in [lo, hi)."""
+        out = torch.zeros(hi - lo, self.E, dtype=torch.float32, device=all_idx.device)
+        self.L.call("dcue_peer_scatter_add_rows", self.hdl.buffer_ptrs_dev, self.capacity, all_idx.data_ptr(), self.world, B, lo, hi,
+                    self.E, out.data_ptr(), self.L.stream())
+        return out
+
+    def check(self):
+        if int(self.counter[2].item()):
+            raise RuntimeError("peer exchange timed out waiting for another rank")
 
 
 class DataParallelDCUE:
@@ -81,6 +136,7 @@ class DataParallelDCUE:
                 self._peer = PeerAllReduce(group, params[0].device)
             except Exception as exc:  # noqa: BLE001  (no peer access / symmetric memory unavailable)
                 print("DataParallelDCUE: peer all-reduce unavailable (%s); using NCCL for the BatchNorm statistics" % exc)
+        self._xch = None          # PeerExchange for the table-gradient rows, created on first use (needs the batch size)
         if hasattr(model.user_embd, "embeddings"):      # replicated table: row exchange instead of a dense all-reduce
             model.user_embd._dp = self if (self.world_size > 1 and row_exchange()) else None
         if broadcast and self.world_size > 1:
@@ -94,6 +150,22 @@ class DataParallelDCUE:
                 self._peer(t)
             else:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def table_exchange(self, B, E, device):
+        """PeerExchange for B (index, gradient row) pairs per rank, or None when peer memory is not in use (then the rows
+        travel by NCCL all-gather)."""
+        if self._peer is None or os.environ.get("DCUE_DP_PEER_ROWS", "1") == "0":
+            return None
+        if self._xch is None or self._xch.capacity < B or self._xch.E != E:
+            self._xch = PeerExchange(self.group, device, B, E)
+        return self._xch
+
+    def check_peers(self):
+        """Host-side check of the peer kernels' time-out flags (a rank that died would otherwise go unnoticed)."""
+        if self._peer is not None:
+            self._peer.check()
+        if self._xch is not None:
+            self._xch.check()
 
     def all_gather_rows(self, t):
         """[n, ...] on every rank -> [world*n, ...] in rank order."""
@@ -136,6 +208,19 @@ def shard_rows(n_rows, rank, world):
     return shard_slice(n_rows, rank, world)
 
 
+def owner_of_rows(idx, n_rows, world):
+    """Owner rank of every global row index under shard_slice's block partition (the arithmetic of csrc/peer.cu
+    block_owner) and the row's position inside the owner's shard."""
+    base, rem = divmod(n_rows, world)
+    cut = (base + 1) * rem
+    small = idx < cut
+    own_a = torch.div(idx, base + 1, rounding_mode="floor")
+    q = torch.div((idx - cut).clamp_min(0), max(base, 1), rounding_mode="floor")
+    owner = torch.where(small, own_a, rem + q)
+    local = torch.where(small, idx - own_a * (base + 1), idx - cut - q * base)
+    return owner, local
+
+
 def local_row_index(all_idx, lo, hi):
     """Map global row indices to this owner's local rows; rows owned by other ranks map to the sentinel
     (hi - lo).  Returns (local_idx int64, owned bool)."""
@@ -144,47 +229,113 @@ def local_row_index(all_idx, lo, hi):
     return local, owned
 
 
-class _ShardedRowsFn(torch.autograd.Function):
-    """rows[b] = table[u[b]] for a table whose rows are block-sharded over the ranks.
-    forward : all_gather(indices) -> every owner gathers the rows it holds (zeros elsewhere)
-              -> all_to_all of the gathered rows back to the requesting ranks -> sum over owners
-    backward: all_gather(indices, gradient rows) -> every owner segment-sums the rows it owns into its
-              dense shard gradient (already the GLOBAL sum: it must not be all-reduced again)."""
+def route_to_owners(idx, n_rows, world):
+    """Stable bucketing of a rank's requests by owner: -> (order, counts) with idx[order] grouped by owner rank (request
+    order kept inside a group) and counts[w] = requests for owner w (the all-to-all split sizes)."""
+    owner, _ = owner_of_rows(idx, n_rows, world)
+    order = torch.sort(owner, stable=True).indices
+    counts = torch.bincount(owner, minlength=world)
+    return order, counts
+
+
+class _RoutedRowsFn(torch.autograd.Function):
+    """rows[b] = table[u[b]] for a block-sharded table with torch.distributed collectives only (any backend): SURVEY 8e row 2
+    as written -- all-to-all of the requested indices to their owners, owner-side gather of exactly the requested rows,
+    all-to-all of the rows back; backward routes (index, gradient row) pairs to the owners the same way and the owner
+    segment-sums them into its dense shard gradient (already the GLOBAL sum: not all-reduced again).  Variable split sizes
+    cost one host read of `world` counts per step; the NVLink peer-memory transport (_PeerUserTowerFn) needs neither."""
 
     @staticmethod
-    def forward(ctx, u, shard, lo, hi, group):
-        from . import ops
+    def forward(ctx, u, shard, n_rows, lo, hi, group, gather_fn, scatter_fn):
         world = dist.get_world_size(group)
-        B, E = u.numel(), shard.shape[1]
-        all_idx = torch.empty(world * B, dtype=torch.int64, device=u.device)
-        dist.all_gather_into_tensor(all_idx, u.contiguous().view(-1), group=group)
-        local, owned = local_row_index(all_idx, lo, hi)
-        safe = torch.where(owned, local, torch.zeros_like(local))
-        part = ops.gather_rows(shard, safe) * owned.unsqueeze(1).to(shard.dtype)      # [world*B, E]
-        recv = torch.empty(world, B, E, dtype=shard.dtype, device=u.device)
-        dist.all_to_all_single(recv.view(world * B, E), part, group=group)           # row exchange over NVLink
-        ctx.save_for_backward(all_idx)
-        ctx.meta = (lo, hi, group, B, E)
-        return recv.sum(dim=0)                                                        # exactly one owner contributes
+        u = u.contiguous().view(-1)
+        order, counts = route_to_owners(u, n_rows, world)
+        send_counts = counts.tolist()
+        recv_counts_t = torch.empty_like(counts)
+        dist.all_to_all_single(recv_counts_t, counts, group=group)
+        recv_counts = recv_counts_t.tolist()
+        req = torch.empty(sum(recv_counts), dtype=torch.int64, device=u.device)
+        dist.all_to_all_single(req, u[order].contiguous(), recv_counts, send_counts, group=group)     # indices -> owners
+        rows_out = gather_fn(shard, req - lo)                                                        # only owned rows
+        back = torch.empty(u.numel(), shard.shape[1], dtype=shard.dtype, device=u.device)
+        dist.all_to_all_single(back, rows_out.contiguous(), send_counts, recv_counts, group=group)   # rows -> requesters
+        rows = torch.empty_like(back)
+        rows[order] = back
+        ctx.save_for_backward(order, req)
+        ctx.meta = (lo, hi, group, send_counts, recv_counts, scatter_fn)
+        return rows
 
     @staticmethod
     def backward(ctx, grows):
-        from . import ops
-        (all_idx,) = ctx.saved_tensors
-        lo, hi, group, B, E = ctx.meta
-        world = dist.get_world_size(group)
-        all_g = torch.empty(world * B, E, dtype=grows.dtype, device=grows.device)
-        dist.all_gather_into_tensor(all_g, grows.contiguous(), group=group)
-        local, _ = local_row_index(all_idx, lo, hi)
-        gshard = ops.scatter_rows(local, all_g, hi - lo)
-        return None, gshard, None, None, None
+        order, req = ctx.saved_tensors
+        lo, hi, group, send_counts, recv_counts, scatter_fn = ctx.meta
+        g_in = torch.empty(req.numel(), grows.shape[1], dtype=grows.dtype, device=grows.device)
+        dist.all_to_all_single(g_in, grows.contiguous()[order].contiguous(), recv_counts, send_counts, group=group)
+        # NOTE the order of summation: requests arrive grouped by requesting rank, in request order -> deterministic
+        gshard = scatter_fn(req - lo, g_in, hi - lo)
+        return None, gshard, None, None, None, None, None, None
+
+
+class _PeerUserTowerFn(torch.autograd.Function):
+    """u_f = linear2(relu(linear1(relu(table[u])))) for a table block-sharded in NVLink peer (symmetric) memory.
+    forward : barrier (every owner finished its previous optimizer step), then ONE gather kernel whose row loads go over
+              NVLink to the owning GPU -- no index exchange, no row all-to-all;
+    backward: the MLP data gradient (masked by the gather's ReLU) is written into this rank's exchange slot, one kernel
+              publishes the indices + barriers + collects all index lists, the owner sums the gradient rows it owns from
+              the peers' slots in (rank, position) order into the dense shard gradient."""
+
+    @staticmethod
+    def forward(ctx, u, shard, w1, b1, w2, b2, table):
+        from . import _lib as L
+        u = u.contiguous().view(-1)
+        B, E, F = u.numel(), shard.shape[1], w2.shape[0]
+        dev, st = shard.device, L.stream()
+        f32 = dict(dtype=torch.float32, device=dev)
+        h0, h1, out = torch.empty(B, E, **f32), torch.empty(B, E, **f32), torch.empty(B, F, **f32)
+        table.xch.barrier(0)
+        L.call("dcue_peer_gather_relu_fwd", table.shard_ptrs_dev, table.user_count, table.world_size, u.data_ptr(), B, E,
+               h0.data_ptr(), None, table.err_flag().data_ptr(), st)
+        L.call("dcue_linear_fwd", h0.data_ptr(), E, w1.data_ptr(), b1.data_ptr(), B, E, E, 1, h1.data_ptr(), E, st)
+        L.call("dcue_linear_fwd", h1.data_ptr(), E, w2.data_ptr(), b2.data_ptr(), B, E, F, 0, out.data_ptr(), F, st)
+        ctx.save_for_backward(u, w1, w2, h0, h1)
+        ctx.table = table
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        from . import _lib as L
+        u, w1, w2, h0, h1 = ctx.saved_tensors
+        table = ctx.table
+        B, E, F = u.numel(), h0.shape[1], w2.shape[0]
+        dev, st = h0.device, L.stream()
+        f32 = dict(dtype=torch.float32, device=dev)
+        gout = gout.contiguous().view(B, F)
+        nscr = max(L.query("dcue_linear_wgrad_ws_bytes", B, E, F), L.query("dcue_linear_wgrad_ws_bytes", B, E, E))
+        scratch = torch.empty(nscr, dtype=torch.uint8, device=dev)
+        gw2, gb2 = torch.empty(F, E, **f32), torch.empty(F, **f32)
+        L.call("dcue_linear_wgrad", gout.data_ptr(), F, h1.data_ptr(), E, B, E, F, gw2.data_ptr(), gb2.data_ptr(),
+               scratch.data_ptr(), nscr, st)
+        dh1 = torch.empty(B, E, **f32)
+        L.call("dcue_linear_dgrad", gout.data_ptr(), F, w2.data_ptr(), B, E, F, h1.data_ptr(), E, dh1.data_ptr(), E, st)
+        gw1, gb1 = torch.empty(E, E, **f32), torch.empty(E, **f32)
+        L.call("dcue_linear_wgrad", dh1.data_ptr(), E, h0.data_ptr(), E, B, E, E, gw1.data_ptr(), gb1.data_ptr(),
+               scratch.data_ptr(), nscr, st)
+        xch = table.xch
+        # single exchange slot: the forward barrier of this step came after every peer's previous scatter
+        L.call("dcue_linear_dgrad", dh1.data_ptr(), E, w1.data_ptr(), B, E, E, h0.data_ptr(), E, xch.rows.data_ptr(), E, st)
+        gshard = xch.scatter_add(xch.exchange_indices(u), B, table.lo, table.hi)
+        return None, gshard, gw1, gb1, gw2, gb2, None
 
 
 class ShardedUserTable(torch.nn.Module):
     """Row-sharded replacement for UserEmbeddings' lookup table (BASELINE cfg4: 1M users x 300 over 8 GPUs).
-    Each rank owns rows [lo, hi) (+ its optimizer state); the MLP stays replicated / data parallel."""
+    Each rank owns rows [lo, hi) (+ its optimizer state); the MLP stays replicated / data parallel.
 
-    def __init__(self, user_embd, group=None):
+    transport="peer" (default on CUDA + NCCL): the shard lives in symmetric memory and rows / gradient rows move by
+    NVLink loads inside the gather / scatter kernels (csrc/peer.cu).  transport="collective": torch.distributed
+    all-to-all of indices and rows (any backend; also what the CPU/gloo tests drive)."""
+
+    def __init__(self, user_embd, group=None, transport=None, capacity=None, gather_fn=None, scatter_fn=None):
         super().__init__()
         from . import ops
         self._ops = ops
@@ -192,19 +343,59 @@ class ShardedUserTable(torch.nn.Module):
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         full = user_embd.embeddings.weight.detach()
-        self.user_count = full.shape[0]
+        self.user_count, E = full.shape
         self.lo, self.hi = shard_rows(self.user_count, self.rank, self.world_size)
-        self.shard = torch.nn.Parameter(full[self.lo:self.hi].clone())
+        if transport is None:
+            transport = "peer" if (full.is_cuda and dist.get_backend(group) == "nccl"
+                                   and os.environ.get("DCUE_SHARD_TRANSPORT", "peer") == "peer") else "collective"
+        self.transport = transport
         self.linear1, self.linear2 = user_embd.linear1, user_embd.linear2
+        self._gather_fn = gather_fn or ops.gather_rows
+        self._scatter_fn = scatter_fn or (lambda idx, rows, n: ops.scatter_rows(idx, rows, n))
+        self._err = None
+        self.xch = None
+        if transport == "peer":
+            import torch.distributed._symmetric_memory as symm
+            pg = group if group is not None else dist.group.WORLD
+            # every rank allocates the same size (symmetric): the largest shard
+            rows_max = self.user_count // self.world_size + (1 if self.user_count % self.world_size else 0)
+            buf = symm.empty(rows_max * E, dtype=torch.float32, device=full.device)
+            self._shard_hdl = symm.rendezvous(buf, pg.group_name)
+            self.shard_ptrs_dev = self._shard_hdl.buffer_ptrs_dev
+            shard = buf[: (self.hi - self.lo) * E].view(self.hi - self.lo, E)
+            shard.copy_(full[self.lo:self.hi])
+            self.shard = torch.nn.Parameter(shard)
+            self._capacity = capacity
+        else:
+            self.shard = torch.nn.Parameter(full[self.lo:self.hi].clone())
+
+    def err_flag(self):
+        if self._err is None or self._err.device != self.shard.device:
+            self._err = torch.zeros(1, dtype=torch.int32, device=self.shard.device)
+        return self._err
+
+    _err_flag = err_flag
 
     def forward(self, user_idx):
         shape = user_idx.shape
-        rows = _ShardedRowsFn.apply(user_idx.reshape(-1).to(self.shard.device), self.shard, self.lo, self.hi, self.group)
-        out = self._ops.UserMLPFn.apply(rows, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias)
+        u = user_idx.reshape(-1).to(self.shard.device)
+        if self.transport == "peer":
+            if self.xch is None or self.xch.capacity < u.numel():
+                self.xch = PeerExchange(self.group, self.shard.device, max(u.numel(), self._capacity or 0), self.shard.shape[1])
+            out = _PeerUserTowerFn.apply(u, self.shard, self.linear1.weight, self.linear1.bias, self.linear2.weight,
+                                         self.linear2.bias, self)
+        else:
+            rows = _RoutedRowsFn.apply(u, self.shard, self.user_count, self.lo, self.hi, self.group, self._gather_fn,
+                                       self._scatter_fn)
+            out = self._ops.UserMLPFn.apply(rows, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias)
         return out.view(*shape, -1)
 
     def raise_if_index_error(self):
-        pass
+        if self._err is not None and int(self._err.item()):
+            self._err.zero_()
+            raise IndexError("index out of range in self")
+        if self.xch is not None:
+            self.xch.check()
 
     def gather_full_table(self):
         """[U,E] table on every rank (for checkpoints in the reference's state_dict layout)."""
@@ -217,22 +408,97 @@ class ShardedUserTable(torch.nn.Module):
         return torch.cat([o[: h - l] for o, (l, h) in zip(out, sizes)])
 
 
-def shard_user_table(model, group=None):
+def shard_user_table(model, group=None, transport=None, capacity=None):
     """Replace model.user_embd by its row-sharded version (call before building the optimizer)."""
-    model.user_embd = ShardedUserTable(model.user_embd, group)
+    model.user_embd = ShardedUserTable(model.user_embd, group, transport, capacity)
     return model
 
 
-def sharded_topk(user_factors, item_factors_local, k, item_offset, group=None):
-    """Song-sharded eval: every rank scores all users against ITS songs, then the per-rank top-k
-    lists are all-gathered and merged (k-way merge kernel).  Returns the global top-k on every rank."""
+# ------------------------------------------------------------------------------ song-sharded eval (cfg5)
+def user_block(n_users, rank, world):
+    """Users whose merged top-k lives on `rank`: contiguous block [lo, hi) of shard_slice."""
+    return shard_slice(n_users, rank, world)
+
+
+def exchange_topk_by_user_block(s, i, group=None):
+    """Per-rank top-k lists [U,k] (this rank's songs) -> [world, U_r, k] lists of the users in THIS rank's block, one part
+    per song shard (all-to-all by user block, SURVEY 8e row 3: each rank receives W x U/W x k pairs instead of the
+    W x U x k of an all-gather)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    U, k = s.shape
+    sizes = [b - a for a, b in (user_block(U, r, world) for r in range(world))]
+    mine = sizes[rank]
+    s_parts = torch.empty(world, mine, k, dtype=s.dtype, device=s.device)
+    i_parts = torch.empty(world, mine, k, dtype=i.dtype, device=i.device)
+    send = [n * k for n in sizes]
+    recv = [mine * k] * world
+    dist.all_to_all_single(s_parts.view(-1), s.contiguous().view(-1), recv, send, group=group)
+    dist.all_to_all_single(i_parts.view(-1), i.contiguous().view(-1), recv, send, group=group)
+    return s_parts, i_parts
+
+
+def sharded_topk(user_factors, item_factors_local, k, item_offset, group=None, gather=False, user_tile=None):
+    """Song-sharded eval (BASELINE cfg5): every rank scores all users against ITS songs (fused score GEMM + top-k), the
+    per-rank lists are exchanged all-to-all BY USER BLOCK and every rank merges only its own U/W users.
+    -> (scores [U_r,k], song idx [U_r,k], (lo, hi)) for this rank's user block; gather=True all-gathers the merged blocks so
+    that every rank returns the full [U,k] (only when the caller needs it: the merged result is 8x smaller than the
+    exchange).  With user_tile the users are processed in tiles so that the exchange of tile t overlaps the scoring of
+    tile t+1 (the all-to-all runs on NCCL's stream)."""
     from . import eval as ev
-    s, i = ev.topk_scores(user_factors, item_factors_local, k, item_offset=item_offset)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
-        return s, i
-    ss = [torch.empty_like(s) for _ in range(world)]
-    ii = [torch.empty_like(i) for _ in range(world)]
-    dist.all_gather(ss, s, group=group)
-    dist.all_gather(ii, i, group=group)
-    return ev.merge_topk(ss, ii)
+        s, i = ev.topk_scores(user_factors, item_factors_local, k, item_offset=item_offset)
+        return (s, i) if gather else (s, i, (0, user_factors.shape[0]))
+    rank = dist.get_rank(group)
+    U = user_factors.shape[0]
+    lo, hi = user_block(U, rank, world)
+    packed_items = ev.normalize_factors(item_factors_local)
+    if user_tile is None:
+        user_tile = int(os.environ.get("DCUE_EVAL_USER_TILE", "0")) or U
+    # a tile = the same sub-range of every rank's block, so that each tile's exchange is itself an all-to-all by block
+    n_tiles = max(1, -(-U // user_tile))
+    out_s = torch.empty(hi - lo, k, dtype=torch.float32, device=user_factors.device)
+    out_i = torch.empty(hi - lo, k, dtype=torch.int64, device=user_factors.device)
+    blocks = [user_block(U, r, world) for r in range(world)]
+    pending = None
+
+    def finish(p):
+        works, s_parts, i_parts, (x, y), _keep = p
+        for w in works:
+            w.wait()                      # stream-side wait: the merge kernel follows the exchange
+        ms, mi = ev.merge_topk_parts(s_parts, i_parts)
+        out_s[x:y], out_i[x:y] = ms, mi
+
+    for t in range(n_tiles):
+        sub = [shard_slice(b - a, t, n_tiles) for a, b in blocks]           # sub-range of every block
+        if n_tiles == 1:
+            uf = user_factors
+        else:
+            rows = torch.cat([torch.arange(a + x, a + y, device=user_factors.device) for (a, _), (x, y) in zip(blocks, sub)])
+            uf = user_factors[rows]
+        s, i = ev.topk_scores(uf, item_factors_local, k, item_offset=item_offset, normalized_items=packed_items)
+        sizes = [y - x for x, y in sub]
+        mine = sizes[rank]
+        s_parts = torch.empty(world, mine, k, dtype=s.dtype, device=s.device)
+        i_parts = torch.empty(world, mine, k, dtype=i.dtype, device=i.device)
+        send, recv = [n * k for n in sizes], [mine * k] * world
+        # asynchronous: the exchange of tile t runs on NCCL's stream while the scorer works on tile t+1
+        works = [dist.all_to_all_single(s_parts.view(-1), s.view(-1), recv, send, group=group, async_op=True),
+                 dist.all_to_all_single(i_parts.view(-1), i.view(-1), recv, send, group=group, async_op=True)]
+        if pending is not None:
+            finish(pending)
+        pending = (works, s_parts, i_parts, sub[rank], (s, i))
+    finish(pending)
+    if not gather:
+        return out_s, out_i, (lo, hi)
+    m = max(b - a for a, b in blocks)
+    pad_s = torch.zeros(m, k, dtype=out_s.dtype, device=out_s.device)
+    pad_i = torch.zeros(m, k, dtype=out_i.dtype, device=out_i.device)
+    pad_s[: hi - lo], pad_i[: hi - lo] = out_s, out_i
+    all_s = torch.empty(world, m, k, dtype=out_s.dtype, device=out_s.device)
+    all_i = torch.empty(world, m, k, dtype=out_i.dtype, device=out_i.device)
+    dist.all_gather_into_tensor(all_s.view(-1), pad_s.view(-1), group=group)
+    dist.all_gather_into_tensor(all_i.view(-1), pad_i.view(-1), group=group)
+    return (torch.cat([all_s[r, : b - a] for r, (a, b) in enumerate(blocks)]),
+            torch.cat([all_i[r, : b - a] for r, (a, b) in enumerate(blocks)]))

@@ -301,6 +301,27 @@ int dcue_peer_allreduce_f64(const void* peer_bufs_dev, const void* peer_signals_
                             double* inout, int n, void* stream);
 int dcue_peer_allreduce_slot_doubles(void);
 
+/* User table over NVLink peer memory (BASELINE cfg4: table row-sharded over the GPUs; cfg3: exchange of the table-gradient
+ * rows).  Every rank owns a zero-initialised symmetric "exchange" buffer of dcue_peer_exchange_bytes(capacity, E) bytes
+ * ([flags][idx: capacity int64][rows: capacity x E f32], the rows start at dcue_peer_exchange_rows_offset(capacity));
+ * peer_bufs_dev = DEVICE array of `world` pointers to them.  counter = 3 zero-initialised device uint32 of the calling rank
+ * (call counters of the two flag channels, [2] = time-out flag as in dcue_peer_allreduce_f64).
+ * dcue_peer_exchange_i64: publish mine[n] in my idx slot, barrier over all ranks (channel 0 or 1), copy every rank's list
+ *   to all_out[world][n] (nullable; n == 0 = pure barrier).  Every rank issues the same sequence of calls per channel.
+ * dcue_peer_gather_relu_fwd: as dcue_gather_relu_fwd for a table whose rows are block-sharded (rank r owns
+ *   [r*U/W + min(r, U%W), ...)) in symmetric memory: peer_shards_dev = `world` pointers to the shards; rows come over NVLink.
+ * dcue_peer_scatter_add_rows: grad_shard[row - lo] = sum of the gradient rows (read from the peers' `rows` slots) whose index
+ *   (all_idx from dcue_peer_exchange_i64) is `row`, for lo <= row < hi, summed in (rank, position) order.  grad_shard zeroed
+ *   by the caller. */
+size_t dcue_peer_exchange_bytes(int capacity_rows, int E);
+size_t dcue_peer_exchange_rows_offset(int capacity_rows);
+int dcue_peer_exchange_i64(const void* peer_bufs_dev, void* counter, int channel, int rank, int world, const int64_t* mine,
+                           int n, int64_t* all_out, void* stream);
+int dcue_peer_gather_relu_fwd(const void* peer_shards_dev, long U, int world, const int64_t* idx, int B, int E, float* out,
+                              float* raw_out, int* err_flag, void* stream);
+int dcue_peer_scatter_add_rows(const void* peer_bufs_dev, int capacity_rows, const int64_t* all_idx, int world, int B, long lo,
+                               long hi, int E, float* grad_shard, void* stream);
+
 /* ---------------------------------------------------------------- eval scorer ------------ */
 
 /* row-normalise factors (x / max(||x||,eps)) into 16-bit K-major rows padded to Kp (mult of 16). */

@@ -59,8 +59,45 @@ def run(model_type):
     return out
 
 
+def run_cfg1(model_type="truedcuemel1dbn", B1=64, N1=20, U1=20000):
+    """BASELINE configs[0] (cfg1) shape: batch 64, 20 negatives, 20 000 users, fp32 CPU reference.  Stores the loss, scores,
+    feature vectors, EVERY tower / user-MLP gradient in full, the touched rows of the dense table gradient and the
+    BatchNorm buffers after the step."""
+    p = fixtures.make_params(model_type, seed=0, user_count=U1)
+    u, pos, neg = fixtures.make_inputs(B1, N1, U1, seed=1)
+    u[1] = u[0]
+    m = DCUENet({"feature_dim": 100, "conv_hidden": 128, "user_embdim": 300, "user_count": U1, "model_type": model_type})
+    m.load_state_dict(p)
+    trainer = DCUE(margin=MARGIN)
+    m.train()
+    m.zero_grad()
+    scores, u_f, pos_f, neg_f = m(u, pos, neg)
+    loss = trainer._loss_func(scores)
+    loss.backward()
+    out = {"model_type": model_type, "B": B1, "N": N1, "U": U1, "margin": MARGIN, "u": u,
+           "train_loss": loss.detach(), "train_scores": scores.detach(), "train_u_f": u_f.detach(),
+           "train_pos_f": pos_f.detach(), "train_neg_f": neg_f.detach()}
+    out["grads"] = {k: v.grad.detach().clone() for k, v in m.named_parameters() if k != "user_embd.embeddings.weight"}
+    tg = m.user_embd.embeddings.weight.grad
+    rows = torch.unique(u)
+    out["table_grad_rows"] = rows
+    out["table_grad"] = tg[rows].clone()
+    out["table_grad_norm"] = tg.double().norm()
+    out["buffers_after"] = {k: v.detach().clone() for k, v in m.named_buffers()}
+    m.load_state_dict(p)
+    m.eval()
+    with torch.no_grad():
+        scores, u_f, pos_f, neg_f = m(u, pos, neg)
+        out.update(eval_scores=scores, eval_pos_f=pos_f, eval_neg_f=neg_f, eval_loss=trainer._loss_func(scores))
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--cfg1" in sys.argv:
+        torch.save(run_cfg1(), os.path.join(OUT, "ref_cfg1_truedcuemel1dbn.pt"))
+        print("wrote cfg1 golden")
+        return
     torch.set_num_threads(1)  # deterministic summation order
     for mt in ("truedcuemel1d", "truedcuemel1dres", "truedcuemel1dbn", "truedcuemel1dresbn"):
         torch.save(run(mt), os.path.join(OUT, "ref_%s.pt" % mt))

@@ -540,3 +540,221 @@ def test_single_pass_center_pack_stats():
     assert relerr(out[1], -(mean - rm.double()) * rstd) < 1e-5
     assert relerr(rmd, 0.9 * rm.double() + 0.1 * mean) < 1e-6              # running_mean tracks the mean of x
     assert relerr(rvd, 0.9 * rv.double() + 0.1 * var * n / (n - 1)) < 1e-6
+
+
+# ------------------------------------------------------------------ round-2 additions
+def test_hinge_tie_at_margin_takes_half_gradient_on_device():
+    """torch.max(0, margin - s) splits the gradient at an exact tie (reference nn/dcue.py:167-170 via torch.max):
+    d loss / d s[b,n] = -0.5/B where s[b,n] == margin.  Scores are computed once on the device and one of them is used as
+    the margin, so the tie is exact in the kernel's own arithmetic."""
+    import math
+    B, N, Fd = 8, 5, 100
+    g = torch.Generator().manual_seed(11)
+    u, feats = torch.randn(B, Fd, generator=g).to(DEV), torch.randn(B * (1 + N), Fd, generator=g).to(DEV)
+    s = ops.ScoreFn.apply(u, feats, B, N)
+    margin = float(s[2, 3])
+
+    def fused(m):
+        ud, fd = u.clone().requires_grad_(True), feats.clone().requires_grad_(True)
+        rows, s2 = ops.HingeScoreFn.apply(ud, fd, B, N, m, B)
+        (rows.sum() / B).backward()
+        assert torch.equal(s2, s)
+        return ud.grad, fd.grad, rows
+
+    du_t, df_t, rows_t = fused(margin)
+    # expected: the un-fused backward with torch.max's sub-gradient as the upstream gradient
+    gs = torch.where(s < margin, torch.ones_like(s), torch.where(s == margin, torch.full_like(s, 0.5), torch.zeros_like(s)))
+    assert float(gs[2, 3]) == 0.5 and int((gs == 0.5).sum()) == 1
+    ud, fd = u.clone().requires_grad_(True), feats.clone().requires_grad_(True)
+    ops.ScoreFn.apply(ud, fd, B, N).backward(-gs / B)
+    assert relerr(du_t, ud.grad) < 1e-6 and relerr(df_t, fd.grad) < 1e-6
+    # and it is exactly the mean of the two one-sided gradients
+    du_lo, df_lo, _ = fused(math.nextafter(margin, -math.inf))
+    du_hi, df_hi, _ = fused(math.nextafter(margin, math.inf))
+    assert relerr(du_t, 0.5 * (du_lo + du_hi)) < 1e-6 and relerr(df_t, 0.5 * (df_lo + df_hi)) < 1e-6
+    assert not torch.equal(du_lo[2], du_hi[2])
+    assert float(rows_t[2]) == float(torch.clamp(margin - s[2], min=0).sum())
+
+
+@pytest.mark.parametrize("B,U,E,masked", [(1024, 20000, 300, True), (257, 50, 300, True), (4096, 3000, 300, False),
+                                          (300, 40, 77, True), (9000, 1000, 300, False)])
+def test_sort_free_scatter_equals_sorted_segment_sum(B, U, E, masked):
+    """dcue_scatter_add_rows (one launch, no sort) == sort + segment sum bit for bit == index_add within fp32 rounding;
+    out-of-range indices are skipped by both kernels and never written outside the table."""
+    g = torch.Generator().manual_seed(B + U)
+    idx = (U * torch.rand(B, generator=g) ** 3).long().clamp_(0, U - 1)
+    idx[5] = U + 7          # out of range: dropped
+    idx[6] = -3
+    rows = torch.randn(B, E, generator=g)
+    mask = torch.randn(B, E, generator=g) if masked else None
+    ref = torch.zeros(U, E, dtype=torch.float64)
+    ok = (idx >= 0) & (idx < U)
+    eff = rows.double() * (mask > 0).double() if masked else rows.double()
+    ref.index_add_(0, idx[ok], eff[ok])
+    idx_d, rows_d = idx.to(DEV), rows.to(DEV)
+    mask_d = None if mask is None else mask.to(DEV)
+    guard = torch.full((U + 64, E), 7.0, device=DEV)          # canary rows after the table
+    out = guard[:U]
+    out.zero_()
+    L.call("dcue_scatter_add_rows", rows_d.data_ptr(), L.ptr(mask_d), idx_d.data_ptr(), B, U, E, out.data_ptr(), L.stream())
+    assert relerr(out, ref) < 1e-6
+    assert bool((guard[U:] == 7.0).all())
+    # sorted path
+    sidx = torch.empty(B, dtype=torch.int64, device=DEV)
+    spos = torch.empty(B, dtype=torch.int32, device=DEV)
+    nscr = L.query("dcue_sort_ws_bytes", B)
+    scr = torch.empty(nscr, dtype=torch.uint8, device=DEV)
+    safe = torch.where(ok, idx, torch.full_like(idx, U)).to(DEV)   # the sort keys must fit the key width: use the sentinel
+    L.call("dcue_sort_indices", safe.data_ptr(), B, U + 1, sidx.data_ptr(), spos.data_ptr(), scr.data_ptr(), nscr, L.stream())
+    guard2 = torch.full((U + 64, E), 7.0, device=DEV)
+    out2 = guard2[:U]
+    out2.zero_()
+    m2 = mask_d if masked else torch.ones_like(rows_d)
+    L.call("dcue_scatter_add_bwd", rows_d.data_ptr(), m2.data_ptr(), sidx.data_ptr(), spos.data_ptr(), B, U, E, out2.data_ptr(),
+           L.stream())
+    assert torch.equal(out, out2)
+    assert bool((guard2[U:] == 7.0).all())
+    assert torch.equal(ops.scatter_rows(idx_d, rows_d, U, mask=mask_d), out)
+
+
+def test_bad_user_index_never_reaches_the_parameters():
+    """an out-of-range user index must not write outside the table gradient, and the guarded fused Adam leaves
+    parameters and moments untouched for that step; IndexError surfaces when the flags are read."""
+    from oracle import fixtures
+    mt, B, N, U = "truedcuemel1dbn", 6, 2, 40
+    params = fixtures.make_params(mt, seed=0, user_count=U)
+    u, pos, neg = fixtures.make_inputs(B, N, U, seed=1)
+    net = pkg.DCUENet({"feature_dim": 100, "conv_hidden": 128, "user_embdim": 300, "user_count": U, "model_type": mt})
+    net.load_state_dict(params)
+    net = net.to(DEV).train()
+    opt = pkg.optim.FusedAdam(net.parameters(), 1e-3, (0.9, 0.99), 1e-8, 0)
+    opt.set_skip_flags(net.error_flags())
+    net.hinge_loss_step(u.to(DEV), pos.to(DEV), neg.to(DEV), 0.2).backward()
+    opt.step()                                       # a good step moves the parameters
+    before = {k: v.detach().clone() for k, v in net.named_parameters()}
+    m_before = {k: opt.state[p]["exp_avg"].clone() for k, p in net.named_parameters()}
+    assert not torch.equal(before["conv.fc.weight"], params["conv.fc.weight"].to(DEV))
+    bad = u.clone()
+    bad[2] = U + 1000
+    net.zero_grad(set_to_none=True)
+    loss = net.hinge_loss_step(bad.to(DEV), pos.to(DEV), neg.to(DEV), 0.2)
+    loss.backward()
+    opt.step()
+    torch.cuda.synchronize()
+    assert torch.isnan(loss)
+    for k, p in net.named_parameters():
+        assert torch.equal(p.detach(), before[k]), k
+        assert torch.equal(opt.state[p]["exp_avg"], m_before[k]), k
+    with pytest.raises(IndexError):
+        net.raise_if_index_error()
+    # after the flag is cleared training continues
+    net.zero_grad(set_to_none=True)
+    net.hinge_loss_step(u.to(DEV), pos.to(DEV), neg.to(DEV), 0.2).backward()
+    opt.step()
+    assert not torch.equal(net.conv.fc.weight.detach(), before["conv.fc.weight"])
+
+
+def test_fused_adam_survives_load_state_dict():
+    """the cached pointer table must follow the state tensors that load_state_dict installs."""
+    torch.manual_seed(0)
+    ps_a = [torch.nn.Parameter(torch.randn(1000, 300, device=DEV)), torch.nn.Parameter(torch.randn(77, device=DEV))]
+    ps_b = [torch.nn.Parameter(p.detach().clone()) for p in ps_a]
+    oa = pkg.optim.FusedAdam(ps_a, 1e-2, (0.9, 0.99), 1e-8, 0.0)
+    ob = torch.optim.Adam(ps_b, 1e-2, (0.9, 0.99), 1e-8, 0.0)
+    grads = [[torch.randn_like(p) for p in ps_a] for _ in range(4)]
+    for p in ps_a + ps_b:
+        p.grad = torch.zeros_like(p)                 # persistent gradient storage (GraphedTrainStep-like)
+
+    def run(opt, ps, gs):
+        for p, g in zip(ps, gs):
+            p.grad.copy_(g)
+        opt.step()
+
+    run(oa, ps_a, grads[0]); run(ob, ps_b, grads[0])
+    run(oa, ps_a, grads[1]); run(ob, ps_b, grads[1])
+    sd = {k: v for k, v in oa.state_dict().items()}
+    import copy
+    oa.load_state_dict(copy.deepcopy(sd))            # new exp_avg / exp_avg_sq tensors
+    run(oa, ps_a, grads[2]); run(ob, ps_b, grads[2])
+    run(oa, ps_a, grads[3]); run(ob, ps_b, grads[3])
+    for a, b in zip(ps_a, ps_b):
+        assert relerr(a, b) < 2e-6
+        assert relerr(oa.state[a]["exp_avg_sq"], ob.state[b]["exp_avg_sq"]) < 2e-6
+
+
+def test_fused_ranger_matches_reference_trajectory():
+    """csrc/optim.cu dcue_ranger_multi_step against the trajectory of the reference's own Ranger (tests/golden/ref_optim.pt,
+    dcrecommend/optim/ranger.py:82-165): 40 steps incl. the rectification switch-on and 6 lookahead syncs."""
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ref_optim.pt"), weights_only=False)
+    w, bb = torch.nn.Parameter(G["w0"].clone().to(DEV)), torch.nn.Parameter(G["b"].clone().to(DEV))
+    A = G["A"].to(DEV)
+    c0 = L.lib().dcue_launch_count()
+    opt = pkg.optim.Ranger([w, bb], lr=1e-2, alpha=0.5, k=6, N_sma_threshhold=5, betas=(0.9, 0.99), eps=1e-5, weight_decay=1e-2)
+    for t in range(40):
+        opt.zero_grad()
+        ((w @ A).tanh().sum(1) + bb).pow(2).sum().backward()
+        opt.step()
+        cur = torch.cat([w.detach().flatten(), bb.detach()]).cpu()
+        assert torch.allclose(cur, G["ranger_traj"][t], rtol=5e-5, atol=5e-6), t
+    assert L.lib().dcue_launch_count() - c0 == 40        # one launch per step for both tensors
+    assert set(opt.state[w].keys()) == {"step", "exp_avg", "exp_avg_sq", "slow_buffer"}
+
+
+@pytest.mark.parametrize("with_group", [False, True])
+def test_device_auc_ap_matches_sklearn(with_group):
+    """csrc/metrics.cu against sklearn.metrics (what the reference's DCUE.score / score_song call, nn/dcue.py:380-476), with
+    tied scores, single-class segments and segments longer than one tile."""
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    import numpy as np
+    rng = np.random.RandomState(5)
+    lens = [1, 2, 7, 40, 300, 2500, 5000, 3, 64]
+    sc, tg, gr, offs = [], [], [], [0]
+    for i, n in enumerate(lens):
+        s = rng.randn(n).astype(np.float32)
+        if i % 2 == 0:
+            s = np.round(s * 4) / 4                  # many exact ties
+        t = (rng.rand(n) < 0.3).astype(np.uint8)
+        if i == 3:
+            t[:] = 1
+        if i == 7:
+            t[:] = 0
+        sc.append(s); tg.append(t); gr.append((rng.rand(n) < 0.5).astype(np.uint8)); offs.append(offs[-1] + n)
+    S, T, Gp = (torch.from_numpy(np.concatenate(x)).to(DEV) for x in (sc, tg, gr))
+    seg = torch.tensor(offs, dtype=torch.int64, device=DEV)
+    m = pkg.nn.dcue.DCUE.ranking_metrics(S, T, seg, Gp if with_group else None).cpu().numpy()
+    for i, n in enumerate(lens):
+        s, t, g = sc[i], tg[i], gr[i] if with_group else np.zeros(n, np.uint8)
+        for h in (0, 1):
+            sel = g == h
+            th, sh = t[sel], s[sel]
+            if sel.sum() == 0:
+                exp = 0.0
+            elif th.sum() == len(th):
+                exp = 1.0
+            elif th.sum() == 0:
+                exp = 0.0
+            else:
+                exp = roc_auc_score(th, sh)
+            assert abs(m[i, h] - exp) < 1e-12, (i, h, m[i, h], exp)
+            assert m[i, 2 + h] == sel.sum() and m[i, 4 + h] == th.sum()
+        if t.sum() > 0:
+            assert abs(m[i, 6] - average_precision_score(t, s)) < 1e-12, (i, m[i, 6])
+        assert m[i, 7] == t.sum()
+
+
+def test_graphed_step_leaves_batchnorm_buffers_alone():
+    """constructing GraphedTrainStep (warm-up forwards + capture) must not advance the running statistics."""
+    from oracle import fixtures
+    mt, B, N, U = "truedcuemel1dbn", 4, 2, 20
+    params = fixtures.make_params(mt, seed=0, user_count=U)
+    u, pos, neg = (t.to(DEV) for t in fixtures.make_inputs(B, N, U, seed=1))
+    net = pkg.DCUENet({"feature_dim": 100, "conv_hidden": 128, "user_embdim": 300, "user_count": U, "model_type": mt})
+    net.load_state_dict(params)
+    net = net.to(DEV).train()
+    step = pkg.GraphedTrainStep(net, 0.2, u, pos, neg)
+    for k, v in net.named_buffers():
+        assert torch.equal(v.cpu(), params[k]), k
+    step(u, pos, neg)
+    torch.cuda.synchronize()
+    assert int(net.conv.bn1.num_batches_tracked) == int(params["conv.bn1.num_batches_tracked"]) + 1
+    step.release()

@@ -215,7 +215,7 @@ def test_cuda_graph_step_equals_eager():
     u0, p0, n0 = (t.to(DEV) for t in batches[0])
     sd = {k: v.clone() for k, v in graphed.state_dict().items()}
     step = pkg.GraphedTrainStep(graphed, 0.2, u0, p0, n0)
-    graphed.load_state_dict(sd)                   # warm-up + capture ran forward passes: restore BatchNorm buffers
+    graphed.load_state_dict(sd)                   # (no longer needed: the constructor restores the BatchNorm buffers)
     for u, pos, neg in batches:
         u, pos, neg = u.to(DEV), pos.to(DEV), neg.to(DEV)
         eager.zero_grad(set_to_none=True)

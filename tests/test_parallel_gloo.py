@@ -76,3 +76,93 @@ def test_data_parallel_plumbing_world2(tmp_path):
     assert r0["g_bn"] == 1.0 and r1["g_bn"] == 2.0            # BN affine grads are already global: untouched
     assert torch.equal(r0["stats"], torch.tensor([3.0, 4.0], dtype=torch.float64))
     assert abs(r0["loss"] - 0.75) < 1e-12 and r0["hooked"] and r1["hooked"]
+
+
+# ------------------------------------------------------------------ round 2: routed sharded table + eval exchange
+def test_owner_arithmetic_and_routing():
+    for U, W in ((1000, 8), (10, 3), (7, 8), (1000003, 8)):
+        idx = torch.arange(U) if U < 10000 else torch.randint(0, U, (4000,), generator=torch.Generator().manual_seed(1))
+        owner, local = par.owner_of_rows(idx, U, W)
+        for r in range(W):
+            lo, hi = par.shard_rows(U, r, W)
+            m = (idx >= lo) & (idx < hi)
+            assert (owner[m] == r).all() and (local[m] == idx[m] - lo).all()
+    idx = torch.tensor([999, 0, 500, 1, 999, 124, 125])
+    order, counts = par.route_to_owners(idx, 1000, 8)
+    owner, _ = par.owner_of_rows(idx, 1000, 8)
+    assert counts.tolist() == torch.bincount(owner, minlength=8).tolist() and counts.sum() == idx.numel()
+    assert (owner[order][1:] >= owner[order][:-1]).all()
+    # stable: requests for one owner keep their request order (determinism of the owner-side sums)
+    for w in range(8):
+        pos = order[owner[order] == w]
+        assert (pos[1:] > pos[:-1]).all()
+
+
+def _table_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    U, E, B = 37, 6, 11
+    g = torch.Generator().manual_seed(0)
+    full = torch.randn(U, E, generator=g)
+
+    class _Emb(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.embeddings = torch.nn.Embedding(U, E)
+            self.embeddings.weight.data.copy_(full)
+            self.linear1, self.linear2 = torch.nn.Linear(E, E), torch.nn.Linear(E, 3)
+
+    def scatter(idx, rows, n):
+        o = torch.zeros(n, rows.shape[1])
+        o.index_add_(0, idx, rows)
+        return o
+
+    tab = par.ShardedUserTable(_Emb(), transport="collective", gather_fn=lambda sh, i: sh[i], scatter_fn=scatter)
+    u = torch.randint(0, U, (B,), generator=torch.Generator().manual_seed(10 + rank))
+    u[0] = 5                      # a row requested by both ranks
+    rows = par._RoutedRowsFn.apply(u, tab.shard, U, tab.lo, tab.hi, None, tab._gather_fn, tab._scatter_fn)
+    gr = torch.randn(B, E, generator=torch.Generator().manual_seed(20 + rank))
+    rows.backward(gr)
+    torch.save(dict(u=u, rows=rows.detach(), gr=gr, gshard=tab.shard.grad, lo=tab.lo, hi=tab.hi, full=full,
+                    table=tab.gather_full_table()), out % rank)
+    dist.destroy_process_group()
+
+
+def test_routed_sharded_table_world2(tmp_path):
+    port = 31500 + os.getpid() % 2000
+    out = str(tmp_path / "t%d.pt")
+    mp.spawn(_table_worker, args=(2, port, out), nprocs=2, join=True)
+    r = [torch.load(out % k) for k in range(2)]
+    full = r[0]["full"]
+    ref = torch.zeros_like(full)
+    for k in range(2):
+        assert torch.equal(r[k]["rows"], full[r[k]["u"]])                     # forward == plain lookup
+        assert torch.equal(r[k]["table"], full)
+        ref.index_add_(0, r[k]["u"], r[k]["gr"])
+    for k in range(2):
+        assert torch.allclose(r[k]["gshard"], ref[r[k]["lo"]:r[k]["hi"]], atol=1e-6)   # owner holds the GLOBAL row sums
+
+
+def _topk_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    U, k = 7, 3
+    s = torch.arange(U * k, dtype=torch.float32).view(U, k) + 100 * rank
+    i = torch.arange(U * k, dtype=torch.int64).view(U, k) + 1000 * rank
+    sp, ip = par.exchange_topk_by_user_block(s, i)
+    torch.save(dict(sp=sp, ip=ip, blk=par.user_block(U, rank, world)), out % rank)
+    dist.destroy_process_group()
+
+
+def test_topk_exchange_by_user_block_world2(tmp_path):
+    port = 33500 + os.getpid() % 2000
+    out = str(tmp_path / "k%d.pt")
+    mp.spawn(_topk_worker, args=(2, port, out), nprocs=2, join=True)
+    U, k = 7, 3
+    for rank in range(2):
+        r = torch.load(out % rank)
+        lo, hi = r["blk"]
+        assert r["sp"].shape == (2, hi - lo, k)
+        for src in range(2):       # part `src` = what rank `src` computed for MY users
+            assert torch.equal(r["sp"][src], torch.arange(U * k, dtype=torch.float32).view(U, k)[lo:hi] + 100 * src)
+            assert torch.equal(r["ip"][src], torch.arange(U * k, dtype=torch.int64).view(U, k)[lo:hi] + 1000 * src)
