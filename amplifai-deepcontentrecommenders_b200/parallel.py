@@ -140,8 +140,10 @@ class DataParallelDCUE:
         if hasattr(model.user_embd, "embeddings"):      # replicated table: row exchange instead of a dense all-reduce
             model.user_embd._dp = self if (self.world_size > 1 and row_exchange()) else None
         if broadcast and self.world_size > 1:
-            for t in list(model.parameters()) + list(model.buffers()):
-                dist.broadcast(t.data, 0, group=group)
+            # replicated state only: a row-sharded table's shard is rank-specific by construction
+            for n, t in list(model.named_parameters()) + list(model.named_buffers()):
+                if not n.endswith("user_embd.shard"):
+                    dist.broadcast(t.data, 0, group=group)
 
     # hook used by ops.SongTowerFn for BatchNorm statistics
     def all_reduce_sum(self, t):

@@ -1,19 +1,27 @@
-"""DCUE training-step benchmark (BASELINE.json metric: DCUE train triplets/sec).
+"""DCUE benchmark (BASELINE.json metric: DCUE train triplets/sec at 1/2/4/8 B200; eval scored users/sec).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
-  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the box's host cores
 
 One "step" = zero_grad + DCUENet forward(u, pos, neg) + hinge loss + backward + optimizer.step +
 scheduler.batch_step over one batch (the loop body of the reference's _train_epoch,
-dcrecommend/nn/dcue.py:202-210).  Workload = BASELINE configs[1]: truedcuemel1dbn, 20k users,
-emb 300, batch 1024 per GPU, 20 sampled negatives, margin 0.2, Adam(1e-5, (0.9, 0.99), 1e-8).
-Prints ONE JSON line on rank 0.
+dcrecommend/nn/dcue.py:202-210).  Workload = BASELINE configs[1] (cfg2): truedcuemel1dbn, 20k users,
+emb 300, batch 1024 per GPU, 20 sampled negatives, margin 0.2, Adam(1e-5, (0.9, 0.99), 1e-8);
+at N > 1 this is cfg3 (data parallel, global batch 1024 N).  Prints ONE JSON line on rank 0.  Besides the
+contract's keys the line carries
+  e2e / e2e_indexed      dense feed through forward(u,pos,neg)-compatible host tensors / index feed
+  operand_bf16           the same step with bf16 conv operands (DCUE_OPERAND=bf16), BASELINE's "bf16 tower"
+  eval                   cfg5: ALL 1M users x 500k songs, fused top-100, song-sharded + all-to-all by user block
+  cfg4                   1M-user table row-sharded over the ranks (NVLink peer memory), negatives 20 -> 200
+  roofline               dominant kernel (CUDA events, live) + whole-step tensor fraction + HBM kernels
+  dp_parity / eval_parity / table_parity   (N > 1) multi-rank results against rank 0 recomputing them on one GPU
+  cpu_baseline, eval.cpu_baseline          the oracle port of the reference on the host cores (N = 1)
 """
 import argparse
+import glob
 import importlib
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -26,20 +34,33 @@ import torch  # noqa: E402
 METRIC, UNIT = "DCUE train triplets/sec", "triplets/s"
 CFG = dict(model_type="truedcuemel1dbn", users=20000, emb=300, feat=100, hidden=128, frames=131, margin=0.2,
            lr=1e-5, betas=(0.9, 0.99), eps=1e-8)
-L1_FLOP_PER_SPEC = 2 * 128 * 128 * 4 * 132  # live MACs*2 of layer1 per spectrogram
+L1_FLOP_PER_SPEC = 2 * 128 * 128 * 4 * 132      # live MACs*2 of layer1 per spectrogram
+STEP_FLOP_PER_SPEC_LIVE = 68.16e6               # forward + dgrad + wgrad, live output columns only
+USER_MLP_FLOP_PER_TRIPLET = 0.72e6
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops", 1590.0), d.get("hbm_gbs", 6650.0), "measured"
-    return 1590.0, 6650.0, "fallback"
+        return dict(burst=d.get("bf16_tflops", 1590.0), sustained=d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)),
+                    hbm=d.get("hbm_gbs", 6650.0), source="measured (MEASURED_PEAKS.json)")
+    return dict(burst=1590.0, sustained=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def host_threads():
+    """All host cores this process may use -- torchrun exports OMP_NUM_THREADS=1, which made the round-1 CPU arm run on one
+    thread at N > 1 and voided those ratios."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled every ~5 ms DURING the timed region (NVML in-process;
-    falls back to `nvidia-smi -lms` when pynvml is unavailable)."""
+    """SM clock and throttle reasons sampled every ~4 ms DURING the timed region (NVML in-process)."""
     BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
@@ -82,9 +103,17 @@ class ClockSampler:
         return {"sm_mhz": clk[len(clk) // 2], "sm_max_mhz": self.maxclk, "reasons": reasons, "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------------------------- CPU arm
+def workload_config(args):
+    return {"workload": "cfg2: DCUE %s, %d users x %d emb, feature %d, batch %d per GPU, 1 pos + %d sampled negs, hinge margin %.1f, Adam lr 1e-5"
+                        % (CFG["model_type"], CFG["users"], CFG["emb"], CFG["feat"], args.batch, args.negs, CFG["margin"]),
+            "global_batch": args.batch * args.gpus, "negatives": args.negs, "parallelism": "dp%d" % args.gpus,
+            "l2": "inputs (%.2f GB/step/GPU fp32 spectrograms) exceed the 126 MB L2; no flush needed" %
+                  (args.batch * (1 + args.negs) * 128 * CFG["frames"] * 4 / 1e9)}
+
+
+# ------------------------------------------------------------------------------------- CPU arm (oracle port)
 class OracleTrainer:
-    """The reference algorithm (oracle port) + torch Adam on host cores."""
+    """The reference algorithm (oracle/dcue_oracle.py, pinned to the reference's own outputs) + torch Adam on host cores."""
 
     def __init__(self, users):
         from oracle import fixtures
@@ -106,8 +135,9 @@ class OracleTrainer:
 
 
 def cpu_arm(batch, negs, steps, warmup, budget_s=None):
-    """-> (triplets/s, seconds per step, steps run).  Uses every host thread torch will take."""
+    """-> (triplets/s, seconds per step, steps run, threads)."""
     from oracle import fixtures
+    threads = host_threads()
     tr = OracleTrainer(CFG["users"])
     u, pos, neg = fixtures.make_inputs(batch, negs, CFG["users"], seed=1)
     for _ in range(warmup):
@@ -119,47 +149,74 @@ def cpu_arm(batch, negs, steps, warmup, budget_s=None):
         if budget_s is not None and time.perf_counter() - t0 > budget_s and n >= 2:
             break
     dt = time.perf_counter() - t0
-    return batch * n / dt, dt / n, n
+    return batch * n / dt, dt / n, n, threads
+
+
+def cpu_eval_arm(n_users=1024, n_items=500000, k=100):
+    """reference-style model.sim on all pairs for a 1 024-user slice x 500k songs (chunked) + top-k,
+    on the host cores -> users/s (oracle.topk_scores restates dcrecommend/nn/dcue.py:513 for all pairs)."""
+    from oracle import dcue_oracle as O
+    threads = host_threads()
+    g = torch.Generator().manual_seed(3)
+    uf = torch.randn(n_users, CFG["feat"], generator=g)
+    itf = torch.randn(n_items, CFG["feat"], generator=g)
+    O.topk_scores(uf[:64], itf, k, chunk=64)
+    t0 = time.perf_counter()
+    O.topk_scores(uf, itf, k, chunk=256)
+    dt = time.perf_counter() - t0
+    return {"value": n_users / dt, "unit": "users/s", "cores": threads, "kind": "port",
+            "sample": "%d-user slice x %d songs, fp32 normalise + matmul + torch.topk(k=%d), chunks of 256 users, %.2f s" %
+                      (n_users, n_items, k, dt)}
 
 
 def run_reference(args):
+    """Reference arm: the reference's algorithm (oracle port: the reference itself is pure Python on torch and cannot travel to
+    the GPU box; the port is pinned to its outputs by tests/golden) on ALL host cores, same config / metric / unit as ours.
+    Each step is one full cfg2 batch when that fits the time budget, else the largest power-of-two slice that does."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_b = 64
-    value, sps, n = cpu_arm(sample_b, args.negs, args.steps, min(args.warmup, 1))
-    cores = torch.get_num_threads()
+    threads = host_threads()
+    # probe at batch 64 to size the sample: K + W steps must end within ~4 minutes
+    v64, s64, _, _ = cpu_arm(64, args.negs, 1, 1)
+    per_triplet = s64 / 64.0
+    total_steps = args.steps + min(args.warmup, 2)
+    sample_b = args.batch
+    while sample_b > 64 and per_triplet * sample_b * total_steps > 240.0:
+        sample_b //= 2
+    while True:
+        try:
+            value, sps, n, _ = cpu_arm(sample_b, args.negs, args.steps, min(args.warmup, 2))
+            break
+        except (RuntimeError, MemoryError) as exc:          # host RAM too small for the full-batch autograd graph
+            if sample_b <= 64 or "alloc" not in str(exc).lower():
+                raise
+            sample_b //= 2
+    sample = ("oracle port of the reference train step (dcrecommend/nn/dcue.py:202-210) on %d host threads; each step = %d of the "
+              "%d triplets of a cfg2 batch x %d negs (BatchNorm statistics over that slice), %d steps, %.2f s/step"
+              % (threads, sample_b, args.batch, args.negs, n, sps))
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
-           "warmup": min(args.warmup, 1), "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": workload_config(args, extra={"sample": "each step = %d of the %d triplets of a batch" % (sample_b, args.batch)}),
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": "oracle port of the reference train step, batch %d x %d negs, %d steps" % (sample_b, args.negs, n)},
+           "warmup": min(args.warmup, 2), "ms_per_step": sps * 1e3 * args.batch / sample_b, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
-def workload_config(args, extra=None):
-    c = {"workload": "cfg2: DCUE %s, %d users x %d emb, feature %d, batch %d per GPU, 1 pos + %d sampled negs, hinge margin %.1f, Adam lr 1e-5"
-                     % (CFG["model_type"], CFG["users"], CFG["emb"], CFG["feat"], args.batch, args.negs, CFG["margin"]),
-         "global_batch": args.batch * args.gpus, "negatives": args.negs, "parallelism": "dp%d" % args.gpus,
-         "l2": "inputs (%.2f GB/step/GPU fp32 spectrograms) exceed the 126 MB L2; no flush needed" %
-               (args.batch * (1 + args.negs) * 128 * CFG["frames"] * 4 / 1e9)}
-    if extra:
-        c.update(extra)
-    return c
-
-
-# ------------------------------------------------------------------------------------- GPU arm
-# DRAM bytes per launch at S = 21504 from the ncu --set full captures in profiles/ (scaled linearly with S)
-NCU_TRAFFIC_S21504 = {"conv1_fwd_pool": 751.0e6 + 422.0e6, "conv1_wgrad_unpool": 1566.6e6 + 8.5e6, "conv1_wgrad": 1500.0e6 + 4.4e6,
-                      "bn_relu_unpool_bwd1": 818.0e6 + 689.0e6}
+# ------------------------------------------------------------------------------------- GPU arm helpers
+def load_ncu_traffic():
+    """DRAM bytes per launch of the big kernels, read from the committed ncu summaries (profiles/*traffic*.json: the newest
+    file wins).  Values are at S = 21 504 spectrograms and scale linearly with S."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*traffic*.json")))
+    if not files:
+        return {}, None
+    d = json.load(open(files[-1]))
+    return d.get("kernels", {}), os.path.basename(files[-1])
 
 
 def kernel_roofline(pkg, S, dev):
-    """CUDA-event timing, on this stream, of the step's heaviest kernels at layer-1 size: the two tcgen05
-    GEMMs (tensor-bound) and the BatchNorm-backward/unpool sweep (HBM-bound).  achieved = algorithmic
-    FLOPs (bytes) per launch / average launch time."""
+    """CUDA-event timing, on this stream, of the step's heaviest kernels at layer-1 size: the tcgen05 GEMMs (tensor-bound)
+    and the BatchNorm-backward/unpool sweep (HBM-bound).  achieved = algorithmic FLOPs (bytes) per launch / average launch time."""
     L, ops = pkg._lib, pkg.ops
     geo = ops.tower_geometry(CFG["frames"])[0]
     st = L.stream()
@@ -215,6 +272,232 @@ def kernel_roofline(pkg, S, dev):
     return res
 
 
+def build_model(pkg, users, dev, seed=0):
+    torch.manual_seed(seed)
+    return pkg.DCUENet({"feature_dim": CFG["feat"], "conv_hidden": CFG["hidden"], "user_embdim": CFG["emb"], "user_count": users,
+                        "model_type": CFG["model_type"]}).to(dev).train()
+
+
+def l2rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def timed_steps(fn, n, barrier, dev, world):
+    """n calls of fn bracketed by barrier + synchronize, CUDA events, MAX over ranks -> total ms."""
+    import torch.distributed as dist
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item()
+
+
+# ------------------------------------------------------------------------------------- multi-rank parity legs
+def dp_parity_leg(pkg, par, dev, rank, world, per_rank=32, negs=4, users=500):
+    """Global batch split over the ranks (SyncBN statistics, peer-memory table-row exchange, flat gradient all-reduce) against
+    rank 0 recomputing the FULL batch on one GPU with the same kernels: loss, every gradient, BatchNorm buffers; then the
+    CUDA-graph replay of the data-parallel step against the eager one."""
+    import torch.distributed as dist
+    Bg = per_rank * world
+    g = torch.Generator().manual_seed(77)
+    u = torch.randint(0, users, (Bg,), generator=g)
+    u[1] = u[0]
+    u[Bg - 1] = u[0]                                   # the same user on the first and the last rank
+    pos = torch.randn(Bg, 128, CFG["frames"], generator=g)
+    neg = torch.randn(Bg, negs, 128, CFG["frames"], generator=g)
+    lo, hi = par.shard_slice(Bg, rank, world)
+    model = build_model(pkg, users, dev, seed=5)
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    dp = par.DataParallelDCUE(model)
+    ul, pl, nl = u[lo:hi].to(dev), pos[lo:hi].to(dev), neg[lo:hi].to(dev)
+    model.zero_grad(set_to_none=True)
+    loss = dp.loss_step(ul, pl, nl, CFG["margin"])
+    loss.backward()
+    dp.reduce_gradients()
+    loss_g = dp.reduce_loss(loss).item()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    bufs = {k: v.detach().clone() for k, v in model.named_buffers()}
+    # every rank must hold the same reduced gradients: compare with rank 0's
+    worst_rank_diff = 0.0
+    for k in sorted(grads):
+        ref = grads[k].clone()
+        dist.broadcast(ref, 0)
+        worst_rank_diff = max(worst_rank_diff, (grads[k] - ref).abs().max().item())
+    wr = torch.tensor([worst_rank_diff], device=dev)
+    dist.all_reduce(wr, op=dist.ReduceOp.MAX)
+    # graph replay of the DP step
+    model.load_state_dict(sd0)
+    gstep = pkg.GraphedTrainStep(model, CFG["margin"], ul, pl, nl, warmup=2, dp=dp)
+    gl = gstep(ul, pl, nl)
+    graph_loss = dp.reduce_loss(gl).item()
+    graph_grad_diff = max((p.grad - grads[k]).abs().max().item() / grads[k].abs().max().clamp_min(1e-30).item()
+                          for k, p in model.named_parameters())
+    gd = torch.tensor([graph_grad_diff], device=dev)
+    dist.all_reduce(gd, op=dist.ReduceOp.MAX)
+    gstep.release()
+    dp.check_peers()
+    out = None
+    if rank == 0:
+        single = build_model(pkg, users, dev, seed=5)
+        single.load_state_dict(sd0)
+        single.zero_grad(set_to_none=True)
+        ls = single.hinge_loss_step(u.to(dev), pos.to(dev), neg.to(dev), CFG["margin"])
+        ls.backward()
+        worst, worst_name = 0.0, ""
+        for k, p in single.named_parameters():
+            e = l2rel(grads[k], p.grad)
+            if e > worst:
+                worst, worst_name = e, k
+        sb = dict(single.named_buffers())
+        buf_err = max(((bufs[k].double() - sb[k].double()).abs().max() / sb[k].double().abs().max().clamp_min(1e-30)).item()
+                      for k in bufs)
+        out = {"global_batch": Bg, "negatives": negs, "loss_rel": abs(loss_g - ls.item()) / abs(ls.item()),
+               "worst_grad_l2": worst, "worst_grad": worst_name, "buffers": buf_err, "max_abs_diff_between_ranks": wr.item(),
+               "graph_vs_eager_loss_rel": abs(graph_loss - loss_g) / abs(loss_g), "graph_vs_eager_grad_relmax": gd.item(),
+               "what": "ranks' slices vs rank 0 recomputing the full batch on one GPU (same kernels, fp16 operands)"}
+    model.conv._dp = None
+    model.user_embd._dp = None
+    dist.barrier()
+    return out
+
+
+def eval_parity_leg(par, ev, dev, rank, world, n_users=3000, n_items=40000, k=100):
+    """sharded_topk (songs over the ranks, all-to-all by user block, per-block merge) against rank 0 scoring all songs alone."""
+    import torch.distributed as dist
+    g = torch.Generator(device=dev).manual_seed(11)
+    uf = torch.randn(n_users, CFG["feat"], generator=g, device=dev)
+    itf = torch.randn(n_items, CFG["feat"], generator=g, device=dev)
+    lo, hi = par.shard_slice(n_items, rank, world)
+    s, i = par.sharded_topk(uf, itf[lo:hi].contiguous(), k, lo, gather=True, user_tile=n_users // 3)
+    out = None
+    if rank == 0:
+        s1, i1 = ev.topk_scores(uf, itf, k)
+        same = (i == i1)
+        # a differing index is only legitimate between tied scores
+        bad = int(((~same) & ((s - s1).abs() > 0)).sum())
+        out = {"users": n_users, "songs": n_items, "k": k, "scores_max_abs_diff": (s - s1).abs().max().item(),
+               "index_mismatch_beyond_ties": bad, "index_equal_frac": same.float().mean().item(),
+               "what": "song-sharded top-k over %d ranks (3 user tiles) vs one GPU scoring all songs" % world}
+    dist.barrier()
+    return out
+
+
+def table_parity_leg(pkg, par, optim, dev, rank, world, users=1003, per_rank=48, negs=3):
+    """Row-sharded user table over NVLink peer memory against the replicated table (both data parallel, same batch):
+    loss, user-MLP gradients, the owner's shard gradient vs the same rows of the dense gradient, and the table after one Adam step."""
+    import torch.distributed as dist
+    Bg = per_rank * world
+    g = torch.Generator().manual_seed(99)
+    u = torch.randint(0, users, (Bg,), generator=g)
+    u[1] = u[0]
+    u[Bg - 1] = u[0]
+    pos = torch.randn(Bg, 128, CFG["frames"], generator=g)
+    neg = torch.randn(Bg, negs, 128, CFG["frames"], generator=g)
+    lo_b, hi_b = par.shard_slice(Bg, rank, world)
+    ul, pl, nl = u[lo_b:hi_b].to(dev), pos[lo_b:hi_b].to(dev), neg[lo_b:hi_b].to(dev)
+
+    def one(sharded):
+        model = build_model(pkg, users, dev, seed=9)
+        if sharded:
+            par.shard_user_table(model)
+        dp = par.DataParallelDCUE(model)
+        opt = optim.FusedAdam(model.parameters(), 1e-3, CFG["betas"], CFG["eps"], 0)
+        model.zero_grad(set_to_none=True)
+        loss = dp.loss_step(ul, pl, nl, CFG["margin"])
+        loss.backward()
+        dp.reduce_gradients()
+        lg = dp.reduce_loss(loss).item()
+        grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+        opt.step()
+        table = model.user_embd.gather_full_table() if sharded else model.user_embd.embeddings.weight.detach().clone()
+        span = (model.user_embd.lo, model.user_embd.hi) if sharded else None
+        model.raise_if_index_error()
+        model.conv._dp = None
+        return lg, grads, table, span
+
+    l_rep, g_rep, t_rep, _ = one(False)
+    l_sh, g_sh, t_sh, (lo, hi) = one(True)
+    errs = torch.tensor([abs(l_sh - l_rep) / abs(l_rep),
+                         max(l2rel(g_sh[k], g_rep[k]) for k in g_sh if k in g_rep),
+                         (g_sh["user_embd.shard"] - g_rep["user_embd.embeddings.weight"][lo:hi]).abs().max().item(),
+                         (t_sh - t_rep).abs().max().item()], device=dev, dtype=torch.float64)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    if rank != 0:
+        return None
+    return {"users": users, "global_batch": Bg, "loss_rel": errs[0].item(), "worst_shared_grad_l2": errs[1].item(),
+            "shard_grad_max_abs_diff": errs[2].item(), "table_after_adam_max_abs_diff": errs[3].item(),
+            "what": "ShardedUserTable(transport=peer) vs replicated table, both data parallel over %d ranks" % world}
+
+
+# ------------------------------------------------------------------------------------- cfg4 leg
+def cfg4_leg(pkg, par, optim, dev, rank, world, args, barrier):
+    """BASELINE configs[3]: 1M users x 300 row-sharded over the ranks, index feed, negatives swept 20 -> 200.  Per N: whole-job
+    triplets/s of the full step (graph: forward + loss + backward [+ collectives]; then the fused Adam), the time of the dense
+    Adam pass alone and of the user-table path alone (gather over NVLink + MLP forward/backward + row exchange + scatter)."""
+    U4, B = 1000000, args.batch
+    model = build_model(pkg, U4, dev, seed=4)
+    if world > 1:
+        par.shard_user_table(model, capacity=B)
+    dp = par.DataParallelDCUE(model)
+    opt = optim.FusedAdam(model.parameters(), CFG["lr"], CFG["betas"], CFG["eps"], 0)
+    opt.set_skip_flags(model.error_flags())
+    pool_songs = 2048
+    g = torch.Generator(device=dev).manual_seed(40 + rank)
+    pool = torch.randn(pool_songs, 128, CFG["frames"], generator=g, device=dev)
+    res = {"users": U4, "emb": CFG["emb"], "batch_per_gpu": B, "table": ("row-sharded over %d ranks, NVLink peer-memory gather / "
+           "gradient-row exchange (csrc/peer.cu)" % world) if world > 1 else "one GPU holds the whole table",
+           "table_rows_per_rank": (U4 + world - 1) // world, "sweep": []}
+    for N in args.cfg4_negs:
+        u = torch.randint(0, U4, (B,), generator=g, device=dev)
+        pi = torch.randint(0, pool_songs, (B,), generator=g, device=dev)
+        ni = torch.randint(0, pool_songs, (B, N), generator=g, device=dev)
+        gstep = pkg.GraphedTrainStep(model, CFG["margin"], u, pi, ni, pool=pool, warmup=2, dp=dp if world > 1 else None)
+
+        def step():
+            gstep()
+            opt.step()
+
+        for _ in range(2):
+            step()
+        n = args.cfg4_steps
+        ms = timed_steps(step, n, barrier, dev, world) / n
+        adam_ms = timed_steps(opt.step, n, barrier, dev, world) / n
+
+        def table_path():
+            out = model.user_embd(u)
+            out.backward(torch.ones_like(out))
+
+        model.zero_grad(set_to_none=True)
+        for _ in range(2):
+            table_path()
+        table_ms = timed_steps(table_path, n, barrier, dev, world) / n
+        model.raise_if_index_error()
+        gstep.release()
+        del gstep
+        pkg.ops.clear_workspaces()
+        torch.cuda.empty_cache()
+        # restore persistent gradient storage for the next capture
+        model.zero_grad(set_to_none=True)
+        res["sweep"].append({"negatives": N, "value": B * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                             "adam_ms": adam_ms, "adam_share": adam_ms / ms, "table_path_ms": table_ms,
+                             "table_path_share": table_ms / ms,
+                             "tflops_live_per_gpu": (B * (1 + N) * STEP_FLOP_PER_SPEC_LIVE) / (ms * 1e-3) / 1e12})
+    model.conv._dp = None
+    del model, opt, pool
+    pkg.ops.clear_workspaces()
+    torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -227,28 +510,33 @@ def run_ours(args):
     pkg = importlib.import_module("amplifai-deepcontentrecommenders_b200")
     par = importlib.import_module("amplifai-deepcontentrecommenders_b200.parallel")
     optim = importlib.import_module("amplifai-deepcontentrecommenders_b200.optim")
+    ev = importlib.import_module("amplifai-deepcontentrecommenders_b200.eval")
     L = pkg._lib
     B, N, U = args.batch, args.negs, CFG["users"]
+    graphs = []
 
-    torch.manual_seed(0)
-    model = pkg.DCUENet({"feature_dim": CFG["feat"], "conv_hidden": CFG["hidden"], "user_embdim": CFG["emb"], "user_count": U,
-                         "model_type": CFG["model_type"]}).to(dev).train()
-    dp = par.DataParallelDCUE(model)
-    # torch.optim.Adam semantics in one multi-tensor launch (DCUE_BENCH_TORCH_ADAM=1: the library optimizer, for A/B)
-    if os.environ.get("DCUE_BENCH_TORCH_ADAM") == "1":
-        opt = torch.optim.Adam(model.parameters(), CFG["lr"], CFG["betas"], CFG["eps"], 0)
-    else:
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make_trainer(seed=0):
+        model = build_model(pkg, U, dev, seed)
+        dp = par.DataParallelDCUE(model)
         opt = optim.FusedAdam(model.parameters(), CFG["lr"], CFG["betas"], CFG["eps"], 0)
-    sched = optim.CyclicLRWithRestarts(opt, B * world, epoch_size=B * world * 100000, restart_period=30, t_mult=2, policy="cosine")
-    sched.step()
+        opt.set_skip_flags(model.error_flags())
+        sched = optim.CyclicLRWithRestarts(opt, B * world, epoch_size=B * world * 100000, restart_period=30, t_mult=2, policy="cosine")
+        sched.step()
+        return model, dp, opt, sched
 
+    model, dp, opt, sched = make_trainer()
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     u = torch.randint(0, U, (B,), generator=g, device=dev)
     pos = torch.randn(B, 128, CFG["frames"], generator=g, device=dev)
     neg = torch.randn(B, N, 128, CFG["frames"], generator=g, device=dev)
     loss_acc = torch.zeros((), device=dev)
 
-    def step(u_, pos_, neg_):
+    def step_eager(u_, pos_, neg_):
         opt.zero_grad(set_to_none=False)
         loss = dp.loss_step(u_, pos_, neg_, CFG["margin"])
         loss.backward()
@@ -257,19 +545,14 @@ def run_ours(args):
         sched.batch_step()
         return loss.detach()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    use_graph = not args.no_graph      # under DP the NCCL collectives are captured into the graph as well
+    use_graph = not args.no_graph      # under DP the collectives are captured into the graph as well
     graph_launches = 0
+    step = step_eager
     if use_graph:
         c0 = L.lib().dcue_launch_count()
         gstep = pkg.GraphedTrainStep(model, CFG["margin"], u, pos, neg, warmup=3, dp=dp if world > 1 else None)
+        graphs.append(gstep)
         graph_launches = (L.lib().dcue_launch_count() - c0) // 4       # 3 warm-up passes + the captured one
-
-        step_eager = step
 
         def step(u_, pos_, neg_):  # noqa: F811  (same step: forward+loss+backward replayed as one CUDA graph)
             if u_ is not u:
@@ -289,13 +572,11 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         loss_acc += step(u, pos, neg)
-        if os.environ.get("DCUE_BENCH_SYNC_EACH_STEP") == "1":   # diagnostic only
-            torch.cuda.synchronize()
     e1.record()
     barrier()
     launches = L.lib().dcue_launch_count() - launches0
-    # under graph replay the library's launch counter does not tick: use the per-step count seen at capture
-    launches_per_step = launches / args.steps if not use_graph else graph_launches
+    # under graph replay the library's launch counter only ticks for the optimizer: add the per-step count seen at capture
+    launches_per_step = launches / args.steps + (graph_launches if use_graph else 0)
     clocks = sampler.stop() if sampler else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
@@ -303,6 +584,7 @@ def run_ours(args):
     ms_total = ms.item()
     value = B * world * args.steps / (ms_total * 1e-3)
     final_loss = dp.reduce_loss(loss_acc / args.steps).item()
+    dp.check_peers()
 
     # ---------------- end to end: pinned host inputs -> H2D -> step -> loss D2H, every step
     hu, hpos, hneg = (t.cpu().pin_memory() for t in (u, pos, neg))
@@ -344,7 +626,7 @@ def run_ours(args):
     h2d = u.numel() * 8 + (pos.numel() + neg.numel()) * 4
     del bufs, hpos, hneg
 
-    # ---------------- end to end on the INDEX feed (SURVEY §8f rank 1): the song pool is resident on the
+    # ---------------- end to end on the INDEX feed (SURVEY 8f rank 1): the song pool is resident on the
     # device like the user table; a step's host inputs are u, positive / negative song indices only
     pool_songs = 4096
     pool = torch.randn(pool_songs, 128, CFG["frames"], generator=g, device=dev)
@@ -352,11 +634,11 @@ def run_ours(args):
     n_idx_batches = 4
     hidx = [(torch.randint(0, U, (B,), generator=gi).pin_memory(), torch.randint(0, pool_songs, (B,), generator=gi).pin_memory(),
              torch.randint(0, pool_songs, (B, N), generator=gi).pin_memory()) for _ in range(n_idx_batches)]
-
     gidx = None
     if use_graph:
         u0_, p0_, n0_ = (t.to(dev) for t in hidx[0])
         gidx = pkg.GraphedTrainStep(model, CFG["margin"], u0_, p0_, n0_, pool=pool, dp=dp if world > 1 else None)
+        graphs.append(gidx)
 
     def idx_step(i):
         hu_, hp_, hn_ = hidx[i % n_idx_batches]
@@ -386,21 +668,57 @@ def run_ours(args):
     e2e_idx_value = B * world * idx_steps / dti.item()
     model.raise_if_index_error()
     h2d_idx = B * 8 * 2 + B * N * 8
-    del pool
 
-    # ---------------- eval scorer (second half of BASELINE.json's metric): cfg5 = all-pairs cosine scores of user
-    # factors against 500k song factors with the fused top-100; songs sharded over the ranks, per-rank lists merged.
-    # A bounded sample of the 1M users (the kernel's cost is linear in users) keeps the default run short.
+    # ---------------- the same step with bf16 conv operands (BASELINE cfg2 says "bf16 tower"; fp16 is this repo's default
+    # because it is 8x closer to fp32 at the same tensor-core rate -- both are measured)
+    for gs_ in graphs:
+        gs_.release()
+    graphs.clear()
+    model.conv._dp = None
+    del model, dp, opt, sched, pool, gidx
+    if use_graph:
+        del gstep
+    pkg.ops.clear_workspaces()
+    torch.cuda.empty_cache()
+    bf16 = None
+    if not args.no_bf16:
+        os.environ["DCUE_OPERAND"] = "bf16"
+        m2, dp2, opt2, sched2 = make_trainer()
+        g2 = pkg.GraphedTrainStep(m2, CFG["margin"], u, pos, neg, warmup=3, dp=dp2 if world > 1 else None)
+
+        def step_bf():
+            g2()
+            opt2.step()
+            sched2.batch_step()
+
+        for _ in range(3):
+            step_bf()
+        nb = max(5, args.steps // 2)
+        msb = timed_steps(step_bf, nb, barrier, dev, world)
+        bf16 = {"value": B * world * nb / (msb * 1e-3), "unit": UNIT, "ms_per_step": msb / nb, "steps": nb, "dtype": "bf16",
+                "final_loss": dp2.reduce_loss(g2.loss.detach()).item(),
+                "note": "DCUE_OPERAND=bf16: same kernels, bf16 conv operands (parity table: profiles/r02_cfg1_error_table.md)"}
+        g2.release()
+        m2.conv._dp = None
+        del m2, dp2, opt2, sched2, g2
+        os.environ.pop("DCUE_OPERAND", None)
+        pkg.ops.clear_workspaces()
+        torch.cuda.empty_cache()
+    del pos, neg
+
+    # ---------------- eval scorer (second half of BASELINE.json's metric): cfg5 = all-pairs cosine scores of ALL 1M user
+    # factors against 500k song factors with the fused top-100; songs sharded over the ranks, the per-rank lists exchanged
+    # all-to-all by user block, every rank merges its own users
     ev_users, ev_items, ev_k = args.eval_users, 500000, 100
     ge = torch.Generator(device=dev).manual_seed(3)
     ufac = torch.randn(ev_users, CFG["feat"], generator=ge, device=dev)
     lo_i, hi_i = par.shard_slice(ev_items, rank, world)
     ifac = torch.randn(ev_items, CFG["feat"], generator=ge, device=dev)[lo_i:hi_i].contiguous()   # same factors on every rank
-    par.sharded_topk(ufac[:4096], ifac, ev_k, lo_i)
+    par.sharded_topk(ufac[:8192], ifac, ev_k, lo_i)
     barrier()
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record()
-    ev_s, ev_i = par.sharded_topk(ufac, ifac, ev_k, lo_i)
+    ev_out = par.sharded_topk(ufac, ifac, ev_k, lo_i, user_tile=args.eval_user_tile if world > 1 else None)
     ee1.record()
     barrier()
     ems = torch.tensor([ee0.elapsed_time(ee1)], device=dev)
@@ -409,47 +727,83 @@ def run_ours(args):
     eval_out = {"metric": "eval scored users/sec (top-%d)" % ev_k, "value": ev_users / (ems.item() * 1e-3), "unit": "users/s",
                 "ms": ems.item(), "users": ev_users, "songs": ev_items, "songs_per_gpu": hi_i - lo_i, "k": ev_k,
                 "tflops_algorithmic": 2.0 * CFG["feat"] * ev_users * ev_items / (ems.item() * 1e-3) / 1e12,
-                "workload": "cfg5 on a %d-user sample: fp16 factors, fp32 accumulate, songs sharded over %d GPU(s), merged top-k"
-                            % (ev_users, world)}
-    del ufac, ifac, ev_s, ev_i
+                "merge": "all-to-all by user block, each rank merges U/%d users (tiles of %s users overlap exchange and scoring)"
+                         % (world, args.eval_user_tile) if world > 1 else "single GPU: no merge",
+                "workload": "cfg5: %d users x %d songs, fp16 factors, fp32 accumulate, songs sharded over %d GPU(s), merged top-k"
+                            % (ev_users, ev_items, world)}
+    del ufac, ifac, ev_out
+    torch.cuda.empty_cache()
+
+    # ---------------- multi-rank parity legs + cfg4
+    parity = {}
+    if world > 1:
+        parity["dp_parity"] = dp_parity_leg(pkg, par, dev, rank, world)
+        parity["eval_parity"] = eval_parity_leg(par, ev, dev, rank, world)
+        parity["table_parity"] = table_parity_leg(pkg, par, optim, dev, rank, world)
+        pkg.ops.clear_workspaces()
+        torch.cuda.empty_cache()
+    cfg4 = None if args.no_cfg4 else cfg4_leg(pkg, par, optim, dev, rank, world, args, barrier)
 
     out = None
     if rank == 0:
-        tf_peak, hbm_peak, which = peaks()
-        kern = kernel_roofline(pkg, B * (1 + N), dev)
-        top = max(kern, key=lambda k: kern[k]["ms"])
-        peak = tf_peak if kern[top]["bound"] == "tensor" else hbm_peak
-        traffic = NCU_TRAFFIC_S21504.get(top)
-        traffic = None if traffic is None else traffic * (B * (1 + N)) / 21504.0
+        pk = peaks()
+        S = B * (1 + N)
+        kern = kernel_roofline(pkg, S, dev)
+        top = max((k for k in kern if kern[k]["bound"] == "tensor"), key=lambda k: kern[k]["ms"])
+        traffic_tab, traffic_src = load_ncu_traffic()
+        traffic = traffic_tab.get(top, {}).get("dram_bytes_per_launch_S21504")
+        traffic = None if traffic is None else traffic * S / 21504.0
+        step_ms = ms_total / args.steps
+        step_flop = S * STEP_FLOP_PER_SPEC_LIVE + B * USER_MLP_FLOP_PER_TRIPLET
+        step_tf = step_flop / (step_ms * 1e-3) / 1e12
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        hbm = None
+        try:
+            import hbm_kernel_bench
+            hbm = {"at_cfg2_batch": hbm_kernel_bench.run(B, tower=True, S=S)["kernels"],
+                   "at_262144_rows": hbm_kernel_bench.run(262144, tower=False)["kernels"],
+                   "note": "embedding / loss kernels move 2-18 MB at the cfg2 batch (launch-latency bound: 4-25 us); the second "
+                           "table times them at a size where bandwidth is the limit.  Peak = measured copy bandwidth."}
+        except Exception as e:  # noqa: BLE001
+            hbm = {"error": str(e)}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f16", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
                        "api": "DCUENet.forward-compatible dense feed: fp32 [B,128,131] + [B,N,128,131] from pinned host memory (PCIe-bound)"},
                "e2e_indexed": {"value": e2e_idx_value, "unit": UNIT, "h2d_bytes_per_step": h2d_idx, "d2h_bytes_per_step": 4,
                                "steps": idx_steps,
                                "api": "hinge_loss_step_indexed: resident pool of %d songs on the device, host sends u + song indices" % pool_songs},
-               "gpu_launches": int(launches_per_step * args.steps), "final_loss": final_loss, "cuda_graph": bool(use_graph),
-               "eval": eval_out,
-               "roofline": {"bound": kern[top]["bound"], "kernel": top, "achieved": kern[top]["achieved"], "peak": peak,
-                            "unit": kern[top]["unit"], "frac": kern[top]["achieved"] / peak, "traffic": traffic,
-                            "peak_source": which + (" (burst bf16 cuBLAS)" if kern[top]["bound"] == "tensor" else " (copy)"),
-                            "kernels": kern}}
+               "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": launches_per_step,
+               "final_loss": final_loss, "cuda_graph": bool(use_graph), "operand_bf16": bf16,
+               "eval": eval_out, "cfg4": cfg4,
+               "roofline": {"bound": "tensor", "kernel": top, "achieved": kern[top]["achieved"], "peak": pk["burst"],
+                            "unit": "TFLOP/s", "frac": kern[top]["achieved"] / pk["burst"], "traffic": traffic,
+                            "traffic_source": traffic_src,
+                            "peak_source": pk["source"] + " (burst bf16 cuBLAS: the kernel is timed alone)",
+                            "step": {"tflops_live": step_tf, "frac_of_sustained": step_tf / pk["sustained"],
+                                     "flop_per_step_live": step_flop, "peak_sustained": pk["sustained"],
+                                     "note": "whole step incl. optimizer vs sustained bf16 cuBLAS (kernels timed inside a long step)"},
+                            "kernels": {k: dict(v, frac=v["achieved"] / (pk["burst"] if v["bound"] == "tensor" else pk["hbm"]))
+                                        for k, v in kern.items()},
+                            "hbm_kernels": hbm}}
+        out.update({k: v for k, v in parity.items() if v is not None})
     if world > 1:
         dist.barrier()
     if rank == 0:
         if world == 1 and not args.no_cpu:
-            v, sps, n = cpu_arm(64, N, 1000, 1, budget_s=args.cpu_seconds)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                   "sample": "oracle port of the reference train step (cfg1: batch 64 x %d negs), %d steps, %.1f s/step" % (N, n, sps)}
+            v, sps, n, threads = cpu_arm(64, N, 1000, 1, budget_s=args.cpu_seconds)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": "oracle port of the reference train step (the reference is pure Python on torch and cannot "
+                                             "travel to this box; the port is pinned to its outputs, tests/golden): cfg1 shape, batch 64 x "
+                                             "%d negs, %d steps, %.2f s/step" % (N, n, sps)}
+            out["eval"]["cpu_baseline"] = cpu_eval_arm()
         print(json.dumps(out), flush=True)
+    # clean shutdown: captured graphs (they hold NCCL work) are gone, so the process group can be destroyed normally
+    torch.cuda.synchronize()
     if world > 1:
-        # CUDA graphs that captured NCCL collectives keep the communicator busy: tearing the process group down with
-        # them alive hung the ranks at exit.  Everything is printed; leave without the collective teardown.
         dist.barrier()
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        os._exit(0)
+        dist.destroy_process_group()
 
 
 def main():
@@ -461,8 +815,12 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="triplets per GPU")
     ap.add_argument("--negs", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--eval-users", type=int, default=151552,
-                    help="users scored in the eval leg (sample of cfg5's 1M): 592 tiles of 256 users = 4 full rounds on 148 SMs")
+    ap.add_argument("--eval-users", type=int, default=1000000, help="users scored in the eval leg (cfg5: 1M)")
+    ap.add_argument("--eval-user-tile", type=int, default=250000, help="users per exchange tile of the song-sharded eval (N > 1)")
+    ap.add_argument("--cfg4-negs", type=int, nargs="*", default=[20, 50, 100, 200])
+    ap.add_argument("--cfg4-steps", type=int, default=5)
+    ap.add_argument("--no-cfg4", action="store_true")
+    ap.add_argument("--no-bf16", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph step")
     args = ap.parse_args()

@@ -31,8 +31,9 @@ def timed(fn, reps=10, flush=None):
     return ts[len(ts) // 2]
 
 
-def main():
-    B = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
+def run(B=262144, tower=True, S=21504):
+    """-> {"hbm_peak_GB/s", "rows", "kernels": {name: {ms, GB/s, frac_of_peak, algorithmic_MB}}}; B = triplets (rows) for the
+    embedding / loss kernels; tower=True adds the song-tower glue sweeps at S spectrograms."""
     pkg = importlib.import_module("amplifai-deepcontentrecommenders_b200")
     L, ops = pkg._lib, pkg.ops
     dev = torch.device("cuda")
@@ -58,16 +59,22 @@ def main():
     report("gather_relu_fwd", B * (8 + 2 * 4 * E),
            timed(lambda: L.call("dcue_gather_relu_fwd", table.data_ptr(), idx.data_ptr(), B, U, E, h0.data_ptr(), None, err.data_ptr(), st),
                  flush=flush))
-    sidx = torch.empty(B, dtype=torch.int64, device=dev)
-    spos = torch.empty(B, dtype=torch.int32, device=dev)
-    nscr = L.query("dcue_sort_ws_bytes", B)
-    scr = torch.empty(nscr, dtype=torch.uint8, device=dev)
-    L.call("dcue_sort_indices", idx.data_ptr(), B, U, sidx.data_ptr(), spos.data_ptr(), scr.data_ptr(), nscr, st)
     dh0 = torch.randn(B, E, device=dev, generator=g)
     gtab = torch.zeros(U, E, device=dev)
-    report("segment_scatter_add_bwd", B * (8 + 4 + 3 * 4 * E),   # grad row + relu mask row read, table row written
-           timed(lambda: L.call("dcue_scatter_add_bwd", dh0.data_ptr(), h0.data_ptr(), sidx.data_ptr(), spos.data_ptr(), B, U, E,
-                                gtab.data_ptr(), st), flush=flush))
+    if B <= L.lib().dcue_scatter_direct_max():
+        # step-sized batch: the sort-free single-launch scatter the training step uses
+        report("scatter_add_rows", B * (8 + 3 * 4 * E),
+               timed(lambda: L.call("dcue_scatter_add_rows", dh0.data_ptr(), h0.data_ptr(), idx.data_ptr(), B, U, E, gtab.data_ptr(), st),
+                     flush=flush))
+    else:
+        sidx = torch.empty(B, dtype=torch.int64, device=dev)
+        spos = torch.empty(B, dtype=torch.int32, device=dev)
+        nscr = L.query("dcue_sort_ws_bytes", B)
+        scr = torch.empty(nscr, dtype=torch.uint8, device=dev)
+        L.call("dcue_sort_indices", idx.data_ptr(), B, U, sidx.data_ptr(), spos.data_ptr(), scr.data_ptr(), nscr, st)
+        report("segment_scatter_add_bwd", B * (8 + 4 + 3 * 4 * E),   # grad row + relu mask row read, table row written
+               timed(lambda: L.call("dcue_scatter_add_bwd", dh0.data_ptr(), h0.data_ptr(), sidx.data_ptr(), spos.data_ptr(), B, U, E,
+                                    gtab.data_ptr(), st), flush=flush))
     del table, gtab, dh0, h0
 
     # ---- fused cosine score + hinge loss + backward, N = 20 negatives, F = 100
@@ -83,8 +90,9 @@ def main():
                                 lrows.data_ptr(), du.data_ptr(), df.data_ptr(), st), flush=flush))
     del feats, df
 
+    if not tower:
+        return {"hbm_peak_GB/s": peak, "rows": B, "kernels": out}
     # ---- song-tower glue at cfg2 size (S = 21 504 spectrograms)
-    S = 21504
     geo = ops.tower_geometry(131)[0]
     pos = torch.randn(S, 128, 131, device=dev, generator=g)
     X = ops.Panel(S, geo["Lp"], dev)
@@ -117,8 +125,8 @@ def main():
     report("bn_bwd_reduce(layer1)", rows * 1024,
            timed(lambda: L.call("dcue_bn_bwd_reduce", dy.data_ptr(), 128, None, 0, z.data_ptr(), bn[2].data_ptr(), bn[3].data_ptr(), S,
                                 geo["P"], 128, sums.data_ptr(), amax.data_ptr(), None, None, ws.data_ptr(), nws, st), flush=flush))
-    print(json.dumps({"hbm_peak_GB/s": peak, "rows": B, "kernels": out}, indent=1))
+    return {"hbm_peak_GB/s": peak, "rows": B, "kernels": out}
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 262144), indent=1))
