@@ -93,8 +93,10 @@ score_kernel(const float* __restrict__ u, const float* __restrict__ feats, const
         float g;  // dL/ds_n
         if (MODE == 2) {
             const float h = margin - s;
-            loss += fmaxf(h, 0.f);
-            g = -(h > 0.f ? 1.f : (h == 0.f ? 0.5f : 0.f)) * inv_batch;
+            // torch.max(0, NaN) is NaN (fmaxf would drop it): a NaN score -- e.g. from a flagged out-of-range user row --
+            // poisons the loss and the gradients instead of looking like a satisfied margin
+            loss += (h != h) ? h : fmaxf(h, 0.f);
+            g = (h != h) ? h : -(h > 0.f ? 1.f : (h == 0.f ? 0.5f : 0.f)) * inv_batch;
         } else {
             g = gscores[(long)b * N + n];
         }
@@ -212,8 +214,8 @@ score_kernel_g8(const float* __restrict__ u, const float* __restrict__ feats, co
         if (MODE == 2) {
             const float h = margin - s;
             if (on) {
-                loss += fmaxf(h, 0.f);
-                g = -(h > 0.f ? 1.f : (h == 0.f ? 0.5f : 0.f)) * inv_batch;
+                loss += (h != h) ? h : fmaxf(h, 0.f);     // NaN propagates like torch.max (see score_kernel)
+                g = (h != h) ? h : -(h > 0.f ? 1.f : (h == 0.f ? 0.5f : 0.f)) * inv_batch;
             }
         } else if (on) {
             g = gscores[(long)b * N + n];

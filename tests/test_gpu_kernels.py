@@ -569,8 +569,10 @@ def test_hinge_tie_at_margin_takes_half_gradient_on_device():
     ops.ScoreFn.apply(ud, fd, B, N).backward(-gs / B)
     assert relerr(du_t, ud.grad) < 1e-6 and relerr(df_t, fd.grad) < 1e-6
     # and it is exactly the mean of the two one-sided gradients
-    du_lo, df_lo, _ = fused(math.nextafter(margin, -math.inf))
-    du_hi, df_hi, _ = fused(math.nextafter(margin, math.inf))
+    import numpy as np
+    m32 = np.float32(margin)                      # the ABI takes a float: step by one fp32 ulp
+    du_lo, df_lo, _ = fused(float(np.nextafter(m32, np.float32(-np.inf))))
+    du_hi, df_hi, _ = fused(float(np.nextafter(m32, np.float32(np.inf))))
     assert relerr(du_t, 0.5 * (du_lo + du_hi)) < 1e-6 and relerr(df_t, 0.5 * (df_lo + df_hi)) < 1e-6
     assert not torch.equal(du_lo[2], du_hi[2])
     assert float(rows_t[2]) == float(torch.clamp(margin - s[2], min=0).sum())
@@ -597,7 +599,7 @@ def test_sort_free_scatter_equals_sorted_segment_sum(B, U, E, masked):
     out = guard[:U]
     out.zero_()
     L.call("dcue_scatter_add_rows", rows_d.data_ptr(), L.ptr(mask_d), idx_d.data_ptr(), B, U, E, out.data_ptr(), L.stream())
-    assert relerr(out, ref) < 1e-6
+    assert relerr(out, ref) < 1e-6 * max(1.0, B / U)          # fp32 running sums over ~B/U duplicates per row
     assert bool((guard[U:] == 7.0).all())
     # sorted path
     sidx = torch.empty(B, dtype=torch.int64, device=DEV)

@@ -83,10 +83,33 @@ def test_factors_predict_score_topk_and_checkpoint(tmp_path):
     cand = [s for _, s, _ in pred.rows]
     ref = O.cosine(t.user_factors.cpu()[3].expand(len(cand), -1), t.item_factors.cpu()[cand])
     assert np.allclose(scores, ref.numpy(), atol=1e-5) and targets == [y for _, _, y in pred.rows]
-    auc, mAP = t.score([0, 1, 2], loader, DataLoader(SynthPredSet(w), batch_size=16))
-    assert 0.0 <= auc <= 1.0 and 0.0 <= mAP <= 1.0
-    sauc, smap = t.score_song(pred.uniq_songs[:3], loader)
-    assert 0.0 <= sauc <= 1.0
+    # score / score_song (device AUC + AP kernel) against the reference's estimator evaluated with sklearn on the
+    # predict() lists (dcrecommend/nn/dcue.py:380-476), pred and truth being different splits
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    truth_loader = DataLoader(SynthPredSet(w, w.pairs[::2]), batch_size=16)
+    pred2 = SynthPredSet(w, w.pairs[1::2])
+    loader2 = DataLoader(pred2, batch_size=16, shuffle=False)
+    users = [0, 1, 2, 5]
+    auc, mAP = t.score(users, loader2, truth_loader)
+    ref_auc, ref_map = [], []
+    for user in users:
+        sp, tp = (np.array(x) for x in t.predict(user, loader2))
+        st, tt = (np.array(x) for x in t.predict(user, truth_loader))
+        halves = [(list(sp[tp == 1]) + list(st[tt == 0]), list(tp[tp == 1]) + list(tt[tt == 0])),
+                  (list(sp[tp == 0]) + list(st[tt == 1]), list(tp[tp == 0]) + list(tt[tt == 1]))]
+        total = len(halves[0][0]) + len(halves[1][0])
+        part = [1 if sum(tg) == len(tg) else 0 if sum(tg) == 0 else roc_auc_score(tg, sc) for sc, tg in halves]
+        ref_auc.append(len(halves[0][0]) / total * part[0] + len(halves[1][0]) / total * part[1])
+        ref_map.append(average_precision_score(halves[0][1] + halves[1][1], halves[0][0] + halves[1][0]))
+    assert abs(auc - np.mean(ref_auc)) < 1e-9 and abs(mAP - np.mean(ref_map)) < 1e-9
+    songs = pred2.uniq_songs[:4]
+    sauc, smap = t.score_song(songs, loader2)
+    ra, rm = [], []
+    for song in songs:
+        sc, tg = t.predict_song(song, loader2)
+        ra.append(1 if sum(tg) == len(tg) else 0 if sum(tg) == 0 else roc_auc_score(tg, sc))
+        rm.append(1 if sum(tg) == len(tg) else 0 if sum(tg) == 0 else average_precision_score(tg, sc))
+    assert abs(sauc - np.mean(ra)) < 1e-9 and abs(smap - np.mean(rm)) < 1e-9
     # top-k recommendation vs the oracle's all-pairs scorer
     ts, ti = t.recommend_topk(k=5)
     vs, vi = O.topk_scores(t.user_factors.cpu(), t.item_factors.cpu(), 5)
@@ -112,5 +135,6 @@ def test_fit_runs_end_to_end(tmp_path):
     np.random.seed(0)
     t.fit(tr, va, va, SynthPredSet(w, w.pairs[96:]), SynthPredSet(w, w.pairs[:96]), SynthItemSet(w), w.n_users,
           w.n_songs, "triplets.txt", "metadata.csv", str(tmp_path))
-    assert t.nn_epoch == 2 and t.user_factors is not None
+    # like the reference, a started sweep over the 10 sub-epoch loaders always finishes (nn_epoch 0 = evaluation only)
+    assert t.nn_epoch == 10 and t.user_factors is not None
     assert os.listdir(os.path.join(str(tmp_path), t._format_model_subdir()))
