@@ -502,7 +502,7 @@ tc_wgrad_kernel(const uint4* __restrict__ dyp, long dy_rows, int fmt_dy, const u
 // straight to registers (32-byte sector per lane, as in bn_relu_unpool_rows_kernel) one tile ahead; the smem stores
 // rotate the row order per lane pair so that a warp store instruction touches every bank once.
 constexpr int WGU_EXP = 8;                          // expander warps
-constexpr int WGU_DY_PANEL = WG_DY_PANEL;           // dY operand panel stride of the fused kernel
+constexpr int WGU_DY_PANEL = WG_DY_PANEL + ROWB;    // dY operand panel stride of the fused kernel (+16 B: bank spread)
 constexpr int WGU_STAGE_BYTES = PANELS * WGU_DY_PANEL + B_STAGE_BYTES;
 constexpr int WGU_THREADS = 64 + WGU_EXP * 32;
 
@@ -523,7 +523,7 @@ tc_wgrad_unpool_kernel(UnpoolSrc src, int fmt, const uint4* __restrict__ xp, lon
                        float* __restrict__ part /* [grid][128][KTAPS][128] */, double* __restrict__ bias_partial /* [grid][128] */) {
     constexpr int TCOLS = KTAPS * 128 <= 128 ? 128 : (KTAPS * 128 <= 256 ? 256 : 512);
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(16) float kconst[3][128];
+    __shared__ float bred[WGU_EXP][128];      // per-warp conv-bias partial sums
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_NSTAGE * WGU_STAGE_BYTES);
     // bars: [0..N) full (X tile by bulk copy), [N..2N) empty, [2N..3N) dyfull (expanders), 3N: done
@@ -592,18 +592,19 @@ tc_wgrad_unpool_kernel(UnpoolSrc src, int fmt, const uint4* __restrict__ xp, lon
         __syncwarp();
     } else {
         // ===== expanders: pooled fp32 inputs -> the 16-bit dY operand tile of every stage =====
-        // lane = pooling window of the 128-row tile, warp e = channel panels 2e, 2e+1 (a 64-byte run of every input row
-        // per lane).  A variant with fully coalesced row loads and a lane-pair exchange was tried and was slower
-        // (525 vs 448 us at layer-1 size: 40 % more instructions, the kernel is issue/latency bound in the expanders).
+        // lane <-> (pooling window, 8-channel panel): q = lane % 16 is the panel, lanes 0-15 / 16-31 take two consecutive windows,
+        // warp e owns windows 4e .. 4e+3 (two chunks per lane and tile).  A warp load instruction therefore covers two
+        // contiguous 512-byte pooled rows (8 cache lines; the previous lane = window mapping touched 32 lines per
+        // instruction and ncu showed l1tex 90 % busy with the tensor pipe at 43 %), every lane owns a complete 16-byte
+        // operand chunk (no lane exchange), and the per-channel BatchNorm constants of its fixed 8 channels live in registers.
+        // The dY panels are WGU_DY_PANEL = 2048 + 16 bytes apart so that the 16 panels of one row hit 16 different bank groups.
         const int e = warp - 2;
+        const int q = lane & 15, hw = lane >> 4;
         const float gs = src.gscale ? src.gscale[0] : 1.f;
-        // per-channel BatchNorm-backward constants live in shared memory (broadcast reads): as registers they pushed the
-        // two prefetch sets into spills
-        float acc[16];
+        float ka[8], kb[8], kc[8], acc[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-        if (lane < 16) {
-            const int c = e * 16 + lane;
+        for (int i = 0; i < 8; ++i) {
+            const int c = q * 8 + i;
             const float sc = src.scale ? src.scale[c] : 1.f;
             float b0 = 0.f, c0 = 0.f;
             if (src.sums) {
@@ -612,94 +613,83 @@ tc_wgrad_unpool_kernel(UnpoolSrc src, int fmt, const uint4* __restrict__ xp, lon
                 b0 = (float)(-(double)sc * rs2);
                 c0 = (float)((double)sc * (rs2 * (double)src.mean[c] - src.sums[c] * inv_n));
             }
-            kconst[0][c] = sc; kconst[1][c] = b0; kconst[2][c] = c0;
+            ka[i] = sc; kb[i] = b0; kc[i] = c0; acc[i] = 0.f;
         }
-        __syncwarp();
         const float invP = 1.f / (float)src.P;
-        // raw inputs of this lane's pooling window, TWO tiles ahead (two register sets: one tile of prefetch left
-        // ~1 us of global-load latency exposed per tile)
+        // raw inputs of this lane's two chunks, TWO tiles ahead (two register sets keep two tiles of loads in flight)
         struct Raw {
-            float4 g4[4], z4[4];
+            float4 g4[2][2], z4[2][2];
             uint2 cd[2];
-            bool valid;
-            long srow;
+            bool valid[2];
+            long srow[2];
         };
-        auto fetch = [&](Raw& w, long tile) {   // 16 channels of dy, z, code -> registers
-            const unsigned r = (unsigned)(tile * BN) + 4u * (unsigned)lane;
-            const unsigned sp = r / (unsigned)src.Lp;
-            const unsigned pw = (r - sp * (unsigned)src.Lp) >> 2;
-            w.valid = tile < tend && (int)sp < src.S && (int)pw < src.P;
-            w.srow = (long)sp;
-            if (w.valid) {
-                const long crow = (long)sp * src.P + pw;
-                const float4* gp = reinterpret_cast<const float4*>(src.dy + crow * src.lddy + e * 16);
-                const float4* zp = reinterpret_cast<const float4*>(src.z + crow * 128 + e * 16);
+        auto fetch = [&](Raw& w, long tile) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { w.g4[i] = __ldg(gp + i); w.z4[i] = __ldg(zp + i); }
-                const uint2* cp = reinterpret_cast<const uint2*>(src.code + crow * 128 + e * 16);
-                w.cd[0] = __ldg(cp);
-                w.cd[1] = __ldg(cp + 1);
+            for (int i = 0; i < 2; ++i) {
+                const unsigned win = (unsigned)(e * 4 + 2 * i + hw);
+                const unsigned r = (unsigned)(tile * BN) + 4u * win;
+                const unsigned sp = r / (unsigned)src.Lp;
+                const unsigned pw = (r - sp * (unsigned)src.Lp) >> 2;
+                w.valid[i] = tile < tend && (int)sp < src.S && (int)pw < src.P;
+                w.srow[i] = (long)sp;
+                if (w.valid[i]) {
+                    const long crow = (long)sp * src.P + pw;
+                    const float4* gp = reinterpret_cast<const float4*>(src.dy + crow * src.lddy + q * 8);
+                    const float4* zp = reinterpret_cast<const float4*>(src.z + crow * 128 + q * 8);
+                    w.g4[i][0] = __ldg(gp); w.g4[i][1] = __ldg(gp + 1);
+                    w.z4[i][0] = __ldg(zp); w.z4[i][1] = __ldg(zp + 1);
+                    w.cd[i] = __ldg(reinterpret_cast<const uint2*>(src.code + crow * 128 + q * 8));
+                }
             }
         };
         Pipe pp;
         auto expand = [&](Raw& w, long tile) {
-            unsigned short h[16];
-            unsigned cw[4] = {0u, 0u, 0u, 0u};
+            unsigned hp[2][4], cw[2][2];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) h[i] = 0;
-            if (w.valid) {
-                float g[16] = {w.g4[0].x, w.g4[0].y, w.g4[0].z, w.g4[0].w, w.g4[1].x, w.g4[1].y, w.g4[1].z, w.g4[1].w,
-                               w.g4[2].x, w.g4[2].y, w.g4[2].z, w.g4[2].w, w.g4[3].x, w.g4[3].y, w.g4[3].z, w.g4[3].w};
-                const float zz[16] = {w.z4[0].x, w.z4[0].y, w.z4[0].z, w.z4[0].w, w.z4[1].x, w.z4[1].y, w.z4[1].z, w.z4[1].w,
-                                      w.z4[2].x, w.z4[2].y, w.z4[2].z, w.z4[2].w, w.z4[3].x, w.z4[3].y, w.z4[3].z, w.z4[3].w};
-                if (src.dtp) {
-                    const float4* tp = reinterpret_cast<const float4*>(src.dtp + w.srow * src.lddtp + e * 16);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 t = __ldg(tp + i);
-                        g[4 * i] = fmaf(t.x, invP, g[4 * i]); g[4 * i + 1] = fmaf(t.y, invP, g[4 * i + 1]);
-                        g[4 * i + 2] = fmaf(t.z, invP, g[4 * i + 2]); g[4 * i + 3] = fmaf(t.w, invP, g[4 * i + 3]);
+            for (int i = 0; i < 2; ++i) {
+                hp[i][0] = hp[i][1] = hp[i][2] = hp[i][3] = 0u;
+                cw[i][0] = cw[i][1] = 0u;
+                if (w.valid[i]) {
+                    float g[8] = {w.g4[i][0].x, w.g4[i][0].y, w.g4[i][0].z, w.g4[i][0].w, w.g4[i][1].x, w.g4[i][1].y, w.g4[i][1].z, w.g4[i][1].w};
+                    const float zz[8] = {w.z4[i][0].x, w.z4[i][0].y, w.z4[i][0].z, w.z4[i][0].w,
+                                         w.z4[i][1].x, w.z4[i][1].y, w.z4[i][1].z, w.z4[i][1].w};
+                    if (src.dtp) {
+                        const float4* tp = reinterpret_cast<const float4*>(src.dtp + w.srow[i] * src.lddtp + q * 8);
+                        const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+                        g[0] = fmaf(t0.x, invP, g[0]); g[1] = fmaf(t0.y, invP, g[1]); g[2] = fmaf(t0.z, invP, g[2]); g[3] = fmaf(t0.w, invP, g[3]);
+                        g[4] = fmaf(t1.x, invP, g[4]); g[5] = fmaf(t1.y, invP, g[5]); g[6] = fmaf(t1.z, invP, g[6]); g[7] = fmaf(t1.w, invP, g[7]);
                     }
-                }
+                    unsigned short h[8];
 #pragma unroll
-                for (int i4 = 0; i4 < 16; i4 += 4) {
-                    const float4 a4 = *reinterpret_cast<const float4*>(&kconst[0][e * 16 + i4]);
-                    const float4 b4 = *reinterpret_cast<const float4*>(&kconst[1][e * 16 + i4]);
-                    const float4 c4 = *reinterpret_cast<const float4*>(&kconst[2][e * 16 + i4]);
-                    const float ka[4] = {a4.x, a4.y, a4.z, a4.w}, kb[4] = {b4.x, b4.y, b4.z, b4.w}, kc[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int i = i4 + t;
-                        const float gg = fmaf(ka[t], g[i], fmaf(kb[t], zz[i], kc[t]));
-                        const float v = zz[i] > 0.f ? gg : 0.f;
-                        acc[i] += v;
-                        h[i] = cvt_f32_to16(v * gs, fmt);
+                    for (int t = 0; t < 8; ++t) {
+                        const float gg = fmaf(ka[t], g[t], fmaf(kb[t], zz[t], kc[t]));
+                        const float v = zz[t] > 0.f ? gg : 0.f;
+                        acc[t] += v;
+                        h[t] = cvt_f32_to16(v * gs, fmt);
                     }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) hp[i][c] = (unsigned)h[2 * c] | ((unsigned)h[2 * c + 1] << 16);
+                    cw[i][0] = w.cd[i].x; cw[i][1] = w.cd[i].y;
                 }
-                cw[0] = w.cd[0].x; cw[1] = w.cd[0].y; cw[2] = w.cd[1].x; cw[3] = w.cd[1].y;
             }
             fetch(w, tile + 2);                       // refill this register set: two tiles of loads stay in flight
             mbar_wait(EMPTY(pp.stage), pp.phase ^ 1); // the MMAs that read this stage (3 tiles ago) have retired
             uint8_t* dy_dst = smem + pp.stage * WGU_STAGE_BYTES;
-            // halves packed two per register once; per row the four code bytes of a word become two 16-bit-lane masks with
-            // word-wide logic (exact zero-byte test + byte permutes) instead of a compare and select per channel
-            unsigned hp[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) hp[c] = (unsigned)h[2 * c] | ((unsigned)h[2 * c + 1] << 16);
+            for (int i = 0; i < 2; ++i) {
+                uint8_t* base = dy_dst + q * WGU_DY_PANEL + (e * 4 + 2 * i + hw) * (4 * ROWB);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint8_t* base = dy_dst + (e * 2 + half) * WGU_DY_PANEL + lane * (4 * ROWB);
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const unsigned j = (unsigned)((jj + (lane >> 1)) & 3);   // lane pairs start on different rows: conflict-free stores
+                for (int j = 0; j < 4; ++j) {
+                    // the four code bytes of a word become two 16-bit-lane masks with word-wide logic (exact zero-byte test +
+                    // byte permutes) instead of a compare and select per channel
                     unsigned out[4];
 #pragma unroll
                     for (int wq = 0; wq < 2; ++wq) {
-                        const unsigned t = cw[half * 2 + wq] ^ (j * 0x01010101u);              // byte == 0 where code == j
+                        const unsigned t = cw[i][wq] ^ ((unsigned)j * 0x01010101u);            // byte == 0 where code == j
                         const unsigned nz = ((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t;             // bit 7 set where the byte is non-zero
                         const unsigned m8 = ((~nz & 0x80808080u) >> 7) * 0xffu;                // 0xff in the matching bytes
-                        out[2 * wq] = hp[half * 4 + 2 * wq] & __byte_perm(m8, 0u, 0x1100);     // channels 0,1 of the word
-                        out[2 * wq + 1] = hp[half * 4 + 2 * wq + 1] & __byte_perm(m8, 0u, 0x3322);   // channels 2,3
+                        out[2 * wq] = hp[i][2 * wq] & __byte_perm(m8, 0u, 0x1100);             // channels 0,1 of the word
+                        out[2 * wq + 1] = hp[i][2 * wq + 1] & __byte_perm(m8, 0u, 0x3322);     // channels 2,3
                     }
                     *reinterpret_cast<uint4*>(base + j * ROWB) = make_uint4(out[0], out[1], out[2], out[3]);
                 }
@@ -717,10 +707,20 @@ tc_wgrad_unpool_kernel(UnpoolSrc src, int fmt, const uint4* __restrict__ xp, lon
             if (tile + 1 < tend) expand(rb, tile + 1);
         }
         if (bias_partial) {
+            // this lane's 8 channels: add the other window half (lane ^ 16), then the 8 warps through shared memory, fixed order
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float t = warp_sum(acc[i]);
-                if (lane == 0) bias_partial[(long)blockIdx.x * 128 + e * 16 + i] = (double)t;
+            for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+            if (hw == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bred[e][q * 8 + i] = acc[i];
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(WGU_EXP * 32) : "memory");
+            const int c = threadIdx.x - 64;
+            if (c < 128) {
+                double t = 0.0;
+#pragma unroll
+                for (int w8 = 0; w8 < WGU_EXP; ++w8) t += (double)bred[w8][c];
+                bias_partial[(long)blockIdx.x * 128 + c] = t;
             }
         }
         if (e < 4) {

@@ -1,12 +1,16 @@
-// fp32 CUDA-core GEMMs for the small dense layers of DCUE: the user MLP
+// fp32-accurate GEMMs for the small dense layers of DCUE: the user MLP
 // (dcrecommend/dcue/embeddings/userembedding.py:42-44), the k=1 conv and the fc of the song
-// tower (truedcuemel1dbn.py:57-59,101).  <0.2 % of the step's FLOPs; kept in fp32 so that the
-// user features match the reference to ~1e-6.
+// tower (truedcuemel1dbn.py:57-59,101).  1.7 % of the step's FLOPs, but as CUDA-core FMAs they took 10 % of the step
+// (round 1: 12 launches, 0.30 ms); they now run on the tensor cores as 3xTF32 (mma.sync.m16n8k8: a = a_hi + a_lo with
+// both halves TF32, a*b ~ a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulate), which keeps ~2^-21 relative accuracy --
+// the user features still match the reference to ~1e-6.  These GEMMs read 10-20 MB each: warp-level MMA from the same
+// shared-memory tiles is enough to make them memory/latency bound; DCUE_LINEAR_IMPL=simt selects the CUDA-core loop (A/B).
 //
 // One strided kernel:  C[i,j] = sum_r A(i,r) * B(r,j)  (+bias[j]) (relu) (* mask[i,j] > 0)
 // 64x64 tile, BK = 16, 256 threads, 4x4 outputs per thread, optional split over r (grid.z)
 // into a workspace that a second kernel reduces in fixed order (deterministic).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -69,11 +73,23 @@ __device__ __forceinline__ void gemm_fetch(const GemmP& p, int tid, int i0, int 
     }
 }
 
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <bool MMA>
 __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
     // double-buffered tiles: the next tile's global loads are in flight while the current one is multiplied
     // (the single-buffered version exposed one DRAM/L2 round trip per 16-deep k step: 35 us for 0.55 GFLOP)
-    __shared__ __align__(16) float As[2][TK][TM + 4];
-    __shared__ __align__(16) float Bs[2][TK][TN + 4];
+    __shared__ __align__(16) float As[2][TK][TM + 8];   // row stride 72 words: the MMA fragment reads hit 32 distinct banks
+    __shared__ __align__(16) float Bs[2][TK][TN + 8];
     const int tid = threadIdx.x;
     const int i0 = blockIdx.y * TM, j0 = blockIdx.x * TN;
     const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 4x4
@@ -82,11 +98,16 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
     const int rbeg = blockIdx.z * rchunk;
     const int rend = min(p.R, rbeg + rchunk);
 
+    // SIMT: thread (ty, tx) owns the 4x4 block at rows ty*4, cols tx*4.
+    // MMA : warp (wm = warp & 1, wn = warp >> 1) owns rows wm*32..+32, cols wn*16..+16 as 2 x 2 m16n8 tiles; acc[mi*2+ni][0..3]
+    //       are the fragment's (row g, col 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1) with g = lane / 4, t = lane % 4.
     float acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    const int lane = tid & 31, wid = tid >> 5;
+    const int wm = wid & 1, wn = wid >> 1, fg = lane >> 2, ft = lane & 3;
 
     const bool a_r_contig = (p.sAr == 1);
     const bool b_j_contig = (p.sBj == 1);
@@ -125,21 +146,74 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
     for (int r0 = rbeg; r0 < rend; r0 += TK) {
         const bool more = r0 + TK < rend;
         if (more) gemm_fetch(p, tid, i0, j0, r0 + TK, rend, a_r_contig, b_j_contig, a_vec, b_vec, f);
+        if (MMA) {
 #pragma unroll
-        for (int k = 0; k < TK; ++k) {
-            const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+            for (int kk = 0; kk < TK; kk += 8) {
+                uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
+                for (int mi = 0; mi < 2; ++mi) {
+                    const int r = wm * 32 + mi * 16 + fg;
+                    split_tf32(As[buf][kk + ft][r], ah[mi][0], al[mi][0]);
+                    split_tf32(As[buf][kk + ft][r + 8], ah[mi][1], al[mi][1]);
+                    split_tf32(As[buf][kk + ft + 4][r], ah[mi][2], al[mi][2]);
+                    split_tf32(As[buf][kk + ft + 4][r + 8], ah[mi][3], al[mi][3]);
+                }
 #pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+                for (int ni = 0; ni < 2; ++ni) {
+                    const int c = wn * 16 + ni * 8 + fg;
+                    split_tf32(Bs[buf][kk + ft][c], bh[ni][0], bl[ni][0]);
+                    split_tf32(Bs[buf][kk + ft + 4][c], bh[ni][1], bl[ni][1]);
+                }
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ++ni) {      // small terms first
+                        mma_tf32(acc[mi * 2 + ni], al[mi], bh[ni]);
+                        mma_tf32(acc[mi * 2 + ni], ah[mi], bl[ni]);
+                        mma_tf32(acc[mi * 2 + ni], ah[mi], bh[ni]);
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < TK; ++k) {
+                const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+                const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+                const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+            }
         }
         if (more) stash(buf ^ 1, f);   // the other buffer was last read before the previous barrier
         __syncthreads();
         buf ^= 1;
     }
     float* C = p.C + (long)blockIdx.z * p.split_stride;
+    if (MMA) {
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int gi = i0 + wm * 32 + mi * 16 + fg + 8 * h;
+                    const int gj = j0 + wn * 16 + ni * 8 + 2 * ft;
+                    if (gi >= p.I) continue;
+#pragma unroll
+                    for (int y = 0; y < 2; ++y) {
+                        if (gj + y >= p.J) continue;
+                        float v = acc[mi * 2 + ni][2 * h + y];
+                        if (p.splits == 1) {
+                            if (p.bias) v += p.bias[gj + y];
+                            if (p.relu) v = v < 0.f ? 0.f : v;  // NaN-propagating (an out-of-range user row must stay loud)
+                            if (p.mask) v = p.mask[gi * p.ldmask + gj + y] > 0.f ? v : 0.f;
+                        }
+                        C[gi * p.ldc + gj + y] = v;
+                    }
+                }
+        return;
+    }
     const int gj0 = j0 + tx * 4;
     const bool c_vec = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && ((p.ldc & 3) == 0) && gj0 + 3 < p.J &&
                        (!p.mask || (((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0) && ((p.ldmask & 3) == 0)));
@@ -211,6 +285,19 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
     }
 }
 
+bool linear_simt() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DCUE_LINEAR_IMPL");
+        v = (e && (e[0] == 's' || e[0] == 'S')) ? 1 : 0;
+    }
+    return v != 0;
+}
+void launch_gemm(const GemmP& p, dim3 grid, cudaStream_t st) {
+    if (linear_simt()) gemm_kernel<false><<<grid, 256, 0, st>>>(p);
+    else gemm_kernel<true><<<grid, 256, 0, st>>>(p);
+}
+
 int wgrad_splits(int M, int K, int N) {
     const int tiles = ceil_div_i(N, TM) * ceil_div_i(K, TN);
     int s = (2 * dcue_num_sms() + tiles - 1) / tiles;
@@ -233,7 +320,7 @@ extern "C" int dcue_linear_fwd(const float* X, int ldx, const float* W, const fl
     p.C = Y; p.ldc = ldy; p.bias = b; p.mask = nullptr; p.ldmask = 0;
     p.I = M; p.J = N; p.R = K; p.relu = relu; p.splits = 1; p.split_stride = 0;
     dim3 grid(ceil_div_i(N, TN), ceil_div_i(M, TM), 1);
-    gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    launch_gemm(p, grid, (cudaStream_t)stream);
     DCUE_LAUNCH_CHECK();
     return 0;
 }
@@ -248,7 +335,7 @@ extern "C" int dcue_linear_dgrad(const float* dY, int lddy, const float* W, int 
     p.C = dX; p.ldc = lddx; p.bias = nullptr; p.mask = mask; p.ldmask = ldmask;
     p.I = M; p.J = K; p.R = N; p.relu = 0; p.splits = 1; p.split_stride = 0;
     dim3 grid(ceil_div_i(K, TN), ceil_div_i(M, TM), 1);
-    gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    launch_gemm(p, grid, (cudaStream_t)stream);
     DCUE_LAUNCH_CHECK();
     return 0;
 }
@@ -275,7 +362,7 @@ extern "C" int dcue_linear_wgrad(const float* dY, int lddy, const float* X, int 
     p.C = splits > 1 ? (float*)ws : dW; p.ldc = K; p.bias = nullptr; p.mask = nullptr; p.ldmask = 0;
     p.I = N; p.J = K; p.R = M; p.relu = 0; p.splits = splits; p.split_stride = (long)N * K;
     dim3 grid(ceil_div_i(K, TN), ceil_div_i(N, TM), splits);
-    gemm_kernel<<<grid, 256, 0, st>>>(p);
+    launch_gemm(p, grid, st);
     DCUE_LAUNCH_CHECK();
     if (splits > 1) {
         const long n = (long)N * K;

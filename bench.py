@@ -322,6 +322,7 @@ def dp_parity_leg(pkg, par, dev, rank, world, per_rank=32, negs=4, users=500):
     loss.backward()
     dp.reduce_gradients()
     loss_g = dp.reduce_loss(loss).item()
+    del loss       # no autograd graph (and no AccumulateGrad node bound to this stream) may survive into the graph capture below
     grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
     bufs = {k: v.detach().clone() for k, v in model.named_buffers()}
     # every rank must hold the same reduced gradients: compare with rank 0's
