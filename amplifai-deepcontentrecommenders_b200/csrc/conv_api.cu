@@ -43,6 +43,17 @@ extern "C" int dcue_conv_pool_fwd(int impl, const void* panel, long panel_rows, 
     return dcue_simt_conv_fwd(panel, panel_rows, fmt, w_packed, bias, tap_bias, g, z, code, sums, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+extern "C" int dcue_conv_pool_fwd_parts(int impl, const void* panel, long panel_rows, int fmt, const void* w_packed,
+                                        const float* bias, const float* tap_bias, int S, int Lp, int Lin, int pad, int P, int pool,
+                                        int k, int Cin, int Cout, float* z, uint8_t* code, void* ws, size_t ws_bytes, void* stream) {
+    return dcue_conv_pool_fwd(impl, panel, panel_rows, fmt, w_packed, bias, tap_bias, S, Lp, Lin, pad, P, pool, k, Cin, Cout, z, code,
+                              DCUE_STATS_PARTIALS, ws, ws_bytes, stream);
+}
+extern "C" size_t dcue_conv_pool_fwd_nparts(int impl, int S, int Lp) {
+    const long rows = (long)S * Lp;
+    return (size_t)(impl == DCUE_IMPL_TC ? dcue_tc_conv_fwd_nparts(rows) : dcue_simt_conv_fwd_nparts(rows));
+}
+
 extern "C" int dcue_conv_dgrad(int impl, const void* dy_panel, long panel_rows, int fmt_dy, const void* w_packed_dgrad,
                                int fmt_w, int S, int Lp, int Lin, int pad, int k, int Cin, int Cout, const float* gscale,
                                float* dx, void* ws, size_t ws_bytes, void* stream) {

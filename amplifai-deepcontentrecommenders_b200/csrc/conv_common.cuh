@@ -28,6 +28,12 @@ __device__ __forceinline__ float missing_taps(const float (&tb)[4], int t, int k
     return a;
 }
 
+// `sums` value that asks the forward kernels to leave their per-block statistic partials ([nparts][2*Cout] doubles) at the
+// start of the workspace instead of reducing them (dcue_conv_pool_fwd_parts + dcue_bn_stats_finalize)
+#define DCUE_STATS_PARTIALS (reinterpret_cast<double*>(uintptr_t(8)))
+int dcue_tc_conv_fwd_nparts(long rows_total);
+int dcue_simt_conv_fwd_nparts(long rows_total);
+
 // CUDA-core path (conv_simt.cu)
 int dcue_simt_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_packed, const float* bias,
                        const float* tap_bias, const ConvGeom& g, float* z, uint8_t* code, double* sums, void* ws, size_t ws_bytes,

@@ -234,11 +234,17 @@ int dcue_simt_conv_fwd(const void* panel, long panel_rows, int fmt, const void* 
     conv_rows_kernel<0><<<grid, 128, smem, st>>>((const uint4*)panel, panel_rows, fmt, (const uint4*)w_packed, fmt, bias,
                                                  g, z, code, sums ? (double*)ws : nullptr, nullptr, tap_bias);
     DCUE_LAUNCH_CHECK();
-    if (sums) {
+    if (sums && sums != DCUE_STATS_PARTIALS) {
         dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 8), 256, 0, st>>>((const double*)ws, grid, 2 * g.Cout, sums);
         DCUE_LAUNCH_CHECK();
     }
     return 0;
+}
+
+int dcue_simt_conv_fwd_nparts(long rows_total) {
+    const long ntiles = (rows_total + TRW - 1) / TRW;
+    const long cap = (long)dcue_num_sms() * 4;
+    return (int)(ntiles < cap ? (ntiles > 0 ? ntiles : 1) : cap);
 }
 
 int dcue_simt_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,

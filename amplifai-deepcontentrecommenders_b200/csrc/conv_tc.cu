@@ -825,12 +825,14 @@ int dcue_tc_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_
     else if (g.pool == 2) e = launch_rows_t<0, 2>(panel, panel_rows, fmt, w_packed, fmt, bias, g, z, code, part, nullptr, tap_bias, dummy, grid, st);
     else e = launch_rows_t<0, 1>(panel, panel_rows, fmt, w_packed, fmt, bias, g, z, code, part, nullptr, tap_bias, dummy, grid, st);
     if (e) return e;
-    if (sums) {
+    if (sums && sums != DCUE_STATS_PARTIALS) {
         dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 8), 256, 0, st>>>((const double*)ws, grid * 4, 2 * g.Cout, sums);
         DCUE_LAUNCH_CHECK();
     }
     return 0;
 }
+
+int dcue_tc_conv_fwd_nparts(long rows_total) { return tc_grid(rows_total) * 4; }
 
 int dcue_tc_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
                        const ConvGeom& g, const float* gscale, float* dx, void* ws, size_t ws_bytes, cudaStream_t st) {

@@ -1,0 +1,71 @@
+// Device-side one-shot all-reduce over NVLink peer memory, shared by peer.cu (stand-alone kernel) and bn.cu (fused into the
+// BatchNorm statistic finalisers).  See peer.cu for the protocol.
+#pragma once
+#include "common.cuh"
+
+constexpr int PEER_SLOT_DOUBLES = 512;
+constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;   // 20 s
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct PeerCtx {
+    double* const* bufs;       // device array of `world` pointers to the symmetric buffers (2 slots of PEER_SLOT_DOUBLES)
+    unsigned* const* sigs;     // device array of `world` pointers to the signal pads
+    unsigned* counter;         // [0] call counter of this rank, [1] time-out flag
+    int rank, world;
+};
+
+// All-reduce (SUM, rank order -> bit-identical on every rank) of vec[0, n) held by ONE thread block (shared or global
+// memory, visible to all its threads); every thread of the block must call this.  `ep_sh` is a shared scratch word.
+__device__ __forceinline__ void peer_allreduce_block(const PeerCtx& pc, double* vec, int n, unsigned* ep_sh) {
+    if (pc.world <= 1) return;
+    __syncthreads();
+    if (threadIdx.x == 0) *ep_sh = ++(*pc.counter);
+    __syncthreads();
+    const unsigned e = *ep_sh;
+    const int slot = (int)(e & 1u) * PEER_SLOT_DOUBLES;
+    double* mine = pc.bufs[pc.rank] + slot;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mine[i] = vec[i];
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < pc.world) {
+        st_release_sys(pc.sigs[threadIdx.x] + pc.rank, e);                 // tell peer `threadIdx.x` that my slot is ready
+        const unsigned* my_pad = pc.sigs[pc.rank] + threadIdx.x;
+        // peer's call e (or a later one) is published.  The wait is bounded: a rank that died or raised would otherwise hang
+        // every other GPU inside this kernel; after PEER_TIMEOUT_NS the flag counter[1] is raised (the result is then invalid)
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        while ((int)(ld_acquire_sys(my_pad) - e) < 0) {
+            __nanosleep(20);
+            if ((++spins & 1023u) == 0) {
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > PEER_TIMEOUT_NS) { atomicExch(reinterpret_cast<int*>(pc.counter) + 1, 1 + (int)threadIdx.x); break; }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < pc.world; ++r) s += ld_relaxed_sys_f64(pc.bufs[r] + slot + i);
+        vec[i] = s;
+    }
+    __syncthreads();
+}

@@ -7,6 +7,9 @@
 #include "common.cuh"
 #include <stdlib.h>
 
+// phase cycle counters of block 0 / appender warp 0 (diagnostics: dcue_topk_debug_cycles)
+__device__ unsigned long long g_topk_dbg[8];
+
 namespace {
 
 constexpr int ROWB = 16;
@@ -529,6 +532,8 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                 sh->done[et] = 0;
             }
             epi_sync();
+            const bool dbg = blockIdx.x == 0 && et == 0;
+            long long c0 = clock64();
             for (long t = 0; t < ntiles; ++t) {
                 mbar_wait(TFULL(acc), acc_phase);
                 tc_fence_after();
@@ -590,7 +595,9 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                 if ((t & (BSTEP - 1)) == BSTEP - 1) boundary(false);
             }
             // ---- finish: every list down to <= 512 entries with nothing pending, then the k best, sorted
+            long long c1 = clock64();
             boundary(true);
+            long long c2 = clock64();
             for (int uu = 0; uu < UPW; ++uu) {
                 const int u = e * UPW + uu;
                 const long gu = ut * NU + u;
@@ -613,7 +620,16 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                 if (n > k) { select_topk_inplace(lst, n, k, lane); n = k; }
                 sort_and_write(lst, n, k, item_offset, out_s + ob, out_i + ob, lane);
             }
+            long long c3 = clock64();
             epi_sync();   // nobody resets the per-user state while another warp still reads it
+            if (dbg) {
+                atomicAdd(&g_topk_dbg[0], (unsigned long long)(c1 - c0));
+                atomicAdd(&g_topk_dbg[1], (unsigned long long)(c2 - c1));
+                atomicAdd(&g_topk_dbg[2], (unsigned long long)(c3 - c2));
+                atomicAdd(&g_topk_dbg[3], (unsigned long long)(clock64() - c3));
+                atomicAdd(&g_topk_dbg[4], 1ull);
+                atomicAdd(&g_topk_dbg[5], (unsigned long long)ntiles);
+            }
         }
         if (et == 0) {
             __threadfence_block();
@@ -824,5 +840,15 @@ extern "C" int dcue_topk_merge(const float* scores, const int64_t* idx, int part
     topk_merge_kernel<<<ceil_div_i(n_users, 128), 128, 0, (cudaStream_t)stream>>>(scores, idx, parts, n_users, k, out_scores,
                                                                                   out_idx);
     DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcue_topk_debug_cycles(unsigned long long* host_out8, int reset) {
+    DCUE_CHECK_ARG(host_out8);
+    DCUE_CUDA(cudaMemcpyFromSymbol(host_out8, g_topk_dbg, sizeof(unsigned long long) * 8));
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        DCUE_CUDA(cudaMemcpyToSymbol(g_topk_dbg, z, sizeof(z)));
+    }
     return 0;
 }

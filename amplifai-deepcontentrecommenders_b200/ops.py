@@ -39,6 +39,20 @@ def fused_wgrad():
     return os.environ.get("DCUE_FUSED_WGRAD", "1") != "0"
 
 
+def fused_finalize():
+    """BatchNorm statistic partials -> (peer all-reduce) -> finalize in ONE kernel per layer (DCUE_FUSED_FINALIZE=0: the
+    separate reduce / all-reduce / finalize launches)."""
+    return os.environ.get("DCUE_FUSED_FINALIZE", "1") != "0"
+
+
+def _peer_args(dp):
+    """(bufs, signals, counter, rank, world) of the NVLink peer all-reduce for the fused finalisers; world 1 = no exchange."""
+    if dp is None or dp.world_size == 1:
+        return (None, None, None, 0, 1)
+    pr = dp._peer
+    return (pr.hdl.buffer_ptrs_dev, pr.hdl.signal_pad_ptrs_dev, pr.counter.data_ptr(), pr.rank, pr.world)
+
+
 def operand_fmt():
     """16-bit format of the forward conv operands: fp16 (default) or bf16 (DCUE_OPERAND=bf16)."""
     return L.FMT_BF16 if os.environ.get("DCUE_OPERAND", "f16").lower() == "bf16" else L.FMT_F16
@@ -193,18 +207,31 @@ class SongTowerFn(torch.autograd.Function):
         dp = mod._dp
         world = 1 if dp is None else dp.world_size
 
-        def bn_finalize(i, count, C_, affine=True, centered=False):
+        # training-mode statistics take the fused finaliser (partials -> [peer all-reduce] -> scale/shift/mean/rstd + running
+        # statistics in one launch) unless the data-parallel group has no peer memory (then: reduce, NCCL, finalize)
+        fused = (has_bn and training and fused_finalize()
+                 and (dp is None or world == 1 or getattr(dp, "_peer", None) is not None))
+        peer = _peer_args(dp)
+
+        def bn_finalize(i, count, C_, affine=True, centered=False, nparts=0):
             """sums[i] -> scale/shift/mean/rstd of BN layer i (batch or running statistics).
             affine=False gives the plain normalisation (scale = rstd, shift = -mean*rstd); centered=True means the
-            statistics were taken on x - running_mean (the single-pass input kernel)."""
+            statistics were taken on x - running_mean (the single-pass input kernel).  nparts > 0: the producer left
+            nparts partial rows at the start of `scratch` (fused finaliser)."""
             bnm = getattr(mod, "bn%d" % i)
+            gam = P["bn%d.weight" % i].data_ptr() if affine else None
+            bet = P["bn%d.bias" % i].data_ptr() if affine else None
+            ctr = bnm.running_mean.data_ptr() if centered else None
+            if nparts:
+                L.call("dcue_bn_stats_finalize", scratch, int(nparts), float(count * world), C_, gam, bet,
+                       bnm.running_mean.data_ptr(), bnm.running_var.data_ptr(), bnm.num_batches_tracked.data_ptr(), BN_MOMENTUM,
+                       BN_EPS, ctr, *peer, ws.sums[i].data_ptr(), ws.bnp[i, 0].data_ptr(), ws.bnp[i, 1].data_ptr(),
+                       ws.bnp[i, 2].data_ptr(), ws.bnp[i, 3].data_ptr(), st)
+                return
             if training and dp is not None:
                 dp.all_reduce_sum(ws.sums[i])
-            L.call("dcue_bn_finalize", ws.sums[i].data_ptr(), float(count * world), C_,
-                   P["bn%d.weight" % i].data_ptr() if affine else None,
-                   P["bn%d.bias" % i].data_ptr() if affine else None, bnm.running_mean.data_ptr(), bnm.running_var.data_ptr(),
-                   bnm.num_batches_tracked.data_ptr(), BN_MOMENTUM, BN_EPS, int(training),
-                   bnm.running_mean.data_ptr() if centered else None,
+            L.call("dcue_bn_finalize", ws.sums[i].data_ptr(), float(count * world), C_, gam, bet, bnm.running_mean.data_ptr(),
+                   bnm.running_var.data_ptr(), bnm.num_batches_tracked.data_ptr(), BN_MOMENTUM, BN_EPS, int(training), ctr,
                    ws.bnp[i, 0].data_ptr(), ws.bnp[i, 1].data_ptr(), ws.bnp[i, 2].data_ptr(), ws.bnp[i, 3].data_ptr(), st)
 
         pos_p, neg_p = pos.data_ptr(), (None if neg is None else neg.data_ptr())
@@ -216,13 +243,16 @@ class SongTowerFn(torch.autograd.Function):
         off_p = None if (src is None or off is None) else off.data_ptr()
         if has_bn:
             rm0 = mod.bn0.running_mean.data_ptr()
+            sums0 = None if fused else ws.sums[0].data_ptr()      # None: partial rows stay in scratch for the fused finaliser
             if src is not None:
                 L.call("dcue_ncl_center_pack_stats_indexed", pos_p, n_songs, T, idx.data_ptr(), off_p, S, C, frames, err.data_ptr(),
-                       rm0, ws.X[0].base, ws.X[0].panel_rows, g0["Lp"], g0["pad"], fmt, ws.sums[0].data_ptr(), scratch, nscr, st)
+                       rm0, ws.X[0].base, ws.X[0].panel_rows, g0["Lp"], g0["pad"], fmt, sums0, scratch, nscr, st)
             else:
                 L.call("dcue_ncl_center_pack_stats", pos_p, S_pos, neg_p, S_neg, C, frames, rm0, ws.X[0].base, ws.X[0].panel_rows,
-                       g0["Lp"], g0["pad"], fmt, ws.sums[0].data_ptr(), scratch, nscr, st)
-            bn_finalize(0, S * frames, C, affine=False, centered=True)   # bnp[0] = (rstd, shift, mean_u, rstd)
+                       g0["Lp"], g0["pad"], fmt, sums0, scratch, nscr, st)
+            # bnp[0] = (rstd, shift, mean_u, rstd)
+            bn_finalize(0, S * frames, C, affine=False, centered=True,
+                        nparts=L.query("dcue_ncl_center_pack_stats_nparts", S, C) if fused else 0)
             L.call("dcue_conv_tap_bias", P["layer1.weight"].data_ptr(), H, 128, g0["k"], P["bn0.bias"].data_ptr(),
                    P["bn0.weight"].data_ptr(), ws.bnp[0, 1].data_ptr(), ws.tapb.data_ptr(), st)
         elif src is not None:
@@ -239,12 +269,17 @@ class SongTowerFn(torch.autograd.Function):
                    P["bn0.weight"].data_ptr() if fold else None, ws.bnp[0, 0].data_ptr() if fold else None,
                    ws.wp[i - 1].data_ptr(), st)
             want_stats = has_bn and training
-            L.call("dcue_conv_pool_fwd", impl, ws.X[i - 1].base, ws.X[i - 1].panel_rows, fmt, ws.wp[i - 1].data_ptr(),
-                   bt.data_ptr(), ws.tapb.data_ptr() if fold else None, S, g["Lp"], g["Lin"], g["pad"], g["P"], g["pool"],
-                   g["k"], 128, H, ws.z[i - 1].data_ptr(),
-                   ws.code[i - 1].data_ptr(), ws.sums[i].data_ptr() if want_stats else None, scratch, nscr, st)
+            if fused:
+                L.call("dcue_conv_pool_fwd_parts", impl, ws.X[i - 1].base, ws.X[i - 1].panel_rows, fmt, ws.wp[i - 1].data_ptr(),
+                       bt.data_ptr(), ws.tapb.data_ptr() if fold else None, S, g["Lp"], g["Lin"], g["pad"], g["P"], g["pool"],
+                       g["k"], 128, H, ws.z[i - 1].data_ptr(), ws.code[i - 1].data_ptr(), scratch, nscr, st)
+            else:
+                L.call("dcue_conv_pool_fwd", impl, ws.X[i - 1].base, ws.X[i - 1].panel_rows, fmt, ws.wp[i - 1].data_ptr(),
+                       bt.data_ptr(), ws.tapb.data_ptr() if fold else None, S, g["Lp"], g["Lin"], g["pad"], g["P"], g["pool"],
+                       g["k"], 128, H, ws.z[i - 1].data_ptr(),
+                       ws.code[i - 1].data_ptr(), ws.sums[i].data_ptr() if want_stats else None, scratch, nscr, st)
             if has_bn:
-                bn_finalize(i, S * g["P"], H)
+                bn_finalize(i, S * g["P"], H, nparts=L.query("dcue_conv_pool_fwd_nparts", impl, S, g["Lp"]) if fused else 0)
                 sc, sh = ws.bnp[i, 0].data_ptr(), ws.bnp[i, 1].data_ptr()
             else:
                 sc = sh = None
@@ -264,8 +299,8 @@ class SongTowerFn(torch.autograd.Function):
         if has_bn:
             if training:  # sum z, sum z^2 via the backward-reduce kernel with mean=0, rstd=1
                 L.call("dcue_bn_bwd_reduce", ws.z5.data_ptr(), F, None, 0, ws.z5.data_ptr(), ws.zero128.data_ptr(),
-                       ws.one128.data_ptr(), S, 1, F, ws.sums[5].data_ptr(), None, None, None, scratch, nscr, st)
-            bn_finalize(5, S, F)
+                       ws.one128.data_ptr(), S, 1, F, None if fused else ws.sums[5].data_ptr(), None, None, None, scratch, nscr, st)
+            bn_finalize(5, S, F, nparts=L.query("dcue_bn_bwd_reduce_nparts", S, 1) if fused else 0)
             sc, sh = ws.bnp[5, 0].data_ptr(), ws.bnp[5, 1].data_ptr()
         else:
             sc = sh = None
@@ -313,15 +348,32 @@ class SongTowerFn(torch.autograd.Function):
         gfmt = fmt
         bn_train = has_bn and training
 
+        fused_fin = fused_finalize() and (dp is None or world == 1 or getattr(dp, "_peer", None) is not None)
+
         def bn_sums(i, dy_ptr, lddy, dtp_ptr, lddtp, z, P_, C_, want_scale=True):
             """Per-channel reductions over the gradient entering layer i's BN (+ DP all-reduce):
             dgamma/dbeta when BN uses batch statistics, and max|dy| for the 16-bit gradient scale."""
             mean_p = ws.bnp[i, 2].data_ptr() if bn_train else ws.zero128.data_ptr()
             rstd_p = ws.bnp[i, 3].data_ptr() if bn_train else ws.one128.data_ptr()
             gw = gb = None
-            direct = bn_train and dp is None  # single GPU: the reducer emits dgamma / dbeta in fp32 directly
             if bn_train:
                 gw, gb = torch.empty(C_, **f32), torch.empty(C_, **f32)
+            if fused_fin:
+                # one sweep leaves per-block partials in scratch, ONE kernel reduces them, all-reduces the sums over NVLink
+                # (data parallel), emits dgamma / dbeta in fp32 and the power-of-two scale of the 16-bit gradient operand
+                L.call("dcue_bn_bwd_reduce", dy_ptr, lddy, dtp_ptr, lddtp, z.data_ptr(), mean_p, rstd_p, S, P_, C_, None, None,
+                       None, None, scratch, nscr, st)
+                peer = _peer_args(dp) if bn_train else (None, None, None, 0, 1)
+                L.call("dcue_bn_bwd_finalize", scratch, L.query("dcue_bn_bwd_reduce_nparts", S, P_), C_,
+                       ws.bnp[i, 0].data_ptr() if has_bn else None, float(S * P_ * world) if bn_train else 0.0, *peer,
+                       b["dsums"][i].data_ptr(), L.ptr(gb), L.ptr(gw), b["amax"][i:].data_ptr() if want_scale else None,
+                       b["gscale"][i].data_ptr() if want_scale else None, st)
+                if bn_train:
+                    grads["bn%d.weight" % i], grads["bn%d.bias" % i] = gw, gb
+                elif has_bn:
+                    grads["bn%d.weight" % i] = grads["bn%d.bias" % i] = None  # eval-mode backward: constants
+                return
+            direct = bn_train and dp is None  # single GPU: the reducer emits dgamma / dbeta in fp32 directly
             L.call("dcue_bn_bwd_reduce", dy_ptr, lddy, dtp_ptr, lddtp, z.data_ptr(), mean_p, rstd_p, S, P_, C_,
                    b["dsums"][i].data_ptr(), b["amax"][i:].data_ptr() if want_scale else None,
                    gb.data_ptr() if direct else None, gw.data_ptr() if direct else None, scratch, nscr, st)

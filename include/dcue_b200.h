@@ -121,6 +121,31 @@ int dcue_bn_finalize(const double* sums, double count, int C, const float* gamma
                      const float* center /* nullable: sums are statistics of x - center (may alias running_mean) */,
                      float* scale, float* shift, float* mean, float* rstd, void* stream);
 
+/* Fused statistic finalisers: ONE launch replaces "reduce the producers' per-block partials" (+ the data-parallel all-reduce
+ * of the sums over NVLink peer memory) + dcue_bn_finalize / dcue_grad_scale.  The producers below leave their partial rows at
+ * the START of their workspace when called in "partials" mode (dcue_conv_pool_fwd_parts; sums == NULL for
+ * dcue_ncl_center_pack_stats[_indexed] and dcue_bn_bwd_reduce); the row count is the matching *_nparts query.
+ * peer_*: as dcue_peer_allreduce_f64 (world == 1: pointers may be NULL).  count = GLOBAL element count per channel.
+ * dcue_bn_stats_finalize (training mode): sums_out (nullable) = global double[2C]; other outputs as dcue_bn_finalize.
+ * dcue_bn_bwd_finalize: partial = dcue_bn_bwd_reduce's rows ([nparts][2C] sums, then [nparts] max|dy|); sums_out = global
+ *   double[2C]; dbeta / dgamma (nullable) fp32 copies; absmax_out (nullable) = local max|dy|; gscale_out (nullable) = {s, 1/s}
+ *   as dcue_grad_scale(absmax, scale, C, count). */
+int dcue_bn_stats_finalize(const double* partial, int nparts, double count, int C, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                           float eps, const float* center, const void* peer_bufs_dev, const void* peer_signals_dev,
+                           void* peer_counter, int rank, int world, double* sums_out, float* scale, float* shift,
+                           float* mean, float* rstd, void* stream);
+int dcue_bn_bwd_finalize(const double* partial, int nparts, int C, const float* scale, double count,
+                         const void* peer_bufs_dev, const void* peer_signals_dev, void* peer_counter, int rank, int world,
+                         double* sums_out, float* dbeta, float* dgamma, float* absmax_out, float* gscale_out, void* stream);
+size_t dcue_ncl_center_pack_stats_nparts(int S, int C);
+size_t dcue_bn_bwd_reduce_nparts(int S, int P);
+size_t dcue_conv_pool_fwd_nparts(int impl, int S, int Lp);
+/* dcue_conv_pool_fwd with the BatchNorm statistic partials ([nparts][2*Cout] doubles) left at the start of ws */
+int dcue_conv_pool_fwd_parts(int impl, const void* panel, long panel_rows, int fmt, const void* w_packed,
+                             const float* bias, const float* tap_bias, int S, int Lp, int Lin, int pad, int P, int pool,
+                             int k, int Cin, int Cout, float* z, uint8_t* code, void* ws, size_t ws_bytes, void* stream);
+
 /* Single pass over the fp32 input (replaces dcue_ncl_stats + dcue_ncl_pack for the BatchNorm towers):
  * u = x - center[c] is written as the 16-bit layer-1 operand panel and its per-channel sum / sum of squares
  * are accumulated in the same sweep (sums = double[2*C]).  center = bn0.running_mean keeps u small whatever
@@ -344,6 +369,9 @@ int dcue_topk_scores_2pass(int impl, const void* users_n, long n_users, const vo
                            int Kp, int fmt, int k, long item_offset, float* top_scores, int64_t* top_idx,
                            int* n_failed, void* ws, size_t ws_bytes, void* stream);
 size_t dcue_topk_2pass_ws_bytes(int impl, long n_users, long n_items, int k);
+/* Diagnostics: cycle counters of the scorer's phases accumulated by block 0's first appender warp since the last reset:
+ * host_out8 (HOST pointer) = {stream loop, final boundary, select+sort+write, trailing barrier, work items, song tiles, 0, 0}. */
+int dcue_topk_debug_cycles(unsigned long long* host_out8, int reset);
 /* merge `parts` per-shard top-k lists [parts][n_users][k] into one (song-sharded eval). */
 int dcue_topk_merge(const float* scores, const int64_t* idx, int parts, long n_users, int k,
                     float* out_scores, int64_t* out_idx, void* stream);
