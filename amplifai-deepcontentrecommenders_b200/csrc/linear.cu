@@ -14,7 +14,8 @@
 
 namespace {
 
-constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int TM = 64, TN = 64, TK = 32;   // k depth per barrier: two 16-deep half tiles (each thread fetches 2 x 16 B per operand)
+constexpr int TKH = 16;
 
 struct GemmP {
     const float* A; long sAi, sAr;
@@ -117,35 +118,42 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
     const bool b_vec = ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0) && (((b_j_contig ? p.sBr : p.sBj) & 3) == 0) &&
                        (b_j_contig || p.sBr == 1) && ((rbeg & 3) == 0);
 
-    auto stash = [&](int buf, const GemmFrag& f) {
+    auto stash = [&](int buf, int koff, const GemmFrag& f) {
         if (a_r_contig) {
-            const int li = tid >> 2, lr = (tid & 3) * 4;
+            const int li = tid >> 2, lr = koff + (tid & 3) * 4;
 #pragma unroll
             for (int q = 0; q < 4; ++q) As[buf][lr + q][li] = f.a[q];
         } else {
-            const int lr = tid >> 4, li = (tid & 15) * 4;
+            const int lr = koff + (tid >> 4), li = (tid & 15) * 4;
             *reinterpret_cast<float4*>(&As[buf][lr][li]) = make_float4(f.a[0], f.a[1], f.a[2], f.a[3]);
         }
         if (b_j_contig) {
-            const int lr = tid >> 4, lj = (tid & 15) * 4;
+            const int lr = koff + (tid >> 4), lj = (tid & 15) * 4;
             *reinterpret_cast<float4*>(&Bs[buf][lr][lj]) = make_float4(f.b[0], f.b[1], f.b[2], f.b[3]);
         } else {
-            const int lj = tid >> 2, lr = (tid & 3) * 4;
+            const int lj = tid >> 2, lr = koff + (tid & 3) * 4;
 #pragma unroll
             for (int q = 0; q < 4; ++q) Bs[buf][lr + q][lj] = f.b[q];
         }
     };
 
-    GemmFrag f;
+    GemmFrag f[2];     // rows beyond rend fetch as zeros
     if (rbeg < rend) {
-        gemm_fetch(p, tid, i0, j0, rbeg, rend, a_r_contig, b_j_contig, a_vec, b_vec, f);
-        stash(0, f);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            gemm_fetch(p, tid, i0, j0, rbeg + h * TKH, rend, a_r_contig, b_j_contig, a_vec, b_vec, f[h]);
+            stash(0, h * TKH, f[h]);
+        }
     }
     __syncthreads();
     int buf = 0;
     for (int r0 = rbeg; r0 < rend; r0 += TK) {
         const bool more = r0 + TK < rend;
-        if (more) gemm_fetch(p, tid, i0, j0, r0 + TK, rend, a_r_contig, b_j_contig, a_vec, b_vec, f);
+        if (more) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                gemm_fetch(p, tid, i0, j0, r0 + TK + h * TKH, rend, a_r_contig, b_j_contig, a_vec, b_vec, f[h]);
+        }
         if (MMA) {
 #pragma unroll
             for (int kk = 0; kk < TK; kk += 8) {
@@ -185,7 +193,10 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
                     for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
             }
         }
-        if (more) stash(buf ^ 1, f);   // the other buffer was last read before the previous barrier
+        if (more) {                    // the other buffer was last read before the previous barrier
+#pragma unroll
+            for (int h = 0; h < 2; ++h) stash(buf ^ 1, h * TKH, f[h]);
+        }
         __syncthreads();
         buf ^= 1;
     }

@@ -1,5 +1,7 @@
 """B200 drop-in for dcrecommend/dcue/dcue.py: Deep Content-User Embedding network
 (Lee et al., DLRS 2018) with forward(u, pos, neg) on hand-written sm_100a kernels."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -50,20 +52,54 @@ class DCUENet(nn.Module):
         self.user_embd = UserEmbeddings({"user_embdim": self.user_embdim, "user_count": self.user_count,
                                          "feature_dim": self.feature_dim})
         self.sim = CosineSimilarity(dim=1)
+        self._side_stream = None
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d["_side_stream"] = None      # CUDA streams do not pickle
+        return d
+
+    # The user tower (gather + 2-layer MLP: a dozen small latency-bound kernels) does not depend on the song tower until the
+    # score kernel, so it runs on a side stream next to the tower's big kernels; autograd replays its backward on that
+    # stream as well.  Inside a CUDA-graph capture this becomes a parallel branch of the graph.  DCUE_USER_STREAM=0: one stream.
+    def _fork_user_tower(self, u):
+        if not self.user_embd_on_side_stream(u):
+            return self.user_embd(u), None
+        cur = torch.cuda.current_stream()
+        if self._side_stream is None or self._side_stream.device != cur.device:
+            self._side_stream = torch.cuda.Stream(device=cur.device)
+        side = self._side_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            u_f = self.user_embd(u)
+        return u_f, side
+
+    @staticmethod
+    def _join_user_tower(u_f, side):
+        if side is not None:
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(side)
+            u_f.record_stream(cur)
+        return u_f
+
+    def user_embd_on_side_stream(self, u):
+        return (torch.is_tensor(u) and u.is_cuda and os.environ.get("DCUE_USER_STREAM", "1") != "0")
 
     def forward(self, u, pos, neg=None):
         """u int64 [B]; pos f32 [B,128,L]; neg f32 [B,N,128,L] ->
         (scores [B,N], u_featvects [B,F], pos_featvects [B,F], neg_featvects [B,N,F]).
         With neg=None the reference raises NameError; here scores is [B,1] = cos(u,pos) and
         neg_featvects is None."""
-        u_featvects = self.user_embd(u)
+        u_featvects, side = self._fork_user_tower(u)
         B = pos.shape[0]
         if neg is not None:
             N = neg.shape[1]
             feats = self.conv.forward_posneg(pos, neg)
+            u_featvects = self._join_user_tower(u_featvects, side)
             scores = ops.ScoreFn.apply(u_featvects, feats, B, N)
             return scores, u_featvects, feats[:B], feats[B:].view(B, N, self.feature_dim)
         pos_featvects = self.conv.forward_posneg(pos, None)
+        u_featvects = self._join_user_tower(u_featvects, side)
         scores = self.sim(u_featvects, pos_featvects).view(B, 1)
         return scores, u_featvects, pos_featvects, None
 
@@ -80,18 +116,20 @@ class DCUENet(nn.Module):
     def forward_indexed(self, u, pool, pos_idx, neg_idx, pos_off=None, neg_off=None, frames=131):
         """forward(u, pos, neg) with pos = pool[pos_idx, :, off:off+frames], neg = pool[neg_idx, ...] taken
         from a resident device pool by index: same outputs, no dense [B,N,128,L] tensor, no H2D copy."""
-        u_featvects = self.user_embd(u)
+        u_featvects, side = self._fork_user_tower(u)
         B, N = neg_idx.shape
         feats = self._indexed_feats(pool, pos_idx.to(pool.device), neg_idx.to(pool.device), pos_off, neg_off, frames)
+        u_featvects = self._join_user_tower(u_featvects, side)
         scores = ops.ScoreFn.apply(u_featvects, feats, B, N)
         return scores, u_featvects, feats[:B], feats[B:].view(B, N, self.feature_dim)
 
     def hinge_loss_step_indexed(self, u, pool, pos_idx, neg_idx, margin, pos_off=None, neg_off=None, frames=131,
                                 batch_total=None):
         """hinge_loss_step on the index feed."""
-        u_featvects = self.user_embd(u)
+        u_featvects, side = self._fork_user_tower(u)
         B, N = neg_idx.shape
         feats = self._indexed_feats(pool, pos_idx.to(pool.device), neg_idx.to(pool.device), pos_off, neg_off, frames)
+        u_featvects = self._join_user_tower(u_featvects, side)
         total = B if batch_total is None else batch_total
         loss_rows, _ = ops.HingeScoreFn.apply(u_featvects, feats, B, N, margin, total)
         return loss_rows.sum() / total
@@ -115,9 +153,10 @@ class DCUENet(nn.Module):
         """forward + DCUE._loss_func (max(0, margin - scores).sum(1).mean()) with the scoring, the
         loss and their backward fused in one kernel.  batch_total = global batch size under data
         parallelism (defaults to the local B)."""
-        u_featvects = self.user_embd(u)
+        u_featvects, side = self._fork_user_tower(u)
         B, N = neg.shape[0], neg.shape[1]
         feats = self.conv.forward_posneg(pos, neg)
+        u_featvects = self._join_user_tower(u_featvects, side)
         total = B if batch_total is None else batch_total
         loss_rows, scores = ops.HingeScoreFn.apply(u_featvects, feats, B, N, margin, total)
         loss = loss_rows.sum() / total
