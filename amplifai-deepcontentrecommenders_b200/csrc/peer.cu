@@ -251,3 +251,109 @@ extern "C" int dcue_peer_scatter_add_rows(const void* peer_bufs_dev, int capacit
     DCUE_LAUNCH_CHECK();
     return 0;
 }
+
+// ====================================================================================================================
+// Flat gradient all-reduce over NVLink peer memory (data-parallel step, BASELINE cfg3): ONE multi-CTA kernel replaces
+// torch.cat + NCCL all-reduce + _foreach_copy_ of the ~1.5 MB of tower / MLP gradients.  Every CTA owns one 16 KB chunk of
+// the flat index space: it gathers the chunk from the gradient tensors (device pointer table) into this rank's symmetric
+// slot, raises the chunk's flag in every peer (release.sys), waits for the peers' flags of the SAME chunk and sums the
+// peers' copies in RANK ORDER straight back into the gradient tensors -- bit-identical on all ranks, and the exchange of
+// chunk c overlaps the gather of chunk c+1 on other SMs.  Two slots by call parity (a rank can only reach call e+2 after
+// every peer has signalled e+1, i.e. finished reading call e).  The call counter lives in device memory and is advanced by
+// the last CTA to finish, so the kernel is CUDA-graph capturable.
+// Symmetric buffer layout: [flags: 2 slots x GR_MAX_CHUNKS x GR_MAX_WORLD uint32][data: 2 slots x GR_MAX_CHUNKS x GR_CHUNK f32]
+// ====================================================================================================================
+namespace {
+
+constexpr int GR_CHUNK = 4096;            // floats per chunk (16 KB)
+constexpr int GR_MAX_CHUNKS = 256;        // 1 Mi floats
+constexpr int GR_MAX_WORLD = 16;
+constexpr size_t GR_FLAG_BYTES = (size_t)2 * GR_MAX_CHUNKS * GR_MAX_WORLD * sizeof(unsigned);
+constexpr size_t GR_DATA_BYTES = (size_t)2 * GR_MAX_CHUNKS * GR_CHUNK * sizeof(float);
+
+struct GradEntry {     // one row of the device table (int64 x 2 on the Python side)
+    float* g;
+    long n;
+};
+
+__global__ void __launch_bounds__(256)
+peer_allreduce_grads_kernel(uint8_t* const* __restrict__ bufs, unsigned* __restrict__ counter /* [0] epoch, [1] ticket, [2] timeout */,
+                            int rank, int world, const GradEntry* __restrict__ tab, const long* __restrict__ prefix /* [n_tensors+1] */,
+                            int n_tensors, long n_total) {
+    __shared__ long pre[64];
+    __shared__ float* gp[64];
+    __shared__ unsigned last;
+    const unsigned e = counter[0] + 1u;          // every CTA reads the epoch before the last one to finish advances it
+    const int c = blockIdx.x;
+    const int slot = (int)(e & 1u);
+    for (int t = threadIdx.x; t <= n_tensors; t += blockDim.x) {
+        pre[t] = prefix[t];
+        if (t < n_tensors) gp[t] = tab[t].g;
+    }
+    __syncthreads();
+    const long f0 = (long)c * GR_CHUNK;
+    const int len = (int)min((long)GR_CHUNK, n_total - f0);
+    float* mine = reinterpret_cast<float*>(bufs[rank] + GR_FLAG_BYTES) + ((size_t)slot * GR_MAX_CHUNKS + c) * GR_CHUNK;
+    // flat index -> (tensor, offset): the chunk spans few tensors, start from the tensor holding f0
+    int t0 = 0;
+    {
+        int lo = 0, hi = n_tensors - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pre[mid] <= f0) lo = mid; else hi = mid - 1; }
+        t0 = lo;
+    }
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        const long f = f0 + i;
+        int t = t0;
+        while (pre[t + 1] <= f) ++t;
+        mine[i] = gp[t][f - pre[t]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        unsigned* peer_flags = reinterpret_cast<unsigned*>(bufs[threadIdx.x]) + ((size_t)slot * GR_MAX_CHUNKS + c) * GR_MAX_WORLD;
+        st_release_sys(peer_flags + rank, e);
+        const unsigned* my_flags = reinterpret_cast<const unsigned*>(bufs[rank]) + ((size_t)slot * GR_MAX_CHUNKS + c) * GR_MAX_WORLD;
+        peer_wait(my_flags + threadIdx.x, e, counter + 2);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < world; ++r) {
+            const float* src = reinterpret_cast<const float*>(bufs[r] + GR_FLAG_BYTES) + ((size_t)slot * GR_MAX_CHUNKS + c) * GR_CHUNK;
+            float v;
+            asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(src + i) : "memory");
+            s += v;
+        }
+        const long f = f0 + i;
+        int t = t0;
+        while (pre[t + 1] <= f) ++t;
+        gp[t][f - pre[t]] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(&counter[1], 1u) == gridDim.x - 1) ? 1u : 0u;
+        if (last) {
+            counter[1] = 0u;
+            __threadfence();
+            counter[0] = e;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" size_t dcue_peer_grads_bytes(void) { return GR_FLAG_BYTES + GR_DATA_BYTES; }
+extern "C" long dcue_peer_grads_max_elems(void) { return (long)GR_MAX_CHUNKS * GR_CHUNK; }
+
+extern "C" int dcue_peer_allreduce_grads(const void* peer_bufs_dev, void* counter, int rank, int world, const void* table_dev,
+                                         const long* prefix_dev, int n_tensors, long n_total, void* stream) {
+    DCUE_CHECK_ARG(peer_bufs_dev && counter && table_dev && prefix_dev && world >= 1 && world <= GR_MAX_WORLD && rank >= 0 &&
+                   rank < world && n_tensors >= 1 && n_tensors <= 63 && n_total >= 0 && n_total <= dcue_peer_grads_max_elems());
+    if (n_total == 0 || world == 1) return 0;
+    const int chunks = (int)((n_total + GR_CHUNK - 1) / GR_CHUNK);
+    peer_allreduce_grads_kernel<<<chunks, 256, 0, (cudaStream_t)stream>>>((uint8_t* const*)peer_bufs_dev, (unsigned*)counter, rank, world,
+                                                                        (const GradEntry*)table_dev, prefix_dev, n_tensors, n_total);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}

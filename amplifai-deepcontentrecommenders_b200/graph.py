@@ -46,6 +46,16 @@ class GraphedTrainStep:
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
         self._grads = [p.grad for p in params]
+        # one more eager pass on the STATIC gradient tensors: everything keyed on their addresses (the peer gradient
+        # all-reduce's pointer table, ...) is built now -- a capture must not contain pageable host-to-device copies
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            torch._foreach_zero_(self._grads)
+            self._loss().backward()
+            if dp is not None:
+                dp.reduce_gradients()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             torch._foreach_zero_(self._grads)

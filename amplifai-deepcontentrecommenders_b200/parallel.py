@@ -118,6 +118,47 @@ class PeerExchange:
             raise RuntimeError("peer exchange timed out waiting for another rank")
 
 
+class PeerGradReduce:
+    """Flat all-reduce of the step's gradient tensors over NVLink peer memory (csrc/peer.cu dcue_peer_allreduce_grads)."""
+
+    def __init__(self, group, device):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib as L
+        self.L = L
+        pg = group if group is not None else dist.group.WORLD
+        self.buf = symm.empty(L.query("dcue_peer_grads_bytes"), dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, pg.group_name)
+        self.rank, self.world = self.hdl.rank, self.hdl.world_size
+        self.counter = torch.zeros(3, dtype=torch.int32, device=device)
+        self.max_elems = int(L.lib().dcue_peer_grads_max_elems())
+        self._key, self._table, self._prefix, self._n = None, None, None, 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+
+    def __call__(self, grads):
+        key = tuple((g.data_ptr(), g.numel()) for g in grads)
+        if key != self._key:
+            for g in grads:
+                if g.dtype != torch.float32 or not g.is_contiguous():
+                    raise RuntimeError("PeerGradReduce needs contiguous fp32 gradients")
+            rows, pre, tot = [], [0], 0
+            for g in grads:
+                rows += [g.data_ptr(), g.numel()]
+                tot += g.numel()
+                pre.append(tot)
+            dev = grads[0].device
+            self._table = torch.tensor(rows, dtype=torch.int64).to(dev)
+            self._prefix = torch.tensor(pre, dtype=torch.int64).to(dev)
+            self._key, self._n = key, tot
+        self.L.call("dcue_peer_allreduce_grads", self.hdl.buffer_ptrs_dev, self.counter.data_ptr(), self.rank, self.world,
+                    self._table.data_ptr(), self._prefix.data_ptr(), len(grads), self._n, self.L.stream())
+
+    def check(self):
+        if int(self.counter[2].item()):
+            raise RuntimeError("peer gradient all-reduce timed out waiting for another rank")
+
+
 class DataParallelDCUE:
     """Wraps a DCUENet for data-parallel training on the current process group."""
 
@@ -137,6 +178,12 @@ class DataParallelDCUE:
             except Exception as exc:  # noqa: BLE001  (no peer access / symmetric memory unavailable)
                 print("DataParallelDCUE: peer all-reduce unavailable (%s); using NCCL for the BatchNorm statistics" % exc)
         self._xch = None          # PeerExchange for the table-gradient rows, created on first use (needs the batch size)
+        self._gred = None         # PeerGradReduce for the flat gradient bucket
+        if self._peer is not None and os.environ.get("DCUE_DP_PEER_GRADS", "1") != "0":
+            try:
+                self._gred = PeerGradReduce(group, params[0].device)
+            except Exception as exc:  # noqa: BLE001
+                print("DataParallelDCUE: peer gradient all-reduce unavailable (%s); using NCCL" % exc)
         if hasattr(model.user_embd, "embeddings"):      # replicated table: row exchange instead of a dense all-reduce
             model.user_embd._dp = self if (self.world_size > 1 and row_exchange()) else None
         if broadcast and self.world_size > 1:
@@ -168,6 +215,8 @@ class DataParallelDCUE:
             self._peer.check()
         if self._xch is not None:
             self._xch.check()
+        if self._gred is not None:
+            self._gred.check()
 
     def all_gather_rows(self, t):
         """[n, ...] on every rank -> [world*n, ...] in rank order."""
@@ -193,6 +242,10 @@ class DataParallelDCUE:
         named = [(n, p) for n, p in self.model.named_parameters() if p.grad is not None]
         keep = set(flat_bucket_names(named))
         grads = [p.grad for n, p in named if n in keep]
+        if (self._gred is not None and len(grads) <= 63 and sum(g.numel() for g in grads) <= self._gred.max_elems
+                and all(g.dtype == torch.float32 and g.is_contiguous() for g in grads)):
+            self._gred(grads)       # one kernel over NVLink peer memory; sums land in the gradient tensors
+            return
         flat = torch.cat([g.reshape(-1) for g in grads])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         torch._foreach_copy_(grads, [c.view_as(g) for c, g in zip(flat.split([g.numel() for g in grads]), grads)])

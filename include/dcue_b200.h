@@ -347,6 +347,17 @@ int dcue_peer_gather_relu_fwd(const void* peer_shards_dev, long U, int world, co
 int dcue_peer_scatter_add_rows(const void* peer_bufs_dev, int capacity_rows, const int64_t* all_idx, int world, int B, long lo,
                                long hi, int E, float* grad_shard, void* stream);
 
+/* Flat SUM all-reduce of a list of fp32 gradient tensors over NVLink peer memory in ONE multi-CTA kernel (replaces
+ * torch.cat + NCCL all-reduce + scatter-back of the data-parallel step's tower / MLP gradients, BASELINE cfg3).
+ * peer_bufs_dev: `world` pointers to zero-initialised symmetric buffers of dcue_peer_grads_bytes() bytes; counter: 3
+ * zero-initialised device uint32 of the calling rank (epoch, CTA ticket, time-out flag); table_dev: n_tensors rows
+ * {float* grad, int64 n}; prefix_dev: int64[n_tensors + 1] exclusive prefix sums of n; n_total <= dcue_peer_grads_max_elems().
+ * The sums are written back into the gradient tensors, bit-identical on every rank.  Every rank issues the same calls. */
+size_t dcue_peer_grads_bytes(void);
+long dcue_peer_grads_max_elems(void);
+int dcue_peer_allreduce_grads(const void* peer_bufs_dev, void* counter, int rank, int world, const void* table_dev,
+                              const long* prefix_dev, int n_tensors, long n_total, void* stream);
+
 /* ---------------------------------------------------------------- eval scorer ------------ */
 
 /* row-normalise factors (x / max(||x||,eps)) into 16-bit K-major rows padded to Kp (mult of 16). */
