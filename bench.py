@@ -553,7 +553,7 @@ def run_ours(args):
         c0 = L.lib().dcue_launch_count()
         gstep = pkg.GraphedTrainStep(model, CFG["margin"], u, pos, neg, warmup=3, dp=dp if world > 1 else None)
         graphs.append(gstep)
-        graph_launches = (L.lib().dcue_launch_count() - c0) // 4       # 3 warm-up passes + the captured one
+        graph_launches = (L.lib().dcue_launch_count() - c0) // 5       # 3 warm-up passes + the priming pass + the captured one
 
         def step(u_, pos_, neg_):  # noqa: F811  (same step: forward+loss+backward replayed as one CUDA graph)
             if u_ is not u:
