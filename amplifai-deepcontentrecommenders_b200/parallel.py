@@ -557,3 +557,28 @@ def sharded_topk(user_factors, item_factors_local, k, item_offset, group=None, g
     dist.all_gather_into_tensor(all_i.view(-1), pad_i.view(-1), group=group)
     return (torch.cat([all_s[r, : b - a] for r, (a, b) in enumerate(blocks)]),
             torch.cat([all_i[r, : b - a] for r, (a, b) in enumerate(blocks)]))
+
+
+_EVAL_GROUPS = {}
+
+
+def eval_layout(song_shards, group=None):
+    """2-D layout of the eval over the ranks: `song_shards` song shards x (world / song_shards) user groups.  Rank r scores the
+    users of group r // song_shards against song shard r % song_shards; the ranks of one user group merge their lists with
+    sharded_topk(group=subgroup).  song_shards == world is BASELINE cfg5's pure song sharding; fewer song shards mean longer
+    song streams per work item (the scorer's per-user-tile start / finish cost is amortised over more songs) at the price of
+    every rank holding I / song_shards song factors.  Collective: every rank must call it with the same arguments.
+    -> dict(song_shard, user_group, n_user_groups, group)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world % song_shards:
+        raise ValueError("song_shards must divide the world size")
+    key = (song_shards, world, id(group))
+    if key not in _EVAL_GROUPS:
+        subs = []
+        for ug in range(world // song_shards):
+            ranks = [ug * song_shards + j for j in range(song_shards)]
+            subs.append(dist.new_group(ranks) if song_shards < world else (group if group is not None else dist.group.WORLD))
+        _EVAL_GROUPS[key] = subs
+    ug = rank // song_shards
+    return dict(song_shard=rank % song_shards, user_group=ug, n_user_groups=world // song_shards, group=_EVAL_GROUPS[key][ug])

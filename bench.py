@@ -750,6 +750,21 @@ def run_ours(args):
                          % (world, args.eval_user_tile) if world > 1 else "single GPU: no merge",
                 "workload": "cfg5: %d users x %d songs, fp16 factors, fp32 accumulate, songs sharded over %d GPU(s), merged top-k"
                             % (ev_users, ev_items, world)}
+    # 2-D variant at N >= 4: 2 song shards x N/2 user groups (longer song streams per work item; every rank holds half the songs)
+    if world >= 4 and not args.no_eval_hybrid:
+        lay = par.eval_layout(2)
+        ulo, uhi = par.shard_slice(ev_users, lay["user_group"], lay["n_user_groups"])
+        slo, shi = par.shard_slice(ev_items, lay["song_shard"], 2)
+        ge2 = torch.Generator(device=dev).manual_seed(3)
+        torch.randn(ev_users, CFG["feat"], generator=ge2, device=dev)            # advance the generator past the user factors
+        ifac2 = torch.randn(ev_items, CFG["feat"], generator=ge2, device=dev)[slo:shi].contiguous()
+        ug = ufac[ulo:uhi].contiguous()
+        par.sharded_topk(ug[:8192], ifac2, ev_k, slo, group=lay["group"])
+        hms = timed_steps(lambda: par.sharded_topk(ug, ifac2, ev_k, slo, group=lay["group"]), 1, barrier, dev, world)
+        eval_out["hybrid_2_song_shards"] = {"value": ev_users / (hms * 1e-3), "unit": "users/s", "ms": hms,
+                                            "layout": "2 song shards x %d user groups (each rank: %d users x %d songs)"
+                                                      % (lay["n_user_groups"], uhi - ulo, shi - slo)}
+        del ifac2, ug
     del ufac, ifac, ev_out
     torch.cuda.empty_cache()
 
@@ -839,6 +854,7 @@ def main():
     ap.add_argument("--cfg4-negs", type=int, nargs="*", default=[20, 50, 100, 200])
     ap.add_argument("--cfg4-steps", type=int, default=5)
     ap.add_argument("--no-cfg4", action="store_true")
+    ap.add_argument("--no-eval-hybrid", action="store_true")
     ap.add_argument("--no-bf16", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph step")

@@ -166,3 +166,28 @@ def test_topk_exchange_by_user_block_world2(tmp_path):
         for src in range(2):       # part `src` = what rank `src` computed for MY users
             assert torch.equal(r["sp"][src], torch.arange(U * k, dtype=torch.float32).view(U, k)[lo:hi] + 100 * src)
             assert torch.equal(r["ip"][src], torch.arange(U * k, dtype=torch.int64).view(U, k)[lo:hi] + 1000 * src)
+
+
+def _layout_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lay = par.eval_layout(2)
+    t = torch.tensor([float(rank)])
+    dist.all_reduce(t, group=lay["group"])            # sums the ranks of my user group only
+    full = par.eval_layout(world)                     # pure song sharding: the whole world is one group
+    t2 = torch.tensor([1.0])
+    dist.all_reduce(t2, group=full["group"])
+    torch.save(dict(lay={k: v for k, v in lay.items() if k != "group"}, s=t.item(), s2=t2.item(),
+                    full={k: v for k, v in full.items() if k != "group"}), out % rank)
+    dist.destroy_process_group()
+
+
+def test_eval_layout_world4(tmp_path):
+    port = 35500 + os.getpid() % 2000
+    out = str(tmp_path / "l%d.pt")
+    mp.spawn(_layout_worker, args=(4, port, out), nprocs=4, join=True)
+    for rank in range(4):
+        r = torch.load(out % rank)
+        assert r["lay"] == dict(song_shard=rank % 2, user_group=rank // 2, n_user_groups=2)
+        assert r["s"] == (1.0 if rank < 2 else 5.0)          # ranks {0,1} and {2,3}
+        assert r["full"] == dict(song_shard=rank, user_group=0, n_user_groups=1) and r["s2"] == 4.0
