@@ -291,7 +291,8 @@ ncl_pack_kernel(SpecSrc src, int S, int C, int L, const float* __restrict__ scal
 // u = x - center[c] (fp32) -> 16-bit panel, and per-channel sum / sum of squares of u in the same pass.
 // block (q, g): panel q (8 channels), spectrograms g, g+G, ...; warps split the spectrograms, lanes walk
 // the frames, so every lane keeps private partial sums for its panel's 8 channels (no atomics).
-__global__ void __launch_bounds__(256)
+// 3 blocks per SM: at 101 registers (2 blocks) only 16 warps x 64 B per lane were in flight -- 74 % of the copy bandwidth
+__global__ void __launch_bounds__(256, 3)
 ncl_center_pack_stats_kernel(SpecSrc src, int S, int C, int L, const float* __restrict__ center, uint4* __restrict__ panel,
                              long panel_rows, int Lp, int pad, int fmt, double* __restrict__ partial /* [G][2][C] */) {
     __shared__ double red[8][16];
@@ -880,7 +881,7 @@ extern "C" int dcue_ncl_stats_indexed(const float* pool, long n_songs, long T, c
 
 static int center_pack_groups(int S, int C) {
     const int npan = C / 8;
-    int G = dcue_num_sms() * 4 / npan;
+    int G = dcue_num_sms() * 3 / npan;     // 3 resident blocks per SM (80 registers): one wave
     if (G > (S + 7) / 8) G = (S + 7) / 8;
     return G < 1 ? 1 : G;
 }
