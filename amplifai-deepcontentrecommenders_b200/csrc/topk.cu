@@ -326,6 +326,7 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                    long n_work, int tile_stride /* score every tile_stride-th 128-song tile (threshold pre-pass) */,
                    const float* __restrict__ init_thr /* nullable: per-user starting threshold, stride thr_ld */, long thr_ld,
                    int* __restrict__ n_failed, int thr_only /* write only the k-th best score per user to out_s[user] */,
+                   int allow_short /* a seeded user with fewer than k candidates is NOT a failure: its short list is written */,
                    int2* __restrict__ lists /* [grid][NU][CAPH] */, float* __restrict__ out_s,
                    int64_t* __restrict__ out_i /* [splits][n_users][k] */) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -614,7 +615,7 @@ topk_stream_kernel(const uint4* __restrict__ users, long n_utiles128, long n_use
                 }
                 const long ob = ((long)sp * n_users + gu) * k;
                 const long avail = iend - ibeg;
-                if (init_thr && n < (avail < k ? (int)avail : k)) {
+                if (init_thr && !allow_short && n < (avail < k ? (int)avail : k)) {
                     // the seeded threshold was too high for this user: mark the row, the caller re-scores it exactly
                     for (int g = lane; g < k; g += 32) { out_s[ob + g] = -INFINITY; out_i[ob + g] = -2; }
                     if (lane == 0) atomicAdd(n_failed, 1);
@@ -740,7 +741,7 @@ namespace {
 // one launch of the streaming scorer (+ the split merge); ws = [candidate lists][split partials]
 int launch_topk(const void* users_n, long n_users, const void* items_n, long n_items, int Kp, int fmt, int k, long item_offset,
                 int tile_stride, const float* init_thr, long thr_ld, int* n_failed, int thr_only, float* top_scores,
-                int64_t* top_idx, void* ws, size_t ws_bytes, cudaStream_t st) {
+                int64_t* top_idx, void* ws, size_t ws_bytes, cudaStream_t st, int allow_short = 0) {
     const int splits = init_thr || tile_stride > 1 ? 1 : topk_splits(n_users, n_items);
     const int grid = topk_grid(n_users, splits);
     long per = (n_items + splits - 1) / splits;
@@ -761,7 +762,7 @@ int launch_topk(const void* users_n, long n_users, const void* items_n, long n_i
     const long n_work = ((n_users + NU - 1) / NU) * splits;
     topk_stream_kernel<<<grid, NTHREADS2, smem, st>>>((const uint4*)users_n, round_up_l(n_users, 128) / 128, n_users,
                                                       (const uint4*)items_n, n_items, Kp, fmt, k, item_offset, per, splits, n_work,
-                                                      tile_stride, init_thr, thr_ld, n_failed, thr_only, (int2*)ws, os, oi);
+                                                      tile_stride, init_thr, thr_ld, n_failed, thr_only, allow_short, (int2*)ws, os, oi);
     DCUE_LAUNCH_CHECK();
     if (splits > 1) {
         topk_merge_kernel<<<ceil_div_i(n_users, 128), 128, 0, st>>>(os, oi, splits, n_users, k, top_scores, top_idx);
@@ -835,6 +836,56 @@ extern "C" int dcue_topk_scores_2pass(int impl, const void* users_n, long n_user
         return e;
     return launch_topk(users_n, n_users, items_n, n_items, Kp, fmt, k, item_offset, 1, thrB, 1, n_failed, 0, top_scores, top_idx, ws,
                        base, st);
+}
+
+// ---- global-threshold protocol of the song-sharded eval (parallel.sharded_topk): every shard returns the r best scores of
+// its song SAMPLE (every s-th tile); the caller merges the shards' lists per user, takes the r-th best of the union -- a
+// threshold that ~4k songs of ALL shards together exceed -- and streams every shard from it with short lists allowed, so a
+// shard keeps ~4k/W candidates per user instead of 4k (8x fewer appends, no selection) and the merge sees ~4k entries.
+extern "C" int dcue_topk_sample_r(long n_users, long n_items, int k) {
+    int s = 0, r = 0;
+    return topk_2pass_plan(n_users, n_items, k, &s, &r) ? r : 0;
+}
+extern "C" size_t dcue_topk_sample_ws_bytes(long n_users, long n_items, int k) {
+    int s = 0, r = 0;
+    if (!topk_2pass_plan(n_users, n_items, k, &s, &r)) return 512;
+    return topk_list_bytes(topk_grid(n_users, 1)) + (size_t)n_users * (sizeof(float) + (size_t)r * sizeof(int64_t)) + 1024;
+}
+extern "C" int dcue_topk_sample(int impl, const void* users_n, long n_users, const void* items_n, long n_items, int Kp, int fmt,
+                                int k, float* sample_scores /* [n_users][r], descending, -inf padded */, void* ws, size_t ws_bytes,
+                                void* stream) {
+    DCUE_CHECK_ARG(users_n && items_n && sample_scores && ws && n_users >= 0 && n_items >= 0 && k > 0 && k <= 256);
+    DCUE_CHECK_ARG(Kp % 16 == 0 && Kp >= 16 && Kp <= 128 && n_items < (1L << 31));
+    if (impl != DCUE_IMPL_TC) DCUE_FAIL(DCUE_E_UNSUPPORTED, "dcue_topk_sample: only the tcgen05 implementation exists");
+    int s = 0, r = 0;
+    if (!topk_2pass_plan(n_users, n_items, k, &s, &r)) DCUE_FAIL(DCUE_E_UNSUPPORTED, "dcue_topk_sample: stream too short to sample");
+    if (n_users == 0) return 0;
+    if (ws_bytes < dcue_topk_sample_ws_bytes(n_users, n_items, k)) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_topk_sample: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t base = topk_list_bytes(topk_grid(n_users, 1));
+    float* thrA = (float*)((char*)ws + base);
+    int64_t* idx_scratch = (int64_t*)((char*)ws + base + round_up_l((long)n_users * sizeof(float), 256));
+    const long tiles = (n_items + TS - 1) / TS;
+    const float* seedB = nullptr;
+    if (tiles / (16L * s) >= 12) {       // long stream: a tiny unseeded level first (see dcue_topk_scores_2pass)
+        if (int e = launch_topk(users_n, n_users, items_n, n_items, Kp, fmt, 20, 0, 16 * s, nullptr, 0, nullptr, 1, thrA, nullptr, ws, base, st))
+            return e;
+        seedB = thrA;
+    }
+    return launch_topk(users_n, n_users, items_n, n_items, Kp, fmt, r, 0, s, seedB, 1, nullptr, 0, sample_scores, idx_scratch, ws, base,
+                       st, /*allow_short=*/1);
+}
+extern "C" size_t dcue_topk_seeded_ws_bytes(long n_users) { return topk_list_bytes(topk_grid(n_users, 1)) + 512; }
+extern "C" int dcue_topk_scores_seeded(int impl, const void* users_n, long n_users, const void* items_n, long n_items, int Kp,
+                                       int fmt, int k, long item_offset, const float* thr /* [n_users] */, float* top_scores,
+                                       int64_t* top_idx, void* ws, size_t ws_bytes, void* stream) {
+    DCUE_CHECK_ARG(users_n && items_n && thr && top_scores && top_idx && ws && n_users >= 0 && n_items >= 0 && k > 0 && k <= 256);
+    DCUE_CHECK_ARG(Kp % 16 == 0 && Kp >= 16 && Kp <= 128 && n_items < (1L << 31));
+    if (impl != DCUE_IMPL_TC) DCUE_FAIL(DCUE_E_UNSUPPORTED, "dcue_topk_scores_seeded: only the tcgen05 implementation exists");
+    if (n_users == 0) return 0;
+    if (ws_bytes < topk_list_bytes(topk_grid(n_users, 1))) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_topk_scores_seeded: workspace too small");
+    return launch_topk(users_n, n_users, items_n, n_items, Kp, fmt, k, item_offset, 1, thr, 1, nullptr, 0, top_scores, top_idx, ws,
+                       topk_list_bytes(topk_grid(n_users, 1)), (cudaStream_t)stream, /*allow_short=*/1);
 }
 
 extern "C" int dcue_topk_merge(const float* scores, const int64_t* idx, int parts, long n_users, int k, float* out_scores,

@@ -59,6 +59,36 @@ def topk_scores(user_factors, item_factors, k, item_offset=0, normalized_items=N
     return scores, idx
 
 
+def sample_scores(users_packed, n_users, items_packed, n_items, k):
+    """Global-threshold protocol, step 1 (csrc/topk.cu dcue_topk_sample): per user the r best scores of this shard's song
+    sample, descending -> [n_users, r] (None when the stream is too short to sample)."""
+    (un, Kp), (inn, Kp2) = users_packed, items_packed
+    assert Kp == Kp2
+    r = int(L.lib().dcue_topk_sample_r(n_users, n_items, k))
+    if r == 0:
+        return None
+    out = torch.empty(n_users, r, dtype=torch.float32, device=un.device)
+    nws = L.query("dcue_topk_sample_ws_bytes", n_users, n_items, k)
+    ws = torch.empty(nws, dtype=torch.uint8, device=un.device)
+    L.call("dcue_topk_sample", L.IMPL_TC, un.data_ptr(), n_users, inn.data_ptr(), n_items, Kp, L.FMT_F16, k, out.data_ptr(),
+           ws.data_ptr(), nws, L.stream())
+    return out
+
+
+def topk_scores_seeded(users_packed, n_users, items_packed, n_items, k, thr, item_offset=0):
+    """Step 2: every song of this shard above the user's threshold (at most the k best), descending; short lists are padded
+    with (-inf, -1)."""
+    (un, Kp), (inn, _) = users_packed, items_packed
+    dev = un.device
+    scores = torch.empty(n_users, k, dtype=torch.float32, device=dev)
+    idx = torch.empty(n_users, k, dtype=torch.int64, device=dev)
+    nws = L.query("dcue_topk_seeded_ws_bytes", n_users)
+    ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+    L.call("dcue_topk_scores_seeded", L.IMPL_TC, un.data_ptr(), n_users, inn.data_ptr(), n_items, Kp, L.FMT_F16, k, item_offset,
+           thr.contiguous().data_ptr(), scores.data_ptr(), idx.data_ptr(), ws.data_ptr(), nws, L.stream())
+    return scores, idx
+
+
 def _topk_exact(user_factors, inn, Kp, n_items, k, item_offset):
     """single-pass scorer (thresholds start at -inf) for a few users."""
     n_users = user_factors.shape[0]

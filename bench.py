@@ -369,9 +369,10 @@ def dp_parity_leg(pkg, par, dev, rank, world, per_rank=32, negs=4, users=500):
     return out
 
 
-def eval_parity_leg(par, ev, dev, rank, world, n_users=3000, n_items=40000, k=100):
+def eval_parity_leg(par, ev, dev, rank, world, n_users=3000, n_items=None, k=100):
     """sharded_topk (songs over the ranks, all-to-all by user block, per-block merge) against rank 0 scoring all songs alone."""
     import torch.distributed as dist
+    n_items = n_items or 40000 * world      # >= 32768 songs per shard: the global-threshold protocol is exercised
     g = torch.Generator(device=dev).manual_seed(11)
     uf = torch.randn(n_users, CFG["feat"], generator=g, device=dev)
     itf = torch.randn(n_items, CFG["feat"], generator=g, device=dev)

@@ -383,6 +383,20 @@ size_t dcue_topk_2pass_ws_bytes(int impl, long n_users, long n_items, int k);
 /* Diagnostics: cycle counters of the scorer's phases accumulated by block 0's first appender warp since the last reset:
  * host_out8 (HOST pointer) = {stream loop, final boundary, select+sort+write, trailing barrier, work items, song tiles, 0, 0}. */
 int dcue_topk_debug_cycles(unsigned long long* host_out8, int reset);
+/* Global-threshold protocol of the song-sharded eval: dcue_topk_sample returns, per user, the r = dcue_topk_sample_r()
+ * best scores of THIS shard's song sample (every s-th 128-song tile; r*s ~ 4k; r == 0: stream too short, do not sample);
+ * the caller merges the shards' lists, takes the r-th best of the union as the user's threshold and calls
+ * dcue_topk_scores_seeded on every shard: all songs above the threshold (at most the k best), descending; a user with fewer
+ * than k of them gets a short list padded with (-inf, -1) -- the merged lists then hold ~4k entries per user, and a user
+ * whose merged list is shorter than k must be re-scored with dcue_topk_scores (probability ~1e-4). */
+int dcue_topk_sample_r(long n_users, long n_items, int k);
+size_t dcue_topk_sample_ws_bytes(long n_users, long n_items, int k);
+int dcue_topk_sample(int impl, const void* users_n, long n_users, const void* items_n, long n_items, int Kp, int fmt,
+                     int k, float* sample_scores, void* ws, size_t ws_bytes, void* stream);
+size_t dcue_topk_seeded_ws_bytes(long n_users);
+int dcue_topk_scores_seeded(int impl, const void* users_n, long n_users, const void* items_n, long n_items, int Kp,
+                            int fmt, int k, long item_offset, const float* thr, float* top_scores,
+                            int64_t* top_idx, void* ws, size_t ws_bytes, void* stream);
 /* merge `parts` per-shard top-k lists [parts][n_users][k] into one (song-sharded eval). */
 int dcue_topk_merge(const float* scores, const int64_t* idx, int parts, long n_users, int k,
                     float* out_scores, int64_t* out_idx, void* stream);
