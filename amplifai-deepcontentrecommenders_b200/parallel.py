@@ -179,7 +179,7 @@ class DataParallelDCUE:
                 print("DataParallelDCUE: peer all-reduce unavailable (%s); using NCCL for the BatchNorm statistics" % exc)
         self._xch = None          # PeerExchange for the table-gradient rows, created on first use (needs the batch size)
         self._gred = None         # PeerGradReduce for the flat gradient bucket
-        if self._peer is not None and os.environ.get("DCUE_DP_PEER_GRADS", "1") != "0":
+        if self._peer is not None and os.environ.get("DCUE_DP_PEER_GRADS", "0") != "0":
             try:
                 self._gred = PeerGradReduce(group, params[0].device)
             except Exception as exc:  # noqa: BLE001
@@ -526,7 +526,7 @@ def sharded_topk(user_factors, item_factors_local, k, item_offset, group=None, g
         out_s[x:y], out_i[x:y] = ms, mi
 
     n_items_local = item_factors_local.shape[0]
-    use_global = (os.environ.get("DCUE_EVAL_GLOBAL_SEED", "1") != "0"
+    use_global = (os.environ.get("DCUE_EVAL_GLOBAL_SEED", "0") != "0"
                   and int(ev.L.lib().dcue_topk_sample_r(max(1, U // n_tiles), n_items_local, k)) > 0)
     failed_rows = []
 
