@@ -155,37 +155,66 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 }
 
 // ------------------------------------------------------------------ fused statistic finalisers
-// ONE launch instead of reduce_partials (+ peer all-reduce) + finalize: a single 1024-thread block sums the producers'
-// per-block partials in a fixed order, (data parallel) all-reduces the 2C sums over NVLink peer memory inside the same
-// kernel, and finishes the per-channel arithmetic.  Round 1 spent ~0.4 ms of the 2.9 ms step in ~70 such tiny launches.
-constexpr int FIN_THREADS = 1024;
+// ONE launch instead of reduce_partials (+ peer all-reduce) + finalize: 2C/8 blocks each sum 8 columns of the producers'
+// per-block partials (32 row lanes, fixed order -> deterministic), the LAST block to finish (self-resetting ticket) gathers
+// the 2C sums, (data parallel) all-reduces them over NVLink peer memory inside the same kernel, and finishes the per-channel
+// arithmetic.  A single-block version of the reduction took 20 us (one SM pulling 1.2 MB of partials through its L2 port).
+constexpr int FIN_THREADS = 256;
 
-// sums_sh[j] = sum_b partial[b][j], j < n <= 256: 4 row groups x 256 columns, combined in fixed order
-__device__ __forceinline__ void block_reduce_partials(const double* __restrict__ partial, int nparts, int n, double* sums_sh,
-                                                      double (*red)[256]) {
-    const int col = threadIdx.x & 255, grp = threadIdx.x >> 8;
+// phase 1: this block's 8 columns -> sums_g; returns true in the last block to finish, with all 2C sums in sums_sh
+__device__ __forceinline__ bool finalize_phase1(const double* __restrict__ partial, int nparts, int n, double* __restrict__ sums_g,
+                                                unsigned* __restrict__ ticket, double* sums_sh) {
+    __shared__ double red[32][9];
+    __shared__ unsigned is_last;
+    const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    const int j = blockIdx.x * 8 + cl;
     double s = 0.0;
-    if (col < n)
-        for (int b = grp; b < nparts; b += 4) s += partial[(long)b * n + col];
-    red[grp][col] = s;
+    if (j < n) {
+        int b = rl;
+        for (; b + 96 < nparts; b += 128) {      // four independent loads in flight per thread
+            const double v0 = partial[(long)b * n + j], v1 = partial[(long)(b + 32) * n + j];
+            const double v2 = partial[(long)(b + 64) * n + j], v3 = partial[(long)(b + 96) * n + j];
+            s += (v0 + v1) + (v2 + v3);
+        }
+        for (; b < nparts; b += 32) s += partial[(long)b * n + j];
+    }
+    red[rl][cl] = s;
     __syncthreads();
-    if (threadIdx.x < n) sums_sh[threadIdx.x] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+    if (rl == 0 && j < n) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t += red[k][cl];
+        sums_g[j] = t;
+    }
+    __threadfence();
     __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(ticket, 1u);
+        is_last = (prev == gridDim.x - 1) ? 1u : 0u;
+        if (is_last) *ticket = 0u;              // self-resetting: the next launch on this stream starts from zero
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sums_sh[i] = __ldcg(sums_g + i);
+    __syncthreads();
+    return true;
 }
 
 __global__ void __launch_bounds__(FIN_THREADS)
 bn_stats_finalize_kernel(const double* __restrict__ partial, int nparts, double count, int C, const float* __restrict__ gamma,
                          const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
                          int64_t* __restrict__ nbt, float momentum, float eps, const float* __restrict__ center, PeerCtx pc,
-                         double* __restrict__ sums_out, float* __restrict__ scale, float* __restrict__ shift,
-                         float* __restrict__ mean_o, float* __restrict__ rstd_o) {
-    __shared__ double red[4][256];
+                         unsigned* __restrict__ ticket, double* __restrict__ sums_out, float* __restrict__ scale,
+                         float* __restrict__ shift, float* __restrict__ mean_o, float* __restrict__ rstd_o) {
     __shared__ double sums_sh[256];
     __shared__ unsigned ep;
-    block_reduce_partials(partial, nparts, 2 * C, sums_sh, red);
-    peer_allreduce_block(pc, sums_sh, 2 * C, &ep);
+    if (!finalize_phase1(partial, nparts, 2 * C, sums_out, ticket, sums_sh)) return;
+    if (pc.world > 1) {
+        peer_allreduce_block(pc, sums_sh, 2 * C, &ep);
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sums_out[i] = sums_sh[i];
+    }
     const int c = threadIdx.x;
-    if (c < 2 * C && sums_out) sums_out[c] = sums_sh[c];
     if (c == 0 && nbt) *nbt += 1;
     if (c >= C) return;
     const double ctr = center ? (double)center[c] : 0.0;   // read before running_mean is updated (may alias)
@@ -208,17 +237,18 @@ bn_stats_finalize_kernel(const double* __restrict__ partial, int nparts, double 
 // BatchNorm-backward sums: partial = [nparts][2C] (sum dy, sum dy*xhat) followed by [nparts] per-block max|dy| (doubles)
 __global__ void __launch_bounds__(FIN_THREADS)
 bn_bwd_finalize_kernel(const double* __restrict__ partial, int nparts, int C, const float* __restrict__ scale, double count, PeerCtx pc,
-                       double* __restrict__ sums_out, float* __restrict__ dbeta, float* __restrict__ dgamma,
-                       float* __restrict__ absmax_out, float* __restrict__ gscale_out) {
-    __shared__ double red[4][256];
+                       unsigned* __restrict__ ticket, double* __restrict__ sums_out, float* __restrict__ dbeta,
+                       float* __restrict__ dgamma, float* __restrict__ absmax_out, float* __restrict__ gscale_out) {
     __shared__ double sums_sh[256];
-    __shared__ float mx[FIN_THREADS / 32];
+    __shared__ float mx[FIN_THREADS / 32], mx2[FIN_THREADS / 32];
     __shared__ unsigned ep;
-    block_reduce_partials(partial, nparts, 2 * C, sums_sh, red);
-    peer_allreduce_block(pc, sums_sh, 2 * C, &ep);
+    if (!finalize_phase1(partial, nparts, 2 * C, sums_out, ticket, sums_sh)) return;
+    if (pc.world > 1) {
+        peer_allreduce_block(pc, sums_sh, 2 * C, &ep);
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sums_out[i] = sums_sh[i];
+    }
     const int c = threadIdx.x;
     if (c < 2 * C) {
-        sums_out[c] = sums_sh[c];
         if (dbeta && c < C) dbeta[c] = (float)sums_sh[c];
         if (dgamma && c >= C) dgamma[c - C] = (float)sums_sh[c];
     }
@@ -233,7 +263,6 @@ bn_bwd_finalize_kernel(const double* __restrict__ partial, int nparts, int C, co
         m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         sm = fmaxf(sm, __shfl_xor_sync(0xffffffffu, sm, o));
     }
-    __shared__ float mx2[FIN_THREADS / 32];
     if ((threadIdx.x & 31) == 0) { mx[threadIdx.x >> 5] = m; mx2[threadIdx.x >> 5] = sm; }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1002,27 +1031,29 @@ extern "C" size_t dcue_ncl_center_pack_stats_nparts(int S, int C) { return (size
 extern "C" int dcue_bn_stats_finalize(const double* partial, int nparts, double count, int C, const float* gamma, const float* beta,
                                       float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
                                       float eps, const float* center, const void* peer_bufs_dev, const void* peer_signals_dev,
-                                      void* peer_counter, int rank, int world, double* sums_out, float* scale, float* shift,
-                                      float* mean, float* rstd, void* stream) {
-    DCUE_CHECK_ARG(partial && nparts > 0 && count > 0 && C > 0 && 2 * C <= 256 && scale && shift && mean && rstd);
+                                      void* peer_counter, int rank, int world, void* ticket, double* sums_out, float* scale,
+                                      float* shift, float* mean, float* rstd, void* stream) {
+    DCUE_CHECK_ARG(partial && nparts > 0 && count > 0 && C > 0 && 2 * C <= 256 && scale && shift && mean && rstd && ticket && sums_out);
     DCUE_CHECK_ARG(world >= 1 && (world == 1 || (peer_bufs_dev && peer_signals_dev && peer_counter && rank >= 0 && rank < world)));
     DCUE_CHECK_ARG(2 * C <= PEER_SLOT_DOUBLES);
     PeerCtx pc{(double* const*)peer_bufs_dev, (unsigned* const*)peer_signals_dev, (unsigned*)peer_counter, rank, world};
-    bn_stats_finalize_kernel<<<1, FIN_THREADS, 0, (cudaStream_t)stream>>>(partial, nparts, count, C, gamma, beta, running_mean,
-                                                                          running_var, num_batches_tracked, momentum, eps, center,
-                                                                          pc, sums_out, scale, shift, mean, rstd);
+    bn_stats_finalize_kernel<<<ceil_div_i(2 * C, 8), FIN_THREADS, 0, (cudaStream_t)stream>>>(
+        partial, nparts, count, C, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, center, pc,
+        (unsigned*)ticket, sums_out, scale, shift, mean, rstd);
     DCUE_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int dcue_bn_bwd_finalize(const double* partial, int nparts, int C, const float* scale, double count,
                                     const void* peer_bufs_dev, const void* peer_signals_dev, void* peer_counter, int rank, int world,
-                                    double* sums_out, float* dbeta, float* dgamma, float* absmax_out, float* gscale_out, void* stream) {
-    DCUE_CHECK_ARG(partial && nparts > 0 && C > 0 && 2 * C <= 256 && sums_out);
+                                    void* ticket, double* sums_out, float* dbeta, float* dgamma, float* absmax_out, float* gscale_out,
+                                    void* stream) {
+    DCUE_CHECK_ARG(partial && nparts > 0 && C > 0 && 2 * C <= 256 && sums_out && ticket);
     DCUE_CHECK_ARG(world >= 1 && (world == 1 || (peer_bufs_dev && peer_signals_dev && peer_counter && rank >= 0 && rank < world)));
     PeerCtx pc{(double* const*)peer_bufs_dev, (unsigned* const*)peer_signals_dev, (unsigned*)peer_counter, rank, world};
-    bn_bwd_finalize_kernel<<<1, FIN_THREADS, 0, (cudaStream_t)stream>>>(partial, nparts, C, scale, count, pc, sums_out, dbeta, dgamma,
-                                                                        absmax_out, gscale_out);
+    bn_bwd_finalize_kernel<<<ceil_div_i(2 * C, 8), FIN_THREADS, 0, (cudaStream_t)stream>>>(partial, nparts, C, scale, count, pc,
+                                                                                         (unsigned*)ticket, sums_out, dbeta, dgamma,
+                                                                                         absmax_out, gscale_out);
     DCUE_LAUNCH_CHECK();
     return 0;
 }

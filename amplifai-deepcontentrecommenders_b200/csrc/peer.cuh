@@ -35,7 +35,6 @@ struct PeerCtx {
 // All-reduce (SUM, rank order -> bit-identical on every rank) of vec[0, n) held by ONE thread block (shared or global
 // memory, visible to all its threads); every thread of the block must call this.  `ep_sh` is a shared scratch word.
 __device__ __forceinline__ void peer_allreduce_block(const PeerCtx& pc, double* vec, int n, unsigned* ep_sh) {
-    if (pc.world <= 1) return;
     __syncthreads();
     if (threadIdx.x == 0) *ep_sh = ++(*pc.counter);
     __syncthreads();

@@ -104,6 +104,7 @@ class TowerWorkspace:
         self.sums = torch.zeros(6, 2 * 128, dtype=torch.float64, device=device)
         self.bnp = torch.zeros(6, 4, 128, **f32)        # scale, shift, mean, rstd per BN layer
         self.tapb = torch.zeros(4, 128, **f32)          # layer-1 per-tap constants of the folded bn0 shift
+        self.ticket = torch.zeros(4, dtype=torch.int32, device=device)    # block ticket of the fused finalisers (self-resetting)
         self.zero128 = torch.zeros(128, **f32)
         self.one128 = torch.ones(128, **f32)
         self.wp = [torch.empty(128 * g["k"] * 128, dtype=torch.int16, device=device) for g in self.geo]
@@ -225,7 +226,7 @@ class SongTowerFn(torch.autograd.Function):
             if nparts:
                 L.call("dcue_bn_stats_finalize", scratch, int(nparts), float(count * world), C_, gam, bet,
                        bnm.running_mean.data_ptr(), bnm.running_var.data_ptr(), bnm.num_batches_tracked.data_ptr(), BN_MOMENTUM,
-                       BN_EPS, ctr, *peer, ws.sums[i].data_ptr(), ws.bnp[i, 0].data_ptr(), ws.bnp[i, 1].data_ptr(),
+                       BN_EPS, ctr, *peer, ws.ticket.data_ptr(), ws.sums[i].data_ptr(), ws.bnp[i, 0].data_ptr(), ws.bnp[i, 1].data_ptr(),
                        ws.bnp[i, 2].data_ptr(), ws.bnp[i, 3].data_ptr(), st)
                 return
             if training and dp is not None:
@@ -366,7 +367,7 @@ class SongTowerFn(torch.autograd.Function):
                 peer = _peer_args(dp) if bn_train else (None, None, None, 0, 1)
                 L.call("dcue_bn_bwd_finalize", scratch, L.query("dcue_bn_bwd_reduce_nparts", S, P_), C_,
                        ws.bnp[i, 0].data_ptr() if has_bn else None, float(S * P_ * world) if bn_train else 0.0, *peer,
-                       b["dsums"][i].data_ptr(), L.ptr(gb), L.ptr(gw), b["amax"][i:].data_ptr() if want_scale else None,
+                       ws.ticket.data_ptr(), b["dsums"][i].data_ptr(), L.ptr(gb), L.ptr(gw), b["amax"][i:].data_ptr() if want_scale else None,
                        b["gscale"][i].data_ptr() if want_scale else None, st)
                 if bn_train:
                     grads["bn%d.weight" % i], grads["bn%d.bias" % i] = gw, gb

@@ -126,18 +126,21 @@ int dcue_bn_finalize(const double* sums, double count, int C, const float* gamma
  * the START of their workspace when called in "partials" mode (dcue_conv_pool_fwd_parts; sums == NULL for
  * dcue_ncl_center_pack_stats[_indexed] and dcue_bn_bwd_reduce); the row count is the matching *_nparts query.
  * peer_*: as dcue_peer_allreduce_f64 (world == 1: pointers may be NULL).  count = GLOBAL element count per channel.
- * dcue_bn_stats_finalize (training mode): sums_out (nullable) = global double[2C]; other outputs as dcue_bn_finalize.
+ * dcue_bn_stats_finalize (training mode): sums_out = global double[2C] (required: the blocks hand their column sums to the
+ *   last block through it); other outputs as dcue_bn_finalize.
  * dcue_bn_bwd_finalize: partial = dcue_bn_bwd_reduce's rows ([nparts][2C] sums, then [nparts] max|dy|); sums_out = global
  *   double[2C]; dbeta / dgamma (nullable) fp32 copies; absmax_out (nullable) = local max|dy|; gscale_out (nullable) = {s, 1/s}
  *   as dcue_grad_scale(absmax, scale, C, count). */
 int dcue_bn_stats_finalize(const double* partial, int nparts, double count, int C, const float* gamma, const float* beta,
                            float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
                            float eps, const float* center, const void* peer_bufs_dev, const void* peer_signals_dev,
-                           void* peer_counter, int rank, int world, double* sums_out, float* scale, float* shift,
-                           float* mean, float* rstd, void* stream);
+                           void* peer_counter, int rank, int world,
+                           void* ticket /* one zero-initialised device uint32 (self-resetting block ticket) */,
+                           double* sums_out, float* scale, float* shift, float* mean, float* rstd, void* stream);
 int dcue_bn_bwd_finalize(const double* partial, int nparts, int C, const float* scale, double count,
                          const void* peer_bufs_dev, const void* peer_signals_dev, void* peer_counter, int rank, int world,
-                         double* sums_out, float* dbeta, float* dgamma, float* absmax_out, float* gscale_out, void* stream);
+                         void* ticket, double* sums_out, float* dbeta, float* dgamma, float* absmax_out, float* gscale_out,
+                         void* stream);
 size_t dcue_ncl_center_pack_stats_nparts(int S, int C);
 size_t dcue_bn_bwd_reduce_nparts(int S, int P);
 size_t dcue_conv_pool_fwd_nparts(int impl, int S, int Lp);
