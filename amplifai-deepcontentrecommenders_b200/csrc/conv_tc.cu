@@ -171,6 +171,13 @@ struct Pipe {
 };
 
 // ----------------------------------------------------------------------------- fwd / dgrad
+// Folded input-BatchNorm shift: conv outputs whose taps hang over the zero padding lack those taps' constants.  Kept out of
+// line so that the (rare, warp-uniform) border windows do not bloat the common epilogue path with predicated code.
+__device__ __noinline__ float border_fix(float tb0, float tb1, float tb2, float tb3, int t, int k, int pad, int Lin) {
+    const float tb[4] = {tb0, tb1, tb2, tb3};
+    return missing_taps(tb, t, k, pad, Lin);
+}
+
 // EPI 0: bias + maxpool(POOL) + relu + argmax code + BN partial sums -> z[S*P, Cout]
 // EPI 1: store the data rows -> dx[S*Lin, Cout]
 // Epilogue work split: 16 warps, warp e owns TMEM lane quarter (warp_id % 4) x column chunk e/4 of
@@ -320,17 +327,16 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
             int s = r / g.Lp;
             int q = r - s * g.Lp;
             if (EPI == 0) {
+                // ncu (round 2): this epilogue, not the MMA, paced the kernel -- 510 instructions per warp and tile, the ALU pipe
+                // saturated (math-pipe-throttle the top stall) because the border correction and the (s, p) index arithmetic
+                // were if-converted into predicated code that issued for every output.  Rows are warp-uniform, so each
+                // pooling window now takes a real branch: 32 of a spectrogram's 34 windows are "interior" (all taps inside the
+                // data, same spectrogram, p < P) and run a short straight-line path with an incrementally advanced pointer.
                 float ts1 = 0.f, ts2 = 0.f;
-#pragma unroll
-                for (int t0 = 0; t0 < 32; t0 += POOL) {
-                    float w[POOL];
-#pragma unroll
-                    for (int i = 0; i < POOL; ++i) w[i] = v[t0 + i];
-                    // folded input-BatchNorm shift: outputs whose taps hang over the zero padding lack those constants
-                    if (has_tb && (q < g.pad || q + POOL - 1 > g.Lin + g.pad - g.k)) {
-#pragma unroll
-                        for (int i = 0; i < POOL; ++i) w[i] -= missing_taps(tb, q + i, g.k, g.pad, g.Lin);
-                    }
+                const int q_hi = g.Lin + g.pad - g.k;            // last conv row whose taps all hit data rows
+                const int q_end = g.P * POOL;                    // rows beyond are dropped by the floor pooling
+                long o = ((long)s * g.P + q / POOL) * g.Cout + m;
+                auto pool_store = [&](const float (&w)[POOL], bool ok, long oo) {
                     float best = w[0];
                     int bi = 0;
 #pragma unroll
@@ -339,21 +345,60 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
                         best = gt ? w[i] : best;
                         bi = gt ? i : bi;
                     }
-                    const int p = q / POOL;  // POOL is a power of two
-                    const bool ok = chan_ok && s < g.S && p < g.P;
                     const float val = ok ? fmaxf(best + bv, 0.f) : 0.f;
-                    const long o = ((long)s * g.P + p) * g.Cout + m;
-                    st_pred_f32(out + o, val, ok);
-                    st_pred_u8(code + o, (uint32_t)bi, ok);
+                    st_pred_f32(out + oo, val, ok);
+                    st_pred_u8(code + oo, (uint32_t)bi, ok);
                     ts1 += val;
                     ts2 = fmaf(val, val, ts2);
-                    q += POOL;
-                    const bool wrap = q >= g.Lp;
-                    q = wrap ? q - g.Lp : q;
-                    s += wrap ? 1 : 0;
+                };
+                if (s < g.S && q >= g.pad && q + 31 <= q_hi && q + 32 <= q_end) {
+                    // the whole 32-row chunk is interior (about 2/3 of the chunks): straight-line, no per-window tests
+#pragma unroll
+                    for (int t0 = 0; t0 < 32; t0 += POOL) {
+                        float w[POOL];
+#pragma unroll
+                        for (int i = 0; i < POOL; ++i) w[i] = v[t0 + i];
+                        pool_store(w, chan_ok, o);
+                        o += g.Cout;
+                    }
+                } else {
+#pragma unroll 1
+                    for (int t0 = 0; t0 < 32; t0 += POOL) {
+                        float w[POOL];
+                        // v[] is indexed with a run-time window here: select with a compile-time switch (no local memory)
+#pragma unroll
+                        for (int i = 0; i < POOL; ++i) w[i] = 0.f;
+#pragma unroll
+                        for (int u = 0; u < 32; u += POOL)
+                            if (u == t0) {
+#pragma unroll
+                                for (int i = 0; i < POOL; ++i) w[i] = v[u + i];
+                            }
+                        const bool ok = chan_ok && s < g.S && q + POOL <= q_end;
+                        if (has_tb && (q < g.pad || q + POOL - 1 > q_hi)) {
+#pragma unroll
+                            for (int i = 0; i < POOL; ++i) w[i] -= border_fix(tb[0], tb[1], tb[2], tb[3], q + i, g.k, g.pad, g.Lin);
+                        }
+                        pool_store(w, ok, o);
+                        q += POOL;
+                        o += g.Cout;
+                        if (q >= g.Lp) {                         // next spectrogram (warp-uniform)
+                            q -= g.Lp;
+                            ++s;
+                            o = ((long)s * g.P + q / POOL) * g.Cout + m;
+                        }
+                    }
                 }
                 st1 += (double)ts1;
                 st2 += (double)ts2;
+            } else if (s < g.S && q >= g.pad && q + 31 < g.Lin + g.pad) {
+                // all 32 rows are data rows of one spectrogram (the common case): one base pointer, no per-row tests
+                float* dst = out + ((long)s * g.Lin + (q - g.pad)) * g.Cout + m;
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    st_pred_f32(dst, v[t] * bv, chan_ok);
+                    dst += g.Cout;
+                }
             } else {
 #pragma unroll
                 for (int t = 0; t < 32; ++t) {
