@@ -267,6 +267,145 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
     }
 }
 
+// ------------------------------------------------------------------ cp.async pipelined 3xTF32 GEMM
+// The register-staged kernel above is bound by global-load latency (two blocks per SM, one 16-byte load per thread and
+// operand in flight: 34 us for an 11 MB GEMM, the same with CUDA-core FMAs or tensor-core MMAs).  Here 64 x 64 x 64 tiles go
+// global -> shared memory with cp.async (16-byte chunks, zero-filled tails) through a 3-stage ring, so a block has two
+// whole k-chunks of both operands in flight while it multiplies the third.  Either operand may be contiguous along the
+// contraction index r (smem [i][r], row stride TKC+4) or along its own index (smem [r][i], row stride 72); both layouts give
+// conflict-free m16n8k8 fragment reads.
+constexpr int TKC = 64, CST = 3;
+constexpr int CP_OP_FLOATS = 64 * 72;                       // one operand tile of one stage (either layout fits)
+constexpr size_t CP_SMEM = (size_t)CST * 2 * CP_OP_FLOATS * sizeof(float);
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+// tile [64 x TKC] of operand X(i, r) = base[i*s_i + r*s_r] at (i0, r0); rows i >= I and columns r >= rend are zero-filled
+__device__ __forceinline__ void cp_load_tile(float* sm, const float* base, long s_i, long s_r, bool r_contig, int i0, int I, int r0,
+                                             int rend, int tid) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int c = tid + it * 256;                        // 1024 16-byte chunks per tile
+        if (r_contig) {
+            const int li = c >> 4, lr = (c & 15) * 4;        // 16 chunks per row of 64 r
+            const int gi = i0 + li, gr = r0 + lr;
+            int bytes = (gi < I && gr < rend) ? min(16, (rend - gr) * 4) : 0;
+            const float* src = bytes ? base + gi * s_i + gr : base;
+            cp_async16(sm + li * (TKC + 4) + lr, src, bytes);
+        } else {
+            const int lr = c >> 4, li = (c & 15) * 4;        // 16 chunks per r-row of 64 i
+            const int gi = i0 + li, gr = r0 + lr;
+            int bytes = (gr < rend && gi < I) ? min(16, (I - gi) * 4) : 0;
+            const float* src = bytes ? base + gr * s_r + gi : base;
+            cp_async16(sm + lr * 72 + li, src, bytes);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) gemm_cpasync_kernel(GemmP p) {
+    extern __shared__ __align__(16) float cps[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int i0 = blockIdx.y * TM, j0 = blockIdx.x * TN;
+    const int wm = wid & 1, wn = wid >> 1, fg = lane >> 2, ft = lane & 3;
+    const int rchunk = ceil_div_i(ceil_div_i(p.R, TKC), p.splits) * TKC;
+    const int rbeg = blockIdx.z * rchunk;
+    const int rend = min(p.R, rbeg + rchunk);
+    const bool a_rc = (p.sAr == 1), b_rc = (p.sBr == 1);
+    const int nk = rbeg < rend ? ceil_div_i(rend - rbeg, TKC) : 0;
+
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+    auto issue = [&](int kc) {
+        if (kc < nk) {
+            float* sa = cps + (size_t)(kc % CST) * 2 * CP_OP_FLOATS;
+            cp_load_tile(sa, p.A, p.sAi, p.sAr, a_rc, i0, p.I, rbeg + kc * TKC, rend, tid);
+            cp_load_tile(sa + CP_OP_FLOATS, p.B, p.sBj, p.sBr, b_rc, j0, p.J, rbeg + kc * TKC, rend, tid);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");     // one group per k-chunk, empty ones included
+    };
+#pragma unroll
+    for (int s = 0; s < CST - 1; ++s) issue(s);
+    for (int kc = 0; kc < nk; ++kc) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(CST - 2) : "memory");   // chunk kc has landed (this thread's copies)
+        __syncthreads();                                                      // ... everyone's; and chunk kc-1 is fully consumed
+        issue(kc + CST - 1);                                                  // refill the slot of chunk kc-1
+        const float* sa = cps + (size_t)(kc % CST) * 2 * CP_OP_FLOATS;
+        const float* sb = sa + CP_OP_FLOATS;
+#pragma unroll
+        for (int kk = 0; kk < TKC; kk += 8) {
+            uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+                const int r = wm * 32 + mi * 16 + fg;
+                float x0, x1, x2, x3;
+                if (a_rc) {
+                    x0 = sa[r * (TKC + 4) + kk + ft]; x1 = sa[(r + 8) * (TKC + 4) + kk + ft];
+                    x2 = sa[r * (TKC + 4) + kk + ft + 4]; x3 = sa[(r + 8) * (TKC + 4) + kk + ft + 4];
+                } else {
+                    x0 = sa[(kk + ft) * 72 + r]; x1 = sa[(kk + ft) * 72 + r + 8];
+                    x2 = sa[(kk + ft + 4) * 72 + r]; x3 = sa[(kk + ft + 4) * 72 + r + 8];
+                }
+                split_tf32(x0, ah[mi][0], al[mi][0]); split_tf32(x1, ah[mi][1], al[mi][1]);
+                split_tf32(x2, ah[mi][2], al[mi][2]); split_tf32(x3, ah[mi][3], al[mi][3]);
+            }
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) {
+                const int c = wn * 16 + ni * 8 + fg;
+                float y0, y1;
+                if (b_rc) { y0 = sb[c * (TKC + 4) + kk + ft]; y1 = sb[c * (TKC + 4) + kk + ft + 4]; }
+                else { y0 = sb[(kk + ft) * 72 + c]; y1 = sb[(kk + ft + 4) * 72 + c]; }
+                split_tf32(y0, bh[ni][0], bl[ni][0]); split_tf32(y1, bh[ni][1], bl[ni][1]);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) {      // small terms first
+                    mma_tf32(acc[mi * 2 + ni], al[mi], bh[ni]);
+                    mma_tf32(acc[mi * 2 + ni], ah[mi], bl[ni]);
+                    mma_tf32(acc[mi * 2 + ni], ah[mi], bh[ni]);
+                }
+        }
+    }
+    float* C = p.C + (long)blockIdx.z * p.split_stride;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int gi = i0 + wm * 32 + mi * 16 + fg + 8 * h;
+                const int gj = j0 + wn * 16 + ni * 8 + 2 * ft;
+                if (gi >= p.I) continue;
+#pragma unroll
+                for (int y = 0; y < 2; ++y) {
+                    if (gj + y >= p.J) continue;
+                    float v = acc[mi * 2 + ni][2 * h + y];
+                    if (p.splits == 1) {
+                        if (p.bias) v += p.bias[gj + y];
+                        if (p.relu) v = v < 0.f ? 0.f : v;  // NaN-propagating (an out-of-range user row must stay loud)
+                        if (p.mask) v = p.mask[gi * p.ldmask + gj + y] > 0.f ? v : 0.f;
+                    }
+                    C[gi * p.ldc + gj + y] = v;
+                }
+            }
+}
+
+// cp.async needs 16-byte aligned rows: the base pointer, the non-unit stride (x4 bytes) and the tile origin along the
+// contiguous index are multiples of 4 floats (true for every DCUE shape: K, N in {100, 128, 300, 612}, ld multiples of 4)
+bool cp_operand_ok(const float* base, long s_i, long s_r) {
+    if (reinterpret_cast<uintptr_t>(base) & 15) return false;
+    if (s_r == 1) return (s_i & 3) == 0;
+    if (s_i == 1) return (s_r & 3) == 0;
+    return false;
+}
+
 __global__ void split_reduce_kernel(const float* __restrict__ part, int splits, long n, float* __restrict__ out) {
     long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -304,9 +443,27 @@ bool linear_simt() {
     }
     return v != 0;
 }
+int linear_impl() {      // 0 = cp.async pipeline (default), 1 = CUDA cores, 2 = register-staged 3xTF32
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DCUE_LINEAR_IMPL");
+        v = !e ? 0 : ((e[0] == 's' || e[0] == 'S') ? 1 : ((e[0] == 'r' || e[0] == 'R') ? 2 : 0));
+    }
+    return v;
+}
 void launch_gemm(const GemmP& p, dim3 grid, cudaStream_t st) {
-    if (linear_simt()) gemm_kernel<false><<<grid, 256, 0, st>>>(p);
-    else gemm_kernel<true><<<grid, 256, 0, st>>>(p);
+    const int impl = linear_impl();
+    if (impl == 1) { gemm_kernel<false><<<grid, 256, 0, st>>>(p); return; }
+    if (impl == 0 && cp_operand_ok(p.A, p.sAi, p.sAr) && cp_operand_ok(p.B, p.sBj, p.sBr)) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(gemm_cpasync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CP_SMEM);
+            attr_done = true;
+        }
+        gemm_cpasync_kernel<<<grid, 256, CP_SMEM, st>>>(p);
+        return;
+    }
+    gemm_kernel<true><<<grid, 256, 0, st>>>(p);
 }
 
 int wgrad_splits(int M, int K, int N) {
