@@ -423,8 +423,16 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int rl = threadIdx.x >> 5;
     float s = 0.f;
-    if (c < N)
-        for (int m = blockIdx.y * 8 + rl; m < M; m += 8 * gridDim.y) s += x[(long)m * ld + c];
+    if (c < N) {
+        const int step = 8 * gridDim.y;
+        int m = blockIdx.y * 8 + rl;
+        for (; m + 3 * step < M; m += 4 * step) {      // four independent loads in flight (the plain loop was latency bound: 22 us)
+            const float v0 = x[(long)m * ld + c], v1 = x[(long)(m + step) * ld + c];
+            const float v2 = x[(long)(m + 2 * step) * ld + c], v3 = x[(long)(m + 3 * step) * ld + c];
+            s += (v0 + v1) + (v2 + v3);
+        }
+        for (; m < M; m += step) s += x[(long)m * ld + c];
+    }
     red[rl][threadIdx.x & 31] = s;
     __syncthreads();
     if (rl == 0 && c < N) {
