@@ -376,14 +376,17 @@ border_row_sums_kernel(const float* __restrict__ dy, int lddy, const float* __re
                        const float* __restrict__ z, const uint8_t* __restrict__ code, const float* __restrict__ scale,
                        const float* __restrict__ mean, const float* __restrict__ rstd, const double* __restrict__ sums,
                        double count, int S, int P, int pool, int4 rows, float* __restrict__ out /* [PRS_SLICES][4][128] */) {
-    __shared__ float red[4][128];
+    // block (pair, slice): border rows come in pairs that share a pooling window (rows 0,1 -> window 0; the two trailing
+    // rows -> the last window), so one load of (dy, z, code) serves both rows of the pair
+    __shared__ float red[2][4][128];
     const int c = threadIdx.x & 127, ph = threadIdx.x >> 7;
-    const int ri = blockIdx.x, zs = blockIdx.y;
-    const int row = ri == 0 ? rows.x : ri == 1 ? rows.y : ri == 2 ? rows.z : rows.w;
-    float a = 0.f;
-    if (row >= 0 && row / pool < P) {
-        const int pe = row / pool;
-        const unsigned ce = (unsigned)(row - pe * pool);
+    const int pr = blockIdx.x, zs = blockIdx.y;
+    const int row_a = pr == 0 ? rows.x : rows.z, row_b = pr == 0 ? rows.y : rows.w;
+    float acc_a = 0.f, acc_b = 0.f;
+    const bool va = row_a >= 0 && row_a / pool < P, vb = row_b >= 0 && row_b / pool < P;
+    if (va || vb) {
+        const int pe_a = va ? row_a / pool : -1, pe_b = vb ? row_b / pool : -1;
+        const unsigned ce_a = va ? (unsigned)(row_a - pe_a * pool) : 255u, ce_b = vb ? (unsigned)(row_b - pe_b * pool) : 255u;
         const float sc = scale ? scale[c] : 1.f;
         float kb = 0.f, kc = 0.f;
         if (sums) {
@@ -395,20 +398,33 @@ border_row_sums_kernel(const float* __restrict__ dy, int lddy, const float* __re
         const float invP = 1.f / (float)P;
         const int per = (S + PRS_SLICES - 1) / PRS_SLICES;
         const int s0 = zs * per, s1 = min(S, s0 + per);
+        const bool shared_window = va && vb && pe_a == pe_b;
 #pragma unroll 4
         for (int sp = s0 + ph; sp < s1; sp += 4) {
-            const long r = (long)sp * P + pe;
-            float g = dy[r * lddy + c];
-            const float zz = z[r * 128 + c];
-            const unsigned cd = code[r * 128 + c];
-            if (dtp) g = fmaf(dtp[(long)sp * lddtp + c], invP, g);
-            const float v = fmaf(sc, g, fmaf(kb, zz, kc));
-            a += (zz > 0.f && cd == ce) ? v : 0.f;
+            const float tpv = dtp ? dtp[(long)sp * lddtp + c] : 0.f;
+            if (va) {
+                const long r = (long)sp * P + pe_a;
+                const float g = fmaf(tpv, invP, dy[r * lddy + c]);
+                const float zz = z[r * 128 + c];
+                const unsigned cd = code[r * 128 + c];
+                const float v = zz > 0.f ? fmaf(sc, g, fmaf(kb, zz, kc)) : 0.f;
+                acc_a += cd == ce_a ? v : 0.f;
+                if (shared_window) acc_b += cd == ce_b ? v : 0.f;
+            }
+            if (vb && !shared_window) {
+                const long r = (long)sp * P + pe_b;
+                const float g = fmaf(tpv, invP, dy[r * lddy + c]);
+                const float zz = z[r * 128 + c];
+                const unsigned cd = code[r * 128 + c];
+                const float v = zz > 0.f ? fmaf(sc, g, fmaf(kb, zz, kc)) : 0.f;
+                acc_b += cd == ce_b ? v : 0.f;
+            }
         }
     }
-    red[ph][c] = a;
+    red[0][ph][c] = acc_a;
+    red[1][ph][c] = acc_b;
     __syncthreads();
-    if (ph == 0) out[(zs * 4 + ri) * 128 + c] = (red[0][c] + red[1][c]) + (red[2][c] + red[3][c]);
+    if (ph < 2) out[(zs * 4 + pr * 2 + ph) * 128 + c] = (red[ph][0][c] + red[ph][1][c]) + (red[ph][2][c] + red[ph][3][c]);
 }
 
 extern "C" int dcue_border_row_sums(const float* dy, int lddy, const float* dtp, int lddtp, const float* z, const uint8_t* code,
@@ -416,7 +432,7 @@ extern "C" int dcue_border_row_sums(const float* dy, int lddy, const float* dtp,
                                     int S, int P, int C, int pool, int r0, int r1, int r2, int r3, float* out, void* stream) {
     DCUE_CHECK_ARG(dy && z && code && out && S >= 0 && P > 0 && C == 128 && pool >= 1 && lddy >= C);
     DCUE_CHECK_ARG(!sums || (mean && rstd && count > 0));
-    dim3 grid(4, PRS_SLICES);
+    dim3 grid(2, PRS_SLICES);
     border_row_sums_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(dy, lddy, dtp, lddtp, z, code, scale, mean, rstd, sums,
                                                                    count > 0 ? count : 1.0, S, P, pool, make_int4(r0, r1, r2, r3), out);
     DCUE_LAUNCH_CHECK();
