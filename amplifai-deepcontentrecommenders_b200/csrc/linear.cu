@@ -25,6 +25,7 @@ struct GemmP {
     const float* mask; long ldmask;
     int I, J, R, relu, splits;
     long split_stride;        // elements between partial buffers
+    int single_tf32;          // 1: one TF32 MMA per product (10-bit mantissa operands, like the 16-bit conv operands); 0: 3xTF32
 };
 
 // Global -> register fetch of this thread's 4 elements of the A (TM x TK) and B (TK x TN) tiles at r0.
@@ -305,6 +306,7 @@ __device__ __forceinline__ void cp_load_tile(float* sm, const float* base, long 
     }
 }
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) gemm_cpasync_kernel(GemmP p) {
     extern __shared__ __align__(16) float cps[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -367,8 +369,10 @@ __global__ void __launch_bounds__(256) gemm_cpasync_kernel(GemmP p) {
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 2; ++ni) {      // small terms first
-                    mma_tf32(acc[mi * 2 + ni], al[mi], bh[ni]);
-                    mma_tf32(acc[mi * 2 + ni], ah[mi], bl[ni]);
+                    if (SPLIT) {
+                        mma_tf32(acc[mi * 2 + ni], al[mi], bh[ni]);
+                        mma_tf32(acc[mi * 2 + ni], ah[mi], bl[ni]);
+                    }
                     mma_tf32(acc[mi * 2 + ni], ah[mi], bh[ni]);
                 }
         }
@@ -465,10 +469,12 @@ void launch_gemm(const GemmP& p, dim3 grid, cudaStream_t st) {
     if (impl == 0 && cp_operand_ok(p.A, p.sAi, p.sAr) && cp_operand_ok(p.B, p.sBj, p.sBr)) {
         static bool attr_done = false;
         if (!attr_done) {
-            cudaFuncSetAttribute(gemm_cpasync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CP_SMEM);
+            cudaFuncSetAttribute(gemm_cpasync_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CP_SMEM);
+            cudaFuncSetAttribute(gemm_cpasync_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CP_SMEM);
             attr_done = true;
         }
-        gemm_cpasync_kernel<<<grid, 256, CP_SMEM, st>>>(p);
+        if (p.single_tf32) gemm_cpasync_kernel<false><<<grid, 256, CP_SMEM, st>>>(p);
+        else gemm_cpasync_kernel<true><<<grid, 256, CP_SMEM, st>>>(p);
         return;
     }
     gemm_kernel<true><<<grid, 256, 0, st>>>(p);
@@ -486,30 +492,30 @@ int wgrad_splits(int M, int K, int N) {
 
 }  // namespace
 
-extern "C" int dcue_linear_fwd(const float* X, int ldx, const float* W, const float* b, int M, int K, int N,
-                               int relu, float* Y, int ldy, void* stream) {
+static int linear_fwd_impl(const float* X, int ldx, const float* W, const float* b, int M, int K, int N,
+                           int relu, float* Y, int ldy, void* stream, int single_tf32) {
     DCUE_CHECK_ARG(X && W && Y && M >= 0 && K > 0 && N > 0 && ldx >= K && ldy >= N);
     if (M == 0) return 0;
     GemmP p{};
     p.A = X; p.sAi = ldx; p.sAr = 1;
     p.B = W; p.sBr = 1; p.sBj = K;  // B(r,j) = W[j,r]
     p.C = Y; p.ldc = ldy; p.bias = b; p.mask = nullptr; p.ldmask = 0;
-    p.I = M; p.J = N; p.R = K; p.relu = relu; p.splits = 1; p.split_stride = 0;
+    p.I = M; p.J = N; p.R = K; p.relu = relu; p.splits = 1; p.split_stride = 0; p.single_tf32 = single_tf32;
     dim3 grid(ceil_div_i(N, TN), ceil_div_i(M, TM), 1);
     launch_gemm(p, grid, (cudaStream_t)stream);
     DCUE_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int dcue_linear_dgrad(const float* dY, int lddy, const float* W, int M, int K, int N,
-                                 const float* mask, int ldmask, float* dX, int lddx, void* stream) {
+static int linear_dgrad_impl(const float* dY, int lddy, const float* W, int M, int K, int N,
+                             const float* mask, int ldmask, float* dX, int lddx, void* stream, int single_tf32) {
     DCUE_CHECK_ARG(dY && W && dX && M >= 0 && K > 0 && N > 0 && lddy >= N && lddx >= K);
     if (M == 0) return 0;
     GemmP p{};
     p.A = dY; p.sAi = lddy; p.sAr = 1;
     p.B = W; p.sBr = K; p.sBj = 1;  // B(r=n, j=k) = W[n,k]
     p.C = dX; p.ldc = lddx; p.bias = nullptr; p.mask = mask; p.ldmask = ldmask;
-    p.I = M; p.J = K; p.R = N; p.relu = 0; p.splits = 1; p.split_stride = 0;
+    p.I = M; p.J = K; p.R = N; p.relu = 0; p.splits = 1; p.split_stride = 0; p.single_tf32 = single_tf32;
     dim3 grid(ceil_div_i(K, TN), ceil_div_i(M, TM), 1);
     launch_gemm(p, grid, (cudaStream_t)stream);
     DCUE_LAUNCH_CHECK();
@@ -520,8 +526,8 @@ extern "C" size_t dcue_linear_wgrad_ws_bytes(int M, int K, int N) {
     return ((size_t)wgrad_splits(M, K, N) * (size_t)N * (size_t)K + (size_t)COLSUM_G * N) * sizeof(float) + 256;
 }
 
-extern "C" int dcue_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, int M, int K, int N,
-                                 float* dW, float* db, void* ws, size_t ws_bytes, void* stream) {
+static int linear_wgrad_impl(const float* dY, int lddy, const float* X, int ldx, int M, int K, int N,
+                             float* dW, float* db, void* ws, size_t ws_bytes, void* stream, int single_tf32) {
     DCUE_CHECK_ARG(dY && X && dW && M >= 0 && K > 0 && N > 0 && lddy >= N && ldx >= K);
     cudaStream_t st = (cudaStream_t)stream;
     if (M == 0) {
@@ -536,7 +542,7 @@ extern "C" int dcue_linear_wgrad(const float* dY, int lddy, const float* X, int 
     p.A = dY; p.sAi = 1; p.sAr = lddy;  // A(i=n, r=m) = dY[m,n]
     p.B = X; p.sBr = ldx; p.sBj = 1;    // B(r=m, j=k) = X[m,k]
     p.C = splits > 1 ? (float*)ws : dW; p.ldc = K; p.bias = nullptr; p.mask = nullptr; p.ldmask = 0;
-    p.I = N; p.J = K; p.R = M; p.relu = 0; p.splits = splits; p.split_stride = (long)N * K;
+    p.I = N; p.J = K; p.R = M; p.relu = 0; p.splits = splits; p.split_stride = (long)N * K; p.single_tf32 = single_tf32;
     dim3 grid(ceil_div_i(K, TN), ceil_div_i(N, TM), splits);
     launch_gemm(p, grid, st);
     DCUE_LAUNCH_CHECK();
@@ -554,4 +560,31 @@ extern "C" int dcue_linear_wgrad(const float* dY, int lddy, const float* X, int 
         DCUE_LAUNCH_CHECK();
     }
     return 0;
+}
+
+extern "C" int dcue_linear_fwd(const float* X, int ldx, const float* W, const float* b, int M, int K, int N,
+                               int relu, float* Y, int ldy, void* stream) {
+    return linear_fwd_impl(X, ldx, W, b, M, K, N, relu, Y, ldy, stream, 0);
+}
+extern "C" int dcue_linear_dgrad(const float* dY, int lddy, const float* W, int M, int K, int N,
+                                 const float* mask, int ldmask, float* dX, int lddx, void* stream) {
+    return linear_dgrad_impl(dY, lddy, W, M, K, N, mask, ldmask, dX, lddx, stream, 0);
+}
+extern "C" int dcue_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, int M, int K, int N,
+                                 float* dW, float* db, void* ws, size_t ws_bytes, void* stream) {
+    return linear_wgrad_impl(dY, lddy, X, ldx, M, K, N, dW, db, ws, ws_bytes, stream, 0);
+}
+// Single-pass TF32 variants (operands rounded to TF32 = 11 significant bits, the precision of the fp16 conv operands; fp32
+// accumulate): the song tower's k = 1 conv and fc, whose inputs already carry 16-bit operand rounding.
+extern "C" int dcue_linear_fwd_tf32(const float* X, int ldx, const float* W, const float* b, int M, int K, int N,
+                                    int relu, float* Y, int ldy, void* stream) {
+    return linear_fwd_impl(X, ldx, W, b, M, K, N, relu, Y, ldy, stream, 1);
+}
+extern "C" int dcue_linear_dgrad_tf32(const float* dY, int lddy, const float* W, int M, int K, int N,
+                                      const float* mask, int ldmask, float* dX, int lddx, void* stream) {
+    return linear_dgrad_impl(dY, lddy, W, M, K, N, mask, ldmask, dX, lddx, stream, 1);
+}
+extern "C" int dcue_linear_wgrad_tf32(const float* dY, int lddy, const float* X, int ldx, int M, int K, int N,
+                                      float* dW, float* db, void* ws, size_t ws_bytes, void* stream) {
+    return linear_wgrad_impl(dY, lddy, X, ldx, M, K, N, dW, db, ws, ws_bytes, stream, 1);
 }

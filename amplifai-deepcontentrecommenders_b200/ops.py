@@ -53,6 +53,12 @@ def _peer_args(dp):
     return (pr.hdl.buffer_ptrs_dev, pr.hdl.signal_pad_ptrs_dev, pr.counter.data_ptr(), pr.rank, pr.world)
 
 
+def tower_linear(name):
+    """The song tower's k = 1 conv and fc run as single-pass TF32 tensor-core GEMMs (their inputs already carry the 16-bit
+    operand rounding of the conv layers); DCUE_TOWER_TF32=0 selects the fp32-accurate 3xTF32 form."""
+    return name + "_tf32" if os.environ.get("DCUE_TOWER_TF32", "1") != "0" else name
+
+
 def operand_fmt():
     """16-bit format of the forward conv operands: fp16 (default) or bf16 (DCUE_OPERAND=bf16)."""
     return L.FMT_BF16 if os.environ.get("DCUE_OPERAND", "f16").lower() == "bf16" else L.FMT_F16
@@ -294,7 +300,7 @@ class SongTowerFn(torch.autograd.Function):
                 L.call("dcue_affine_pack", ws.z[3].data_ptr(), S, 1, H, sc, sh, None, 0, 1, 0, fmt, ws.y4.data_ptr(), tp,
                        ldtp, st)
         # ---- layer5 (k=1 conv == linear) + relu (+bn5), fc
-        L.call("dcue_linear_fwd", ws.y4.data_ptr(), H, P["layer5.weight"].data_ptr(), P["layer5.bias"].data_ptr(), S, H, F,
+        L.call(tower_linear("dcue_linear_fwd"), ws.y4.data_ptr(), H, P["layer5.weight"].data_ptr(), P["layer5.bias"].data_ptr(), S, H, F,
                1, ws.z5.data_ptr(), F, st)
         y5 = ws.fc_in[:, 4 * H:] if res else ws.fc_in
         if has_bn:
@@ -310,7 +316,7 @@ class SongTowerFn(torch.autograd.Function):
                ws.fc_in.shape[1], st)
         out = torch.empty(S, F, dtype=torch.float32, device=dev)
         Kfc = ws.fc_in.shape[1]
-        L.call("dcue_linear_fwd", ws.fc_in.data_ptr(), Kfc, P["fc.weight"].data_ptr(), P["fc.bias"].data_ptr(), S, Kfc, F,
+        L.call(tower_linear("dcue_linear_fwd"), ws.fc_in.data_ptr(), Kfc, P["fc.weight"].data_ptr(), P["fc.bias"].data_ptr(), S, Kfc, F,
                0, out.data_ptr(), F, st)
 
         needs_bwd = any(ctx.needs_input_grad)
@@ -392,11 +398,11 @@ class SongTowerFn(torch.autograd.Function):
 
         # ---- fc
         gW, gb_ = torch.empty(F, Kfc, **f32), torch.empty(F, **f32)
-        L.call("dcue_linear_wgrad", gout.data_ptr(), F, ws.fc_in.data_ptr(), Kfc, S, Kfc, F, gW.data_ptr(), gb_.data_ptr(),
+        L.call(tower_linear("dcue_linear_wgrad"), gout.data_ptr(), F, ws.fc_in.data_ptr(), Kfc, S, Kfc, F, gW.data_ptr(), gb_.data_ptr(),
                scratch, nscr, st)
         grads["fc.weight"], grads["fc.bias"] = gW, gb_
         dfc = torch.empty(S, Kfc, **f32)
-        L.call("dcue_linear_dgrad", gout.data_ptr(), F, P["fc.weight"].data_ptr(), S, Kfc, F, None, 0, dfc.data_ptr(), Kfc, st)
+        L.call(tower_linear("dcue_linear_dgrad"), gout.data_ptr(), F, P["fc.weight"].data_ptr(), S, Kfc, F, None, 0, dfc.data_ptr(), Kfc, st)
         dy5 = dfc[:, 4 * H:] if res else dfc
         # ---- bn5 + relu5 -> dz5 ; layer5
         dz5 = torch.empty(S, F, **f32)
@@ -407,11 +413,11 @@ class SongTowerFn(torch.autograd.Function):
                ws.bnp[5, 3].data_ptr() if has_bn else None, b["dsums"][5].data_ptr() if bn_train else None,
                float(S * world), S, 1, F, 1, 1, None, 0, gfmt, None, dz5.data_ptr(), None, None, scratch, nscr, st)
         gW5, gb5 = torch.empty(F, H, 1, **f32), torch.empty(F, **f32)
-        L.call("dcue_linear_wgrad", dz5.data_ptr(), F, ws.y4.data_ptr(), H, S, H, F, gW5.data_ptr(), gb5.data_ptr(), scratch,
+        L.call(tower_linear("dcue_linear_wgrad"), dz5.data_ptr(), F, ws.y4.data_ptr(), H, S, H, F, gW5.data_ptr(), gb5.data_ptr(), scratch,
                nscr, st)
         grads["layer5.weight"], grads["layer5.bias"] = gW5, gb5
         dy = torch.empty(S, H, **f32)  # gradient w.r.t. the stage-4 BN output
-        L.call("dcue_linear_dgrad", dz5.data_ptr(), F, P["layer5.weight"].data_ptr(), S, H, F, None, 0, dy.data_ptr(), H, st)
+        L.call(tower_linear("dcue_linear_dgrad"), dz5.data_ptr(), F, P["layer5.weight"].data_ptr(), S, H, F, None, 0, dy.data_ptr(), H, st)
         # ---- stages 4..1
         for i in range(4, 0, -1):
             g = geo[i - 1]

@@ -92,6 +92,17 @@ int dcue_linear_dgrad(const float* dY, int lddy, const float* W, int M, int K, i
 int dcue_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, int M, int K, int N,
                       float* dW, float* db, void* ws, size_t ws_bytes, void* stream);
 size_t dcue_linear_wgrad_ws_bytes(int M, int K, int N);
+/* The same three GEMMs with ONE TF32 tensor-core pass per product instead of the fp32-accurate 3xTF32 split: operands are
+ * rounded to TF32 (11 significant bits -- the precision of the fp16 conv operands), accumulation is fp32.  Used for the song
+ * tower's k = 1 conv and fc (truedcuemel1dbn.py:57-59, :101), whose inputs already carry 16-bit operand rounding; the user
+ * MLP keeps the fp32-accurate form.  When the cp.async path is not applicable (unaligned operands, DCUE_LINEAR_IMPL) these
+ * fall back to the fp32-accurate kernels. */
+int dcue_linear_fwd_tf32(const float* X, int ldx, const float* W, const float* b, int M, int K, int N,
+                         int relu, float* Y, int ldy, void* stream);
+int dcue_linear_dgrad_tf32(const float* dY, int lddy, const float* W, int M, int K, int N,
+                           const float* mask, int ldmask, float* dX, int lddx, void* stream);
+int dcue_linear_wgrad_tf32(const float* dY, int lddy, const float* X, int ldx, int M, int K, int N,
+                           float* dW, float* db, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- song tower ------------- */
 

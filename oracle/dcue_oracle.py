@@ -20,7 +20,8 @@ Reference anchors (all under /root/reference):
   * DCUE._loss_func                dcrecommend/nn/dcue.py:167-170
   * DCUE.predict (model.sim)       dcrecommend/nn/dcue.py:495-513
 
-``operand_dtype`` / ``grad_dtype`` reproduce the roundings of the B200 path:
+``operand_dtype`` / ``grad_dtype`` reproduce the roundings of the B200 path (and switch the k = 1 conv and the fc to
+TF32-rounded operands, the single-pass tensor-core form those two GEMMs take there):
 conv operands (activations entering layer1..4 and their weights) are rounded to
 ``operand_dtype`` (fp16 on B200) and the gradient entering each conv backward is
 rounded to ``grad_dtype`` ("fp16_scaled": fp16 under a per-layer power-of-two scale);
@@ -49,6 +50,36 @@ def _round(x, dt):
         m, e = torch.frexp(x.double())
         return torch.ldexp(torch.round(m * 2048.0) / 2048.0, e).to(x.dtype)
     return x.to(dt).to(x.dtype)
+
+
+def _round_tf32(x):
+    """Round to TF32 (10 explicit mantissa bits) like PTX cvt.rna.tf32.f32: nearest, ties away from zero.  The B200 path runs
+    the tower's k = 1 conv and fc as single-pass TF32 tensor-core GEMMs (csrc/linear.cu dcue_linear_*_tf32)."""
+    f = x.detach().to(torch.float32).contiguous()
+    bits = f.view(torch.int32)
+    r = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+    r = torch.where(torch.isfinite(f), r, f)
+    return r.to(x.dtype)
+
+
+class _RoundedLinear(torch.autograd.Function):
+    """y = x @ w.T + b over the last dim with TF32-rounded operands; the gradient operand is rounded the same way in both
+    backward GEMMs (dX = g_r @ w_r, dW = g_r.T @ x_r); the bias gradient uses the unrounded gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xr, wr = _round_tf32(x), _round_tf32(w)
+        ctx.save_for_backward(xr, wr)
+        return F.linear(xr, wr, b)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xr, wr = ctx.saved_tensors
+        gr = _round_tf32(gy)
+        gx = gr @ wr
+        gw = gr.reshape(-1, gr.shape[-1]).t() @ xr.reshape(-1, xr.shape[-1])
+        gb = gy.reshape(-1, gy.shape[-1]).sum(0)
+        return gx, gw, gb
 
 
 class _RoundedConv(torch.autograd.Function):
@@ -177,7 +208,11 @@ def tower_forward(p, x, model_type, training=True, prefix="conv.", operand_dtype
             x = _bn(x, q, "bn%d" % i, training, stats)
         if res:
             tps.append(x.mean(dim=2, keepdim=True))  # AvgPool1d over the whole time extent
-    x = F.conv1d(x, q["layer5.weight"], q["layer5.bias"])
+    tf32 = operand_dtype in (torch.float16, torch.bfloat16)          # B200 evaluation: single-pass TF32 for layer5 / fc
+    if tf32:   # k = 1 conv == linear over the channel dim
+        x = _RoundedLinear.apply(x.permute(0, 2, 1), q["layer5.weight"][:, :, 0], q["layer5.bias"]).permute(0, 2, 1)
+    else:
+        x = F.conv1d(x, q["layer5.weight"], q["layer5.bias"])
     x = F.relu(x)
     if bn:
         x = _bn(x, q, "bn5", training, stats)
@@ -186,7 +221,10 @@ def tower_forward(p, x, model_type, training=True, prefix="conv.", operand_dtype
     if stats is not None:
         for k, v in stats.items():
             new_stats[prefix + k] = v
-    out = F.linear(x.permute(0, 2, 1), q["fc.weight"], q["fc.bias"])
+    if tf32:
+        out = _RoundedLinear.apply(x.permute(0, 2, 1), q["fc.weight"], q["fc.bias"])
+    else:
+        out = F.linear(x.permute(0, 2, 1), q["fc.weight"], q["fc.bias"])
     return out.reshape(out.shape[0], out.shape[-1]) if out.shape[1] == 1 else out
 
 
