@@ -311,7 +311,9 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
             __syncwarp();
             if (lane == 0) mbar_arrive(WFULL);
         }
-        double st1 = 0.0, st2 = 0.0;
+        // BatchNorm partial sums across the CTA's tiles: compensated (Kahan) fp32 instead of fp64 -- the two DADDs per warp and
+        // tile took 11 % of the kernel's stall samples (the fp64 pipe is narrow) and the compensated sum is as accurate here
+        float st1 = 0.f, st1c = 0.f, st2 = 0.f, st2c = 0.f;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -389,8 +391,14 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
                         }
                     }
                 }
-                st1 += (double)ts1;
-                st2 += (double)ts2;
+                {
+                    const float y1 = ts1 - st1c, t1 = st1 + y1;
+                    st1c = (t1 - st1) - y1;
+                    st1 = t1;
+                    const float y2 = ts2 - st2c, t2 = st2 + y2;
+                    st2c = (t2 - st2) - y2;
+                    st2 = t2;
+                }
             } else if (s < g.S && q >= g.pad && q + 31 < g.Lin + g.pad) {
                 // all 32 rows are data rows of one spectrogram (the common case): one base pointer, no per-row tests
                 float* dst = out + ((long)s * g.Lin + (q - g.pad)) * g.Cout + m;
@@ -416,8 +424,8 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
         if (EPI == 0 && partial && chan_ok) {
             // 4 chunk-warps per channel: partial rows are (block, chunk)
             const long prow = (long)blockIdx.x * 4 + chunk;
-            partial[(prow * 2 + 0) * g.Cout + m] = st1;
-            partial[(prow * 2 + 1) * g.Cout + m] = st2;
+            partial[(prow * 2 + 0) * g.Cout + m] = (double)st1 - (double)st1c;
+            partial[(prow * 2 + 1) * g.Cout + m] = (double)st2 - (double)st2c;
         }
     }
     tc_fence_before();
