@@ -321,7 +321,7 @@ extern "C" int dcue_conv_tap_bias(const float* W, int Cout, int Cin, int k, cons
 // out[z][i][c] = inv_scale * (sum over the z-th slice of the spectrograms) panel[s*Lp + rows[i]][c] for up to 4 rows per
 // spectrogram; the PRS_SLICES partial sums are added in fixed order by the consumer (dcue_bn_fold_grads).
 // (The one-block-per-(panel,row) version ran 64 blocks of 84 strided loads each: 60 us for 22 MB.)
-constexpr int PRS_SLICES = 64;
+constexpr int PRS_SLICES = 148;     // one slice per SM for the border-row kernels
 __global__ void __launch_bounds__(256)
 panel_row_sums_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt, int S, int Lp, int4 rows,
                       const float* __restrict__ gscale, float* __restrict__ out /* [PRS_SLICES][4][128] */) {

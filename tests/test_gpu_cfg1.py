@@ -131,12 +131,16 @@ def test_cfg1_train_step_error_table(fmt, monkeypatch):
     assert a["u_f_relmax"] < 1e-5
     assert a["pos_f_relmax"] < bd["feat"] and a["neg_f_relmax"] < bd["feat"]
     assert a["scores_absmax"] < bd["score_abs"]
+    # a hinge decision that flips (a score within the operand rounding of the margin; 0-2 of 1 280 here, depending on the
+    # accumulation order of the day) switches one (user, negative) pair's whole gradient on or off: ~1e-2 of the user-side
+    # gradients per flip at this batch size -- allowed for explicitly, and reported in the table
+    flips = a["hinge_decisions_flipped"]
     for k, e in a["grads"].items():
         if k.startswith("user_embd."):
-            assert e["l2"] < bd["mlp_l2"], (k, e)
+            assert e["l2"] < bd["mlp_l2"] + 1e-2 * flips, (k, e, flips)
         else:
             assert e["l2"] < bd["grad_l2"] and e["cos"] > bd["grad_cos"], (k, e)
-    assert a["table_rows_l2"] < bd["table_l2"] and a["table_norm_rel"] < bd["table_l2"]
+    assert a["table_rows_l2"] < bd["table_l2"] + 1e-2 * flips and a["table_norm_rel"] < bd["table_l2"]
     assert a["table_untouched_rows_nonzero"] == 0
     for k, e in a["buffers"].items():
         assert e < bd["buf"], (k, e)
