@@ -364,18 +364,12 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
                         o += g.Cout;
                     }
                 } else {
-#pragma unroll 1
+                    // chunk touching a spectrogram border (about 1/3 of the chunks): per-window tests, all warp-uniform
+#pragma unroll
                     for (int t0 = 0; t0 < 32; t0 += POOL) {
                         float w[POOL];
-                        // v[] is indexed with a run-time window here: select with a compile-time switch (no local memory)
 #pragma unroll
-                        for (int i = 0; i < POOL; ++i) w[i] = 0.f;
-#pragma unroll
-                        for (int u = 0; u < 32; u += POOL)
-                            if (u == t0) {
-#pragma unroll
-                                for (int i = 0; i < POOL; ++i) w[i] = v[u + i];
-                            }
+                        for (int i = 0; i < POOL; ++i) w[i] = v[t0 + i];
                         const bool ok = chan_ok && s < g.S && q + POOL <= q_end;
                         if (has_tb && (q < g.pad || q + POOL - 1 > q_hi)) {
 #pragma unroll
