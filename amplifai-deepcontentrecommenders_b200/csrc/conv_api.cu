@@ -21,7 +21,7 @@ static int check_geom(const ConvGeom& g, long panel_rows) {
 
 extern "C" size_t dcue_conv_ws_bytes(int impl, int S, int Lp, int k, int Cin, int Cout) {
     (void)S; (void)Lp; (void)Cin; (void)Cout;
-    size_t stats = (size_t)dcue_num_sms() * 4 * 2 * 128 * sizeof(double) + 256;
+    size_t stats = (size_t)dcue_num_sms() * 4 * (2 * 128 + 1) * sizeof(double) + 256;
     size_t wg = (size_t)32 * 128 * k * 128 * sizeof(float);
     size_t tc = impl == DCUE_IMPL_TC ? dcue_tc_ws_bytes(k) : 0;
     size_t m = stats > wg ? stats : wg;
@@ -68,6 +68,21 @@ extern "C" int dcue_conv_dgrad(int impl, const void* dy_panel, long panel_rows, 
     if (impl == DCUE_IMPL_TC)
         return dcue_tc_conv_dgrad(shifted, panel_rows, fmt_dy, w_packed_dgrad, fmt_w, g, gscale, dx, ws, ws_bytes, (cudaStream_t)stream);
     return dcue_simt_conv_dgrad(shifted, panel_rows, fmt_dy, w_packed_dgrad, fmt_w, g, gscale, dx, (cudaStream_t)stream);
+}
+
+extern "C" int dcue_conv_dgrad_stats(const void* dy_panel, long panel_rows, int fmt_dy, const void* w_packed_dgrad, int fmt_w, int S, int Lp,
+                                     int Lin, int pad, int k, int Cin, int Cout, const float* gscale, float* dx, const float* z,
+                                     const float* mean, const float* rstd, const float* dtp, int lddtp, void* ws, size_t ws_bytes,
+                                     void* stream) {
+    DCUE_CHECK_ARG(dy_panel && w_packed_dgrad && dx && z && mean && rstd && Lin > 0 && pad >= 0 && Lin + pad <= Lp &&
+                   k - 1 <= DCUE_FRONT_HALO);
+    DCUE_CHECK_ARG(Cout % 8 == 0 && Cin == 128 && (!dtp || lddtp >= Cin));
+    ConvGeom g{S, Lp, Lin, pad, k, 1, 0, Cout, Cin, (long)S * Lp};
+    if (int e = check_geom(g, panel_rows)) return e;
+    if (S == 0) return 0;
+    const char* shifted = (const char*)dy_panel - (size_t)(k - 1) * 16;
+    return dcue_tc_conv_dgrad_stats(shifted, panel_rows, fmt_dy, w_packed_dgrad, fmt_w, g, gscale, dx, z, mean, rstd, dtp, lddtp, ws,
+                                    ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int dcue_conv_wgrad(int impl, const void* dy_panel, long dy_panel_rows, int fmt_dy, const void* x_panel,

@@ -52,6 +52,9 @@ int dcue_tc_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy
 int dcue_tc_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const void* x_panel, long x_rows, int fmt_x,
                        long rows_total, int k, int Cin, int Cout, const float* gscale, float* dW, void* ws,
                        size_t ws_bytes, cudaStream_t st);
+int dcue_tc_conv_dgrad_stats(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
+                             const ConvGeom& g, const float* gscale, float* dx, const float* z, const float* mean, const float* rstd,
+                             const float* dtp, int lddtp, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t dcue_tc_ws_bytes(int k);
 size_t dcue_tc_wgrad_unpool_ws_bytes(int k);
 int dcue_tc_conv_wgrad_unpool(const float* dy, int lddy, const float* dtp, int lddtp, const float* z, const uint8_t* code,

@@ -191,12 +191,26 @@ constexpr int NTHREADS_ROWS = 64 + NEPI * 32;
 // ATMEM: the packed weights live in TMEM columns [0, k*64) (TS-mode MMA) instead of shared memory, which
 // leaves room for NST = 6 activation stages instead of 2 (the 2-stage ring was load-latency bound) and
 // removes the A-operand shared-memory reads.
+// EPI 1 with BnBwdStats (partial != NULL): the data gradient dx this kernel writes IS the gradient dy entering the previous
+// stage's BatchNorm, so the BatchNorm-backward reductions (sum dy, sum dy*xhat, max|dy|; dcue_bn_bwd_reduce) are taken in
+// this epilogue while dx is still in registers -- one extra coalesced read of z instead of a separate sweep over dx and z
+// (103 us at layer 1).  Partial rows as in the forward: [(block, chunk)][2][Cout] doubles, then [(block, chunk)] max|dy|.
+struct BnBwdStats {
+    const float* z;        // [S*Lin, Cout] pre-BatchNorm activations of the previous stage (same row space as dx)
+    const float* mean;     // per channel (batch statistics) -- or zeros / ones for the plain sums
+    const float* rstd;
+    const float* dtp;      // nullable [S, lddtp]: gradient of the time average, added as dtp / Lin to every row
+    int lddtp;
+    float inv_rows;        // 1 / Lin
+};
+
 template <int EPI, int POOL, bool ATMEM>
 __global__ void __launch_bounds__(NTHREADS_ROWS, 1)
 tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in, const uint4* __restrict__ wp, int fmt_w,
                     const float* __restrict__ bias, ConvGeom g, float* __restrict__ out, uint8_t* __restrict__ code,
                     double* __restrict__ partial, const float* __restrict__ gscale, const float* __restrict__ tap_bias,
-                    float* __restrict__ dummy) {
+                    float* __restrict__ dummy, BnBwdStats bs) {
+    __shared__ float smax[4][4];
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NST = ATMEM ? 6 : NSTAGE;
@@ -314,6 +328,9 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
         // BatchNorm partial sums across the CTA's tiles: compensated (Kahan) fp32 instead of fp64 -- the two DADDs per warp and
         // tile took 11 % of the kernel's stall samples (the fp64 pipe is narrow) and the compensated sum is as accurate here
         float st1 = 0.f, st1c = 0.f, st2 = 0.f, st2c = 0.f;
+        const bool dstats = EPI == 1 && partial != nullptr;
+        float bmean = 0.f, brstd = 1.f, amax = 0.f;
+        if (dstats && chan_ok) { bmean = bs.mean[m]; brstd = bs.rstd[m]; }
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -395,31 +412,88 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
                 }
             } else if (s < g.S && q >= g.pad && q + 31 < g.Lin + g.pad) {
                 // all 32 rows are data rows of one spectrogram (the common case): one base pointer, no per-row tests
-                float* dst = out + ((long)s * g.Lin + (q - g.pad)) * g.Cout + m;
+                const long o0 = ((long)s * g.Lin + (q - g.pad)) * g.Cout + m;
+                float* dst = out + o0;
+                if (dstats) {
+                    const float* zp = bs.z + o0;
+                    const float tpv = (bs.dtp && chan_ok) ? bs.dtp[(long)s * bs.lddtp + m] * bs.inv_rows : 0.f;
+                    float ts1 = 0.f, ts2 = 0.f;
 #pragma unroll
-                for (int t = 0; t < 32; ++t) {
-                    st_pred_f32(dst, v[t] * bv, chan_ok);
-                    dst += g.Cout;
+                    for (int t0 = 0; t0 < 32; t0 += 8) {
+                        float zz[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) zz[i] = chan_ok ? __ldg(zp + (long)(t0 + i) * g.Cout) : 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float val = v[t0 + i] * bv;
+                            st_pred_f32(dst + (long)(t0 + i) * g.Cout, val, chan_ok);
+                            const float gg = chan_ok ? val + tpv : 0.f;
+                            ts1 += gg;
+                            ts2 = fmaf(gg, (zz[i] - bmean) * brstd, ts2);
+                            amax = fmaxf(amax, fabsf(gg));
+                        }
+                    }
+                    const float y1 = ts1 - st1c, t1 = st1 + y1;
+                    st1c = (t1 - st1) - y1;
+                    st1 = t1;
+                    const float y2 = ts2 - st2c, t2 = st2 + y2;
+                    st2c = (t2 - st2) - y2;
+                    st2 = t2;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) {
+                        st_pred_f32(dst, v[t] * bv, chan_ok);
+                        dst += g.Cout;
+                    }
                 }
             } else {
+                float ts1 = 0.f, ts2 = 0.f;
 #pragma unroll
                 for (int t = 0; t < 32; ++t) {
                     const int tt = q - g.pad;
                     const bool ok = chan_ok && s < g.S && tt >= 0 && tt < g.Lin;
-                    st_pred_f32(out + ((long)s * g.Lin + tt) * g.Cout + m, v[t] * bv, ok);
+                    const long oo = ((long)s * g.Lin + tt) * g.Cout + m;
+                    const float val = v[t] * bv;
+                    st_pred_f32(out + oo, val, ok);
+                    if (dstats && ok) {
+                        const float gg = val + (bs.dtp ? bs.dtp[(long)s * bs.lddtp + m] * bs.inv_rows : 0.f);
+                        ts1 += gg;
+                        ts2 = fmaf(gg, (__ldg(bs.z + oo) - bmean) * brstd, ts2);
+                        amax = fmaxf(amax, fabsf(gg));
+                    }
                     ++q;
                     const bool wrap = q == g.Lp;
                     q = wrap ? 0 : q;
                     s += wrap ? 1 : 0;
                 }
+                if (dstats) {
+                    const float y1 = ts1 - st1c, t1 = st1 + y1;
+                    st1c = (t1 - st1) - y1;
+                    st1 = t1;
+                    const float y2 = ts2 - st2c, t2 = st2 + y2;
+                    st2c = (t2 - st2) - y2;
+                    st2 = t2;
+                }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (EPI == 0 && partial && chan_ok) {
+        if ((EPI == 0 || dstats) && partial && chan_ok) {
             // 4 chunk-warps per channel: partial rows are (block, chunk)
             const long prow = (long)blockIdx.x * 4 + chunk;
             partial[(prow * 2 + 0) * g.Cout + m] = (double)st1 - (double)st1c;
             partial[(prow * 2 + 1) * g.Cout + m] = (double)st2 - (double)st2c;
+        }
+        if (dstats) {
+            // max|dy| of the (block, chunk) row: the four lane-quarter warps of a chunk combine through shared memory
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+            if (lane == 0) smax[chunk][quarter] = amax;
+            asm volatile("bar.sync 3, %0;" ::"n"(NEPI * 32) : "memory");
+            if (quarter == 0 && lane == 0) {
+                const float mx = fmaxf(fmaxf(smax[chunk][0], smax[chunk][1]), fmaxf(smax[chunk][2], smax[chunk][3]));
+                double* pmax = partial + (size_t)gridDim.x * 4 * 2 * g.Cout;
+                pmax[(long)blockIdx.x * 4 + chunk] = (double)mx;
+            }
         }
     }
     tc_fence_before();
@@ -825,19 +899,19 @@ int tc_grid(long rows_total) {
 template <int EPI, int POOL>
 int launch_rows_t(const void* panel, long panel_rows, int fmt_in, const void* w_packed, int fmt_w, const float* bias,
                   const ConvGeom& g, float* out, uint8_t* code, double* partial, const float* gscale,
-                  const float* tap_bias, float* dummy, int grid, cudaStream_t st) {
+                  const float* tap_bias, float* dummy, int grid, cudaStream_t st, BnBwdStats bs = BnBwdStats{}) {
     const bool atm = use_atmem();
     const size_t smem = rows_smem_bytes(g.k, atm);
     if (atm) {
         DCUE_CUDA(cudaFuncSetAttribute(tc_conv_rows_kernel<EPI, POOL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_conv_rows_kernel<EPI, POOL, true><<<grid, NTHREADS_ROWS, smem, st>>>((const uint4*)panel, panel_rows, fmt_in,
                                                                                 (const uint4*)w_packed, fmt_w, bias, g, out,
-                                                                                code, partial, gscale, tap_bias, dummy);
+                                                                                code, partial, gscale, tap_bias, dummy, bs);
     } else {
         DCUE_CUDA(cudaFuncSetAttribute(tc_conv_rows_kernel<EPI, POOL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_conv_rows_kernel<EPI, POOL, false><<<grid, NTHREADS_ROWS, smem, st>>>((const uint4*)panel, panel_rows, fmt_in,
                                                                                  (const uint4*)w_packed, fmt_w, bias, g, out,
-                                                                                 code, partial, gscale, tap_bias, dummy);
+                                                                                 code, partial, gscale, tap_bias, dummy, bs);
     }
     DCUE_LAUNCH_CHECK();
     return 0;
@@ -852,7 +926,7 @@ __global__ void dcue_cvt_d2f_kernel(const double* __restrict__ in, int n, float*
 
 size_t dcue_tc_ws_bytes(int k) {
     // [grid*4][2][128] stat partials + one scratch line for dead-lane stores
-    const size_t stats = (size_t)dcue_num_sms() * 4 * 2 * 128 * sizeof(double) + 256;
+    const size_t stats = (size_t)dcue_num_sms() * 4 * (2 * 128 + 1) * sizeof(double) + 256;
     const size_t wg = (size_t)dcue_num_sms() * 128 * k * 128 * sizeof(float);
     return stats > wg ? stats : wg;
 }
@@ -888,6 +962,21 @@ int dcue_tc_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy
     if (!ws || ws_bytes < 256) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_dgrad(tc): workspace too small");
     return launch_rows_t<1, 1>(dy_panel_shifted, panel_rows, fmt_dy, w_packed, fmt_w, nullptr, g, dx, nullptr, nullptr, gscale,
                                nullptr, (float*)ws, tc_grid(g.rows_total), st);
+}
+
+// dgrad + the BatchNorm-backward partial sums of the stage below, left at the start of ws for dcue_bn_bwd_finalize:
+// [grid*4][2*Cout] doubles (sum dy, sum dy*xhat) followed by [grid*4] doubles (max|dy|)
+int dcue_tc_conv_dgrad_stats(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
+                             const ConvGeom& g, const float* gscale, float* dx, const float* z, const float* mean, const float* rstd,
+                             const float* dtp, int lddtp, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (g.Cin != 128) DCUE_FAIL(DCUE_E_UNSUPPORTED, "tcgen05 dgrad needs Cout == 128 (got %d)", g.Cin);
+    if (fmt_dy != fmt_w) DCUE_FAIL(DCUE_E_UNSUPPORTED, "tcgen05 kind::f16 needs both operands in the same 16-bit format");
+    const int grid = tc_grid(g.rows_total);
+    const size_t need = (size_t)grid * 4 * (2 * g.Cout + 1) * sizeof(double);
+    if (!ws || ws_bytes < need) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_dgrad_stats(tc): workspace too small");
+    BnBwdStats bs{z, mean, rstd, dtp, lddtp, 1.f / (float)g.Lin};
+    return launch_rows_t<1, 1>(dy_panel_shifted, panel_rows, fmt_dy, w_packed, fmt_w, nullptr, g, dx, nullptr, (double*)ws, gscale,
+                               nullptr, nullptr, grid, st, bs);
 }
 
 int dcue_tc_conv_wgrad(const void* dy_panel, long dy_rows, int fmt_dy, const void* x_panel, long x_rows, int fmt_x,

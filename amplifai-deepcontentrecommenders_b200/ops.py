@@ -59,6 +59,12 @@ def tower_linear(name):
     return name + "_tf32" if os.environ.get("DCUE_TOWER_TF32", "1") != "0" else name
 
 
+def dgrad_stats():
+    """BatchNorm-backward reductions of stage i-1 taken in the epilogue of stage i's data-gradient kernel
+    (DCUE_DGRAD_STATS=0: the separate dcue_bn_bwd_reduce sweep)."""
+    return os.environ.get("DCUE_DGRAD_STATS", "1") != "0"
+
+
 def operand_fmt():
     """16-bit format of the forward conv operands: fp16 (default) or bf16 (DCUE_OPERAND=bf16)."""
     return L.FMT_BF16 if os.environ.get("DCUE_OPERAND", "f16").lower() == "bf16" else L.FMT_F16
@@ -357,7 +363,7 @@ class SongTowerFn(torch.autograd.Function):
 
         fused_fin = fused_finalize() and (dp is None or world == 1 or getattr(dp, "_peer", None) is not None)
 
-        def bn_sums(i, dy_ptr, lddy, dtp_ptr, lddtp, z, P_, C_, want_scale=True):
+        def bn_sums(i, dy_ptr, lddy, dtp_ptr, lddtp, z, P_, C_, want_scale=True, pre_nparts=0):
             """Per-channel reductions over the gradient entering layer i's BN (+ DP all-reduce):
             dgamma/dbeta when BN uses batch statistics, and max|dy| for the 16-bit gradient scale."""
             mean_p = ws.bnp[i, 2].data_ptr() if bn_train else ws.zero128.data_ptr()
@@ -368,13 +374,17 @@ class SongTowerFn(torch.autograd.Function):
             if fused_fin:
                 # one sweep leaves per-block partials in scratch, ONE kernel reduces them, all-reduces the sums over NVLink
                 # (data parallel), emits dgamma / dbeta in fp32 and the power-of-two scale of the 16-bit gradient operand
-                L.call("dcue_bn_bwd_reduce", dy_ptr, lddy, dtp_ptr, lddtp, z.data_ptr(), mean_p, rstd_p, S, P_, C_, None, None,
-                       None, None, scratch, nscr, st)
+                if dy_ptr is not None:      # None: the producing dgrad already left the partial rows in scratch
+                    L.call("dcue_bn_bwd_reduce", dy_ptr, lddy, dtp_ptr, lddtp, z.data_ptr(), mean_p, rstd_p, S, P_, C_, None, None,
+                           None, None, scratch, nscr, st)
+                    nparts = L.query("dcue_bn_bwd_reduce_nparts", S, P_)
+                else:
+                    nparts = pre_nparts
                 peer = _peer_args(dp) if bn_train else (None, None, None, 0, 1)
-                L.call("dcue_bn_bwd_finalize", scratch, L.query("dcue_bn_bwd_reduce_nparts", S, P_), C_,
+                L.call("dcue_bn_bwd_finalize", scratch, nparts, C_,
                        ws.bnp[i, 0].data_ptr() if has_bn else None, float(S * P_ * world) if bn_train else 0.0, *peer,
-                       ws.ticket.data_ptr(), b["dsums"][i].data_ptr(), L.ptr(gb), L.ptr(gw), b["amax"][i:].data_ptr() if want_scale else None,
-                       b["gscale"][i].data_ptr() if want_scale else None, st)
+                       ws.ticket.data_ptr(), b["dsums"][i].data_ptr(), L.ptr(gb), L.ptr(gw),
+                       b["amax"][i:].data_ptr() if want_scale else None, b["gscale"][i].data_ptr() if want_scale else None, st)
                 if bn_train:
                     grads["bn%d.weight" % i], grads["bn%d.bias" % i] = gw, gb
                 elif has_bn:
@@ -419,10 +429,15 @@ class SongTowerFn(torch.autograd.Function):
         dy = torch.empty(S, H, **f32)  # gradient w.r.t. the stage-4 BN output
         L.call(tower_linear("dcue_linear_dgrad"), dz5.data_ptr(), F, P["layer5.weight"].data_ptr(), S, H, F, None, 0, dy.data_ptr(), H, st)
         # ---- stages 4..1
+        stats_in_scratch = 0
         for i in range(4, 0, -1):
             g = geo[i - 1]
             dtp = dfc[:, (i - 1) * H:].data_ptr() if res else None
-            bn_sums(i, dy.data_ptr(), H, dtp, Kfc, ws.z[i - 1], g["P"], H)
+            if stats_in_scratch:     # the dgrad of the stage above took the reductions in its epilogue
+                bn_sums(i, None, H, dtp, Kfc, ws.z[i - 1], g["P"], H, pre_nparts=stats_in_scratch)
+                stats_in_scratch = 0
+            else:
+                bn_sums(i, dy.data_ptr(), H, dtp, Kfc, ws.z[i - 1], g["P"], H)
             gsc = b["gscale"][i].data_ptr()
             gb_i = torch.empty(H, **f32)
             gW_i = torch.empty(H, 128, g["k"], **f32)
@@ -466,8 +481,19 @@ class SongTowerFn(torch.autograd.Function):
                 L.call("dcue_pack_conv_weight", P["layer%d.weight" % i].data_ptr(), H, 128, g["k"], 1, fmt, None, None,
                        b["wpd"][i - 1].data_ptr(), st)
                 dx = b["dx"][i - 1]
-                L.call("dcue_conv_dgrad", impl, dYp.base, dYp.panel_rows, gfmt, b["wpd"][i - 1].data_ptr(), fmt, S, g["Lp"],
-                       g["Lin"], g["pad"], g["k"], 128, H, gsc, dx.data_ptr(), scratch, nscr, st)
+                if fused_fin and impl == L.IMPL_TC and dgrad_stats():
+                    # dx is the gradient entering stage i-1's BatchNorm: its backward reductions are taken in this epilogue
+                    j = i - 1
+                    mean_j = ws.bnp[j, 2].data_ptr() if bn_train else ws.zero128.data_ptr()
+                    rstd_j = ws.bnp[j, 3].data_ptr() if bn_train else ws.one128.data_ptr()
+                    dtp_j = dfc[:, (j - 1) * H:].data_ptr() if res else None
+                    L.call("dcue_conv_dgrad_stats", dYp.base, dYp.panel_rows, gfmt, b["wpd"][i - 1].data_ptr(), fmt, S, g["Lp"],
+                           g["Lin"], g["pad"], g["k"], 128, H, gsc, dx.data_ptr(), ws.z[j - 1].data_ptr(), mean_j, rstd_j,
+                           dtp_j, Kfc, scratch, nscr, st)
+                    stats_in_scratch = L.query("dcue_conv_pool_fwd_nparts", impl, S, g["Lp"])
+                else:
+                    L.call("dcue_conv_dgrad", impl, dYp.base, dYp.panel_rows, gfmt, b["wpd"][i - 1].data_ptr(), fmt, S, g["Lp"],
+                           g["Lin"], g["pad"], g["k"], 128, H, gsc, dx.data_ptr(), scratch, nscr, st)
                 dy = dx
         ctx.ws = None
         _release(ws)

@@ -223,6 +223,16 @@ int dcue_conv_dgrad(int impl, const void* dy_panel, long panel_rows, int fmt_dy,
                     const float* gscale /* {s, 1/s} of the scaled dY operand, nullable */, float* dx,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* dcue_conv_dgrad (tcgen05 only, Cin == 128) that ALSO takes the BatchNorm-backward reductions of the stage below in its
+ * epilogue: the dx it writes is the gradient dy entering that stage's BatchNorm, z / mean / rstd are that stage's
+ * pre-BatchNorm activations [S*Lin, Cin] and statistics (zeros / ones for plain sums), dtp (nullable, [S, lddtp]) the gradient
+ * of the time average (added as dtp / Lin).  Leaves dcue_bn_bwd_reduce's partial rows at the start of ws
+ * (dcue_conv_pool_fwd_nparts(DCUE_IMPL_TC, S, Lp) rows) for dcue_bn_bwd_finalize: replaces a separate sweep over dx and z. */
+int dcue_conv_dgrad_stats(const void* dy_panel, long panel_rows, int fmt_dy, const void* w_packed_dgrad, int fmt_w, int S, int Lp,
+                          int Lin, int pad, int k, int Cin, int Cout, const float* gscale, float* dx, const float* z,
+                          const float* mean, const float* rstd, const float* dtp, int lddtp, void* ws, size_t ws_bytes,
+                          void* stream);
+
 /* Conv1d weight gradient dW[co,ci,j] = sum_r dY[r,co] X[r+j,ci] over all flat rows
  * (reference layout [Cout,Cin,k] fp32 out). */
 int dcue_conv_wgrad(int impl, const void* dy_panel, long dy_panel_rows, int fmt_dy, const void* x_panel,
