@@ -129,6 +129,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // predicated global stores: dead lanes issue nothing.  (They used to write one shared scratch word instead; ncu
 // showed every SM serialising on that single L2 sector -- the layer-2 dgrad spent its whole 270 us there.)
 __device__ __forceinline__ void st_pred_f32(float* p, float v, bool ok) {
@@ -191,7 +205,7 @@ constexpr int NTHREADS_ROWS = 64 + NEPI * 32;
 // ATMEM: the packed weights live in TMEM columns [0, k*64) (TS-mode MMA) instead of shared memory, which
 // leaves room for NST = 6 activation stages instead of 2 (the 2-stage ring was load-latency bound) and
 // removes the A-operand shared-memory reads.
-// EPI 1 with BnBwdStats (partial != NULL): the data gradient dx this kernel writes IS the gradient dy entering the previous
+// EPI 2 = EPI 1 with BnBwdStats: the data gradient dx this kernel writes IS the gradient dy entering the previous
 // stage's BatchNorm, so the BatchNorm-backward reductions (sum dy, sum dy*xhat, max|dy|; dcue_bn_bwd_reduce) are taken in
 // this epilogue while dx is still in registers -- one extra coalesced read of z instead of a separate sweep over dx and z
 // (103 us at layer 1).  Partial rows as in the forward: [(block, chunk)][2][Cout] doubles, then [(block, chunk)] max|dy|.
@@ -211,6 +225,7 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
                     double* __restrict__ partial, const float* __restrict__ gscale, const float* __restrict__ tap_bias,
                     float* __restrict__ dummy, BnBwdStats bs) {
     __shared__ float smax[4][4];
+    __shared__ double sred[4][2][128];
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NST = ATMEM ? 6 : NSTAGE;
@@ -328,23 +343,50 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
         // BatchNorm partial sums across the CTA's tiles: compensated (Kahan) fp32 instead of fp64 -- the two DADDs per warp and
         // tile took 11 % of the kernel's stall samples (the fp64 pipe is narrow) and the compensated sum is as accurate here
         float st1 = 0.f, st1c = 0.f, st2 = 0.f, st2c = 0.f;
-        const bool dstats = EPI == 1 && partial != nullptr;
+        constexpr bool dstats = EPI == 2;      // own instantiation: the statistics cost registers the plain dgrad keeps free
         float bmean = 0.f, brstd = 1.f, amax = 0.f;
         if (dstats && chan_ok) { bmean = bs.mean[m]; brstd = bs.rstd[m]; }
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            mbar_wait(TFULL(acc), acc_phase);
-            tc_fence_after();
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ACC0 + acc * BN + chunk * 32), v);
-            // accumulator columns are in registers: release the TMEM buffer before the global stores
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(TEMPTY(acc));
             const int r = (int)(tile * BN) + chunk * 32;
             int s = r / g.Lp;
             int q = r - s * g.Lp;
+            // EPI 1 with statistics: the 32 z values this thread needs are requested BEFORE waiting for the accumulator, all at
+            // once (32 x 128 B per warp in flight).  Valid rows (pad <= q < pad + Lin, s < S) map to CONSECUTIVE output rows, so one
+            // running offset serves every chunk -- with Lin = 33 only 2 of 36 chunk positions lie inside one spectrogram and the
+            // first version's per-row fallback (dependent loads behind the stores) made the layer-2 launch 5x slower.
+            float zz[EPI == 2 ? 32 : 1];
+            long o_first = 0;
+            uint32_t vm = 0, wm = 0;      // bit t: row t is a data row / a new spectrogram starts after row t (warp-uniform)
+            if (dstats) {
+                const int tt0 = min(max(q - g.pad, 0), g.Lin);
+                o_first = ((long)s * g.Lin + tt0) * g.Cout + m;
+                int s2 = s, q2 = q;
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    vm |= (s2 < g.S && q2 >= g.pad && q2 < g.pad + g.Lin) ? (1u << t) : 0u;
+                    ++q2;
+                    if (q2 == g.Lp) { q2 = 0; ++s2; wm |= 1u << t; }
+                }
+                const float* zp = bs.z + o_first;
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    const int nb = __popc(vm & ((1u << t) - 1u));          // data rows before t
+                    zz[t] = (((vm >> t) & 1u) && chan_ok) ? __ldg(zp + (long)nb * g.Cout) : bmean;
+                }
+            }
+            mbar_wait(TFULL(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t tsrc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ACC0 + acc * BN + chunk * 32);
+            float v[32];
+            if constexpr (!dstats) {
+                tmem_ld32(tsrc, v);
+                // accumulator columns are in registers: release the TMEM buffer before the global stores
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(TEMPTY(acc));
+            }
             if (EPI == 0) {
                 // ncu (round 2): this epilogue, not the MMA, paced the kernel -- 510 instructions per warp and tile, the ALU pipe
                 // saturated (math-pipe-throttle the top stall) because the border correction and the (s, p) index arithmetic
@@ -410,89 +452,93 @@ tc_conv_rows_kernel(const uint4* __restrict__ panel, long panel_rows, int fmt_in
                     st2c = (t2 - st2) - y2;
                     st2 = t2;
                 }
-            } else if (s < g.S && q >= g.pad && q + 31 < g.Lin + g.pad) {
-                // all 32 rows are data rows of one spectrogram (the common case): one base pointer, no per-row tests
-                const long o0 = ((long)s * g.Lin + (q - g.pad)) * g.Cout + m;
-                float* dst = out + o0;
-                if (dstats) {
-                    const float* zp = bs.z + o0;
-                    const float tpv = (bs.dtp && chan_ok) ? bs.dtp[(long)s * bs.lddtp + m] * bs.inv_rows : 0.f;
-                    float ts1 = 0.f, ts2 = 0.f;
+            } else if (dstats) {
+                // two 16-column halves: 32 z values + 16 accumulator columns live instead of 64 registers
+                float* dst = out + o_first;
+                float ts1 = 0.f, ts2 = 0.f;
+                float tpv = 0.f;
+                int s_tp = -1;
 #pragma unroll
-                    for (int t0 = 0; t0 < 32; t0 += 8) {
-                        float zz[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) zz[i] = chan_ok ? __ldg(zp + (long)(t0 + i) * g.Cout) : 0.f;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float val = v[t0 + i] * bv;
-                            st_pred_f32(dst + (long)(t0 + i) * g.Cout, val, chan_ok);
-                            const float gg = chan_ok ? val + tpv : 0.f;
-                            ts1 += gg;
-                            ts2 = fmaf(gg, (zz[i] - bmean) * brstd, ts2);
-                            amax = fmaxf(amax, fabsf(gg));
-                        }
+                for (int h = 0; h < 2; ++h) {
+                    float vh[16];
+                    tmem_ld16(tsrc + (uint32_t)(h * 16), vh);
+                    if (h == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(TEMPTY(acc));
                     }
-                    const float y1 = ts1 - st1c, t1 = st1 + y1;
-                    st1c = (t1 - st1) - y1;
-                    st1 = t1;
-                    const float y2 = ts2 - st2c, t2 = st2 + y2;
-                    st2c = (t2 - st2) - y2;
-                    st2 = t2;
-                } else {
 #pragma unroll
-                    for (int t = 0; t < 32; ++t) {
-                        st_pred_f32(dst, v[t] * bv, chan_ok);
-                        dst += g.Cout;
+                    for (int t = 0; t < 16; ++t) {
+                        const int tt = h * 16 + t;
+                        const bool okr = (vm >> tt) & 1u;                                 // warp-uniform
+                        const bool ok = okr && chan_ok;
+                        if (bs.dtp && okr) {                                              // residual towers: once per spectrogram
+                            const int st = s + __popc(wm & ((1u << tt) - 1u));
+                            if (st != s_tp) {
+                                tpv = chan_ok ? __ldg(bs.dtp + (long)st * bs.lddtp + m) * bs.inv_rows : 0.f;
+                                s_tp = st;
+                            }
+                        }
+                        const float val = vh[t] * bv;
+                        st_pred_f32(dst + (long)__popc(vm & ((1u << tt) - 1u)) * g.Cout, val, ok);
+                        const float gg = ok ? val + tpv : 0.f;
+                        ts1 += gg;
+                        ts2 = fmaf(gg, (zz[tt] - bmean) * brstd, ts2);
+                        amax = fmaxf(amax, fabsf(gg));
                     }
                 }
+                const float y1 = ts1 - st1c, t1 = st1 + y1;
+                st1c = (t1 - st1) - y1;
+                st1 = t1;
+                const float y2 = ts2 - st2c, t2 = st2 + y2;
+                st2c = (t2 - st2) - y2;
+                st2 = t2;
+            } else if (s < g.S && q >= g.pad && q + 31 < g.Lin + g.pad) {
+                // all 32 rows are data rows of one spectrogram: one base pointer, no per-row tests
+                float* dst = out + ((long)s * g.Lin + (q - g.pad)) * g.Cout + m;
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    st_pred_f32(dst, v[t] * bv, chan_ok);
+                    dst += g.Cout;
+                }
             } else {
-                float ts1 = 0.f, ts2 = 0.f;
 #pragma unroll
                 for (int t = 0; t < 32; ++t) {
                     const int tt = q - g.pad;
                     const bool ok = chan_ok && s < g.S && tt >= 0 && tt < g.Lin;
                     const long oo = ((long)s * g.Lin + tt) * g.Cout + m;
-                    const float val = v[t] * bv;
-                    st_pred_f32(out + oo, val, ok);
-                    if (dstats && ok) {
-                        const float gg = val + (bs.dtp ? bs.dtp[(long)s * bs.lddtp + m] * bs.inv_rows : 0.f);
-                        ts1 += gg;
-                        ts2 = fmaf(gg, (__ldg(bs.z + oo) - bmean) * brstd, ts2);
-                        amax = fmaxf(amax, fabsf(gg));
-                    }
+                    st_pred_f32(out + oo, v[t] * bv, ok);
                     ++q;
                     const bool wrap = q == g.Lp;
                     q = wrap ? 0 : q;
                     s += wrap ? 1 : 0;
                 }
-                if (dstats) {
-                    const float y1 = ts1 - st1c, t1 = st1 + y1;
-                    st1c = (t1 - st1) - y1;
-                    st1 = t1;
-                    const float y2 = ts2 - st2c, t2 = st2 + y2;
-                    st2c = (t2 - st2) - y2;
-                    st2 = t2;
-                }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if ((EPI == 0 || dstats) && partial && chan_ok) {
-            // 4 chunk-warps per channel: partial rows are (block, chunk)
-            const long prow = (long)blockIdx.x * 4 + chunk;
-            partial[(prow * 2 + 0) * g.Cout + m] = (double)st1 - (double)st1c;
-            partial[(prow * 2 + 1) * g.Cout + m] = (double)st2 - (double)st2c;
-        }
-        if (dstats) {
-            // max|dy| of the (block, chunk) row: the four lane-quarter warps of a chunk combine through shared memory
+        if ((EPI == 0 || dstats) && partial) {
+            // the four chunk-warps of a channel combine through shared memory (fixed order): ONE partial row per block, so
+            // the finaliser reads 148 rows instead of 592
+            sred[chunk][0][m] = (double)st1 - (double)st1c;
+            sred[chunk][1][m] = (double)st2 - (double)st2c;
+            if (dstats) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-            if (lane == 0) smax[chunk][quarter] = amax;
+                for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+                if (lane == 0) smax[chunk][quarter] = amax;
+            }
             asm volatile("bar.sync 3, %0;" ::"n"(NEPI * 32) : "memory");
-            if (quarter == 0 && lane == 0) {
-                const float mx = fmaxf(fmaxf(smax[chunk][0], smax[chunk][1]), fmaxf(smax[chunk][2], smax[chunk][3]));
-                double* pmax = partial + (size_t)gridDim.x * 4 * 2 * g.Cout;
-                pmax[(long)blockIdx.x * 4 + chunk] = (double)mx;
+            if (chunk == 0 && chan_ok) {
+                partial[((long)blockIdx.x * 2 + 0) * g.Cout + m] = (sred[0][0][m] + sred[1][0][m]) + (sred[2][0][m] + sred[3][0][m]);
+                partial[((long)blockIdx.x * 2 + 1) * g.Cout + m] = (sred[0][1][m] + sred[1][1][m]) + (sred[2][1][m] + sred[3][1][m]);
+            }
+            if (dstats && warp == 2 && lane == 0) {
+                float mx = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) mx = fmaxf(mx, smax[c][qq]);
+                double* pmax = partial + (size_t)gridDim.x * 2 * g.Cout;
+                pmax[blockIdx.x] = (double)mx;
             }
         }
     }
@@ -947,13 +993,13 @@ int dcue_tc_conv_fwd(const void* panel, long panel_rows, int fmt, const void* w_
     else e = launch_rows_t<0, 1>(panel, panel_rows, fmt, w_packed, fmt, bias, g, z, code, part, nullptr, tap_bias, dummy, grid, st);
     if (e) return e;
     if (sums && sums != DCUE_STATS_PARTIALS) {
-        dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 8), 256, 0, st>>>((const double*)ws, grid * 4, 2 * g.Cout, sums);
+        dcue_reduce_partials_d<<<ceil_div_i(2 * g.Cout, 8), 256, 0, st>>>((const double*)ws, grid, 2 * g.Cout, sums);
         DCUE_LAUNCH_CHECK();
     }
     return 0;
 }
 
-int dcue_tc_conv_fwd_nparts(long rows_total) { return tc_grid(rows_total) * 4; }
+int dcue_tc_conv_fwd_nparts(long rows_total) { return tc_grid(rows_total); }
 
 int dcue_tc_conv_dgrad(const void* dy_panel_shifted, long panel_rows, int fmt_dy, const void* w_packed, int fmt_w,
                        const ConvGeom& g, const float* gscale, float* dx, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -975,7 +1021,7 @@ int dcue_tc_conv_dgrad_stats(const void* dy_panel_shifted, long panel_rows, int 
     const size_t need = (size_t)grid * 4 * (2 * g.Cout + 1) * sizeof(double);
     if (!ws || ws_bytes < need) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_conv_dgrad_stats(tc): workspace too small");
     BnBwdStats bs{z, mean, rstd, dtp, lddtp, 1.f / (float)g.Lin};
-    return launch_rows_t<1, 1>(dy_panel_shifted, panel_rows, fmt_dy, w_packed, fmt_w, nullptr, g, dx, nullptr, (double*)ws, gscale,
+    return launch_rows_t<2, 1>(dy_panel_shifted, panel_rows, fmt_dy, w_packed, fmt_w, nullptr, g, dx, nullptr, (double*)ws, gscale,
                                nullptr, nullptr, grid, st, bs);
 }
 

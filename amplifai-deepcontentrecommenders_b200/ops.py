@@ -61,8 +61,9 @@ def tower_linear(name):
 
 def dgrad_stats():
     """BatchNorm-backward reductions of stage i-1 taken in the epilogue of stage i's data-gradient kernel
-    (DCUE_DGRAD_STATS=0: the separate dcue_bn_bwd_reduce sweep)."""
-    return os.environ.get("DCUE_DGRAD_STATS", "1") != "0"
+    (DCUE_DGRAD_STATS=1).  Off by default: measured slower than the separate dcue_bn_bwd_reduce sweep
+    (layer-2 data gradient 124 -> ~600 us against 103 us saved)."""
+    return os.environ.get("DCUE_DGRAD_STATS", "0") != "0"
 
 
 def operand_fmt():

@@ -265,6 +265,57 @@ def test_conv_backward_kernels(impl, gi, S):
     assert relerr(dx.view(S, geo["Lin"], 128), xr.grad.permute(0, 2, 1)) < 5e-5
 
 
+@pytest.mark.parametrize("gi,S,with_tp", [(1, 9, False), (1, 700, True), (2, 333, False), (3, 1500, True), (1, 1, False)])
+def test_dgrad_with_batchnorm_backward_sums_in_the_epilogue(gi, S, with_tp):
+    """dcue_conv_dgrad_stats = dcue_conv_dgrad + the reductions dcue_bn_bwd_reduce takes over (dx, z) of the stage below
+    (sum g, sum g*xhat, max|g| with g = dx + dtp / Lin): dx must equal the plain kernel's bit for bit, the sums must match
+    fp64 math on that dx.  Lin = 33 / 8 / 2: almost every 32-row chunk crosses a spectrogram border."""
+    geo = ops.tower_geometry(131)[gi]
+    Lin, Lp = geo["Lin"], geo["Lp"]
+    g = torch.Generator().manual_seed(4100 + gi)
+    dyp = torch.zeros(S, Lp, 128)
+    dyp[:, :geo["Lout"]] = torch.randn(S, geo["Lout"], 128, generator=g) * (torch.rand(S, geo["Lout"], 128, generator=g) < 0.3)
+    dY = ops.Panel(S, Lp, DEV)
+    st = L.stream()
+    # rows of the dY panel are flat (s, q) with the data in q < Lout: pack through the NCL packer with pad 0
+    src = dyp[:, :geo["Lout"]].permute(0, 2, 1).contiguous().to(DEV)
+    L.call("dcue_ncl_pack", src.data_ptr(), S, None, 0, 128, geo["Lout"], None, None, dY.base, dY.panel_rows, Lp, 0, L.FMT_F16, st)
+    w = (torch.randn(128, 128, geo["k"], generator=g) * 0.06).to(DEV)
+    wpd = torch.empty(128 * geo["k"] * 128, dtype=torch.int16, device=DEV)
+    L.call("dcue_pack_conv_weight", w.data_ptr(), 128, 128, geo["k"], 1, L.FMT_F16, None, None, wpd.data_ptr(), st)
+    gsc = torch.tensor([4.0, 0.25], device=DEV)
+    z = torch.relu(torch.randn(S * Lin, 128, generator=g) + 0.2).to(DEV)
+    mean = (torch.randn(128, generator=g) * 0.1 + 0.4).to(DEV)
+    rstd = (torch.rand(128, generator=g) + 0.7).to(DEV)
+    dtp = (torch.randn(S, 640, generator=g) * 0.3).to(DEV) if with_tp else None
+    nws = max(L.query("dcue_conv_ws_bytes", L.IMPL_TC, S, Lp, geo["k"], 128, 128), L.query("dcue_bn_bwd_ws_bytes", 128), 1 << 21)
+    ws = torch.empty(nws, dtype=torch.uint8, device=DEV)
+    dx0 = torch.full((S * Lin, 128), float("nan"), device=DEV)
+    L.call("dcue_conv_dgrad", L.IMPL_TC, dY.base, dY.panel_rows, L.FMT_F16, wpd.data_ptr(), L.FMT_F16, S, Lp, Lin, geo["pad"],
+           geo["k"], 128, 128, gsc.data_ptr(), dx0.data_ptr(), ws.data_ptr(), nws, st)
+    dx1 = torch.full((S * Lin, 128), float("nan"), device=DEV)
+    L.call("dcue_conv_dgrad_stats", dY.base, dY.panel_rows, L.FMT_F16, wpd.data_ptr(), L.FMT_F16, S, Lp, Lin, geo["pad"], geo["k"],
+           128, 128, gsc.data_ptr(), dx1.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+           None if dtp is None else dtp[:, 128:].data_ptr(), 640, ws.data_ptr(), nws, st)
+    nparts = L.query("dcue_conv_pool_fwd_nparts", L.IMPL_TC, S, Lp)
+    ticket = torch.zeros(4, dtype=torch.int32, device=DEV)
+    sums = torch.zeros(256, dtype=torch.float64, device=DEV)
+    db, dg = torch.empty(128, device=DEV), torch.empty(128, device=DEV)
+    amax, gs2 = torch.zeros(1, device=DEV), torch.zeros(2, device=DEV)
+    L.call("dcue_bn_bwd_finalize", ws.data_ptr(), nparts, 128, None, 0.0, None, None, None, 0, 1, ticket.data_ptr(),
+           sums.data_ptr(), db.data_ptr(), dg.data_ptr(), amax.data_ptr(), gs2.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dx0).all() and torch.equal(dx0, dx1)
+    geff = dx0.double().cpu()
+    if with_tp:
+        geff = geff + dtp[:, 128:256].double().cpu().repeat_interleave(Lin, 0) / Lin
+    xhat = (z.double().cpu() - mean.double().cpu()) * rstd.double().cpu()
+    assert relerr(sums[:128], geff.sum(0)) < 2e-5
+    assert relerr(sums[128:], (geff * xhat).sum(0)) < 2e-5
+    assert abs(amax.item() - geff.abs().max().item()) <= 1e-6 * geff.abs().max().item()
+    assert relerr(db, geff.sum(0)) < 2e-5 and relerr(dg, (geff * xhat).sum(0)) < 2e-5
+
+
 @pytest.mark.parametrize("gi,S,with_tp", [(0, 7, False), (1, 40, True), (3, 300, True), (0, 70, False)])
 def test_bn_backward_unpool_and_affine_pack(gi, S, with_tp):
     """BatchNorm-backward + ReLU mask + max-unpool into the 16-bit dY panel (truedcuemel1dbn.py:80-95 autograd) and
