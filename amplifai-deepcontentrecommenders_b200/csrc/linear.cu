@@ -25,6 +25,7 @@ struct GemmP {
     const float* mask; long ldmask;
     int I, J, R, relu, splits;
     long split_stride;        // elements between partial buffers
+    float* rowsum;            // nullable [splits][I]: per-split row sums of A (cp.async kernel only)
     int single_tf32;          // 1: one TF32 MMA per product (10-bit mantissa operands, like the 16-bit conv operands); 0: 3xTF32
 };
 
@@ -270,14 +271,18 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
 
 // ------------------------------------------------------------------ cp.async pipelined 3xTF32 GEMM
 // The register-staged kernel above is bound by global-load latency (two blocks per SM, one 16-byte load per thread and
-// operand in flight: 34 us for an 11 MB GEMM, the same with CUDA-core FMAs or tensor-core MMAs).  Here 64 x 64 x 64 tiles go
-// global -> shared memory with cp.async (16-byte chunks, zero-filled tails) through a 3-stage ring, so a block has two
-// whole k-chunks of both operands in flight while it multiplies the third.  Either operand may be contiguous along the
-// contraction index r (smem [i][r], row stride TKC+4) or along its own index (smem [r][i], row stride 72); both layouts give
-// conflict-free m16n8k8 fragment reads.
-constexpr int TKC = 64, CST = 3;
-constexpr int CP_OP_FLOATS = 64 * 72;                       // one operand tile of one stage (either layout fits)
+// operand in flight: 34 us for an 11 MB GEMM, the same with CUDA-core FMAs or tensor-core MMAs).  Here 64 x 64 x 32 tiles go
+// global -> shared memory with cp.async (16-byte chunks, zero-filled tails) through a 3-stage ring.  Either operand may be
+// contiguous along the contraction index r (smem [i][r], row stride TKC+4) or along its own index (smem [r][i], row stride
+// 72); both layouts give conflict-free m16n8k8 fragment reads.
+// Round 2 (ncu: 2 060 instructions per warp for 64 MMAs, issue slots 55 % busy, 16 warps per SM): the operand layouts are
+// template parameters (no per-load selects), 4 warps own 32 x 32 each (5 instead of 7 instructions per MMA), 55 KB of shared
+// memory let 4 blocks share an SM, and the weight-gradient form also takes the bias gradient (row sums of its A operand, from
+// the unrounded fp32 values already in registers) -- no separate column-sum launches.
+constexpr int TKC = 32, CST = 3;
+constexpr int CP_OP_FLOATS = 64 * (TKC + 4);                // one operand tile of one stage (either layout fits: 32 x 72 = 64 x 36)
 constexpr size_t CP_SMEM = (size_t)CST * 2 * CP_OP_FLOATS * sizeof(float);
+constexpr int CP_THREADS = 128;
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -285,29 +290,29 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, i
 }
 
 // tile [64 x TKC] of operand X(i, r) = base[i*s_i + r*s_r] at (i0, r0); rows i >= I and columns r >= rend are zero-filled
-__device__ __forceinline__ void cp_load_tile(float* sm, const float* base, long s_i, long s_r, bool r_contig, int i0, int I, int r0,
-                                             int rend, int tid) {
+template <bool RC>
+__device__ __forceinline__ void cp_load_tile(float* sm, const float* base, long s_i, long s_r, int i0, int I, int r0, int rend, int tid) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int c = tid + it * 256;                        // 1024 16-byte chunks per tile
-        if (r_contig) {
-            const int li = c >> 4, lr = (c & 15) * 4;        // 16 chunks per row of 64 r
+    for (int it = 0; it < (64 * TKC / 4) / CP_THREADS; ++it) {
+        const int c = tid + it * CP_THREADS;                 // 512 16-byte chunks per tile
+        if (RC) {
+            const int li = c / (TKC / 4), lr = (c % (TKC / 4)) * 4;
             const int gi = i0 + li, gr = r0 + lr;
-            int bytes = (gi < I && gr < rend) ? min(16, (rend - gr) * 4) : 0;
+            const int bytes = (gi < I && gr < rend) ? min(16, (rend - gr) * 4) : 0;
             const float* src = bytes ? base + gi * s_i + gr : base;
             cp_async16(sm + li * (TKC + 4) + lr, src, bytes);
         } else {
             const int lr = c >> 4, li = (c & 15) * 4;        // 16 chunks per r-row of 64 i
             const int gi = i0 + li, gr = r0 + lr;
-            int bytes = (gr < rend && gi < I) ? min(16, (I - gi) * 4) : 0;
+            const int bytes = (gr < rend && gi < I) ? min(16, (I - gi) * 4) : 0;
             const float* src = bytes ? base + gr * s_r + gi : base;
             cp_async16(sm + lr * 72 + li, src, bytes);
         }
     }
 }
 
-template <bool SPLIT>
-__global__ void __launch_bounds__(256) gemm_cpasync_kernel(GemmP p) {
+template <bool SPLIT, bool ARC, bool BRC>
+__global__ void __launch_bounds__(CP_THREADS) gemm_cpasync_kernel(GemmP p) {
     extern __shared__ __align__(16) float cps[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int i0 = blockIdx.y * TM, j0 = blockIdx.x * TN;
@@ -315,20 +320,23 @@ __global__ void __launch_bounds__(256) gemm_cpasync_kernel(GemmP p) {
     const int rchunk = ceil_div_i(ceil_div_i(p.R, TKC), p.splits) * TKC;
     const int rbeg = blockIdx.z * rchunk;
     const int rend = min(p.R, rbeg + rchunk);
-    const bool a_rc = (p.sAr == 1), b_rc = (p.sBr == 1);
     const int nk = rbeg < rend ? ceil_div_i(rend - rbeg, TKC) : 0;
+    const bool want_rowsum = p.rowsum != nullptr && blockIdx.x == 0 && wn == 0;
 
-    float acc[4][4];
+    float acc[2][4][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+    float rs[2][2] = {{0.f, 0.f}, {0.f, 0.f}};               // row sums of A: rows (mi, g) and (mi, g + 8)
 
     auto issue = [&](int kc) {
         if (kc < nk) {
             float* sa = cps + (size_t)(kc % CST) * 2 * CP_OP_FLOATS;
-            cp_load_tile(sa, p.A, p.sAi, p.sAr, a_rc, i0, p.I, rbeg + kc * TKC, rend, tid);
-            cp_load_tile(sa + CP_OP_FLOATS, p.B, p.sBj, p.sBr, b_rc, j0, p.J, rbeg + kc * TKC, rend, tid);
+            cp_load_tile<ARC>(sa, p.A, p.sAi, p.sAr, i0, p.I, rbeg + kc * TKC, rend, tid);
+            cp_load_tile<BRC>(sa + CP_OP_FLOATS, p.B, p.sBj, p.sBr, j0, p.J, rbeg + kc * TKC, rend, tid);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");     // one group per k-chunk, empty ones included
     };
@@ -342,38 +350,40 @@ __global__ void __launch_bounds__(256) gemm_cpasync_kernel(GemmP p) {
         const float* sb = sa + CP_OP_FLOATS;
 #pragma unroll
         for (int kk = 0; kk < TKC; kk += 8) {
-            uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
+            uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi) {
                 const int r = wm * 32 + mi * 16 + fg;
                 float x0, x1, x2, x3;
-                if (a_rc) {
+                if (ARC) {
                     x0 = sa[r * (TKC + 4) + kk + ft]; x1 = sa[(r + 8) * (TKC + 4) + kk + ft];
                     x2 = sa[r * (TKC + 4) + kk + ft + 4]; x3 = sa[(r + 8) * (TKC + 4) + kk + ft + 4];
                 } else {
                     x0 = sa[(kk + ft) * 72 + r]; x1 = sa[(kk + ft) * 72 + r + 8];
                     x2 = sa[(kk + ft + 4) * 72 + r]; x3 = sa[(kk + ft + 4) * 72 + r + 8];
                 }
+                rs[mi][0] += x0 + x2;
+                rs[mi][1] += x1 + x3;
                 split_tf32(x0, ah[mi][0], al[mi][0]); split_tf32(x1, ah[mi][1], al[mi][1]);
                 split_tf32(x2, ah[mi][2], al[mi][2]); split_tf32(x3, ah[mi][3], al[mi][3]);
             }
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni) {
-                const int c = wn * 16 + ni * 8 + fg;
+            for (int ni = 0; ni < 4; ++ni) {
+                const int c = wn * 32 + ni * 8 + fg;
                 float y0, y1;
-                if (b_rc) { y0 = sb[c * (TKC + 4) + kk + ft]; y1 = sb[c * (TKC + 4) + kk + ft + 4]; }
+                if (BRC) { y0 = sb[c * (TKC + 4) + kk + ft]; y1 = sb[c * (TKC + 4) + kk + ft + 4]; }
                 else { y0 = sb[(kk + ft) * 72 + c]; y1 = sb[(kk + ft + 4) * 72 + c]; }
                 split_tf32(y0, bh[ni][0], bl[ni][0]); split_tf32(y1, bh[ni][1], bl[ni][1]);
             }
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) {      // small terms first
+                for (int ni = 0; ni < 4; ++ni) {      // small terms first
                     if (SPLIT) {
-                        mma_tf32(acc[mi * 2 + ni], al[mi], bh[ni]);
-                        mma_tf32(acc[mi * 2 + ni], ah[mi], bl[ni]);
+                        mma_tf32(acc[mi][ni], al[mi], bh[ni]);
+                        mma_tf32(acc[mi][ni], ah[mi], bl[ni]);
                     }
-                    mma_tf32(acc[mi * 2 + ni], ah[mi], bh[ni]);
+                    mma_tf32(acc[mi][ni], ah[mi], bh[ni]);
                 }
         }
     }
@@ -381,16 +391,16 @@ __global__ void __launch_bounds__(256) gemm_cpasync_kernel(GemmP p) {
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 2; ++ni)
+        for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int gi = i0 + wm * 32 + mi * 16 + fg + 8 * h;
-                const int gj = j0 + wn * 16 + ni * 8 + 2 * ft;
+                const int gj = j0 + wn * 32 + ni * 8 + 2 * ft;
                 if (gi >= p.I) continue;
 #pragma unroll
                 for (int y = 0; y < 2; ++y) {
                     if (gj + y >= p.J) continue;
-                    float v = acc[mi * 2 + ni][2 * h + y];
+                    float v = acc[mi][ni][2 * h + y];
                     if (p.splits == 1) {
                         if (p.bias) v += p.bias[gj + y];
                         if (p.relu) v = v < 0.f ? 0.f : v;  // NaN-propagating (an out-of-range user row must stay loud)
@@ -399,6 +409,19 @@ __global__ void __launch_bounds__(256) gemm_cpasync_kernel(GemmP p) {
                     C[gi * p.ldc + gj + y] = v;
                 }
             }
+    if (p.rowsum != nullptr) {
+        // bias gradient of the weight-gradient form: sum over r of A(i, r), this block's r range -> rowsum[z][i]
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float t = rs[mi][h];
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                t += __shfl_xor_sync(0xffffffffu, t, 2);
+                const int gi = i0 + wm * 32 + mi * 16 + fg + 8 * h;
+                if (want_rowsum && ft == 0 && gi < p.I) p.rowsum[(long)blockIdx.z * p.I + gi] = t;
+            }
+    }
 }
 
 // cp.async needs 16-byte aligned rows: the base pointer, the non-unit stride (x4 bytes) and the tile origin along the
@@ -416,6 +439,24 @@ __global__ void split_reduce_kernel(const float* __restrict__ part, int splits, 
     float s = 0.f;
     for (int k = 0; k < splits; ++k) s += part[(long)k * n + i];
     out[i] = s;
+}
+// the same for two partial arrays in one launch (weight gradient [splits][n] and bias gradient [splits][n2])
+__global__ void split_reduce2_kernel(const float* __restrict__ part, int splits, long n, float* __restrict__ out,
+                                     const float* __restrict__ part2, long n2, float* __restrict__ out2) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n + n2) return;
+    const bool second = i >= n;
+    const float* src = second ? part2 + (i - n) : part + i;
+    const long stride = second ? n2 : n;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= splits; k += 4) {
+        s0 += src[(long)k * stride]; s1 += src[(long)(k + 1) * stride];
+        s2 += src[(long)(k + 2) * stride]; s3 += src[(long)(k + 3) * stride];
+    }
+    for (; k < splits; ++k) s0 += src[(long)k * stride];
+    const float s = (s0 + s1) + (s2 + s3);
+    if (second) out2[i - n] = s; else out[i] = s;
 }
 
 // column sums of a [M, N] matrix (row stride ld): block (column chunk, row chunk g) writes
@@ -463,21 +504,37 @@ int linear_impl() {      // 0 = cp.async pipeline (default), 1 = CUDA cores, 2 =
     }
     return v;
 }
-void launch_gemm(const GemmP& p, dim3 grid, cudaStream_t st) {
+template <bool SPLIT, bool ARC, bool BRC>
+void launch_cp(const GemmP& p, dim3 grid, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(gemm_cpasync_kernel<SPLIT, ARC, BRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CP_SMEM);
+        attr_done = true;
+    }
+    gemm_cpasync_kernel<SPLIT, ARC, BRC><<<grid, CP_THREADS, CP_SMEM, st>>>(p);
+}
+template <bool SPLIT>
+void launch_cp_layout(const GemmP& p, dim3 grid, cudaStream_t st) {
+    const bool arc = p.sAr == 1, brc = p.sBr == 1;
+    if (arc && brc) launch_cp<SPLIT, true, true>(p, grid, st);
+    else if (arc) launch_cp<SPLIT, true, false>(p, grid, st);
+    else if (brc) launch_cp<SPLIT, false, true>(p, grid, st);
+    else launch_cp<SPLIT, false, false>(p, grid, st);
+}
+// -> true when the cp.async kernel ran (it honours p.rowsum); the other kernels ignore p.rowsum
+bool launch_gemm(const GemmP& p, dim3 grid, cudaStream_t st) {
     const int impl = linear_impl();
-    if (impl == 1) { gemm_kernel<false><<<grid, 256, 0, st>>>(p); return; }
+    if (impl == 1) { gemm_kernel<false><<<grid, 256, 0, st>>>(p); return false; }
     if (impl == 0 && cp_operand_ok(p.A, p.sAi, p.sAr) && cp_operand_ok(p.B, p.sBj, p.sBr)) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(gemm_cpasync_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CP_SMEM);
-            cudaFuncSetAttribute(gemm_cpasync_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CP_SMEM);
-            attr_done = true;
-        }
-        if (p.single_tf32) gemm_cpasync_kernel<false><<<grid, 256, CP_SMEM, st>>>(p);
-        else gemm_cpasync_kernel<true><<<grid, 256, CP_SMEM, st>>>(p);
-        return;
+        if (p.single_tf32) launch_cp_layout<false>(p, grid, st);
+        else launch_cp_layout<true>(p, grid, st);
+        return true;
     }
     gemm_kernel<true><<<grid, 256, 0, st>>>(p);
+    return false;
+}
+bool cp_path(const GemmP& p) {
+    return linear_impl() == 0 && cp_operand_ok(p.A, p.sAi, p.sAr) && cp_operand_ok(p.B, p.sBj, p.sBr);
 }
 
 int wgrad_splits(int M, int K, int N) {
@@ -543,16 +600,19 @@ static int linear_wgrad_impl(const float* dY, int lddy, const float* X, int ldx,
     p.B = X; p.sBr = ldx; p.sBj = 1;    // B(r=m, j=k) = X[m,k]
     p.C = splits > 1 ? (float*)ws : dW; p.ldc = K; p.bias = nullptr; p.mask = nullptr; p.ldmask = 0;
     p.I = N; p.J = K; p.R = M; p.relu = 0; p.splits = splits; p.split_stride = (long)N * K; p.single_tf32 = single_tf32;
+    float* part = (float*)ws + (size_t)splits * N * K;      // bias-gradient partials: [splits][N] (fused) or [COLSUM_G][N]
+    const bool fuse_db = db != nullptr && cp_path(p);        // splits <= 64 = COLSUM_G rows fit the same region
+    p.rowsum = fuse_db ? (splits > 1 ? part : db) : nullptr;
     dim3 grid(ceil_div_i(K, TN), ceil_div_i(N, TM), splits);
     launch_gemm(p, grid, st);
     DCUE_LAUNCH_CHECK();
+    const long n = (long)N * K;
     if (splits > 1) {
-        const long n = (long)N * K;
-        split_reduce_kernel<<<ceil_div_i(n, 256), 256, 0, st>>>((const float*)ws, splits, n, dW);
+        if (fuse_db) split_reduce2_kernel<<<ceil_div_i(n + N, 256), 256, 0, st>>>((const float*)ws, splits, n, dW, part, N, db);
+        else split_reduce_kernel<<<ceil_div_i(n, 256), 256, 0, st>>>((const float*)ws, splits, n, dW);
         DCUE_LAUNCH_CHECK();
     }
-    if (db) {
-        float* part = (float*)ws + (size_t)splits * N * K;
+    if (db && !fuse_db) {
         dim3 cg(ceil_div_i(N, 32), COLSUM_G);
         colsum_kernel<<<cg, 256, 0, st>>>(dY, lddy, M, N, part);
         DCUE_LAUNCH_CHECK();
