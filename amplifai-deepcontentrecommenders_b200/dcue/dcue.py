@@ -83,7 +83,10 @@ class DCUENet(nn.Module):
         return u_f
 
     def user_embd_on_side_stream(self, u):
-        return (torch.is_tensor(u) and u.is_cuda and os.environ.get("DCUE_USER_STREAM", "1") != "0")
+        """DCUE_USER_STREAM=1 runs the user tower on a side stream next to the song tower.  Off by default: the round-2 kernel
+        timeline showed its low-occupancy GEMM blocks taking register-file room on ~80 SMs, so the one-wave input pass (3
+        blocks per SM by design) needed a second wave -- 554 instead of 372 us -- for 35 us of user-tower work hidden."""
+        return (torch.is_tensor(u) and u.is_cuda and os.environ.get("DCUE_USER_STREAM", "0") != "0")
 
     def forward(self, u, pos, neg=None):
         """u int64 [B]; pos f32 [B,128,L]; neg f32 [B,N,128,L] ->

@@ -38,31 +38,46 @@ class GraphedTrainStep:
                     dp.reduce_gradients()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        # The graph zeroes the EXISTING .grad tensors and the backward accumulates into them in place, so the
-        # optimizer (and any other GraphedTrainStep of the same model) keeps seeing the same gradient storage.
-        # Do not call zero_grad(set_to_none=True) on the model afterwards.
         params = [p for p in model.parameters() if p.requires_grad]
-        for p in params:
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
-        self._grads = [p.grad for p in params]
-        # one more eager pass on the STATIC gradient tensors: everything keyed on their addresses (the peer gradient
-        # all-reduce's pointer table, ...) is built now -- a capture must not contain pageable host-to-device copies
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            torch._foreach_zero_(self._grads)
-            self._loss().backward()
-            if dp is not None:
-                dp.reduce_gradients()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
+        self._params = params
+        # Gradient storage.  Default ("owned"): the capture starts with every .grad = None, so autograd ASSIGNS the tensors
+        # the backward kernels produce (graph-pool memory: the same addresses on every replay) instead of accumulating into
+        # pre-existing ones -- the round-2 timeline showed 29 ATen add kernels + the zero fill per step (~75 us of 2.6 ms)
+        # doing nothing but that.  __call__ re-binds p.grad to this graph's tensors, so several graphs over one model (dense
+        # and index feed) and eager steps in between (zero_grad(set_to_none=False)) keep working.
+        # DCUE_GRAPH_GRADS=accumulate (and the peer-memory gradient all-reduce, whose pointer table is keyed on the gradient
+        # addresses before the capture): the graph zeroes the EXISTING .grad tensors and accumulates into them in place.
+        peer_grads = dp is not None and getattr(dp, "_gred", None) is not None
+        self.owned = os.environ.get("DCUE_GRAPH_GRADS", "owned") != "accumulate" and not peer_grads
+        if not self.owned:
+            for p in params:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            self._grads = [p.grad for p in params]
+            # one more eager pass on the STATIC gradient tensors: everything keyed on their addresses (the peer gradient
+            # all-reduce's pointer table, ...) is built now -- a capture must not contain pageable host-to-device copies
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                torch._foreach_zero_(self._grads)
+                self._loss().backward()
+                if dp is not None:
+                    dp.reduce_gradients()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+        self.passes = warmup + (1 if self.owned else 2)      # forward+backward passes run by this constructor (launch accounting)
         self.graph = torch.cuda.CUDAGraph()
+        if self.owned:
+            for p in params:
+                p.grad = None
         with torch.cuda.graph(self.graph):
-            torch._foreach_zero_(self._grads)
+            if not self.owned:
+                torch._foreach_zero_(self._grads)
             self.loss = self._loss()
             self.loss.backward()
             if dp is not None:
                 dp.reduce_gradients()
+        if self.owned:
+            self._grads = [p.grad for p in params]
         with torch.no_grad():
             for b, saved in buffers:
                 b.copy_(saved)
@@ -102,4 +117,8 @@ class GraphedTrainStep:
             self._launches += 1
         else:
             self.graph.replay()
+        if self.owned:
+            for p, g in zip(self._params, self._grads):
+                if p.grad is not g:
+                    p.grad = g
         return self.loss

@@ -311,6 +311,56 @@ def timed_steps(fn, n, barrier, dev, world):
 
 
 # ------------------------------------------------------------------------------------- multi-rank parity legs
+def timeline_leg(step, u, pos, neg, path, rank, steps=4):
+    """Kernel timeline of the (graph-replayed) step from CUPTI activity records (torch.profiler): per kernel its stream, start
+    offset, duration and the idle gap before it on its stream -- the in-graph, warm-cache view that ncu's serialised launch
+    list cannot give.  One text file per rank: `path`.rank<r>.txt (diagnostic; never part of a timed region)."""
+    import json as _json
+    import tempfile
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(steps):
+            step(u, pos, neg)
+        torch.cuda.synchronize()
+    with tempfile.NamedTemporaryFile(suffix=".json") as f:
+        prof.export_chrome_trace(f.name)
+        tr = _json.load(open(f.name))
+    ks = sorted((e for e in tr["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in e),
+                key=lambda e: e["ts"])
+    starts = [i for i, e in enumerate(ks) if "gather_relu" in e["name"]]
+    if len(starts) < 3:
+        return None
+    a, b = starts[-2], starts[-1]
+    evs = ks[a:b]
+    t0 = evs[0]["ts"]
+    last_end = {}
+    lines, busy = [], {}
+    for e in evs:
+        st = e.get("args", {}).get("stream", 0)
+        gap = e["ts"] - last_end[st] if st in last_end else 0.0
+        last_end[st] = e["ts"] + e["dur"]
+        busy[st] = busy.get(st, 0.0) + e["dur"]
+        name = e["name"].replace("(anonymous namespace)::", "").replace("void ", "")
+        lines.append("%9.1f %8.1f %7.1f  s%-3s %s" % (e["ts"] - t0, e["dur"], gap, st, name[:100]))
+    span = ks[b]["ts"] - t0
+    agg = {}
+    for e in evs:
+        n = e["name"].replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:70]
+        c = agg.setdefault(n, [0, 0.0])
+        c[0] += 1
+        c[1] += e["dur"]
+    out = "%s.rank%d.txt" % (path, rank)
+    with open(out, "w") as f:
+        f.write("step span %.1f us, %d kernels; busy per stream: %s\n" % (span, len(evs), {k: round(v, 1) for k, v in busy.items()}))
+        f.write("--- per kernel (count, total us, share of span)\n")
+        for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("%-72s n=%3d %9.1f us %5.1f%%\n" % (n, c, t, 100 * t / span))
+        f.write("--- timeline: start_us dur_us gap_before_us stream kernel\n")
+        f.write("\n".join(lines) + "\n")
+    return {"span_us": span, "kernels": len(evs), "file": out}
+
+
 def dp_parity_leg(pkg, par, dev, rank, world, per_rank=32, negs=4, users=500):
     """Global batch split over the ranks (SyncBN statistics, peer-memory table-row exchange, flat gradient all-reduce) against
     rank 0 recomputing the FULL batch on one GPU with the same kernels: loss, every gradient, BatchNorm buffers; then the
@@ -565,7 +615,7 @@ def run_ours(args):
         c0 = L.lib().dcue_launch_count()
         gstep = pkg.GraphedTrainStep(model, CFG["margin"], u, pos, neg, warmup=3, dp=dp if world > 1 else None)
         graphs.append(gstep)
-        graph_launches = (L.lib().dcue_launch_count() - c0) // 5       # 3 warm-up passes + the priming pass + the captured one
+        graph_launches = (L.lib().dcue_launch_count() - c0) // gstep.passes   # warm-up passes (+ priming pass) + the captured one
 
         def step(u_, pos_, neg_):  # noqa: F811  (same step: forward+loss+backward replayed as one CUDA graph)
             if u_ is not u:
@@ -576,17 +626,30 @@ def run_ours(args):
             return loss.detach().clone()
 
     # ---------------- device-resident timing ("value")
-    for _ in range(args.warmup + int(os.environ.get("DCUE_BENCH_SETTLE", "0"))):
+    # the last two warm-up steps run AFTER the sampler process has been forked: the first step after the fork measured 7-15 ms
+    # (copy-on-write faults of the launching process), which must not land in the timed region
+    late = min(2, args.warmup)
+    for _ in range(args.warmup - late + int(os.environ.get("DCUE_BENCH_SETTLE", "0"))):
+        step(u, pos, neg)
+    # the sampler process takes ~0.1 s to start (python + NVML init): start it BEFORE the barrier, or the other ranks enter
+    # the timed loop first and spend that time spinning on rank 0's peer flags inside their own timed region
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(late):
         step(u, pos, neg)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = L.lib().dcue_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    per_step = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)] if os.environ.get("DCUE_BENCH_PER_STEP") else None
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         loss_acc += step(u, pos, neg)
+        if per_step:
+            per_step[i].record()
     e1.record()
     barrier()
+    if per_step and rank == 0:      # diagnostic: device time of every step of the timed region
+        ts = [e0.elapsed_time(e) for e in per_step]
+        print("per-step ms:", " ".join("%.3f" % (b - a) for a, b in zip([0.0] + ts[:-1], ts)), file=sys.stderr, flush=True)
     launches = L.lib().dcue_launch_count() - launches0
     # under graph replay the library's launch counter only ticks for the optimizer: add the per-step count seen at capture
     launches_per_step = launches / args.steps + (graph_launches if use_graph else 0)
@@ -598,6 +661,10 @@ def run_ours(args):
     value = B * world * args.steps / (ms_total * 1e-3)
     final_loss = dp.reduce_loss(loss_acc / args.steps).item()
     dp.check_peers()
+
+    if args.timeline:
+        timeline_leg(step, u, pos, neg, args.timeline, rank)
+        barrier()
 
     # ---------------- end to end: pinned host inputs -> H2D -> step -> loss D2H, every step
     hu, hpos, hneg = (t.cpu().pin_memory() for t in (u, pos, neg))
@@ -869,6 +936,7 @@ def main():
     ap.add_argument("--no-eval-hybrid", action="store_true")
     ap.add_argument("--no-bf16", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--timeline", default=None, help="write a CUPTI kernel timeline of one step to PATH.rank<r>.txt (diagnostic)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph step")
     args = ap.parse_args()
     if args.impl == "reference":
