@@ -184,8 +184,16 @@ __global__ void dcue_wgrad_reduce_kernel(const float* __restrict__ part, int npa
     // fixed summation order (deterministic); eight independent loads in flight (the plain loop was L2-latency bound: 17 us)
     const float* src = part + ((long)co * k + j) * 128 + ci;
     const long stride = 128L * k * 128;
+    // (in-graph timeline: 10 us for 38 MB of L2-resident partials = 19 dependent batches of 8 loads; 32 in flight -> 5 batches)
     float s = 0.f;
     int p = 0;
+    for (; p + 32 <= nparts; p += 32) {
+        float v[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) v[u] = __ldcg(src + (long)(p + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 32; ++u) s += v[u];
+    }
     for (; p + 8 <= nparts; p += 8) {
         float v[8];
 #pragma unroll

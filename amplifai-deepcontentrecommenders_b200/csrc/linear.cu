@@ -279,7 +279,10 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
 // template parameters (no per-load selects), 4 warps own 32 x 32 each (5 instead of 7 instructions per MMA), 55 KB of shared
 // memory let 4 blocks share an SM, and the weight-gradient form also takes the bias gradient (row sums of its A operand, from
 // the unrounded fp32 values already in registers) -- no separate column-sum launches.
-constexpr int TKC = 32, CST = 3;
+#ifndef DCUE_GEMM_STAGES
+#define DCUE_GEMM_STAGES 3
+#endif
+constexpr int TKC = 32, CST = DCUE_GEMM_STAGES;
 constexpr int CP_OP_FLOATS = 64 * (TKC + 4);                // one operand tile of one stage (either layout fits: 32 x 72 = 64 x 36)
 constexpr size_t CP_SMEM = (size_t)CST * 2 * CP_OP_FLOATS * sizeof(float);
 constexpr int CP_THREADS = 128;

@@ -89,15 +89,29 @@ peer_exchange_i64_kernel(uint8_t* const* __restrict__ bufs, unsigned* __restrict
         peer_wait(my_flags + threadIdx.x, e, counter + 2);
     }
     __syncthreads();
-    if (all_out)
-        for (int r = 0; r < world; ++r) {
-            const int64_t* src = reinterpret_cast<const int64_t*>(bufs[r] + XCH_FLAG_BYTES);
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                int64_t v;
-                asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(src + i) : "memory");
-                all_out[(long)r * n + i] = v;
+    if (all_out) {
+        // eight NVLink reads in flight per thread (one at a time, each followed by its store, made this single-block kernel
+        // 57 us on 8 GPUs: 32 serial round trips)
+        const int total = world * n;
+        for (int b0 = threadIdx.x; b0 < total; b0 += 8 * blockDim.x) {
+            int64_t v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int g = b0 + q * blockDim.x;
+                v[q] = 0;
+                if (g < total) {
+                    const int r = g / n, i = g - r * n;
+                    const int64_t* src = reinterpret_cast<const int64_t*>(bufs[r] + XCH_FLAG_BYTES) + i;
+                    asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v[q]) : "l"(src) : "memory");
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int g = b0 + q * blockDim.x;
+                if (g < total) all_out[g] = v[q];
             }
         }
+    }
 }
 
 // owner / local row of a global row under the contiguous block partition of parallel.shard_slice
@@ -155,29 +169,44 @@ peer_gather_relu_kernel(const float* const* __restrict__ shards, long base, long
     }
 }
 
-// warp per entry j of the world*B exchanged (index, gradient row) pairs; see dup_scan_scatter_kernel (embed.cu)
+// First pass of the exchanged-row reduction: per table row its FIRST entry (as n - j, so that zero = none) and its number of
+// entries.  Integer atomics: the result does not depend on the order.
+__global__ void __launch_bounds__(256)
+peer_mark_rows_kernel(const int64_t* __restrict__ all_idx, int n, long lo, long hi, unsigned* __restrict__ meta /* [hi-lo][2] */) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int64_t row = all_idx[j];
+    if (row < lo || row >= hi) return;
+    atomicMax(meta + 2 * (row - lo), (unsigned)(n - j));
+    atomicAdd(meta + 2 * (row - lo) + 1, 1u);
+}
+
+// warp per entry j of the world*B exchanged (index, gradient row) pairs; only the FIRST entry of a row works: it sums the
+// row's entries in increasing j (= (rank, position)) order -- deterministic, no sort.  A row with one entry (most of them) is a
+// copy; a duplicated row scans the index list from j on and stops at its last entry.  (Round 2: without the marks every warp
+// scanned all n indices -- O(n^2 / 32) ballots, 122 us at n = 8 x 1024.)
 __global__ void __launch_bounds__(256)
 peer_scatter_add_rows_kernel(uint8_t* const* __restrict__ bufs, long rows_off_bytes, const int64_t* __restrict__ all_idx, int world, int B,
-                             long lo, long hi, int E, float* __restrict__ gshard) {
+                             long lo, long hi, int E, const unsigned* __restrict__ meta, float* __restrict__ gshard) {
     const int lane = threadIdx.x & 31;
     const int n = world * B;
     const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (j >= n) return;
     const int64_t row = all_idx[j];
     if (row < lo || row >= hi) return;
+    if ((int)(n - meta[2 * (row - lo)]) != j) return;          // an earlier entry owns this row
+    const int cnt = (int)meta[2 * (row - lo) + 1];
     float* dst = gshard + (row - lo) * (long)E;
     for (int c0 = 0; c0 < E; c0 += 512) {
         float4 a[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) a[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int j0 = 0; j0 < n; j0 += 32) {
+        int found = 0;
+        for (int j0 = j & ~31; j0 < n && found < cnt; j0 += 32) {
             const int jj = j0 + lane;
-            unsigned m = __ballot_sync(0xffffffffu, jj < n && __ldg(all_idx + jj) == row);
-            if (j0 + 32 <= j) {
-                if (m) return;
-                continue;
-            }
-            if (j0 <= j && (m & ((1u << (j - j0)) - 1u))) return;
+            unsigned m = cnt == 1 ? (j0 == (j & ~31) ? 1u << (j & 31) : 0u)
+                                  : __ballot_sync(0xffffffffu, jj >= j && jj < n && __ldg(all_idx + jj) == row);
+            found += __popc(m);
             while (m) {
                 const int pj = j0 + __ffs(m) - 1;
                 m &= m - 1;
@@ -243,11 +272,19 @@ extern "C" int dcue_peer_gather_relu_fwd(const void* peer_shards_dev, long U, in
 }
 
 extern "C" int dcue_peer_scatter_add_rows(const void* peer_bufs_dev, int capacity_rows, const int64_t* all_idx, int world, int B, long lo,
-                                          long hi, int E, float* grad_shard, void* stream) {
+                                          long hi, int E, float* grad_shard, void* ws, size_t ws_bytes, void* stream) {
     DCUE_CHECK_ARG(peer_bufs_dev && all_idx && grad_shard && world >= 1 && B >= 0 && B <= capacity_rows && hi >= lo && E > 0);
     if (B == 0 || hi == lo) return 0;
-    peer_scatter_add_rows_kernel<<<ceil_div_i((long)world * B, 8), 256, 0, (cudaStream_t)stream>>>(
-        (uint8_t* const*)peer_bufs_dev, (long)dcue_peer_exchange_rows_offset(capacity_rows), all_idx, world, B, lo, hi, E, grad_shard);
+    const size_t need = (size_t)(hi - lo) * 2 * sizeof(unsigned);
+    if (!ws || ws_bytes < need) DCUE_FAIL(DCUE_E_WORKSPACE, "dcue_peer_scatter_add_rows: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long n = (long)world * B;
+    DCUE_CUDA(cudaMemsetAsync(ws, 0, need, st));
+    peer_mark_rows_kernel<<<ceil_div_i(n, 256), 256, 0, st>>>(all_idx, (int)n, lo, hi, (unsigned*)ws);
+    DCUE_LAUNCH_CHECK();
+    peer_scatter_add_rows_kernel<<<ceil_div_i(n, 8), 256, 0, st>>>(
+        (uint8_t* const*)peer_bufs_dev, (long)dcue_peer_exchange_rows_offset(capacity_rows), all_idx, world, B, lo, hi, E,
+        (const unsigned*)ws, grad_shard);
     DCUE_LAUNCH_CHECK();
     return 0;
 }
@@ -271,24 +308,29 @@ constexpr int GR_MAX_WORLD = 16;
 constexpr size_t GR_FLAG_BYTES = (size_t)2 * GR_MAX_CHUNKS * GR_MAX_WORLD * sizeof(unsigned);
 constexpr size_t GR_DATA_BYTES = (size_t)2 * GR_MAX_CHUNKS * GR_CHUNK * sizeof(float);
 
-struct GradEntry {     // one row of the device table (int64 x 2 on the Python side)
+struct GradEntry {     // one row of the HOST table (int64 x 2 on the Python side)
     float* g;
     long n;
+};
+// The tensor list travels as a kernel ARGUMENT (1 KB): no device table, no host-to-device copy, so the call can be captured
+// into a CUDA graph together with the backward pass that allocates the gradient tensors.
+struct GradList {
+    float* g[64];
+    long pre[65];
 };
 
 __global__ void __launch_bounds__(256)
 peer_allreduce_grads_kernel(uint8_t* const* __restrict__ bufs, unsigned* __restrict__ counter /* [0] epoch, [1] ticket, [2] timeout */,
-                            int rank, int world, const GradEntry* __restrict__ tab, const long* __restrict__ prefix /* [n_tensors+1] */,
-                            int n_tensors, long n_total) {
-    __shared__ long pre[64];
+                            int rank, int world, const __grid_constant__ GradList gl, int n_tensors, long n_total) {
+    __shared__ long pre[65];
     __shared__ float* gp[64];
     __shared__ unsigned last;
     const unsigned e = counter[0] + 1u;          // every CTA reads the epoch before the last one to finish advances it
     const int c = blockIdx.x;
     const int slot = (int)(e & 1u);
     for (int t = threadIdx.x; t <= n_tensors; t += blockDim.x) {
-        pre[t] = prefix[t];
-        if (t < n_tensors) gp[t] = tab[t].g;
+        pre[t] = gl.pre[t];
+        if (t < n_tensors) gp[t] = gl.g[t];
     }
     __syncthreads();
     const long f0 = (long)c * GR_CHUNK;
@@ -316,18 +358,37 @@ peer_allreduce_grads_kernel(uint8_t* const* __restrict__ bufs, unsigned* __restr
         peer_wait(my_flags + threadIdx.x, e, counter + 2);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < len; i += blockDim.x) {
-        float s = 0.f;
-        for (int r = 0; r < world; ++r) {
-            const float* src = reinterpret_cast<const float*>(bufs[r] + GR_FLAG_BYTES) + ((size_t)slot * GR_MAX_CHUNKS + c) * GR_CHUNK;
-            float v;
-            asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(src + i) : "memory");
-            s += v;
+    // 16-byte NVLink reads, all ranks in flight, added in rank order (one 4-byte read at a time, each followed by its add,
+    // serialised world x 16 round trips per thread: that version lost to NCCL's LL ring).  The slot is a whole chunk, so the
+    // vector read past `len` stays inside it; those lanes are not written back.
+    for (int i4 = threadIdx.x * 4; i4 < len; i4 += blockDim.x * 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r0 = 0; r0 < world; r0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r0 + q < world) {
+                    const float* src = reinterpret_cast<const float*>(bufs[r0 + q] + GR_FLAG_BYTES) +
+                                       ((size_t)slot * GR_MAX_CHUNKS + c) * GR_CHUNK + i4;
+                    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(v[q].x), "=f"(v[q].y), "=f"(v[q].z), "=f"(v[q].w) : "l"(src) : "memory");
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (r0 + q < world) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
         }
-        const long f = f0 + i;
+        const float av[4] = {acc.x, acc.y, acc.z, acc.w};
         int t = t0;
-        while (pre[t + 1] <= f) ++t;
-        gp[t][f - pre[t]] = s;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long f = f0 + i4 + k;
+            if (i4 + k < len) {
+                while (pre[t + 1] <= f) ++t;
+                gp[t][f - pre[t]] = av[k];
+            }
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -346,14 +407,25 @@ peer_allreduce_grads_kernel(uint8_t* const* __restrict__ bufs, unsigned* __restr
 extern "C" size_t dcue_peer_grads_bytes(void) { return GR_FLAG_BYTES + GR_DATA_BYTES; }
 extern "C" long dcue_peer_grads_max_elems(void) { return (long)GR_MAX_CHUNKS * GR_CHUNK; }
 
-extern "C" int dcue_peer_allreduce_grads(const void* peer_bufs_dev, void* counter, int rank, int world, const void* table_dev,
-                                         const long* prefix_dev, int n_tensors, long n_total, void* stream) {
-    DCUE_CHECK_ARG(peer_bufs_dev && counter && table_dev && prefix_dev && world >= 1 && world <= GR_MAX_WORLD && rank >= 0 &&
-                   rank < world && n_tensors >= 1 && n_tensors <= 63 && n_total >= 0 && n_total <= dcue_peer_grads_max_elems());
+extern "C" int dcue_peer_allreduce_grads(const void* peer_bufs_dev, void* counter, int rank, int world, const void* table_host,
+                                         int n_tensors, void* stream) {
+    DCUE_CHECK_ARG(peer_bufs_dev && counter && table_host && world >= 1 && world <= GR_MAX_WORLD && rank >= 0 && rank < world &&
+                   n_tensors >= 1 && n_tensors <= 63);
+    GradList gl{};
+    const GradEntry* tab = (const GradEntry*)table_host;
+    long n_total = 0;
+    for (int t = 0; t < n_tensors; ++t) {
+        DCUE_CHECK_ARG(tab[t].g != nullptr && tab[t].n >= 0);
+        gl.g[t] = tab[t].g;
+        gl.pre[t] = n_total;
+        n_total += tab[t].n;
+    }
+    gl.pre[n_tensors] = n_total;
+    DCUE_CHECK_ARG(n_total <= dcue_peer_grads_max_elems());
     if (n_total == 0 || world == 1) return 0;
     const int chunks = (int)((n_total + GR_CHUNK - 1) / GR_CHUNK);
     peer_allreduce_grads_kernel<<<chunks, 256, 0, (cudaStream_t)stream>>>((uint8_t* const*)peer_bufs_dev, (unsigned*)counter, rank, world,
-                                                                        (const GradEntry*)table_dev, prefix_dev, n_tensors, n_total);
+                                                                        gl, n_tensors, n_total);
     DCUE_LAUNCH_CHECK();
     return 0;
 }

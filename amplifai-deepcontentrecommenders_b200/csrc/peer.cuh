@@ -61,9 +61,18 @@ __device__ __forceinline__ void peer_allreduce_block(const PeerCtx& pc, double* 
         }
     }
     __syncthreads();
+    // all ranks' values in flight at once, then added in rank order (the plain loop made every NVLink read wait for the
+    // previous add: 8 serial round trips = +12 us per BatchNorm finaliser on 8 GPUs, round-2 timeline)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double s = 0.0;
-        for (int r = 0; r < pc.world; ++r) s += ld_relaxed_sys_f64(pc.bufs[r] + slot + i);
+        for (int r0 = 0; r0 < pc.world; r0 += 8) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = r0 + q < pc.world ? ld_relaxed_sys_f64(pc.bufs[r0 + q] + slot + i) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (r0 + q < pc.world) s += v[q];
+        }
         vec[i] = s;
     }
     __syncthreads();

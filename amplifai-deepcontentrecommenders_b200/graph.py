@@ -45,10 +45,8 @@ class GraphedTrainStep:
         # pre-existing ones -- the round-2 timeline showed 29 ATen add kernels + the zero fill per step (~75 us of 2.6 ms)
         # doing nothing but that.  __call__ re-binds p.grad to this graph's tensors, so several graphs over one model (dense
         # and index feed) and eager steps in between (zero_grad(set_to_none=False)) keep working.
-        # DCUE_GRAPH_GRADS=accumulate (and the peer-memory gradient all-reduce, whose pointer table is keyed on the gradient
-        # addresses before the capture): the graph zeroes the EXISTING .grad tensors and accumulates into them in place.
-        peer_grads = dp is not None and getattr(dp, "_gred", None) is not None
-        self.owned = os.environ.get("DCUE_GRAPH_GRADS", "owned") != "accumulate" and not peer_grads
+        # DCUE_GRAPH_GRADS=accumulate: the graph zeroes the EXISTING .grad tensors and accumulates into them in place.
+        self.owned = os.environ.get("DCUE_GRAPH_GRADS", "owned") != "accumulate"
         if not self.owned:
             for p in params:
                 if p.grad is None:

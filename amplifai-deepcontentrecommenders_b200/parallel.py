@@ -109,8 +109,9 @@ class PeerExchange:
     def scatter_add(self, all_idx, B, lo, hi):
         """Dense [hi-lo, E] sum of every rank's rows slot entries whose index falls in [lo, hi)."""
         out = torch.zeros(hi - lo, self.E, dtype=torch.float32, device=all_idx.device)
+        ws = torch.empty(2 * (hi - lo), dtype=torch.int32, device=all_idx.device)
         self.L.call("dcue_peer_scatter_add_rows", self.hdl.buffer_ptrs_dev, self.capacity, all_idx.data_ptr(), self.world, B, lo, hi,
-                    self.E, out.data_ptr(), self.L.stream())
+                    self.E, out.data_ptr(), ws.data_ptr(), ws.numel() * 4, self.L.stream())
         return out
 
     def check(self):
@@ -132,27 +133,18 @@ class PeerGradReduce:
         self.rank, self.world = self.hdl.rank, self.hdl.world_size
         self.counter = torch.zeros(3, dtype=torch.int32, device=device)
         self.max_elems = int(L.lib().dcue_peer_grads_max_elems())
-        self._key, self._table, self._prefix, self._n = None, None, None, 0
         torch.cuda.synchronize(device)
         dist.barrier(group=group)
 
     def __call__(self, grads):
-        key = tuple((g.data_ptr(), g.numel()) for g in grads)
-        if key != self._key:
-            for g in grads:
-                if g.dtype != torch.float32 or not g.is_contiguous():
-                    raise RuntimeError("PeerGradReduce needs contiguous fp32 gradients")
-            rows, pre, tot = [], [0], 0
-            for g in grads:
-                rows += [g.data_ptr(), g.numel()]
-                tot += g.numel()
-                pre.append(tot)
-            dev = grads[0].device
-            self._table = torch.tensor(rows, dtype=torch.int64).to(dev)
-            self._prefix = torch.tensor(pre, dtype=torch.int64).to(dev)
-            self._key, self._n = key, tot
+        rows = []
+        for g in grads:
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                raise RuntimeError("PeerGradReduce needs contiguous fp32 gradients")
+            rows += [g.data_ptr(), g.numel()]
+        table = torch.tensor(rows, dtype=torch.int64)          # host: the list is passed to the kernel by value
         self.L.call("dcue_peer_allreduce_grads", self.hdl.buffer_ptrs_dev, self.counter.data_ptr(), self.rank, self.world,
-                    self._table.data_ptr(), self._prefix.data_ptr(), len(grads), self._n, self.L.stream())
+                    table.data_ptr(), len(grads), self.L.stream())
 
     def check(self):
         if int(self.counter[2].item()):
@@ -179,7 +171,7 @@ class DataParallelDCUE:
                 print("DataParallelDCUE: peer all-reduce unavailable (%s); using NCCL for the BatchNorm statistics" % exc)
         self._xch = None          # PeerExchange for the table-gradient rows, created on first use (needs the batch size)
         self._gred = None         # PeerGradReduce for the flat gradient bucket
-        if self._peer is not None and os.environ.get("DCUE_DP_PEER_GRADS", "0") != "0":
+        if self._peer is not None and os.environ.get("DCUE_DP_PEER_GRADS", "1") != "0":
             try:
                 self._gred = PeerGradReduce(group, params[0].device)
             except Exception as exc:  # noqa: BLE001

@@ -361,7 +361,7 @@ int dcue_peer_allreduce_slot_doubles(void);
  *   [r*U/W + min(r, U%W), ...)) in symmetric memory: peer_shards_dev = `world` pointers to the shards; rows come over NVLink.
  * dcue_peer_scatter_add_rows: grad_shard[row - lo] = sum of the gradient rows (read from the peers' `rows` slots) whose index
  *   (all_idx from dcue_peer_exchange_i64) is `row`, for lo <= row < hi, summed in (rank, position) order.  grad_shard zeroed
- *   by the caller. */
+ *   by the caller; ws = 8 * (hi - lo) bytes of scratch (first entry and entry count of every row). */
 size_t dcue_peer_exchange_bytes(int capacity_rows, int E);
 size_t dcue_peer_exchange_rows_offset(int capacity_rows);
 int dcue_peer_exchange_i64(const void* peer_bufs_dev, void* counter, int channel, int rank, int world, const int64_t* mine,
@@ -369,18 +369,20 @@ int dcue_peer_exchange_i64(const void* peer_bufs_dev, void* counter, int channel
 int dcue_peer_gather_relu_fwd(const void* peer_shards_dev, long U, int world, const int64_t* idx, int B, int E, float* out,
                               float* raw_out, int* err_flag, void* stream);
 int dcue_peer_scatter_add_rows(const void* peer_bufs_dev, int capacity_rows, const int64_t* all_idx, int world, int B, long lo,
-                               long hi, int E, float* grad_shard, void* stream);
+                               long hi, int E, float* grad_shard, void* ws /* 8 * (hi - lo) bytes */, size_t ws_bytes,
+                               void* stream);
 
 /* Flat SUM all-reduce of a list of fp32 gradient tensors over NVLink peer memory in ONE multi-CTA kernel (replaces
  * torch.cat + NCCL all-reduce + scatter-back of the data-parallel step's tower / MLP gradients, BASELINE cfg3).
  * peer_bufs_dev: `world` pointers to zero-initialised symmetric buffers of dcue_peer_grads_bytes() bytes; counter: 3
- * zero-initialised device uint32 of the calling rank (epoch, CTA ticket, time-out flag); table_dev: n_tensors rows
- * {float* grad, int64 n}; prefix_dev: int64[n_tensors + 1] exclusive prefix sums of n; n_total <= dcue_peer_grads_max_elems().
+ * zero-initialised device uint32 of the calling rank (epoch, CTA ticket, time-out flag); table_host: n_tensors <= 63 rows
+ * {float* grad, int64 n} in HOST memory (they travel as a kernel argument: graph-capturable, no copy); sum of n <=
+ * dcue_peer_grads_max_elems().
  * The sums are written back into the gradient tensors, bit-identical on every rank.  Every rank issues the same calls. */
 size_t dcue_peer_grads_bytes(void);
 long dcue_peer_grads_max_elems(void);
-int dcue_peer_allreduce_grads(const void* peer_bufs_dev, void* counter, int rank, int world, const void* table_dev,
-                              const long* prefix_dev, int n_tensors, long n_total, void* stream);
+int dcue_peer_allreduce_grads(const void* peer_bufs_dev, void* counter, int rank, int world, const void* table_host,
+                              int n_tensors, void* stream);
 
 /* ---------------------------------------------------------------- eval scorer ------------ */
 
