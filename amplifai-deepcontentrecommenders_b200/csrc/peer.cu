@@ -2,11 +2,11 @@
 //
 // Data-parallel DCUE needs 13 all-reduces of 2 KB per step (BatchNorm batch statistics forward, the two
 // BatchNorm-backward sums per layer: SyncBN semantics, parallel.py) and each sits on the critical path between two
-// kernels; an NCCL all-reduce of that size costs ~20-40 us of launch + protocol latency.  Here every rank copies its
-// vector into its own symmetric slot, raises a flag in every peer's signal pad (release, system scope), waits for the
-// peers' flags (acquire) and sums all slots in RANK ORDER -- so the result is bit-identical on every rank.
-// Slots are double buffered by call parity: a rank can only reach call e+2 (which reuses slot e&1) after every rank has
-// signalled e+1, i.e. finished reading call e.  The call counter lives in device memory and is advanced by the kernel
+// kernels; an NCCL all-reduce of that size costs ~20-40 us of launch + protocol latency.  Here every rank PUSHES its
+// vector into its slot of every rank's symmetric buffer, raises a flag in every peer's signal pad (release, system scope),
+// waits for the peers' flags (acquire) and sums the slots of its own buffer in RANK ORDER -- bit-identical on every rank.
+// Slots are double buffered by call parity: a rank can only reach call e+2 (which reuses parity e&1) after every rank has
+// signalled e+1, i.e. finished call e.  The call counter lives in device memory and is advanced by the kernel
 // itself, so the kernel is CUDA-graph capturable (every rank issues the same sequence of calls).
 #include "common.cuh"
 #include "peer.cuh"
@@ -24,10 +24,11 @@ peer_allreduce_f64_kernel(double* const* __restrict__ bufs, unsigned* const* __r
 }  // namespace
 
 extern "C" int dcue_peer_allreduce_slot_doubles(void) { return PEER_SLOT_DOUBLES; }
+extern "C" long dcue_peer_allreduce_buffer_doubles(void) { return 2L * PEER_MAX_WORLD * PEER_SLOT_DOUBLES; }
 
 extern "C" int dcue_peer_allreduce_f64(const void* peer_bufs_dev, const void* peer_signals_dev, void* counter, int rank, int world,
                                        double* inout, int n, void* stream) {
-    DCUE_CHECK_ARG(peer_bufs_dev && peer_signals_dev && counter && inout && world >= 1 && world <= 64 && rank >= 0 && rank < world);
+    DCUE_CHECK_ARG(peer_bufs_dev && peer_signals_dev && counter && inout && world >= 1 && world <= PEER_MAX_WORLD && rank >= 0 && rank < world);
     DCUE_CHECK_ARG(n >= 0 && n <= PEER_SLOT_DOUBLES);
     if (n == 0) return 0;
     peer_allreduce_f64_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((double* const*)peer_bufs_dev, (unsigned* const*)peer_signals_dev,

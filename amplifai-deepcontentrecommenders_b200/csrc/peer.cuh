@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 constexpr int PEER_SLOT_DOUBLES = 512;
+constexpr int PEER_MAX_WORLD = 16;                // source slots per call parity in every rank's buffer
 constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;   // 20 s
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -26,7 +27,7 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
 }
 
 struct PeerCtx {
-    double* const* bufs;       // device array of `world` pointers to the symmetric buffers (2 slots of PEER_SLOT_DOUBLES)
+    double* const* bufs;       // device array of `world` pointers to the symmetric buffers: [2 parities][PEER_MAX_WORLD][PEER_SLOT_DOUBLES]
     unsigned* const* sigs;     // device array of `world` pointers to the signal pads
     unsigned* counter;         // [0] call counter of this rank, [1] time-out flag
     int rank, world;
@@ -34,18 +35,25 @@ struct PeerCtx {
 
 // All-reduce (SUM, rank order -> bit-identical on every rank) of vec[0, n) held by ONE thread block (shared or global
 // memory, visible to all its threads); every thread of the block must call this.  `ep_sh` is a shared scratch word.
+// PUSH protocol: every rank stores its vector into slot [parity][rank] of EVERY rank's buffer (fire-and-forget NVLink writes),
+// fences, raises its flag in every peer (release.sys) and waits for the peers' flags; the sum then reads only LOCAL memory.
+// (The first version pulled: flag, then NVLink reads of the peers' slots -- one more round trip on the critical path of each
+// of the 11 BatchNorm exchanges of a step.)  Slots are double buffered by call parity: a rank can only reach call e+2 (which
+// rewrites parity e&1 in its peers) after every peer has signalled e+1, i.e. has finished call e.
 __device__ __forceinline__ void peer_allreduce_block(const PeerCtx& pc, double* vec, int n, unsigned* ep_sh) {
     __syncthreads();
     if (threadIdx.x == 0) *ep_sh = ++(*pc.counter);
     __syncthreads();
     const unsigned e = *ep_sh;
-    const int slot = (int)(e & 1u) * PEER_SLOT_DOUBLES;
-    double* mine = pc.bufs[pc.rank] + slot;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) mine[i] = vec[i];
+    const long slot = ((long)(e & 1u) * PEER_MAX_WORLD + pc.rank) * PEER_SLOT_DOUBLES;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = vec[i];
+        for (int r = 0; r < pc.world; ++r) pc.bufs[r][slot + i] = v;
+    }
     __threadfence_system();
     __syncthreads();
     if ((int)threadIdx.x < pc.world) {
-        st_release_sys(pc.sigs[threadIdx.x] + pc.rank, e);                 // tell peer `threadIdx.x` that my slot is ready
+        st_release_sys(pc.sigs[threadIdx.x] + pc.rank, e);                 // tell peer `threadIdx.x` that my vector has landed
         const unsigned* my_pad = pc.sigs[pc.rank] + threadIdx.x;
         // peer's call e (or a later one) is published.  The wait is bounded: a rank that died or raised would otherwise hang
         // every other GPU inside this kernel; after PEER_TIMEOUT_NS the flag counter[1] is raised (the result is then invalid)
@@ -61,14 +69,13 @@ __device__ __forceinline__ void peer_allreduce_block(const PeerCtx& pc, double* 
         }
     }
     __syncthreads();
-    // all ranks' values in flight at once, then added in rank order (the plain loop made every NVLink read wait for the
-    // previous add: 8 serial round trips = +12 us per BatchNorm finaliser on 8 GPUs, round-2 timeline)
+    const double* mine = pc.bufs[pc.rank] + (long)(e & 1u) * PEER_MAX_WORLD * PEER_SLOT_DOUBLES;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double s = 0.0;
         for (int r0 = 0; r0 < pc.world; r0 += 8) {
             double v[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = r0 + q < pc.world ? ld_relaxed_sys_f64(pc.bufs[r0 + q] + slot + i) : 0.0;
+            for (int q = 0; q < 8; ++q) v[q] = r0 + q < pc.world ? ld_relaxed_sys_f64(mine + (long)(r0 + q) * PEER_SLOT_DOUBLES + i) : 0.0;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
                 if (r0 + q < pc.world) s += v[q];

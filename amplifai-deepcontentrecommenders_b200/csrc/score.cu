@@ -313,3 +313,49 @@ extern "C" int dcue_score_hinge_fwdbwd(const float* u, const float* feats, int B
     return launch<2>(u, feats, nullptr, B, N, F, eps, margin, 1.f / (float)batch_total, scores, loss_rows, du,
                      dfeats, (cudaStream_t)stream);
 }
+
+// ------------------------------------------------------------------ loss scalar + gradient rescale (no ATen glue in the step)
+namespace {
+// loss = sum_b loss_rows[b] / batch_total, one block, fixed order (deterministic)
+__global__ void __launch_bounds__(256) loss_mean_kernel(const float* __restrict__ rows, int B, float inv_total, float* __restrict__ out) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < B; i += 256) s += (double)rows[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = (float)(red[0] * (double)inv_total);
+}
+// a_out = a * g, b_out = b * g with g a device scalar (the incoming gradient of the loss): both in one launch
+__global__ void __launch_bounds__(256) scale_pair_kernel(const float* __restrict__ a, long na, const float* __restrict__ b, long nb,
+                                                         const float* __restrict__ g, float* __restrict__ ao, float* __restrict__ bo) {
+    const float gs = __ldg(g);
+    const long n = na + nb;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        if (i < na) ao[i] = a[i] * gs;
+        else bo[i - na] = b[i - na] * gs;
+    }
+}
+}  // namespace
+
+extern "C" int dcue_loss_mean(const float* loss_rows, int B, int batch_total, float* loss_out, void* stream) {
+    DCUE_CHECK_ARG(loss_rows && loss_out && B >= 0 && batch_total > 0);
+    loss_mean_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(loss_rows, B, 1.f / (float)batch_total, loss_out);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dcue_scale_pair(const float* a, long na, const float* b, long nb, const float* g_dev, float* a_out, float* b_out,
+                               void* stream) {
+    DCUE_CHECK_ARG(g_dev && na >= 0 && nb >= 0 && (na == 0 || (a && a_out)) && (nb == 0 || (b && b_out)));
+    const long n = na + nb;
+    if (n == 0) return 0;
+    long blocks = (n + 255) / 256;
+    if (blocks > 148L * 8) blocks = 148L * 8;
+    scale_pair_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(a, na, b, nb, g_dev, a_out, b_out);
+    DCUE_LAUNCH_CHECK();
+    return 0;
+}

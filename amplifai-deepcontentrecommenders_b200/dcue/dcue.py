@@ -134,8 +134,8 @@ class DCUENet(nn.Module):
         feats = self._indexed_feats(pool, pos_idx.to(pool.device), neg_idx.to(pool.device), pos_off, neg_off, frames)
         u_featvects = self._join_user_tower(u_featvects, side)
         total = B if batch_total is None else batch_total
-        loss_rows, _ = ops.HingeScoreFn.apply(u_featvects, feats, B, N, margin, total)
-        return loss_rows.sum() / total
+        loss, _ = ops.HingeLossFn.apply(u_featvects, feats, B, N, margin, total)
+        return loss
 
     def raise_if_index_error(self):
         self.user_embd.raise_if_index_error()
@@ -161,8 +161,7 @@ class DCUENet(nn.Module):
         feats = self.conv.forward_posneg(pos, neg)
         u_featvects = self._join_user_tower(u_featvects, side)
         total = B if batch_total is None else batch_total
-        loss_rows, scores = ops.HingeScoreFn.apply(u_featvects, feats, B, N, margin, total)
-        loss = loss_rows.sum() / total
+        loss, scores = ops.HingeLossFn.apply(u_featvects, feats, B, N, margin, total)
         if return_all:
             return loss, scores, u_featvects, feats[:B], feats[B:].view(B, N, self.feature_dim)
         return loss

@@ -702,3 +702,35 @@ class HingeScoreFn(torch.autograd.Function):
         du, df = ctx.saved_tensors
         scale = g_rows.reshape(-1)[:1] * float(ctx.batch_total)
         return du * scale, df * scale, None, None, None, None
+
+
+class HingeLossFn(torch.autograd.Function):
+    """HingeScoreFn + the mean over the (global) batch as ONE differentiable op: forward = the fused score/hinge kernel and a
+    one-block sum (scalar loss on the device), backward = one kernel scaling the stored gradients by the incoming gradient.
+    Replaces `loss_rows.sum() / total` and its autograd chain (8 ATen launches per step in the round-2 timeline).
+    Returns (loss [], scores [B, N])."""
+
+    @staticmethod
+    def forward(ctx, u_f, feats, B, N, margin, batch_total):
+        u_f, feats = u_f.contiguous(), feats.contiguous()
+        F = u_f.shape[1]
+        dev = u_f.device
+        scores = torch.empty(B, N, dtype=torch.float32, device=dev)
+        loss_rows = torch.empty(B, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        du, df = torch.empty_like(u_f), torch.empty_like(feats)
+        L.call("dcue_score_hinge_fwdbwd", u_f.data_ptr(), feats.data_ptr(), B, N, F, COS_EPS, float(margin), int(batch_total),
+               scores.data_ptr(), loss_rows.data_ptr(), du.data_ptr(), df.data_ptr(), L.stream())
+        L.call("dcue_loss_mean", loss_rows.data_ptr(), B, int(batch_total), loss.data_ptr(), L.stream())
+        ctx.save_for_backward(du, df)
+        ctx.mark_non_differentiable(scores)
+        return loss, scores
+
+    @staticmethod
+    def backward(ctx, g, _g_scores):
+        du, df = ctx.saved_tensors          # d(loss)/d(u_f), d(loss)/d(feats) for an incoming gradient of 1
+        g = g.to(torch.float32).contiguous()
+        gu, gf = torch.empty_like(du), torch.empty_like(df)
+        L.call("dcue_scale_pair", du.data_ptr(), du.numel(), df.data_ptr(), df.numel(), g.data_ptr(), gu.data_ptr(), gf.data_ptr(),
+               L.stream())
+        return gu, gf, None, None, None, None

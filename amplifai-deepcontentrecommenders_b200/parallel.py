@@ -51,7 +51,8 @@ class PeerAllReduce:
         self.L = L
         self.slot = L.lib().dcue_peer_allreduce_slot_doubles()
         pg = group if group is not None else dist.group.WORLD
-        self.buf = symm.empty(2 * self.slot, dtype=torch.float64, device=device)
+        self.buf = symm.empty(int(L.lib().dcue_peer_allreduce_buffer_doubles()), dtype=torch.float64, device=device)
+        self.buf.zero_()
         self.hdl = symm.rendezvous(self.buf, pg.group_name)
         self.counter = torch.zeros(2, dtype=torch.int32, device=device)     # [call counter, time-out flag]
         self.rank, self.world = self.hdl.rank, self.hdl.world_size
@@ -171,6 +172,8 @@ class DataParallelDCUE:
                 print("DataParallelDCUE: peer all-reduce unavailable (%s); using NCCL for the BatchNorm statistics" % exc)
         self._xch = None          # PeerExchange for the table-gradient rows, created on first use (needs the batch size)
         self._gred = None         # PeerGradReduce for the flat gradient bucket
+        # one-shot peer all-reduce of the flat gradient bucket: +1.1 % step rate on 2 GPUs, equal to NCCL's LL ring + cat/copy
+        # on 8 (2.770 vs 2.780 ms per step, round 2); DCUE_DP_PEER_GRADS=0 selects NCCL
         if self._peer is not None and os.environ.get("DCUE_DP_PEER_GRADS", "1") != "0":
             try:
                 self._gred = PeerGradReduce(group, params[0].device)

@@ -317,6 +317,13 @@ int dcue_score_hinge_fwdbwd(const float* u, const float* feats, int B, int N, in
                             float margin, int batch_total, float* scores, float* loss_rows, float* du,
                             float* dfeats, void* stream);
 
+/* The scalar loss of DCUE._loss_func from the kernel's per-row sums: loss_out[0] = sum_b loss_rows[b] / batch_total (one block,
+ * fixed order), and the backward's rescale by the incoming gradient g (a DEVICE scalar): a_out = a * g, b_out = b * g in one
+ * launch -- together they replace the ~8 ATen kernels of `loss_rows.sum() / B` and its autograd (dcrecommend/nn/dcue.py:167-170,208). */
+int dcue_loss_mean(const float* loss_rows, int B, int batch_total, float* loss_out, void* stream);
+int dcue_scale_pair(const float* a, long na, const float* b, long nb, const float* g_dev, float* a_out, float* b_out,
+                    void* stream);
+
 /* ---------------------------------------------------------------- optimizer ---------------- */
 
 /* torch.optim.Adam.step() for ALL parameter tensors in one launch (dcrecommend/nn/dcue.py:143-147, :209).
@@ -349,6 +356,7 @@ int dcue_ranger_multi_step(const void* table_dev, const int* blk_first_dev, int 
 int dcue_peer_allreduce_f64(const void* peer_bufs_dev, const void* peer_signals_dev, void* counter, int rank, int world,
                             double* inout, int n, void* stream);
 int dcue_peer_allreduce_slot_doubles(void);
+long dcue_peer_allreduce_buffer_doubles(void);   /* doubles every rank's symmetric buffer must hold (zero-initialised) */
 
 /* User table over NVLink peer memory (BASELINE cfg4: table row-sharded over the GPUs; cfg3: exchange of the table-gradient
  * rows).  Every rank owns a zero-initialised symmetric "exchange" buffer of dcue_peer_exchange_bytes(capacity, E) bytes

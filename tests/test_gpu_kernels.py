@@ -457,7 +457,8 @@ def test_peer_allreduce_single_rank_plumbing():
     """dcue_peer_allreduce_f64 with world = 1 (own buffer as the only peer): identity, the call counter advances and the
     two slots alternate -- the multi-rank behaviour is covered on real GPUs by tools/dp_parity.py (torchrun)."""
     slot = L.lib().dcue_peer_allreduce_slot_doubles()
-    buf = torch.zeros(2 * slot, dtype=torch.float64, device=DEV)
+    nbuf = int(L.lib().dcue_peer_allreduce_buffer_doubles())      # [2 parities][max world][slot]
+    buf = torch.zeros(nbuf, dtype=torch.float64, device=DEV)
     sig = torch.zeros(64, dtype=torch.int32, device=DEV)
     counter = torch.zeros(1, dtype=torch.int32, device=DEV)
     bufs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=DEV)
@@ -468,7 +469,8 @@ def test_peer_allreduce_single_rank_plumbing():
         L.call("dcue_peer_allreduce_f64", bufs.data_ptr(), sigs.data_ptr(), counter.data_ptr(), 0, 1, x.data_ptr(), 256, L.stream())
         torch.cuda.synchronize()
         assert torch.equal(x, ref) and counter.item() == call and sig[0].item() == call
-        assert torch.equal(buf[(call & 1) * slot:(call & 1) * slot + 256], ref)
+        par = (call & 1) * (nbuf // 2)                                # rank 0's slot of this call's parity
+        assert torch.equal(buf[par:par + 256], ref)
 
 
 def test_fused_adam_matches_torch_adam():
