@@ -813,3 +813,23 @@ def test_graphed_step_leaves_batchnorm_buffers_alone():
     torch.cuda.synchronize()
     assert int(net.conv.bn1.num_batches_tracked) == int(params["conv.bn1.num_batches_tracked"]) + 1
     step.release()
+
+
+@pytest.mark.gpu
+def test_fused_loss_scalar_and_gradient_rescale():
+    """ops.HingeLossFn (score/hinge kernel + dcue_loss_mean, backward = dcue_scale_pair) against HingeScoreFn + torch's
+    sum / division, for an incoming gradient other than 1 and for a data-parallel batch_total > B."""
+    g = torch.Generator().manual_seed(77)
+    B, N, Fd = 37, 20, 100
+    u, f = torch.randn(B, Fd, generator=g), torch.randn(B * (N + 1), Fd, generator=g)
+    for total, gin in ((B, 1.0), (4 * B, 0.37)):
+        u1, f1 = u.to(DEV).requires_grad_(True), f.to(DEV).requires_grad_(True)
+        rows, s1 = ops.HingeScoreFn.apply(u1, f1, B, N, 0.2, total)
+        l1 = rows.sum() / total
+        (l1 * gin).backward()
+        u2, f2 = u.to(DEV).requires_grad_(True), f.to(DEV).requires_grad_(True)
+        l2, s2 = ops.HingeLossFn.apply(u2, f2, B, N, 0.2, total)
+        (l2 * gin).backward()
+        assert torch.equal(s1, s2)
+        assert abs(l1.item() - l2.item()) <= 2e-6 * abs(l1.item())
+        assert relerr(u2.grad, u1.grad) < 1e-6 and relerr(f2.grad, f1.grad) < 1e-6

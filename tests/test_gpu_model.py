@@ -229,3 +229,33 @@ def test_cuda_graph_step_equals_eager():
         assert torch.equal(p, q), k
     for (k, p), (_, q) in zip(eager.named_buffers(), graphed.named_buffers()):
         assert torch.equal(p, q), k
+
+
+@pytest.mark.gpu
+def test_two_graphs_and_eager_steps_share_one_model():
+    """Graph-owned gradients: two GraphedTrainSteps over ONE model (different batch contents), replayed alternately with
+    an eager step in between, must leave the model exactly where a purely eager run leaves it -- every replay re-binds
+    p.grad to its own graph's tensors, and zero_grad(set_to_none=False) + backward accumulate into whichever is bound."""
+    mt, B, N, U = "truedcuemel1dbn", 6, 3, 40
+    params = fixtures.make_params(mt, seed=0, user_count=U)
+    batches = [tuple(t.to(DEV) for t in fixtures.make_inputs(B, N, U, seed=30 + i)) for i in range(5)]
+    eager, graphed = _build(mt, U, params).train(), _build(mt, U, params).train()
+    oe = torch.optim.Adam(eager.parameters(), 1e-3)
+    og = torch.optim.Adam(graphed.parameters(), 1e-3)
+    ga = pkg.GraphedTrainStep(graphed, 0.2, *batches[0])
+    gb = pkg.GraphedTrainStep(graphed, 0.2, *batches[1])
+    for i, (u, pos, neg) in enumerate(batches):
+        eager.zero_grad(set_to_none=True)
+        le = eager.hinge_loss_step(u, pos, neg, 0.2)
+        le.backward()
+        oe.step()
+        if i == 2:                                   # an eager step on the graphed model, gradients kept allocated
+            og.zero_grad(set_to_none=False)
+            lg = graphed.hinge_loss_step(u, pos, neg, 0.2)
+            lg.backward()
+        else:
+            lg = (ga if i % 2 == 0 else gb)(u, pos, neg)
+        og.step()
+        assert le.item() == lg.item(), i
+    for (k, p), (_, q) in zip(eager.named_parameters(), graphed.named_parameters()):
+        assert torch.equal(p, q), k
