@@ -840,6 +840,14 @@ def run_ours(args):
                          % (world, args.eval_user_tile) if world > 1 else "single GPU: no merge",
                 "workload": "cfg5: %d users x %d songs, fp16 factors, fp32 accumulate, songs sharded over %d GPU(s), merged top-k"
                             % (ev_users, ev_items, world)}
+    # The scorer reads every fp32 score from tensor memory exactly once; TMEM reads run at 64 B/clk/SM (tcgen05.ld, measured in
+    # B300_MICROARCH.md), which for a 128 x 256 tile is 2 048 clocks against 900 for its MMAs: that, not the tensor pipe, is the
+    # roofline of this formulation.  All-pairs bytes / (time x SMs of all ranks x SM clock).
+    sm_clk = ((clocks or {}).get("sm_mhz") or 1965) * 1e6
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    tmem_bpc = 4.0 * ev_users * ev_items / (ems.item() * 1e-3) / (n_sm * world) / sm_clk
+    eval_out["roofline"] = {"bound": "tmem_read", "achieved": tmem_bpc, "peak": 64.0, "unit": "B/clk/SM", "frac": tmem_bpc / 64.0,
+                            "peak_source": "B300_MICROARCH.md (LDTM throughput 64 B/cyc/SM)", "algorithmic": "4 B per (user, song) score"}
     # 2-D variant at N >= 4: 2 song shards x N/2 user groups (longer song streams per work item; every rank holds half the songs)
     if world >= 4 and not args.no_eval_hybrid:
         lay = par.eval_layout(2)
