@@ -292,27 +292,52 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, i
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 
-// tile [64 x TKC] of operand X(i, r) = base[i*s_i + r*s_r] at (i0, r0); rows i >= I and columns r >= rend are zero-filled
+// This thread's four 16-byte chunks of a [64 x TKC] operand tile X(i, r) = base[i*s_i + r*s_r]: everything that does not depend
+// on the k-chunk is computed ONCE (the first version redid the index arithmetic for every chunk: 25 instructions per cp.async,
+// as many as the tile's MMAs).  Rows i >= I and columns r >= rend are zero-filled (cp.async src-size).
 template <bool RC>
-__device__ __forceinline__ void cp_load_tile(float* sm, const float* base, long s_i, long s_r, int i0, int I, int r0, int rend, int tid) {
+struct TileLoader {
+    const float* g[4];     // global address of the chunk at r0 = 0 (any valid address when the chunk is out of range)
+    int lim[4];            // RC: the chunk's offset lr along r, or INT_MAX/2 when its row is out of range
+                           // !RC: bytes to copy (0..16, fixed by the i-range), the row offset lr is it * 8 + tid / 16
+    uint32_t soff[4];      // float offset inside the operand's shared-memory tile
+    int lr0;
+    __device__ __forceinline__ void init(const float* base, long s_i, long s_r, int i0, int I, int tid) {
 #pragma unroll
-    for (int it = 0; it < (64 * TKC / 4) / CP_THREADS; ++it) {
-        const int c = tid + it * CP_THREADS;                 // 512 16-byte chunks per tile
-        if (RC) {
-            const int li = c / (TKC / 4), lr = (c % (TKC / 4)) * 4;
-            const int gi = i0 + li, gr = r0 + lr;
-            const int bytes = (gi < I && gr < rend) ? min(16, (rend - gr) * 4) : 0;
-            const float* src = bytes ? base + gi * s_i + gr : base;
-            cp_async16(sm + li * (TKC + 4) + lr, src, bytes);
-        } else {
-            const int lr = c >> 4, li = (c & 15) * 4;        // 16 chunks per r-row of 64 i
-            const int gi = i0 + li, gr = r0 + lr;
-            const int bytes = (gr < rend && gi < I) ? min(16, (I - gi) * 4) : 0;
-            const float* src = bytes ? base + gr * s_r + gi : base;
-            cp_async16(sm + lr * 72 + li, src, bytes);
+        for (int it = 0; it < 4; ++it) {
+            const int c = tid + it * CP_THREADS;
+            if (RC) {
+                const int li = c / (TKC / 4), lr = (c % (TKC / 4)) * 4;
+                const int gi = i0 + li;
+                g[it] = gi < I ? base + gi * s_i + lr : base;
+                lim[it] = gi < I ? lr : (1 << 29);
+                soff[it] = (uint32_t)(li * (TKC + 4) + lr);
+            } else {
+                const int lr = c >> 4, li = (c & 15) * 4;
+                const int gi = i0 + li;
+                const int nb = min(16, (I - gi) * 4);
+                g[it] = nb > 0 ? base + lr * s_r + gi : base;
+                lim[it] = nb > 0 ? nb : 0;
+                soff[it] = (uint32_t)(lr * 72 + li);
+            }
+        }
+        lr0 = tid >> 4;
+    }
+    // chunk starting at r0 (rem = rend - r0 > 0 columns left) into the stage's tile `sm`
+    __device__ __forceinline__ void issue(float* sm, long s_r, int r0, int rem) const {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            if (RC) {
+                int bytes = (rem - lim[it]) * 4;
+                bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+                cp_async16(sm + soff[it], bytes ? g[it] + r0 : g[it], bytes);
+            } else {
+                const int bytes = (lr0 + it * (CP_THREADS / 16)) < rem ? lim[it] : 0;
+                cp_async16(sm + soff[it], bytes ? g[it] + r0 * s_r : g[it], bytes);
+            }
         }
     }
-}
+};
 
 template <bool SPLIT, bool ARC, bool BRC>
 __global__ void __launch_bounds__(CP_THREADS) gemm_cpasync_kernel(GemmP p) {
@@ -335,11 +360,16 @@ __global__ void __launch_bounds__(CP_THREADS) gemm_cpasync_kernel(GemmP p) {
             for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
     float rs[2][2] = {{0.f, 0.f}, {0.f, 0.f}};               // row sums of A: rows (mi, g) and (mi, g + 8)
 
+    TileLoader<ARC> la;
+    TileLoader<BRC> lb;
+    la.init(p.A, p.sAi, p.sAr, i0, p.I, tid);
+    lb.init(p.B, p.sBj, p.sBr, j0, p.J, tid);
     auto issue = [&](int kc) {
         if (kc < nk) {
             float* sa = cps + (size_t)(kc % CST) * 2 * CP_OP_FLOATS;
-            cp_load_tile<ARC>(sa, p.A, p.sAi, p.sAr, i0, p.I, rbeg + kc * TKC, rend, tid);
-            cp_load_tile<BRC>(sa + CP_OP_FLOATS, p.B, p.sBj, p.sBr, j0, p.J, rbeg + kc * TKC, rend, tid);
+            const int r0 = rbeg + kc * TKC;
+            la.issue(sa, p.sAr, r0, rend - r0);
+            lb.issue(sa + CP_OP_FLOATS, p.sBr, r0, rend - r0);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");     // one group per k-chunk, empty ones included
     };
@@ -391,27 +421,49 @@ __global__ void __launch_bounds__(CP_THREADS) gemm_cpasync_kernel(GemmP p) {
         }
     }
     float* C = p.C + (long)blockIdx.z * p.split_stride;
+    // Epilogue (round 2: the per-element bias / relu / mask / bounds tests of the first version were 800 of the kernel's ~1 900
+    // executed instructions): one warp-uniform mode switch, the bias pair of every column loaded once, 8-byte stores.
+    const int mode = p.splits > 1 ? 0 : (p.mask ? 2 : ((p.bias || p.relu) ? 1 : 0));
+    const bool st2 = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 7) == 0);
+    float b0[4] = {0.f, 0.f, 0.f, 0.f}, b1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (mode == 1 && p.bias) {
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int gj = j0 + wn * 32 + ni * 8 + 2 * ft;
+            if (gj < p.J) b0[ni] = p.bias[gj];
+            if (gj + 1 < p.J) b1[ni] = p.bias[gj + 1];
+        }
+    }
+    const bool relu = mode == 1 && p.relu;
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni)
+        for (int h = 0; h < 2; ++h) {
+            const int gi = i0 + wm * 32 + mi * 16 + fg + 8 * h;
+            if (gi >= p.I) continue;
+            float* crow = C + gi * p.ldc;
+            const float* mrow = mode == 2 ? p.mask + gi * p.ldmask : nullptr;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int gi = i0 + wm * 32 + mi * 16 + fg + 8 * h;
+            for (int ni = 0; ni < 4; ++ni) {
                 const int gj = j0 + wn * 32 + ni * 8 + 2 * ft;
-                if (gi >= p.I) continue;
-#pragma unroll
-                for (int y = 0; y < 2; ++y) {
-                    if (gj + y >= p.J) continue;
-                    float v = acc[mi][ni][2 * h + y];
-                    if (p.splits == 1) {
-                        if (p.bias) v += p.bias[gj + y];
-                        if (p.relu) v = v < 0.f ? 0.f : v;  // NaN-propagating (an out-of-range user row must stay loud)
-                        if (p.mask) v = p.mask[gi * p.ldmask + gj + y] > 0.f ? v : 0.f;
-                    }
-                    C[gi * p.ldc + gj + y] = v;
+                if (gj >= p.J) continue;
+                float v0 = acc[mi][ni][2 * h] + b0[ni], v1 = acc[mi][ni][2 * h + 1] + b1[ni];
+                if (relu) {                              // NaN-propagating (an out-of-range user row must stay loud)
+                    v0 = v0 < 0.f ? 0.f : v0;
+                    v1 = v1 < 0.f ? 0.f : v1;
+                }
+                const bool two = gj + 1 < p.J;
+                if (mode == 2) {
+                    v0 = mrow[gj] > 0.f ? v0 : 0.f;
+                    if (two) v1 = mrow[gj + 1] > 0.f ? v1 : 0.f;
+                }
+                if (two && st2) *reinterpret_cast<float2*>(crow + gj) = make_float2(v0, v1);
+                else {
+                    crow[gj] = v0;
+                    if (two) crow[gj + 1] = v1;
                 }
             }
+        }
     if (p.rowsum != nullptr) {
         // bias gradient of the weight-gradient form: sum over r of A(i, r), this block's r range -> rowsum[z][i]
 #pragma unroll
