@@ -457,6 +457,29 @@ __global__ void time_mean_kernel(const float* __restrict__ z, int S, int P, int 
     tp[s * ldtp + c] = scale ? fmaf(a, scale[c], shift[c]) : a;
 }
 
+// the same, four channels per thread (16-byte accesses; the scalar kernel spent 13 us on 8.6 MB at S = 21 504)
+__global__ void __launch_bounds__(256)
+time_mean4_kernel(const float* __restrict__ z, int S, int P, int C, const float* __restrict__ scale,
+                  const float* __restrict__ shift, float* __restrict__ tp, int ldtp) {
+    const int C4 = C >> 2;
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= (long)S * C4) return;
+    const int c = (int)(i % C4) * 4;
+    const long s = i / C4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < P; ++p) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(z + (s * P + p) * C + c));
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    const float inv = (float)P;
+    a.x /= inv; a.y /= inv; a.z /= inv; a.w /= inv;          // same rounding as the scalar kernel (a / P)
+    if (scale) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c)), sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+        a.x = fmaf(a.x, sc.x, sh.x); a.y = fmaf(a.y, sc.y, sh.y); a.z = fmaf(a.z, sc.z, sh.z); a.w = fmaf(a.w, sc.w, sh.w);
+    }
+    *reinterpret_cast<float4*>(tp + s * ldtp + c) = a;
+}
+
 // BN backward reductions: per block partial of sum dy, sum dy*xhat  (C <= 128, C % 4 == 0)
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ dtp, int lddtp, const float* __restrict__ z,
@@ -1013,7 +1036,11 @@ extern "C" int dcue_affine_pack(const float* z, int S, int P, int C, const float
     }
     if (tp) {
         DCUE_CHECK_ARG(ldtp >= C);
-        time_mean_kernel<<<ceil_div_i((long)S * C, 256), 256, 0, st>>>(z, S, P, C, scale, shift, tp, ldtp);
+        if ((C & 3) == 0 && (ldtp & 3) == 0 && (((uintptr_t)z | (uintptr_t)tp) & 15) == 0 &&
+            (!scale || (((uintptr_t)scale | (uintptr_t)shift) & 15) == 0))
+            time_mean4_kernel<<<ceil_div_i((long)S * (C / 4), 256), 256, 0, st>>>(z, S, P, C, scale, shift, tp, ldtp);
+        else
+            time_mean_kernel<<<ceil_div_i((long)S * C, 256), 256, 0, st>>>(z, S, P, C, scale, shift, tp, ldtp);
         DCUE_LAUNCH_CHECK();
     }
     return 0;
