@@ -495,7 +495,10 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __rest
 #pragma unroll
         for (int j = 0; j < 4; ++j) { m[j] = mean[cl + j]; rs[j] = rstd[cl + j]; }
         const float invP = 1.f / (float)P;
-        for (long r = (long)blockIdx.x * 8 + rg; r < rows; r += (long)gridDim.x * 8) {
+        // rows are walked from the END: dy was written front to back by the data-gradient kernel just before, so its last
+        // ~100 MB are still in the 126 MB L2 when this sweep starts
+        for (long rf = (long)blockIdx.x * 8 + rg; rf < rows; rf += (long)gridDim.x * 8) {
+            const long r = rows - 1 - rf;
             const float4 g = *reinterpret_cast<const float4*>(dy + r * lddy + cl);
             const float4 zz = *reinterpret_cast<const float4*>(z + r * C + cl);
             float gv[4] = {g.x, g.y, g.z, g.w};
