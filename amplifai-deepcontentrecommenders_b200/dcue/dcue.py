@@ -64,7 +64,10 @@ class DCUENet(nn.Module):
     # stream as well.  Inside a CUDA-graph capture this becomes a parallel branch of the graph.  DCUE_USER_STREAM=0: one stream.
     def _fork_user_tower(self, u):
         if not self.user_embd_on_side_stream(u):
-            return self.user_embd(u), None
+            # one stream: the user tower is evaluated by _join_user_tower, i.e. AFTER the song tower.  Autograd runs the backward
+            # of the later forward op first, so the user tower's backward -- and with it the data-parallel exchange of the table
+            # gradient rows, which then overlaps the whole song-tower backward on a side stream (ops.UserTowerFn) -- comes first
+            return None, None
         cur = torch.cuda.current_stream()
         if self._side_stream is None or self._side_stream.device != cur.device:
             self._side_stream = torch.cuda.Stream(device=cur.device)
@@ -74,8 +77,9 @@ class DCUENet(nn.Module):
             u_f = self.user_embd(u)
         return u_f, side
 
-    @staticmethod
-    def _join_user_tower(u_f, side):
+    def _join_user_tower(self, u_f, side, u):
+        if u_f is None:
+            return self.user_embd(u)
         if side is not None:
             cur = torch.cuda.current_stream()
             cur.wait_stream(side)
@@ -98,11 +102,11 @@ class DCUENet(nn.Module):
         if neg is not None:
             N = neg.shape[1]
             feats = self.conv.forward_posneg(pos, neg)
-            u_featvects = self._join_user_tower(u_featvects, side)
+            u_featvects = self._join_user_tower(u_featvects, side, u)
             scores = ops.ScoreFn.apply(u_featvects, feats, B, N)
             return scores, u_featvects, feats[:B], feats[B:].view(B, N, self.feature_dim)
         pos_featvects = self.conv.forward_posneg(pos, None)
-        u_featvects = self._join_user_tower(u_featvects, side)
+        u_featvects = self._join_user_tower(u_featvects, side, u)
         scores = self.sim(u_featvects, pos_featvects).view(B, 1)
         return scores, u_featvects, pos_featvects, None
 
@@ -122,7 +126,7 @@ class DCUENet(nn.Module):
         u_featvects, side = self._fork_user_tower(u)
         B, N = neg_idx.shape
         feats = self._indexed_feats(pool, pos_idx.to(pool.device), neg_idx.to(pool.device), pos_off, neg_off, frames)
-        u_featvects = self._join_user_tower(u_featvects, side)
+        u_featvects = self._join_user_tower(u_featvects, side, u)
         scores = ops.ScoreFn.apply(u_featvects, feats, B, N)
         return scores, u_featvects, feats[:B], feats[B:].view(B, N, self.feature_dim)
 
@@ -132,7 +136,7 @@ class DCUENet(nn.Module):
         u_featvects, side = self._fork_user_tower(u)
         B, N = neg_idx.shape
         feats = self._indexed_feats(pool, pos_idx.to(pool.device), neg_idx.to(pool.device), pos_off, neg_off, frames)
-        u_featvects = self._join_user_tower(u_featvects, side)
+        u_featvects = self._join_user_tower(u_featvects, side, u)
         total = B if batch_total is None else batch_total
         loss, _ = ops.HingeLossFn.apply(u_featvects, feats, B, N, margin, total)
         return loss
@@ -159,7 +163,7 @@ class DCUENet(nn.Module):
         u_featvects, side = self._fork_user_tower(u)
         B, N = neg.shape[0], neg.shape[1]
         feats = self.conv.forward_posneg(pos, neg)
-        u_featvects = self._join_user_tower(u_featvects, side)
+        u_featvects = self._join_user_tower(u_featvects, side, u)
         total = B if batch_total is None else batch_total
         loss, scores = ops.HingeLossFn.apply(u_featvects, feats, B, N, margin, total)
         if return_all:

@@ -171,6 +171,7 @@ class DataParallelDCUE:
             except Exception as exc:  # noqa: BLE001  (no peer access / symmetric memory unavailable)
                 print("DataParallelDCUE: peer all-reduce unavailable (%s); using NCCL for the BatchNorm statistics" % exc)
         self._xch = None          # PeerExchange for the table-gradient rows, created on first use (needs the batch size)
+        self._xstream, self._xpending = None, None      # side stream of the row exchange and its pending join
         self._gred = None         # PeerGradReduce for the flat gradient bucket
         # one-shot peer all-reduce of the flat gradient bucket: +1.1 % step rate on 2 GPUs, equal to NCCL's LL ring + cat/copy
         # on 8 (2.770 vs 2.780 ms per step, round 2); DCUE_DP_PEER_GRADS=0 selects NCCL
@@ -204,6 +205,24 @@ class DataParallelDCUE:
             self._xch = PeerExchange(self.group, device, B, E)
         return self._xch
 
+    def exchange_stream(self, table):
+        """Side stream for the table-gradient row exchange of this backward pass, or None (exchange on the current stream):
+        DCUE_DP_EXCHANGE_STREAM=0, or autograd is going to ACCUMULATE into an existing table.grad (see ops.UserTowerFn)."""
+        if os.environ.get("DCUE_DP_EXCHANGE_STREAM", "1") == "0" or table.grad is not None:
+            return None
+        if self._xstream is None:
+            self._xstream = torch.cuda.Stream(device=table.device)
+        return self._xstream
+
+    def exchange_pending(self, stream, keep):
+        self._xpending = (stream, keep)      # tensors the side stream still reads stay referenced until the join
+
+    def join_exchange(self):
+        """The current stream waits for the side-stream row exchange of the last backward (no-op when none is pending)."""
+        if self._xpending is not None:
+            torch.cuda.current_stream().wait_stream(self._xpending[0])
+            self._xpending = None
+
     def check_peers(self):
         """Host-side check of the peer kernels' time-out flags (a rank that died would otherwise go unnoticed)."""
         if self._peer is not None:
@@ -223,17 +242,25 @@ class DataParallelDCUE:
     def loss_step(self, u, pos, neg, margin):
         """Local slice of the global batch -> loss contribution whose gradients sum to the global
         gradient.  Returns the local partial loss (sum over ranks == reference loss)."""
+        self.join_exchange()            # a backward whose reduce_gradients() was skipped must not leave the stream dangling
         return self.model.hinge_loss_step(u, pos, neg, margin, batch_total=pos.shape[0] * self.world_size)
 
     def loss_step_indexed(self, u, pool, pos_idx, neg_idx, margin, pos_off=None, neg_off=None, frames=131):
         """loss_step on the index feed (resident song pool)."""
+        self.join_exchange()
         return self.model.hinge_loss_step_indexed(u, pool, pos_idx, neg_idx, margin, pos_off, neg_off, frames,
                                                   batch_total=pos_idx.shape[0] * self.world_size)
 
     def reduce_gradients(self):
-        """One flat SUM all-reduce over all non-BatchNorm gradients."""
+        """One flat SUM all-reduce over all non-BatchNorm gradients (+ the join of the side-stream table-row exchange)."""
         if self.world_size == 1:
             return
+        try:
+            self._reduce_flat()
+        finally:
+            self.join_exchange()        # after the flat bucket has been launched: the two exchanges overlap as well
+
+    def _reduce_flat(self):
         named = [(n, p) for n, p in self.model.named_parameters() if p.grad is not None]
         keep = set(flat_bucket_names(named))
         grads = [p.grad for n, p in named if n in keep]
