@@ -332,7 +332,10 @@ def timeline_leg(step, u, pos, neg, path, rank, steps=4):
         tr = _json.load(open(f.name))
     ks = sorted((e for e in tr["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in e),
                 key=lambda e: e["ts"])
-    starts = [i for i, e in enumerate(ks) if "gather_relu" in e["name"]]
+    # a step starts at the single-pass input kernel (the first launch of the forward); older layouts: the user-tower gather
+    starts = [i for i, e in enumerate(ks) if "center_pack_stats" in e["name"]]
+    if len(starts) < 3:
+        starts = [i for i, e in enumerate(ks) if "gather_relu" in e["name"]]
     if len(starts) < 3:
         return None
     a, b = starts[-2], starts[-1]
