@@ -1,4 +1,4 @@
-"""CPU restatements of two pieces of device-side logic, checked against numpy.  (1) The selection logic of the top-k scorer (csrc/topk.cu):
+"""CPU restatements of pieces of device-side logic, checked against numpy (round-2 additions: sections 3 and 4 below).  (1) The selection logic of the top-k scorer (csrc/topk.cu):
   * the order-preserving float -> uint32 key map and the bit-by-bit radix select of the k-th largest key
     (select_topk_inplace: common bits skipped, `rem` copies of the threshold key kept),
   * the seeding arithmetic of dcue_topk_scores_2pass (r-th best of every s-th tile => about 4k candidates, and how
@@ -111,3 +111,100 @@ def test_unpool_row_mask_bit_trick():
                         want_lo = (0xFFFF if b0 == j else 0) | (0xFFFF0000 if b1 == j else 0)
                         want_hi = (0xFFFF if b2 == j else 0) | (0xFFFF0000 if b3 == j else 0)
                         assert (lo, hi) == (want_lo, want_hi)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# (3) round 2: the cp.async tile loader of the dense-layer GEMM (csrc/linear.cu TileLoader) computes each thread's chunk
+# address / byte count once and derives the per-k-chunk values from (r0, rem = rend - r0) alone; (4) the exchanged-row
+# reduction of the data-parallel table gradient (csrc/peer.cu peer_mark_rows_kernel + peer_scatter_add_rows_kernel) marks
+# the first entry and the entry count of every row with integer atomics, and only first entries sum (in entry order).
+TKC, CP_THREADS = 32, 128
+
+
+def _bytes_reference(rc, tid, it, i0, I, r0, rend):
+    """The first version's per-chunk arithmetic (cp_load_tile): -> (bytes, element offset of the source or None)."""
+    c = tid + it * CP_THREADS
+    if rc:
+        li, lr = c // (TKC // 4), (c % (TKC // 4)) * 4
+        gi, gr = i0 + li, r0 + lr
+        nb = min(16, (rend - gr) * 4) if (gi < I and gr < rend) else 0
+        return nb, ((gi, gr) if nb else None)
+    lr, li = c >> 4, (c & 15) * 4
+    gi, gr = i0 + li, r0 + lr
+    nb = min(16, (I - gi) * 4) if (gr < rend and gi < I) else 0
+    return nb, ((gi, gr) if nb else None)
+
+
+def _bytes_hoisted(rc, tid, it, i0, I, r0, rend):
+    """TileLoader.init + TileLoader.issue."""
+    c = tid + it * CP_THREADS
+    rem = rend - r0
+    if rc:
+        li, lr = c // (TKC // 4), (c % (TKC // 4)) * 4
+        gi = i0 + li
+        lim = lr if gi < I else (1 << 29)
+        nb = max(0, min(16, (rem - lim) * 4))
+        return nb, ((gi, lr + r0) if nb else None)
+    lr, li = c >> 4, (c & 15) * 4
+    gi = i0 + li
+    fixed = max(0, min(16, (I - gi) * 4))
+    lr_issue = (tid >> 4) + it * (CP_THREADS // 16)
+    assert lr_issue == lr
+    nb = fixed if lr_issue < rem else 0
+    return nb, ((gi, lr + r0) if nb else None)
+
+
+def test_gemm_tile_loader_hoisting_is_equivalent():
+    rng = np.random.default_rng(0)
+    cases = [(0, 64, 0, 32), (0, 100, 96, 100), (64, 100, 96, 100), (64, 100, 64, 97), (0, 3, 0, 5), (128, 300, 288, 300)]
+    cases += [(int(64 * rng.integers(0, 6)), int(rng.integers(1, 400)), int(32 * rng.integers(0, 10)), int(rng.integers(1, 330)))
+              for _ in range(60)]
+    for i0, I, r0, rend in cases:
+        if r0 >= rend:
+            continue
+        for rc in (True, False):
+            for tid in range(CP_THREADS):
+                for it in range(4):
+                    assert _bytes_reference(rc, tid, it, i0, I, r0, rend) == _bytes_hoisted(rc, tid, it, i0, I, r0, rend), \
+                        (rc, tid, it, i0, I, r0, rend)
+
+
+def _marked_row_reduction(all_idx, rows, lo, hi):
+    """peer_mark_rows_kernel + peer_scatter_add_rows_kernel on numpy arrays (float32 adds in entry order)."""
+    n = len(all_idx)
+    first = np.zeros(hi - lo, dtype=np.int64)       # n - j of the first entry (atomicMax), 0 = no entry
+    cnt = np.zeros(hi - lo, dtype=np.int64)
+    for j in np.random.default_rng(1).permutation(n):        # any order: max / count do not depend on it
+        r = all_idx[j]
+        if lo <= r < hi:
+            first[r - lo] = max(first[r - lo], n - j)
+            cnt[r - lo] += 1
+    out = np.zeros((hi - lo, rows.shape[1]), dtype=np.float32)
+    for j in range(n):
+        r = all_idx[j]
+        if not (lo <= r < hi) or n - first[r - lo] != j:
+            continue                                           # an earlier entry owns this row
+        acc = np.zeros(rows.shape[1], dtype=np.float32)
+        found = 0
+        for jj in range(j, n):                                 # the kernel scans 32 entries per ballot and stops at `cnt`
+            if all_idx[jj] == r:
+                acc = acc + rows[jj]
+                found += 1
+                if found == cnt[r - lo]:
+                    break
+        out[r - lo] = acc
+    return out
+
+
+def test_marked_row_reduction_equals_ordered_scatter_add():
+    rng = np.random.default_rng(3)
+    for n, U, lo, hi in ((64, 10, 0, 10), (2048, 500, 0, 500), (512, 40, 10, 30), (300, 1000, 0, 1000)):
+        idx = rng.integers(0, U, n)
+        idx[1] = idx[0]
+        idx[n - 1] = idx[0]                                    # a row with entries at both ends
+        rows = rng.standard_normal((n, 12)).astype(np.float32)
+        ref = np.zeros((hi - lo, 12), dtype=np.float32)
+        for j in range(n):                                     # sequential fp32 adds in entry order = the kernel's order
+            if lo <= idx[j] < hi:
+                ref[idx[j] - lo] = ref[idx[j] - lo] + rows[j]
+        assert np.array_equal(_marked_row_reduction(idx, rows, lo, hi), ref)
