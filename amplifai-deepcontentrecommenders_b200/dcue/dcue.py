@@ -77,8 +77,12 @@ class DCUENet(nn.Module):
             u_f = self.user_embd(u)
         return u_f, side
 
-    def _join_user_tower(self, u_f, side, u):
+    def _join_user_tower(self, u_f, side, u, feats=None):
         if u_f is None:
+            # the song tower is already in the autograd graph: the user tower's backward will run before the song tower's
+            # and may overlap it on a side stream (ops.UserTowerFn.backward)
+            if feats is not None and feats.requires_grad and hasattr(self.user_embd, "embeddings"):
+                self.user_embd._overlap_bwd = True
             return self.user_embd(u)
         if side is not None:
             cur = torch.cuda.current_stream()
@@ -102,11 +106,11 @@ class DCUENet(nn.Module):
         if neg is not None:
             N = neg.shape[1]
             feats = self.conv.forward_posneg(pos, neg)
-            u_featvects = self._join_user_tower(u_featvects, side, u)
+            u_featvects = self._join_user_tower(u_featvects, side, u, feats)
             scores = ops.ScoreFn.apply(u_featvects, feats, B, N)
             return scores, u_featvects, feats[:B], feats[B:].view(B, N, self.feature_dim)
         pos_featvects = self.conv.forward_posneg(pos, None)
-        u_featvects = self._join_user_tower(u_featvects, side, u)
+        u_featvects = self._join_user_tower(u_featvects, side, u, pos_featvects)
         scores = self.sim(u_featvects, pos_featvects).view(B, 1)
         return scores, u_featvects, pos_featvects, None
 
@@ -126,7 +130,7 @@ class DCUENet(nn.Module):
         u_featvects, side = self._fork_user_tower(u)
         B, N = neg_idx.shape
         feats = self._indexed_feats(pool, pos_idx.to(pool.device), neg_idx.to(pool.device), pos_off, neg_off, frames)
-        u_featvects = self._join_user_tower(u_featvects, side, u)
+        u_featvects = self._join_user_tower(u_featvects, side, u, feats)
         scores = ops.ScoreFn.apply(u_featvects, feats, B, N)
         return scores, u_featvects, feats[:B], feats[B:].view(B, N, self.feature_dim)
 
@@ -136,7 +140,7 @@ class DCUENet(nn.Module):
         u_featvects, side = self._fork_user_tower(u)
         B, N = neg_idx.shape
         feats = self._indexed_feats(pool, pos_idx.to(pool.device), neg_idx.to(pool.device), pos_off, neg_off, frames)
-        u_featvects = self._join_user_tower(u_featvects, side, u)
+        u_featvects = self._join_user_tower(u_featvects, side, u, feats)
         total = B if batch_total is None else batch_total
         loss, _ = ops.HingeLossFn.apply(u_featvects, feats, B, N, margin, total)
         return loss
@@ -163,7 +167,7 @@ class DCUENet(nn.Module):
         u_featvects, side = self._fork_user_tower(u)
         B, N = neg.shape[0], neg.shape[1]
         feats = self.conv.forward_posneg(pos, neg)
-        u_featvects = self._join_user_tower(u_featvects, side, u)
+        u_featvects = self._join_user_tower(u_featvects, side, u, feats)
         total = B if batch_total is None else batch_total
         loss, scores = ops.HingeLossFn.apply(u_featvects, feats, B, N, margin, total)
         if return_all:

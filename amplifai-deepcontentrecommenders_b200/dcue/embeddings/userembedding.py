@@ -40,8 +40,9 @@ class UserEmbeddings(nn.Module):
         """user_idx: int64 tensor of any shape -> [..., feature_dim].  An out-of-range index (where
         nn.Embedding raises IndexError) yields NaN rows and sets a device flag without a host sync;
         call raise_if_index_error() -- the trainer does, whenever it reads the loss."""
+        overlap, self._overlap_bwd = getattr(self, "_overlap_bwd", False), False     # set by DCUENet for this one call
         return ops.UserTowerFn.apply(user_idx, self.embeddings.weight, self.linear1.weight, self.linear1.bias,
-                                     self.linear2.weight, self.linear2.bias, self._err_flag(), getattr(self, "_dp", None))
+                                     self.linear2.weight, self.linear2.bias, self._err_flag(), getattr(self, "_dp", None), overlap)
 
     def raise_if_index_error(self):
         if self._err is not None and int(self._err.item()):

@@ -11,6 +11,8 @@ import os
 
 import torch
 
+from . import ops
+
 
 class GraphedTrainStep:
     """step = GraphedTrainStep(model, margin, u, pos, neg)   # example batch fixes the shapes
@@ -72,6 +74,7 @@ class GraphedTrainStep:
                 torch._foreach_zero_(self._grads)
             self.loss = self._loss()
             self.loss.backward()
+            ops.join_backward_side()        # every side stream of the backward pass re-joins before the capture ends
             if dp is not None:
                 dp.reduce_gradients()
         if self.owned:

@@ -181,6 +181,33 @@ def _check_input(x, name):
     return x.contiguous()
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# The user tower's backward (gather-side scatter + 4 small GEMMs: 66 us of latency-bound launches) overlaps the first kernels
+# of the song tower's backward on a side stream.  It is forked only when DCUENet evaluated the user tower AFTER a song tower
+# that needs gradients (autograd then runs the user tower's backward first and the song tower's backward -- which joins the
+# stream at its end -- later in the same pass) and when autograd will ADOPT every gradient (all .grad None): an accumulating
+# `grad += g` would run on the main stream without waiting for the side stream.  DCUE_USER_BWD_STREAM=0 disables it.
+_BWD_SIDE = {"stream": None, "pending": None}
+
+
+def _bwd_side_stream(device):
+    st = _BWD_SIDE["stream"]
+    if st is None or st.device != device:
+        st = _BWD_SIDE["stream"] = torch.cuda.Stream(device=device)
+    return st
+
+
+def join_backward_side():
+    """The current stream waits for a user-tower backward that is still running on the side stream (no-op otherwise).
+    Called at the end of SongTowerFn.backward; also by GraphedTrainStep, DataParallelDCUE.reduce_gradients, the fused
+    optimizers and the next forward, so that no consumer can get ahead of it."""
+    pend = _BWD_SIDE["pending"]
+    if pend is not None:
+        _BWD_SIDE["pending"] = None
+        if pend[0].device == torch.cuda.current_stream().device:
+            torch.cuda.current_stream().wait_stream(pend[0])
+
+
 class SongTowerFn(torch.autograd.Function):
     """feats[S,F] = tower(cat(pos, neg))  without materialising the concatenation."""
 
@@ -188,6 +215,7 @@ class SongTowerFn(torch.autograd.Function):
     def forward(ctx, pos, neg, src, mod, training, *params):
         """Dense feed: pos [B,128,L] (+ neg [.., 128, L]).  Index feed: pos = resident pool [n_songs,128,T],
         neg = None, src = (idx int64 [S], off int32 [S] or None, frames, err_flag int32 [1])."""
+        join_backward_side()
         has_bn, res = mod._has_bn, mod._res
         H, F = mod.hidden_size, mod.output_size
         if H != 128:
@@ -498,6 +526,7 @@ class SongTowerFn(torch.autograd.Function):
                 dy = dx
         ctx.ws = None
         _release(ws)
+        join_backward_side()        # the user tower's backward (side stream) ends inside this backward pass
         return (None, None, None, None, None) + tuple(grads.get(n) for n in mod._param_names)
 
 
@@ -505,8 +534,11 @@ class UserTowerFn(torch.autograd.Function):
     """u_f = linear2(relu(linear1(relu(table[idx]))))  (userembedding.py:40-44)."""
 
     @staticmethod
-    def forward(ctx, idx, table, w1, b1, w2, b2, err, dp=None):
+    def forward(ctx, idx, table, w1, b1, w2, b2, err, dp=None, overlap_backward=False):
         ctx.dp = dp
+        ctx.overlap = bool(overlap_backward)
+        ctx.biases = (b1, b2)
+        join_backward_side()
         if not table.is_cuda:
             raise RuntimeError("the DCUE B200 path has no CPU fallback: move the model to a CUDA device")
         if idx.dtype != torch.int64:
@@ -527,6 +559,26 @@ class UserTowerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
+        idx, table, w1, w2, h0, h1 = ctx.saved_tensors
+        fork = (ctx.overlap and table.is_cuda and os.environ.get("DCUE_USER_BWD_STREAM", "1") != "0"
+                and all(t.grad is None for t in (table, w1, w2) + tuple(ctx.biases)))
+        if not fork:
+            return UserTowerFn._backward(ctx, gout)
+        cur = torch.cuda.current_stream()
+        side = _bwd_side_stream(table.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            out = UserTowerFn._backward(ctx, gout)
+        for t in (gout, idx, h0, h1):
+            t.record_stream(side)             # allocated on the main stream, read on the side stream
+        for t in out:
+            if t is not None:
+                t.record_stream(cur)          # produced on the side stream, consumed on the main stream after the join
+        _BWD_SIDE["pending"] = (side, (gout, idx, h0, h1))    # inputs only: a second reference to a gradient makes autograd clone it
+        return out
+
+    @staticmethod
+    def _backward(ctx, gout):
         idx, table, w1, w2, h0, h1 = ctx.saved_tensors
         B, (U, E), F = idx.numel(), table.shape, w2.shape[0]
         dev, st = table.device, L.stream()
@@ -582,7 +634,7 @@ class UserTowerFn(torch.autograd.Function):
             dh0 = torch.empty(B, E, **f32)  # ReLU mask of the gather is applied in the scatter kernel
             L.call("dcue_linear_dgrad", dh1.data_ptr(), E, w1.data_ptr(), B, E, E, None, 0, dh0.data_ptr(), E, st)
             gtable = scatter_rows(idx, dh0, U, mask=h0)     # dense gradient, like nn.Embedding(sparse=False)
-        return None, gtable, gw1, gb1, gw2, gb2, None, None
+        return None, gtable, gw1, gb1, gw2, gb2, None, None, None
 
 
 class UserMLPFn(torch.autograd.Function):

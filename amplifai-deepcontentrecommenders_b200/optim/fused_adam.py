@@ -59,6 +59,8 @@ class FusedAdam(Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        from .. import ops
+        ops.join_backward_side()          # gradients of a backward side stream are complete before they are read
         for gi, group in enumerate(self.param_groups):
             params = [p for p in group["params"] if p.grad is not None]
             if not params:

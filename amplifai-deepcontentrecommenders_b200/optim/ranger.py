@@ -91,6 +91,9 @@ class Ranger(Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
+        if any(p.is_cuda for g in self.param_groups for p in g["params"][:1]):
+            from .. import ops
+            ops.join_backward_side()
         for gi, group in enumerate(self.param_groups):
             beta1, beta2 = group["betas"]
             # parameters of one group may be at different steps (e.g. late-added): bucket by step

@@ -255,6 +255,8 @@ class DataParallelDCUE:
         """One flat SUM all-reduce over all non-BatchNorm gradients (+ the join of the side-stream table-row exchange)."""
         if self.world_size == 1:
             return
+        from . import ops
+        ops.join_backward_side()            # user-tower gradients computed on the backward side stream are in the flat bucket
         try:
             self._reduce_flat()
         finally:
