@@ -204,8 +204,8 @@ def join_backward_side():
     pend = _BWD_SIDE["pending"]
     if pend is not None:
         _BWD_SIDE["pending"] = None
-        if pend[0].device == torch.cuda.current_stream().device:
-            torch.cuda.current_stream().wait_stream(pend[0])
+        # the consumer's stream on the side stream's device (the caller may have another device current)
+        torch.cuda.current_stream(pend[0].device).wait_stream(pend[0])
 
 
 class SongTowerFn(torch.autograd.Function):
